@@ -1,0 +1,286 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: qEI value + gradient evaluations per second.
+
+    python bench.py --gpus N --steps K --warmup W              # the CUDA path
+    python bench.py --impl reference --steps K --warmup W      # the reference op sequence on host cores
+
+Metric (BASELINE.json): (restart x q x MC-sample) acquisition value+gradient evaluations per
+second for qEI at n_train=4096, d=6, q=8, 128 MC samples.  One "step" = one value+gradient
+pass over all of this rank's restarts (S per GPU, weak scaling: restarts are independent
+units) followed by the rank-local arg-min and, for N > 1, the single all-gather that picks
+the global best.  Prints ONE JSON line (rank 0).
+
+  value : inputs (X, z) resident in HBM, timed with CUDA events on the library's stream.
+  e2e   : the same through the host-pointer C-ABI call (maf_acq_value_grad) with pinned host
+          buffers: H2D of X and z, D2H of losses and gradient inside the timed region.
+  roofline : the FP64 tensor-pipe (DMMA) contraction V^T = K10 L0^-T / Kbar = Vbar^T L0^-1;
+          algorithmic flops 2 n^2 q per restart per value+grad, durations from
+          CUDA events around every launch of that kernel.
+  cpu_baseline : the torch-CPU float64 restatement of the reference op sequence (oracle/), timed
+          on this box's host cores on a bounded sample (rank 0, N=1 only).
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(n=4096, d=6, q=8, M=128, S_per_gpu=65536, kernel="matern52", acq="ei", seed=0)
+METRIC = "qEI value+grad evals/sec (restarts x q x MC) @ n=4096,d=6,q=8"
+UNIT = "evals/s"
+
+
+def load_fp64_peak():
+    """FP64 roofline denominator.  MEASURED_PEAKS.json (driver-written) has only HBM and bf16
+    entries, so the FP64 figure is this repo's own cuBLAS DGEMM measurement on the same pool
+    (scripts/microbench_fp64.cu -> profiles/fp64_peaks.json); else nominal."""
+    p = os.path.join(ROOT, "profiles", "fp64_peaks.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["cublas_dgemm_tflops"]), "own cuBLAS DGEMM measurement (profiles/fp64_peaks.json); MEASURED_PEAKS.json has no fp64 entry"
+        except Exception:
+            pass
+    return 37.0, "nominal B200 fp64 (no measurement found)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons during the timed region (nvidia-smi, 200 ms)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop_evt = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                self.samples.append(float(f[0]))
+                self.max_mhz = float(f[1])
+                for nm, v in zip(names, f[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def make_inputs(S, w=WORKLOAD):
+    from maximizingacquisitionfunctions_b200.synthetic import synthetic_inputs
+    return synthetic_inputs(w["n"], w["d"], w["q"], S, w["M"], seed=w["seed"])
+
+
+def oracle_state(w, X0, y0):
+    """CPU-baseline legs only: the oracle's view of the same model (the one place bench.py touches oracle/)."""
+    from oracle import maf_oracle as orc
+    gp = orc.GP(log_lenscales=math.log(math.sqrt(w["d"]) / 4), log_amplitude=0.0, log_noise=math.log(1e-3),
+                mean=0.0, kernel_id=w["kernel"], jitter=1e-6)
+    return orc, orc.prepare_train(gp, X0, y0), orc.Acq(w["acq"])
+
+
+def cpu_reference_rate(w, threads, target_s=12.0, s_first=256):
+    """evals/s of the torch-CPU restatement of the reference op sequence (value + autograd
+    gradient, 4096-restart shards like sharded_fn) on a bounded sample of the same workload."""
+    import torch
+    torch.set_num_threads(threads)
+    X0, y0, X, z = make_inputs(max(s_first, 4096), w)
+    orc, ts, acq = oracle_state(w, X0, y0)
+    t0 = time.perf_counter()
+    orc.value_and_grad(ts, acq, X[:s_first], z)
+    t1 = time.perf_counter() - t0
+    S = int(min(4096, max(s_first, s_first * target_s / max(t1, 1e-3))))
+    S = max(s_first, S // s_first * s_first)
+    t0 = time.perf_counter()
+    orc.value_and_grad(ts, acq, X[:S], z)
+    dt = time.perf_counter() - t0
+    return S * w["q"] * w["M"] / dt, S, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port: TensorFlow 1.x cannot be installed)."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    import torch
+    w = WORKLOAD
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    S = 512
+    X0, y0, X, z = make_inputs(S, w)
+    orc, ts, acq = oracle_state(w, X0, y0)
+    for _ in range(args.warmup):
+        orc.value_and_grad(ts, acq, X[:64], z)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.value_and_grad(ts, acq, X, z)
+    dt = time.perf_counter() - t0
+    val = args.steps * S * w["q"] * w["M"] / dt
+    sample = "S=%d restarts per step (of %d), n=%d,d=%d,q=%d,M=%d, value+autograd gradient" % (
+        S, w["S_per_gpu"], w["n"], w["d"], w["q"], w["M"])
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "qEI n=4096 d=6 q=8 M=128 matern52 (torch-CPU restatement of the reference TF op sequence; TF 1.x not installable)",
+                   "S_per_step": S},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", type=str, default="b200", choices=["b200", "reference"])
+    ap.add_argument("--restarts", type=int, default=WORKLOAD["S_per_gpu"], help="restarts per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    from maximizingacquisitionfunctions_b200 import dist as mdist
+    from maximizingacquisitionfunctions_b200.engine import Engine, acq_params
+
+    rank, ws, local = mdist.world()
+    if ws > 1:
+        mdist.init_process_group("nccl")
+    import torch
+    torch.cuda.set_device(local)
+
+    w = dict(WORKLOAD)
+    S = int(args.restarts)
+    n, d, q, M = w["n"], w["d"], w["q"], w["M"]
+    # every rank owns S restarts (weak scaling); its shard of the global restart index space
+    X0, y0, _, z = make_inputs(1, w)
+    X = np.random.RandomState(w["seed"] + 2 + 1000 * rank).rand(S, q, d)
+    eng = Engine(local)
+    eng.set_model(w["kernel"], np.full(d, math.sqrt(d) / 4), 1.0, 1e-3, 0.0, 1e-6)
+    t0 = time.perf_counter()
+    eng.set_train(X0, y0)
+    setup_s = time.perf_counter() - t0
+    prm = acq_params(w["acq"])
+
+    # ---- value: inputs resident in HBM -------------------------------------------------------
+    dX = eng.alloc(X.nbytes).upload(X)
+    dz = eng.alloc(z.nbytes).upload(z)
+    dloss = eng.alloc(S * 8)
+    dgrad = eng.alloc(X.nbytes)
+
+    def step_dev():
+        eng.value_and_grad_dev(prm, S, q, 0, dX, M, dz, dloss, dgrad)
+        idx, val = eng.argmin_last()              # rank-local selection (device kernel + 16-byte D2H)
+        if ws > 1:
+            mdist.select_global_best(val, rank * S + idx, X[idx])
+        return idx, val
+
+    for _ in range(args.warmup):
+        step_dev()
+    eng.profile_enable(True)
+    eng.profile_reset()
+    mdist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = eng.launch_count
+    eng.timer_start()
+    for _ in range(args.steps):
+        step_dev()
+    ms = eng.timer_stop()
+    torch.cuda.synchronize()
+    mdist.barrier()
+    launches = eng.launch_count - launches0
+    clocks = sampler.stop()
+    prof = eng.profile_read()
+    eng.profile_enable(False)
+    ms = mdist.max_over_ranks(ms)
+    value = ws * S * q * M * args.steps / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (FP64 DMMA contraction) --------------------------------
+    gemm_ms = prof["gemm_fwd"][0] + prof["gemm_bwd"][0]
+    gemm_launches = prof["gemm_fwd"][1] + prof["gemm_bwd"][1]
+    npad = (n + 127) // 128 * 128
+    flops_per_step = 2.0 * npad * npad * q * S            # n^2 q per triangular GEMM, two GEMMs
+    peak, peak_src = load_fp64_peak()
+    achieved = flops_per_step * args.steps / (gemm_ms * 1e-3) * 1e-12 if gemm_ms > 0 else 0.0
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "gemm_nt_f64_kernel (DMMA.8x8x4)", "peak_source": peak_src,
+                "kernel_ms_per_launch": gemm_ms / max(gemm_launches, 1), "kernel_share_of_step": gemm_ms / ms,
+                "per_kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()}}
+
+    # ---- e2e: host buffers through the C ABI -----------------------------------------------------
+    hX = eng.pinned_empty((S, q, d))
+    hz = eng.pinned_empty((M, q))
+    hloss = eng.pinned_empty((S,))
+    hgrad = eng.pinned_empty((S, q, d))
+    hX[...] = X
+    hz[...] = z
+    e2e_steps = max(2, min(args.steps, 3))
+    eng.value_and_grad(prm, hX, hz, out_loss=hloss, out_grad=hgrad)
+    mdist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        eng.value_and_grad(prm, hX, hz, out_loss=hloss, out_grad=hgrad)
+        i = int(np.argmin(hloss))
+        if ws > 1:
+            mdist.select_global_best(float(hloss[i]), rank * S + i, hX[i])
+    torch.cuda.synchronize()
+    e2e_s = mdist.max_over_ranks(time.perf_counter() - t0)
+    e2e = {"value": ws * S * q * M * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(hX.nbytes + hz.nbytes),
+           "d2h_bytes_per_step": int(hloss.nbytes + hgrad.nbytes), "steps": e2e_steps}
+
+    # ---- CPU baseline (rank 0, N=1) ------------------------------------------------------------------
+    cpu = None
+    if rank == 0 and ws == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        rate, S_cpu, dt = cpu_reference_rate(w, threads)
+        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "S=%d restarts (of %d), one value+autograd-gradient pass in %.1f s, same n/d/q/M/z" % (S_cpu, S, dt)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "qEI value+grad, n=%d d=%d q=%d M=%d matern52, S=%d restarts per GPU" % (n, d, q, M, S),
+                       "parallelism": "restarts sharded x%d, replicated training factor, one all-gather per step" % ws,
+                       "l2_policy": "working set per chunk (K10 + V^T = %.1f GB) >> 126 MB L2; no flush needed" % (2 * min(S * q, 65536) * npad * 8 / 1e9),
+                       "setup_s_not_timed": setup_s},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if ws > 1:
+        import torch.distributed as tdist
+        tdist.barrier()
+        tdist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

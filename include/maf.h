@@ -1,0 +1,159 @@
+/*
+ * maf.h -- C ABI of the B200-native acquisition-maximisation hot path.
+ *
+ * The reference (j-wilson/MaximizingAcquisitionFunctions) is pure Python on
+ * TensorFlow 1.x and has no FFI of its own; its "operator interface" for this
+ * path is the set of Python call sites listed next to each entry point below
+ * (file:line relative to the reference root).  A maintainer binds these with
+ * ctypes; the in-tree binding is
+ * maximizingacquisitionfunctions_b200/_native.py.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure;
+ *     maf_last_error(ctx) returns a human-readable reason;
+ *   - arrays are C-contiguous float64, caller-owned; "host" entry points take
+ *     host pointers and do their own H2D/D2H copies on the context's stream and
+ *     synchronise before returning; "_dev" entry points take device pointers,
+ *     enqueue on the context's stream and do NOT synchronise;
+ *   - one CUDA stream per context, no global state; a context is not
+ *     thread-safe;
+ *   - candidates ("pools") are X[S][q][d]: S restarts of q points; rows
+ *     0..p-1 of each pool are pending points (constant, no gradient), rows
+ *     p..q-1 are trainable (reference: bayesian_optimization.prepare,
+ *     src/agents/bayesian_optimization.py:1051-1125).
+ *   - limits: 1 <= q <= MAF_MAX_Q, 1 <= d <= MAF_MAX_D.
+ */
+#ifndef MAF_H_
+#define MAF_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MAF_MAX_Q 16
+#define MAF_MAX_D 16
+
+typedef struct maf_ctx maf_ctx;
+
+enum maf_dtype { MAF_F64 = 0, MAF_F32 = 1 };
+/* src/models/kernels.py:32-49 */
+enum maf_kernel { MAF_KERNEL_SE = 0, MAF_KERNEL_MATERN52 = 1, MAF_KERNEL_MATERN32 = 2 };
+/* src/losses/{negative_ei,negative_pi,simple_regret,confidence_bound}.py */
+enum maf_acq { MAF_ACQ_EI = 0, MAF_ACQ_PI = 1, MAF_ACQ_SR = 2, MAF_ACQ_CB = 3 };
+
+typedef struct maf_acq_params {
+  int32_t acq;        /* enum maf_acq */
+  int32_t lower;      /* CB: 1 = lower bound (default of the reference), 0 = upper */
+  double level;       /* EI/PI improvement level; NaN => min(y0) (negative_ei.py:31-34) */
+  double temperature; /* PI: NaN => hard indicator, else soft_less temperature (math_ops.py:56-69) */
+  double beta;        /* CB: confidence parameter (confidence_bound.py:27-33) */
+} maf_acq_params;
+
+/* ---- life cycle ------------------------------------------------------- */
+int maf_create(int device, int dtype, maf_ctx** out);
+int maf_destroy(maf_ctx* ctx);
+const char* maf_last_error(const maf_ctx* ctx);
+const char* maf_version(void);
+/* the context's CUDA stream (cudaStream_t as void*) and a full sync */
+void* maf_stream(maf_ctx* ctx);
+int maf_sync(maf_ctx* ctx);
+
+/* ---- model + training set --------------------------------------------- */
+/* Replaces gaussian_process.__init__/state (src/models/gaussian_process.py:37-75,
+ * 377-411): ARD lengthscales[d], amplitude a (cov = a^2 * kappa), noise variance
+ * (NaN => noiseless), constant prior mean (NaN => empirical mean of y0, :229-231),
+ * jitter (1e-6 f64 / 1e-4 f32, :42-44). */
+int maf_set_model(maf_ctx* ctx, int kernel_id, int d, const double* lenscales,
+                  double amplitude, double noise, double mean, double jitter);
+
+/* Replaces model.compute_cholesky(X0, noisy=True) + the cached-factor feed in
+ * bayesian_optimization.appraise_inputs (src/agents/bayesian_optimization.py:188-198;
+ * src/models/gaussian_process.py:352-360): builds K00 + (noise + jitter) I, its
+ * Cholesky factor L0, the explicit inverse factor L0^-1 and gamma = L0^-1 (y0 - m)
+ * on the device.  Non-zero return if K00 is not positive definite. */
+int maf_set_train(maf_ctx* ctx, int n, const double* X0 /*[n][d]*/, const double* y0 /*[n]*/);
+/* copies of the cached factors, for tests: L0[n][n] lower, Linv[n][n] lower */
+int maf_get_factors(maf_ctx* ctx, double* L0, double* Linv, double* gamma);
+
+/* ---- GP posterior ------------------------------------------------------ */
+/* Replaces gaussian_process.predict/_predict_nd (src/models/gaussian_process.py:
+ * 109-117,172-223) for rank-3 pools against a rank-2 training set.
+ * mu[S][q]; full_cov != 0: cov[S][q][q], else cov[S][q] (marginal variances). */
+int maf_posterior(maf_ctx* ctx, int S, int q, const double* X, int full_cov,
+                  double* mu, double* cov);
+
+/* ---- acquisition value + gradient -------------------------------------- */
+/* Replaces loss_fn(pools, ...) -> myopic_loss.evaluate/monte_carlo/closed_form
+ * (src/losses/myopic_loss.py:63-244) plus the tf.gradients pass that
+ * optimizer.minimize builds (src/agents/bayesian_optimization.py:420-426).
+ * q == 1 with z == NULL evaluates the closed form (myopic_loss.py:84-90),
+ * otherwise the MC estimator with base samples z[M][q] (shared by all restarts),
+ * optional weights[M] (sum_m w_m u_m instead of the mean) and incumbents[M].
+ * out_loss[S]; out_grad[S][q-p][d] = d(sum_s loss_s)/dX (NULL => value only). */
+int maf_acq_value_grad(maf_ctx* ctx, const maf_acq_params* prm, int S, int q, int p_pending,
+                       const double* X, int M, const double* z, const double* weights,
+                       const double* incumbents, double* out_loss, double* out_grad);
+/* same, device pointers, asynchronous on maf_stream(ctx) */
+int maf_acq_value_grad_dev(maf_ctx* ctx, const maf_acq_params* prm, int S, int q, int p_pending,
+                           const double* dX, int M, const double* dz, const double* dweights,
+                           const double* dincumbents, double* dout_loss, double* dout_grad);
+/* extras of the last evaluation (myopic_loss.py:179 returns (means, cov, chol)):
+ * mu[S][q], cov[S][q][q], chol[S][q][q] (NULL to skip) */
+int maf_last_extras(maf_ctx* ctx, double* mu, double* cov, double* chol);
+
+/* ---- multi-start Adam loop --------------------------------------------- */
+/* Replaces bayesian_optimization._optimize_inputs_sgd (src/agents/
+ * bayesian_optimization.py:377-482): TF-1 Adam on sum_s loss_s, then
+ * clip_by_value(x, 0, 1); a fresh z[M][q] per step.  maf_adam_begin uploads
+ * the starts X[S][q][d] (pending rows included) and zeroes the slots;
+ * maf_adam_steps runs `steps` updates with z_steps[steps][M][q] and may be called
+ * repeatedly (the host owns the time limit); out_loss_trace[steps][S] may be NULL;
+ * maf_adam_end downloads the iterate. */
+int maf_adam_begin(maf_ctx* ctx, const maf_acq_params* prm, int S, int q, int p_pending,
+                   const double* X, double lr, double beta1, double beta2, double eps);
+int maf_adam_steps(maf_ctx* ctx, int steps, int M, const double* z_steps, double* out_loss_trace);
+int maf_adam_end(maf_ctx* ctx, double* X_out);
+
+/* ---- selection --------------------------------------------------------- */
+/* np.argmin semantics (first minimum; src/agents/bayesian_optimization.py:152) over
+ * a host loss vector is the caller's; this is the device-side variant over the losses
+ * of the last evaluation: index and value of the first minimum (NaNs never win). */
+int maf_argmin_last(maf_ctx* ctx, int64_t* idx, double* value);
+
+/* ---- profiling (CUDA events on the context's stream) -------------------- */
+enum maf_prof_slot {
+  MAF_PROF_CROSS_FWD = 0, MAF_PROF_GEMM_FWD = 1, MAF_PROF_POSTERIOR = 2, MAF_PROF_MC = 3,
+  MAF_PROF_VBAR = 4, MAF_PROF_GEMM_BWD = 5, MAF_PROF_CROSS_BWD = 6, MAF_PROF_ADAM = 7,
+  MAF_PROF_NSLOTS = 8
+};
+int maf_profile_enable(maf_ctx* ctx, int on);
+/* accumulated device milliseconds and launch counts per slot since the last reset */
+int maf_profile_read(maf_ctx* ctx, double* ms /*[MAF_PROF_NSLOTS]*/, int64_t* launches /*[MAF_PROF_NSLOTS]*/);
+int maf_profile_reset(maf_ctx* ctx);
+/* total kernels launched by this context since creation */
+int64_t maf_launch_count(const maf_ctx* ctx);
+/* a pair of CUDA events on the context's stream: start is recorded now; stop records the
+ * second event, waits for it and returns the device time between the two */
+int maf_timer_start(maf_ctx* ctx);
+int maf_timer_stop(maf_ctx* ctx, double* ms);
+
+/* ---- raw building blocks (exported for tests / micro-benchmarks) -------- */
+/* C[J][N] = A[J][K] * T[N][K]^T, row-major device pointers, J,N,K multiples of 128;
+ * tri: 0 full, 1 T lower-triangular (K==N), 2 T upper-triangular (K==N). */
+int maf_gemm_nt_dev(maf_ctx* ctx, int J, int N, int K, const double* dA, int lda,
+                    const double* dT, int ldt, double* dC, int ldc, int tri);
+void* maf_dev_alloc(maf_ctx* ctx, size_t bytes);
+int maf_dev_free(maf_ctx* ctx, void* p);
+int maf_h2d(maf_ctx* ctx, void* dst, const void* src, size_t bytes);
+int maf_d2h(maf_ctx* ctx, void* dst, const void* src, size_t bytes);
+/* page-locked host memory (so that the host entry points copy at full PCIe rate) */
+void* maf_host_alloc(maf_ctx* ctx, size_t bytes);
+int maf_host_free(maf_ctx* ctx, void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAF_H_ */

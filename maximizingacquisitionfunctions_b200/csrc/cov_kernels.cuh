@@ -1,0 +1,153 @@
+// Covariance kernels: K00 build, fused ARD cross-covariance K(Xcand, Xtrain) forward,
+// and its reverse-mode reduction to d loss / d Xcand.
+// Reference: gaussian_process.covar_fn (src/models/gaussian_process.py:244-269),
+// kernels.py:32-49, utils.pdist2 (src/utils/linalg_ops.py:102-109).
+#pragma once
+#include "common.cuh"
+
+// X0 [n][d] (AoS, raw) -> X0s [d][npad] (SoA, multiplied by 1/l; pad = 0).
+__global__ void scale_train_kernel(const double* __restrict__ X0, int n, int npad, ModelParams mp,
+                                   double* __restrict__ X0s) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= npad) return;
+  for (int c = 0; c < mp.d; ++c)
+    X0s[(size_t)c * npad + k] = (k < n) ? X0[(size_t)k * mp.d + c] * mp.inv_ls[c] : 0.0;
+}
+
+// K00[i][j] = (a^2 kappa(r2_ij) + noise*delta_ij) + jitter*delta_ij ; identity on the pad.
+// (noise_fn :272-280 then jitter_diagonal linalg_ops.py:112-128, same order of additions.)
+__global__ void k00_kernel(const double* __restrict__ X0s, int n, int npad, ModelParams mp,
+                           double* __restrict__ K00) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  int i = blockIdx.y;
+  if (j >= npad) return;
+  double v;
+  if (i < n && j < n) {
+    double r2 = 0.0;
+    for (int c = 0; c < mp.d; ++c) {
+      double df = X0s[(size_t)c * npad + i] - X0s[(size_t)c * npad + j];
+      r2 += df * df;
+    }
+    v = mp.amp2 * kern_val(mp.kernel_id, r2);
+    if (i == j) v = (v + mp.noise) + mp.jitter;
+  } else {
+    v = (i == j) ? 1.0 : 0.0;
+  }
+  K00[(size_t)i * npad + j] = v;
+}
+
+// ---------------------------------------------------------------------------
+// Forward: K10[j][k] = a^2 kappa(|xs_j - x0s_k|^2), j < J candidate rows, k < n.
+// One thread per training point k (its scaled coordinates live in registers for
+// the whole tile), CROSS_TJ candidate rows per CTA broadcast from shared memory;
+// stores are coalesced along k.  Rows j >= J and columns k >= n are written as 0 so
+// the GEMM can run on whole 128x128 tiles.
+// D > 0: compile-time dimension; D == 0: runtime d <= MAF_MAX_D.
+// ---------------------------------------------------------------------------
+#define CROSS_TJ 32
+#define CROSS_TK 256
+
+template <int D>
+__global__ void __launch_bounds__(CROSS_TK)
+cross_fwd_kernel(const double* __restrict__ X, int J, const double* __restrict__ X0s, int n, int npad,
+                 ModelParams mp, double* __restrict__ K10) {
+  constexpr int DD = D > 0 ? D : MAF_MAX_D;
+  const int d = D > 0 ? D : mp.d;
+  __shared__ double xs[CROSS_TJ][DD];
+  const int k = blockIdx.x * CROSS_TK + threadIdx.x;
+  const int j0 = blockIdx.y * CROSS_TJ;
+  for (int t = threadIdx.x; t < CROSS_TJ * d; t += CROSS_TK) {
+    int jj = t / d, c = t - jj * d;
+    int j = j0 + jj;
+    xs[jj][c] = (j < J) ? X[(size_t)j * d + c] * mp.inv_ls[c] : 0.0;
+  }
+  __syncthreads();
+  double x0[DD];
+#pragma unroll
+  for (int c = 0; c < DD; ++c) x0[c] = (c < d) ? X0s[(size_t)c * npad + k] : 0.0;
+  const bool kvalid = k < n;
+#pragma unroll 4
+  for (int jj = 0; jj < CROSS_TJ; ++jj) {
+    double r2 = 0.0;
+#pragma unroll
+    for (int c = 0; c < DD; ++c) {
+      if (c < d) {
+        double df = xs[jj][c] - x0[c];
+        r2 += df * df;
+      }
+    }
+    double v = (kvalid && (j0 + jj) < J) ? mp.amp2 * kern_val(mp.kernel_id, r2) : 0.0;
+    K10[(size_t)(j0 + jj) * npad + k] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Backward: grad[s][i-p][c] = 2 a^2 / l_c * ( sum_k Kbar10[j][k] kappa'(r2_jk) (xs_jc - x0s_kc)
+//                       + sum_{i' != i} (Sbar_ii' + Sbar_i'i) kappa'(r2_ii') (xs_ic - xs_i'c) )
+// One warp per candidate row (block = one restart, q warps); lanes stride over k with
+// coalesced reads of Kbar10 and of the SoA training set; warp-shuffle reduction.
+// ---------------------------------------------------------------------------
+template <int D>
+__global__ void cross_bwd_kernel(const double* __restrict__ X, int S, int q, int p,
+                                 const double* __restrict__ X0s, int n, int npad, ModelParams mp,
+                                 const double* __restrict__ Kbar /*[S*q][npad]*/,
+                                 const double* __restrict__ Sigbar /*[S][q][q]*/,
+                                 double* __restrict__ grad /*[S][q-p][d]*/) {
+  constexpr int DD = D > 0 ? D : MAF_MAX_D;
+  const int d = D > 0 ? D : mp.d;
+  const int s = blockIdx.x;
+  const int i = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (i >= q || i < p) return;
+  const size_t j = (size_t)s * q + i;
+  double xi[DD], acc[DD];
+#pragma unroll
+  for (int c = 0; c < DD; ++c) {
+    xi[c] = (c < d) ? X[j * d + c] * mp.inv_ls[c] : 0.0;
+    acc[c] = 0.0;
+  }
+  const double* kb = Kbar + j * npad;
+  for (int k = lane; k < n; k += 32) {
+    double x0[DD];
+    double r2 = 0.0;
+#pragma unroll
+    for (int c = 0; c < DD; ++c) {
+      if (c < d) {
+        x0[c] = X0s[(size_t)c * npad + k];
+        double df = xi[c] - x0[c];
+        r2 += df * df;
+      }
+    }
+    double g = kb[k] * kern_dr2(mp.kernel_id, r2);
+#pragma unroll
+    for (int c = 0; c < DD; ++c)
+      if (c < d) acc[c] += g * (xi[c] - x0[c]);
+  }
+  // self-covariance term (K11 = a^2 kappa(r2(X_s, X_s)); diagonal has zero gradient)
+  if (lane < q && lane != i) {
+    const double* xo = X + ((size_t)s * q + lane) * d;
+    double xj[DD];
+    double r2 = 0.0;
+#pragma unroll
+    for (int c = 0; c < DD; ++c) {
+      if (c < d) {
+        xj[c] = xo[c] * mp.inv_ls[c];
+        double df = xi[c] - xj[c];
+        r2 += df * df;
+      }
+    }
+    const double* sb = Sigbar + (size_t)s * q * q;
+    double g = (sb[i * q + lane] + sb[lane * q + i]) * kern_dr2(mp.kernel_id, r2);
+#pragma unroll
+    for (int c = 0; c < DD; ++c)
+      if (c < d) acc[c] += g * (xi[c] - xj[c]);
+  }
+#pragma unroll
+  for (int c = 0; c < DD; ++c) {
+    if (c < d) {
+      double v = warp_sum(acc[c]);
+      if (lane == 0)
+        grad[((size_t)s * (q - p) + (i - p)) * d + c] = 2.0 * mp.amp2 * mp.inv_ls[c] * v;
+    }
+  }
+}

@@ -1,0 +1,841 @@
+// C ABI of the B200-native acquisition-maximisation path (see include/maf.h).
+// Host orchestration only: every number is produced by the kernels in the .cuh files.
+#include <cublas_v2.h>
+#include <cusolverDn.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "cov_kernels.cuh"
+#include "gemm_f64.cuh"
+#include "mc_kernels.cuh"
+#include "posterior.cuh"
+
+#define MAF_VERSION_STR "maf_b200 0.1 (sm_100a, fp64 DMMA)"
+
+struct ProfSlot {
+  std::vector<cudaEvent_t> ev;   // pairs (start, stop)
+  size_t used = 0;
+  double ms = 0.0;
+  int64_t launches = 0;
+};
+
+struct Buf {
+  double* p = nullptr;
+  size_t cap = 0;   // doubles
+};
+
+struct maf_ctx {
+  int device = 0;
+  int dtype = MAF_F64;
+  cudaStream_t stream = nullptr;
+  cublasHandle_t cublas = nullptr;
+  cusolverDnHandle_t cusolver = nullptr;
+  std::string err;
+  int64_t launch_count = 0;
+
+  // model
+  bool model_set = false;
+  ModelParams mp{};
+  double mean_param = 0.0;     // NaN => empirical
+  // training set
+  bool train_set = false;
+  int n = 0, npad = 0;
+  double mean_val = 0.0, y_min = 0.0;
+  double *X0s = nullptr, *L0 = nullptr, *Linv = nullptr, *LinvT = nullptr, *gamma = nullptr;
+  size_t cap_train = 0;        // npad the factor buffers were sized for
+  int cap_train_d = 0;
+  // GEMM workspace (chunk of candidate rows)
+  size_t chunk_rows = 65536;
+  Buf K10, Vt;
+  // per-restart buffers
+  Buf dX, dz, dw, dinc, dmu, dSig, dchol, dmubar, dSigbar, dloss, dgrad;
+  int last_S = 0, last_q = 0;
+  bool last_has_chol = false;
+  double* d_argmin_val = nullptr;
+  long long* d_argmin_idx = nullptr;
+  // Adam state
+  bool adam_on = false;
+  maf_acq_params adam_prm{};
+  int adam_S = 0, adam_q = 0, adam_p = 0;
+  Buf adam_X, adam_m, adam_v, adam_g, adam_z;
+  double adam_lr = 0, adam_b1 = 0, adam_b2 = 0, adam_eps = 0, adam_b1p = 0, adam_b2p = 0;
+  // profiling
+  cudaEvent_t timer_ev[2] = {nullptr, nullptr};
+  bool prof = false;
+  ProfSlot slots[MAF_PROF_NSLOTS];
+};
+
+static int fail(maf_ctx* ctx, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf;
+  return 1;
+}
+
+#define CK(expr)                                                                           \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess)                                                                 \
+      return fail(ctx, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+#define CKB(expr)                                                                          \
+  do {                                                                                     \
+    int _s = (int)(expr);                                                                  \
+    if (_s != 0) return fail(ctx, "%s failed with status %d (%s:%d)", #expr, _s, __FILE__, __LINE__); \
+  } while (0)
+#define CKL() CK(cudaGetLastError())
+
+static int ensure(maf_ctx* ctx, Buf& b, size_t need) {
+  if (b.p != nullptr && b.cap >= need) return 0;
+  if (b.p) CK(cudaFree(b.p));
+  b.p = nullptr;
+  b.cap = 0;
+  size_t bytes = std::max<size_t>(need, 1) * sizeof(double);
+  cudaError_t e = cudaMalloc((void**)&b.p, bytes);
+  if (e != cudaSuccess) return fail(ctx, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+  b.cap = need;
+  return 0;
+}
+
+// ---- profiling helpers ------------------------------------------------------------------
+struct ProfScope {
+  maf_ctx* ctx;
+  int slot;
+  cudaEvent_t stop = nullptr;
+  ProfScope(maf_ctx* c, int s) : ctx(c), slot(s) {
+    ctx->launch_count++;
+    ctx->slots[slot].launches++;
+    if (!ctx->prof) return;
+    ProfSlot& ps = ctx->slots[slot];
+    if (ps.used + 2 > ps.ev.size()) {
+      cudaEvent_t a, b;
+      cudaEventCreate(&a);
+      cudaEventCreate(&b);
+      ps.ev.push_back(a);
+      ps.ev.push_back(b);
+    }
+    cudaEventRecord(ps.ev[ps.used], ctx->stream);
+    stop = ps.ev[ps.used + 1];
+    ps.used += 2;
+  }
+  ~ProfScope() {
+    if (stop) cudaEventRecord(stop, ctx->stream);
+  }
+};
+
+static void prof_collect(maf_ctx* ctx) {
+  cudaStreamSynchronize(ctx->stream);
+  for (int s = 0; s < MAF_PROF_NSLOTS; ++s) {
+    ProfSlot& ps = ctx->slots[s];
+    for (size_t i = 0; i + 1 < ps.used; i += 2) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, ps.ev[i], ps.ev[i + 1]) == cudaSuccess) ps.ms += ms;
+    }
+    ps.used = 0;
+  }
+}
+
+// ---- small setup kernels ------------------------------------------------------------------
+__global__ void tril_identity_kernel(double* L, double* Y, int npad) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  int i = blockIdx.y;
+  if (j >= npad) return;
+  if (j > i) L[(size_t)i * npad + j] = 0.0;
+  Y[(size_t)i * npad + j] = (i == j) ? 1.0 : 0.0;
+}
+
+__global__ void transpose_kernel(const double* __restrict__ A, double* __restrict__ B, int n) {
+  __shared__ double t[32][33];
+  int x = blockIdx.x * 32 + threadIdx.x, y0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) t[r][threadIdx.x] = A[(size_t)(y0 + r) * n + x];
+  __syncthreads();
+  int xo = blockIdx.y * 32 + threadIdx.x, yo0 = blockIdx.x * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) B[(size_t)(yo0 + r) * n + xo] = t[threadIdx.x][r];
+}
+
+// gamma_i = sum_{k<=i} Linv[i][k] rho_k ; one warp per row.
+__global__ void trmv_lower_kernel(const double* __restrict__ Linv, const double* __restrict__ rho, int npad,
+                                  double* __restrict__ gamma) {
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (row >= npad) return;
+  double a = 0.0;
+  for (int k = lane; k <= row; k += 32) a += Linv[(size_t)row * npad + k] * rho[k];
+  a = warp_sum(a);
+  if (lane == 0) gamma[row] = a;
+}
+
+__global__ void diag_extract_kernel(const double* __restrict__ Sig, int S, int q, double* __restrict__ var) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= S * q) return;
+  int s = t / q, i = t - s * q;
+  var[t] = Sig[(size_t)s * q * q + i * q + i];
+}
+
+// ---- dispatch helpers ---------------------------------------------------------------------
+#define DISPATCH_Q(q, ...)                                                         \
+  switch (q) {                                                                     \
+    case 1: { constexpr int Q = 1; __VA_ARGS__; } break;                           \
+    case 2: { constexpr int Q = 2; __VA_ARGS__; } break;                           \
+    case 3: { constexpr int Q = 3; __VA_ARGS__; } break;                           \
+    case 4: { constexpr int Q = 4; __VA_ARGS__; } break;                           \
+    case 5: { constexpr int Q = 5; __VA_ARGS__; } break;                           \
+    case 6: { constexpr int Q = 6; __VA_ARGS__; } break;                           \
+    case 7: { constexpr int Q = 7; __VA_ARGS__; } break;                           \
+    case 8: { constexpr int Q = 8; __VA_ARGS__; } break;                           \
+    case 9: { constexpr int Q = 9; __VA_ARGS__; } break;                           \
+    case 10: { constexpr int Q = 10; __VA_ARGS__; } break;                         \
+    case 11: { constexpr int Q = 11; __VA_ARGS__; } break;                         \
+    case 12: { constexpr int Q = 12; __VA_ARGS__; } break;                         \
+    case 13: { constexpr int Q = 13; __VA_ARGS__; } break;                         \
+    case 14: { constexpr int Q = 14; __VA_ARGS__; } break;                         \
+    case 15: { constexpr int Q = 15; __VA_ARGS__; } break;                         \
+    case 16: { constexpr int Q = 16; __VA_ARGS__; } break;                         \
+    default: return fail(ctx, "q=%d outside 1..%d", q, MAF_MAX_Q);                 \
+  }
+
+#define DISPATCH_D(d, ...)                                                         \
+  switch (d) {                                                                     \
+    case 1: { constexpr int D = 1; __VA_ARGS__; } break;                           \
+    case 2: { constexpr int D = 2; __VA_ARGS__; } break;                           \
+    case 3: { constexpr int D = 3; __VA_ARGS__; } break;                           \
+    case 4: { constexpr int D = 4; __VA_ARGS__; } break;                           \
+    case 5: { constexpr int D = 5; __VA_ARGS__; } break;                           \
+    case 6: { constexpr int D = 6; __VA_ARGS__; } break;                           \
+    case 7: { constexpr int D = 7; __VA_ARGS__; } break;                           \
+    case 8: { constexpr int D = 8; __VA_ARGS__; } break;                           \
+    default: { constexpr int D = 0; __VA_ARGS__; } break;                          \
+  }
+
+static int launch_gemm(maf_ctx* ctx, int slot, int J, int N, int K, const double* A, int lda,
+                       const double* T, int ldt, double* C, int ldc, int tri) {
+  if (J % GEMM_BM || N % GEMM_BN || K % GEMM_BK) return fail(ctx, "gemm dims must be multiples of 128");
+  if (tri != 0 && K != N) return fail(ctx, "triangular gemm needs K == N");
+  dim3 grid(N / GEMM_BN, J / GEMM_BM);
+  ProfScope ps(ctx, slot);
+  gemm_nt_f64_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, ctx->stream>>>(A, lda, T, ldt, C, ldc, K, tri);
+  CKL();
+  return 0;
+}
+
+// ---- life cycle ---------------------------------------------------------------------------
+extern "C" const char* maf_version(void) { return MAF_VERSION_STR; }
+
+extern "C" const char* maf_last_error(const maf_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" int maf_create(int device, int dtype, maf_ctx** out) {
+  if (!out) return 1;
+  *out = nullptr;
+  maf_ctx* ctx = new maf_ctx();
+  *out = ctx;   // returned even on failure so that the caller can read the error
+  ctx->device = device;
+  ctx->dtype = dtype;
+  if (dtype != MAF_F64) return fail(ctx, "only MAF_F64 is implemented in this build");
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(ctx, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+  CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  CKB(cublasCreate(&ctx->cublas));
+  CKB(cublasSetStream(ctx->cublas, ctx->stream));
+  CKB(cusolverDnCreate(&ctx->cusolver));
+  CKB(cusolverDnSetStream(ctx->cusolver, ctx->stream));
+  CK(cudaFuncSetAttribute(gemm_nt_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CK(cudaMalloc((void**)&ctx->d_argmin_val, sizeof(double)));
+  CK(cudaMalloc((void**)&ctx->d_argmin_idx, sizeof(long long)));
+  const char* cr = getenv("MAF_CHUNK_ROWS");
+  if (cr) {
+    long v = atol(cr);
+    if (v >= 128) ctx->chunk_rows = (size_t)v / 128 * 128;
+  }
+  return 0;
+}
+
+extern "C" int maf_destroy(maf_ctx* ctx) {
+  if (!ctx) return 0;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  double* raw[] = {ctx->X0s, ctx->L0, ctx->Linv, ctx->LinvT, ctx->gamma, ctx->d_argmin_val};
+  for (double* b : raw)
+    if (b) cudaFree(b);
+  Buf* bufs[] = {&ctx->K10, &ctx->Vt, &ctx->dX, &ctx->dz, &ctx->dw, &ctx->dinc, &ctx->dmu, &ctx->dSig, &ctx->dchol,
+                 &ctx->dmubar, &ctx->dSigbar, &ctx->dloss, &ctx->dgrad, &ctx->adam_X, &ctx->adam_m, &ctx->adam_v,
+                 &ctx->adam_g, &ctx->adam_z};
+  for (Buf* b : bufs)
+    if (b->p) cudaFree(b->p);
+  if (ctx->d_argmin_idx) cudaFree(ctx->d_argmin_idx);
+  for (auto& ps : ctx->slots)
+    for (auto e : ps.ev) cudaEventDestroy(e);
+  for (auto e : ctx->timer_ev)
+    if (e) cudaEventDestroy(e);
+  if (ctx->cusolver) cusolverDnDestroy(ctx->cusolver);
+  if (ctx->cublas) cublasDestroy(ctx->cublas);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return 0;
+}
+
+extern "C" void* maf_stream(maf_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+extern "C" int maf_sync(maf_ctx* ctx) {
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+extern "C" void* maf_dev_alloc(maf_ctx* ctx, size_t bytes) {
+  void* p = nullptr;
+  cudaSetDevice(ctx->device);
+  if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) {
+    fail(ctx, "maf_dev_alloc(%zu) failed", bytes);
+    return nullptr;
+  }
+  return p;
+}
+extern "C" int maf_dev_free(maf_ctx* ctx, void* p) {
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaFree(p));
+  return 0;
+}
+extern "C" int maf_h2d(maf_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+extern "C" int maf_d2h(maf_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// ---- model + training set -------------------------------------------------------------------
+extern "C" int maf_set_model(maf_ctx* ctx, int kernel_id, int d, const double* lenscales, double amplitude,
+                             double noise, double mean, double jitter) {
+  if (!ctx) return 1;
+  if (d < 1 || d > MAF_MAX_D) return fail(ctx, "d=%d outside 1..%d", d, MAF_MAX_D);
+  if (kernel_id < 0 || kernel_id > 2) return fail(ctx, "unknown kernel id %d", kernel_id);
+  ModelParams mp{};
+  mp.kernel_id = kernel_id;
+  mp.d = d;
+  for (int c = 0; c < d; ++c) {
+    if (!(lenscales[c] > 0.0)) return fail(ctx, "lengthscale %d must be positive", c);
+    mp.inv_ls[c] = 1.0 / lenscales[c];
+  }
+  mp.amp2 = amplitude * amplitude;
+  mp.noise = (noise == noise) ? noise : 0.0;
+  mp.jitter = jitter;
+  ctx->mp = mp;
+  ctx->mean_param = mean;
+  ctx->model_set = true;
+  ctx->train_set = false;   // factors depend on the hyper-parameters
+  return 0;
+}
+
+extern "C" int maf_set_train(maf_ctx* ctx, int n, const double* X0, const double* y0) {
+  if (!ctx) return 1;
+  if (!ctx->model_set) return fail(ctx, "maf_set_model must be called first");
+  if (n < 1) return fail(ctx, "n must be >= 1");
+  CK(cudaSetDevice(ctx->device));
+  const int d = ctx->mp.d;
+  const int npad = round_up(n, 128);
+  ctx->train_set = false;
+  if ((size_t)npad != ctx->cap_train || d != ctx->cap_train_d) {
+    double** bufs[] = {&ctx->X0s, &ctx->L0, &ctx->Linv, &ctx->LinvT, &ctx->gamma};
+    for (double** b : bufs) {
+      if (*b) CK(cudaFree(*b));
+      *b = nullptr;
+    }
+    ctx->cap_train = 0;
+    size_t nn = (size_t)npad * npad;
+    CK(cudaMalloc((void**)&ctx->X0s, sizeof(double) * (size_t)d * npad));
+    CK(cudaMalloc((void**)&ctx->L0, sizeof(double) * nn));
+    CK(cudaMalloc((void**)&ctx->Linv, sizeof(double) * nn));
+    CK(cudaMalloc((void**)&ctx->LinvT, sizeof(double) * nn));
+    CK(cudaMalloc((void**)&ctx->gamma, sizeof(double) * npad));
+    ctx->cap_train = npad;
+    ctx->cap_train_d = d;
+  }
+  ctx->n = n;
+  ctx->npad = npad;
+
+  // host-side scalars: prior mean (constant or empirical, gaussian_process.py:226-231) and min(y0)
+  double mean = ctx->mean_param;
+  if (!(mean == mean)) {
+    double acc = 0.0;
+    for (int i = 0; i < n; ++i) acc += y0[i];
+    mean = acc / n;
+  }
+  ctx->mean_val = mean;
+  double ymin = y0[0];
+  for (int i = 1; i < n; ++i) ymin = std::min(ymin, y0[i]);
+  ctx->y_min = ymin;
+  std::vector<double> rho(npad, 0.0);
+  for (int i = 0; i < n; ++i) rho[i] = y0[i] - mean;
+
+  // raw X0 -> LinvT scratch, rho -> gamma scratch (Linv row 0 reused below)
+  double* scratch = ctx->LinvT;
+  CK(cudaMemcpyAsync(scratch, X0, sizeof(double) * (size_t)n * d, cudaMemcpyHostToDevice, ctx->stream));
+  {
+    ProfScope ps(ctx, MAF_PROF_CROSS_FWD);
+    scale_train_kernel<<<(npad + 255) / 256, 256, 0, ctx->stream>>>(scratch, n, npad, ctx->mp, ctx->X0s);
+    CKL();
+  }
+  {
+    ProfScope ps(ctx, MAF_PROF_CROSS_FWD);
+    dim3 grid((npad + 255) / 256, npad);
+    k00_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->X0s, n, npad, ctx->mp, ctx->L0);
+    CKL();
+  }
+  // Cholesky: the row-major buffer viewed column-major is K00 itself (symmetric);
+  // FILL_MODE_UPPER there == lower triangle of the row-major view.
+  int lwork = 0;
+  CKB(cusolverDnDpotrf_bufferSize(ctx->cusolver, CUBLAS_FILL_MODE_UPPER, npad, ctx->L0, npad, &lwork));
+  double* work = nullptr;
+  int* dinfo = nullptr;
+  CK(cudaMalloc((void**)&work, sizeof(double) * std::max(lwork, 1)));
+  CK(cudaMalloc((void**)&dinfo, sizeof(int)));
+  int st = (int)cusolverDnDpotrf(ctx->cusolver, CUBLAS_FILL_MODE_UPPER, npad, ctx->L0, npad, work, lwork, dinfo);
+  int info = 0;
+  cudaMemcpyAsync(&info, dinfo, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(work);
+  cudaFree(dinfo);
+  ctx->launch_count++;
+  if (st != 0) return fail(ctx, "cusolverDnDpotrf failed with status %d", st);
+  if (info != 0) return fail(ctx, "Cholesky decomposition was not successful (leading minor %d of K00 is not positive definite)", info);
+  {
+    ProfScope ps(ctx, MAF_PROF_CROSS_FWD);
+    dim3 grid((npad + 255) / 256, npad);
+    tril_identity_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->L0, ctx->Linv, npad);
+    CKL();
+  }
+  // Linv: column-major view of L0 is U = L^T; solve U X = I  =>  X = U^-1 whose row-major view is L^-1.
+  const double one = 1.0;
+  CKB(cublasDtrsm(ctx->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, npad,
+                  npad, &one, ctx->L0, npad, ctx->Linv, npad));
+  ctx->launch_count++;
+  {
+    ProfScope ps(ctx, MAF_PROF_CROSS_FWD);
+    dim3 grid(npad / 32, npad / 32), block(32, 8);
+    transpose_kernel<<<grid, block, 0, ctx->stream>>>(ctx->Linv, ctx->LinvT, npad);
+    CKL();
+  }
+  // gamma = Linv rho  (rho staged in the GEMM-independent dSig-free scratch: reuse X0s? no -> temp)
+  double* drho = nullptr;
+  CK(cudaMalloc((void**)&drho, sizeof(double) * npad));
+  CK(cudaMemcpyAsync(drho, rho.data(), sizeof(double) * npad, cudaMemcpyHostToDevice, ctx->stream));
+  {
+    ProfScope ps(ctx, MAF_PROF_CROSS_FWD);
+    trmv_lower_kernel<<<(npad + 7) / 8, 256, 0, ctx->stream>>>(ctx->Linv, drho, npad, ctx->gamma);
+    CKL();
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaFree(drho));
+  ctx->train_set = true;
+  ctx->adam_on = false;
+  return 0;
+}
+
+extern "C" int maf_get_factors(maf_ctx* ctx, double* L0, double* Linv, double* gamma) {
+  if (!ctx || !ctx->train_set) return fail(ctx, "no training set");
+  CK(cudaSetDevice(ctx->device));
+  const int n = ctx->n, npad = ctx->npad;
+  if (L0) CK(cudaMemcpy2DAsync(L0, sizeof(double) * n, ctx->L0, sizeof(double) * npad, sizeof(double) * n, n, cudaMemcpyDeviceToHost, ctx->stream));
+  if (Linv) CK(cudaMemcpy2DAsync(Linv, sizeof(double) * n, ctx->Linv, sizeof(double) * npad, sizeof(double) * n, n, cudaMemcpyDeviceToHost, ctx->stream));
+  if (gamma) CK(cudaMemcpyAsync(gamma, ctx->gamma, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// ---- the pipeline -------------------------------------------------------------------------------
+static int resolve_acq(maf_ctx* ctx, const maf_acq_params* prm, AcqDev* out) {
+  if (!prm) return fail(ctx, "null acquisition parameters");
+  if (prm->acq < 0 || prm->acq > 3) return fail(ctx, "unknown acquisition id %d", prm->acq);
+  AcqDev a{};
+  a.acq = prm->acq;
+  a.lower = prm->lower ? 1 : 0;
+  a.level = (prm->level == prm->level) ? prm->level : ctx->y_min;
+  a.soft = (prm->temperature == prm->temperature) ? 1 : 0;
+  a.inv_temp = a.soft ? 1.0 / prm->temperature : 0.0;
+  a.beta = prm->beta;
+  a.cb_scale = std::pow(0.5 * 3.141592653589793 * prm->beta, 0.5);
+  *out = a;
+  return 0;
+}
+
+// forward (+ optional backward) over one chunk of restarts
+static int run_chunk(maf_ctx* ctx, const AcqDev& ap, bool posterior_only, bool closed_form, int sc, int q, int p,
+                     const double* dX, int M, const double* dz, const double* dw, const double* dinc, double* mu,
+                     double* Sig, double* chol, double* mubar, double* Sigbar, double* dloss, double* dgrad) {
+  const int d = ctx->mp.d, n = ctx->n, npad = ctx->npad;
+  const int J = sc * q, Jpad = round_up(J, 128);
+  double* K10 = ctx->K10.p;
+  double* Vt = ctx->Vt.p;
+  {
+    ProfScope ps(ctx, MAF_PROF_CROSS_FWD);
+    dim3 grid((npad + CROSS_TK - 1) / CROSS_TK, Jpad / CROSS_TJ);
+    DISPATCH_D(d, cross_fwd_kernel<D><<<grid, CROSS_TK, 0, ctx->stream>>>(dX, J, ctx->X0s, n, npad, ctx->mp, K10));
+    CKL();
+  }
+  if (launch_gemm(ctx, MAF_PROF_GEMM_FWD, Jpad, npad, npad, K10, npad, ctx->Linv, npad, Vt, npad, 1)) return 1;
+  {
+    ProfScope ps(ctx, MAF_PROF_POSTERIOR);
+    DISPATCH_Q(q, posterior_kernel<Q><<<sc, POST_THREADS, 0, ctx->stream>>>(Vt, npad, ctx->gamma, dX, ctx->mp, ctx->mean_val, mu, Sig));
+    CKL();
+  }
+  if (posterior_only) return 0;
+  const int need_grad = dgrad != nullptr;
+  {
+    ProfScope ps(ctx, MAF_PROF_MC);
+    if (closed_form) {
+      closed_form_kernel<<<(sc + 127) / 128, 128, 0, ctx->stream>>>(sc, mu, Sig, ap, need_grad, dloss, mubar, Sigbar);
+    } else {
+      DISPATCH_Q(q, {
+        const size_t smem = sizeof(McSmem<Q>);
+        static bool attr_set = false;
+        if (!attr_set && smem > 48 * 1024) {
+          CK(cudaFuncSetAttribute(mc_acq_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          attr_set = true;
+        }
+        mc_acq_kernel<Q><<<(sc + MC_WARPS - 1) / MC_WARPS, MC_WARPS * 32, smem, ctx->stream>>>(
+            sc, M, mu, Sig, dz, dw, dinc, ap, ctx->mp.jitter, need_grad, dloss, mubar, Sigbar, chol);
+      });
+    }
+    CKL();
+  }
+  if (!need_grad) return 0;
+  {
+    ProfScope ps(ctx, MAF_PROF_VBAR);
+    DISPATCH_Q(q, vbar_kernel<Q><<<sc, 256, 0, ctx->stream>>>(Vt, npad, ctx->gamma, mubar, Sigbar));
+    CKL();
+  }
+  if (launch_gemm(ctx, MAF_PROF_GEMM_BWD, Jpad, npad, npad, Vt, npad, ctx->LinvT, npad, K10, npad, 2)) return 1;
+  {
+    ProfScope ps(ctx, MAF_PROF_CROSS_BWD);
+    DISPATCH_D(d, cross_bwd_kernel<D><<<sc, 32 * q, 0, ctx->stream>>>(dX, sc, q, p, ctx->X0s, n, npad, ctx->mp, K10, Sigbar, dgrad));
+    CKL();
+  }
+  return 0;
+}
+
+static int check_shape(maf_ctx* ctx, int S, int q, int p) {
+  if (!ctx->train_set) return fail(ctx, "maf_set_train must be called first");
+  if (S < 1) return fail(ctx, "S must be >= 1");
+  if (q < 1 || q > MAF_MAX_Q) return fail(ctx, "q=%d outside 1..%d", q, MAF_MAX_Q);
+  if (p < 0 || p >= q) return fail(ctx, "p_pending=%d must satisfy 0 <= p < q=%d", p, q);
+  return 0;
+}
+
+// All restarts, in chunks of at most chunk_rows candidate rows.  Device pointers; asynchronous.
+static int run_all(maf_ctx* ctx, const maf_acq_params* prm, bool posterior_only, int S, int q, int p,
+                   const double* dX, int M, const double* dz, const double* dw, const double* dinc,
+                   double* dloss, double* dgrad) {
+  if (check_shape(ctx, S, q, p)) return 1;
+  CK(cudaSetDevice(ctx->device));
+  AcqDev ap{};
+  bool closed_form = false;
+  if (!posterior_only) {
+    if (resolve_acq(ctx, prm, &ap)) return 1;
+    closed_form = (q == 1 && dz == nullptr);
+    if (!closed_form && (dz == nullptr || M < 1))
+      return fail(ctx, "base samples z[M][q] are required for the Monte-Carlo path");
+  }
+  const int d = ctx->mp.d, npad = ctx->npad;
+  const size_t sq = (size_t)S * q, sqq = sq * q;
+  if (ensure(ctx, ctx->dmu, sq) || ensure(ctx, ctx->dmubar, sq) || ensure(ctx, ctx->dSig, sqq) ||
+      ensure(ctx, ctx->dSigbar, sqq) || ensure(ctx, ctx->dchol, sqq))
+    return 1;
+  int sc_max = (int)std::max<size_t>(1, ctx->chunk_rows / q);
+  sc_max = std::min(sc_max, S);
+  const size_t need = (size_t)round_up(sc_max * q, 128) * npad;
+  if (ensure(ctx, ctx->K10, need) || ensure(ctx, ctx->Vt, need)) return 1;
+  for (int s0 = 0; s0 < S; s0 += sc_max) {
+    const int sc = std::min(sc_max, S - s0);
+    const size_t oq = (size_t)s0 * q, oqq = oq * q;
+    if (run_chunk(ctx, ap, posterior_only, closed_form, sc, q, p, dX + oq * d, M, dz, dw, dinc, ctx->dmu.p + oq,
+                  ctx->dSig.p + oqq, closed_form ? nullptr : ctx->dchol.p + oqq, ctx->dmubar.p + oq,
+                  ctx->dSigbar.p + oqq, dloss ? dloss + s0 : nullptr,
+                  dgrad ? dgrad + (size_t)s0 * (q - p) * d : nullptr))
+      return 1;
+  }
+  ctx->last_S = S;
+  ctx->last_q = q;
+  ctx->last_has_chol = !posterior_only && !closed_form;
+  return 0;
+}
+
+extern "C" int maf_posterior(maf_ctx* ctx, int S, int q, const double* X, int full_cov, double* mu, double* cov) {
+  if (!ctx) return 1;
+  if (!X) return fail(ctx, "null pointer");
+  if (check_shape(ctx, S, q, 0)) return 1;
+  CK(cudaSetDevice(ctx->device));
+  const size_t nx = (size_t)S * q * ctx->mp.d;
+  if (ensure(ctx, ctx->dX, nx)) return 1;
+  CK(cudaMemcpyAsync(ctx->dX.p, X, nx * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if (run_all(ctx, nullptr, true, S, q, 0, ctx->dX.p, 0, nullptr, nullptr, nullptr, nullptr, nullptr)) return 1;
+  if (mu) CK(cudaMemcpyAsync(mu, ctx->dmu.p, sizeof(double) * S * q, cudaMemcpyDeviceToHost, ctx->stream));
+  if (cov) {
+    if (full_cov) {
+      CK(cudaMemcpyAsync(cov, ctx->dSig.p, sizeof(double) * S * q * q, cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+      {
+        ProfScope ps(ctx, MAF_PROF_POSTERIOR);
+        diag_extract_kernel<<<(S * q + 255) / 256, 256, 0, ctx->stream>>>(ctx->dSig.p, S, q, ctx->dSigbar.p);
+        CKL();
+      }
+      CK(cudaMemcpyAsync(cov, ctx->dSigbar.p, sizeof(double) * S * q, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+extern "C" int maf_acq_value_grad_dev(maf_ctx* ctx, const maf_acq_params* prm, int S, int q, int p_pending,
+                                      const double* dX, int M, const double* dz, const double* dweights,
+                                      const double* dincumbents, double* dout_loss, double* dout_grad) {
+  if (!ctx) return 1;
+  if (!dX || !dout_loss) return fail(ctx, "null device pointer");
+  if (check_shape(ctx, S, q, p_pending)) return 1;
+  if (ensure(ctx, ctx->dloss, (size_t)S)) return 1;   // copy kept for maf_argmin_last
+  if (run_all(ctx, prm, false, S, q, p_pending, dX, M, dz, dweights, dincumbents, dout_loss, dout_grad)) return 1;
+  if (dout_loss != ctx->dloss.p)
+    CK(cudaMemcpyAsync(ctx->dloss.p, dout_loss, sizeof(double) * S, cudaMemcpyDeviceToDevice, ctx->stream));
+  return 0;
+}
+
+extern "C" int maf_acq_value_grad(maf_ctx* ctx, const maf_acq_params* prm, int S, int q, int p_pending,
+                                  const double* X, int M, const double* z, const double* weights,
+                                  const double* incumbents, double* out_loss, double* out_grad) {
+  if (!ctx) return 1;
+  if (!X || !out_loss) return fail(ctx, "null pointer");
+  if (check_shape(ctx, S, q, p_pending)) return 1;
+  CK(cudaSetDevice(ctx->device));
+  const int d = ctx->mp.d;
+  const size_t nx = (size_t)S * q * d, ng = (size_t)S * (q - p_pending) * d;
+  if (ensure(ctx, ctx->dX, nx) || ensure(ctx, ctx->dloss, (size_t)S)) return 1;
+  if (out_grad && ensure(ctx, ctx->dgrad, ng)) return 1;
+  CK(cudaMemcpyAsync(ctx->dX.p, X, nx * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  const double *dz = nullptr, *dw = nullptr, *dinc = nullptr;
+  if (z) {
+    if (M < 1) return fail(ctx, "M must be >= 1 when z is given");
+    if (ensure(ctx, ctx->dz, (size_t)M * q)) return 1;
+    CK(cudaMemcpyAsync(ctx->dz.p, z, sizeof(double) * M * q, cudaMemcpyHostToDevice, ctx->stream));
+    dz = ctx->dz.p;
+    if (weights) {
+      if (ensure(ctx, ctx->dw, (size_t)M)) return 1;
+      CK(cudaMemcpyAsync(ctx->dw.p, weights, sizeof(double) * M, cudaMemcpyHostToDevice, ctx->stream));
+      dw = ctx->dw.p;
+    }
+    if (incumbents) {
+      if (ensure(ctx, ctx->dinc, (size_t)M)) return 1;
+      CK(cudaMemcpyAsync(ctx->dinc.p, incumbents, sizeof(double) * M, cudaMemcpyHostToDevice, ctx->stream));
+      dinc = ctx->dinc.p;
+    }
+  }
+  if (run_all(ctx, prm, false, S, q, p_pending, ctx->dX.p, M, dz, dw, dinc, ctx->dloss.p,
+              out_grad ? ctx->dgrad.p : nullptr))
+    return 1;
+  CK(cudaMemcpyAsync(out_loss, ctx->dloss.p, sizeof(double) * S, cudaMemcpyDeviceToHost, ctx->stream));
+  if (out_grad) CK(cudaMemcpyAsync(out_grad, ctx->dgrad.p, sizeof(double) * ng, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+extern "C" int maf_last_extras(maf_ctx* ctx, double* mu, double* cov, double* chol) {
+  if (!ctx) return 1;
+  if (ctx->last_S == 0) return fail(ctx, "no evaluation to report");
+  CK(cudaSetDevice(ctx->device));
+  const size_t sq = (size_t)ctx->last_S * ctx->last_q;
+  if (mu) CK(cudaMemcpyAsync(mu, ctx->dmu.p, sizeof(double) * sq, cudaMemcpyDeviceToHost, ctx->stream));
+  if (cov) CK(cudaMemcpyAsync(cov, ctx->dSig.p, sizeof(double) * sq * ctx->last_q, cudaMemcpyDeviceToHost, ctx->stream));
+  if (chol) {
+    if (!ctx->last_has_chol) return fail(ctx, "the last evaluation did not factorise the covariance");
+    CK(cudaMemcpyAsync(chol, ctx->dchol.p, sizeof(double) * sq * ctx->last_q, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+extern "C" int maf_argmin_last(maf_ctx* ctx, int64_t* idx, double* value) {
+  if (!ctx) return 1;
+  if (ctx->last_S == 0 || !ctx->dloss.p) return fail(ctx, "no evaluation to report");
+  CK(cudaSetDevice(ctx->device));
+  {
+    ProfScope ps(ctx, MAF_PROF_ADAM);
+    argmin_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->dloss.p, ctx->last_S, ctx->d_argmin_val, ctx->d_argmin_idx);
+    CKL();
+  }
+  long long hi = -1;
+  double hv = 0.0;
+  CK(cudaMemcpyAsync(&hi, ctx->d_argmin_idx, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(&hv, ctx->d_argmin_val, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (idx) *idx = (int64_t)hi;
+  if (value) *value = hv;
+  return 0;
+}
+
+// ---- Adam loop ---------------------------------------------------------------------------------
+extern "C" int maf_adam_begin(maf_ctx* ctx, const maf_acq_params* prm, int S, int q, int p_pending, const double* X,
+                              double lr, double beta1, double beta2, double eps) {
+  if (!ctx) return 1;
+  if (!prm || !X) return fail(ctx, "null pointer");
+  if (check_shape(ctx, S, q, p_pending)) return 1;
+  CK(cudaSetDevice(ctx->device));
+  const int d = ctx->mp.d;
+  const size_t nx = (size_t)S * q * d, nt = (size_t)S * (q - p_pending) * d;
+  if (ensure(ctx, ctx->adam_X, nx) || ensure(ctx, ctx->adam_m, nt) || ensure(ctx, ctx->adam_v, nt) ||
+      ensure(ctx, ctx->adam_g, nt))
+    return 1;
+  CK(cudaMemcpyAsync(ctx->adam_X.p, X, nx * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemsetAsync(ctx->adam_m.p, 0, sizeof(double) * nt, ctx->stream));
+  CK(cudaMemsetAsync(ctx->adam_v.p, 0, sizeof(double) * nt, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->adam_prm = *prm;
+  ctx->adam_S = S;
+  ctx->adam_q = q;
+  ctx->adam_p = p_pending;
+  ctx->adam_lr = lr;
+  ctx->adam_b1 = beta1;
+  ctx->adam_b2 = beta2;
+  ctx->adam_eps = eps;
+  ctx->adam_b1p = beta1;
+  ctx->adam_b2p = beta2;
+  ctx->adam_on = true;
+  return 0;
+}
+
+extern "C" int maf_adam_steps(maf_ctx* ctx, int steps, int M, const double* z_steps, double* out_loss_trace) {
+  if (!ctx) return 1;
+  if (!ctx->adam_on) return fail(ctx, "maf_adam_begin must be called first");
+  if (steps < 0 || M < 1 || !z_steps) return fail(ctx, "bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  const int S = ctx->adam_S, q = ctx->adam_q, p = ctx->adam_p, d = ctx->mp.d;
+  const size_t nt = (size_t)S * (q - p) * d;
+  const size_t zsz = (size_t)M * q;
+  if (ensure(ctx, ctx->adam_z, zsz * std::max(steps, 1)) || ensure(ctx, ctx->dloss, (size_t)S)) return 1;
+  CK(cudaMemcpyAsync(ctx->adam_z.p, z_steps, sizeof(double) * zsz * steps, cudaMemcpyHostToDevice, ctx->stream));
+  double* dtrace = nullptr;
+  if (out_loss_trace && steps > 0) CK(cudaMalloc((void**)&dtrace, sizeof(double) * (size_t)steps * S));
+  int rc = 0;
+  for (int t = 0; t < steps && rc == 0; ++t) {
+    double* lossp = dtrace ? dtrace + (size_t)t * S : ctx->dloss.p;
+    rc = run_all(ctx, &ctx->adam_prm, false, S, q, p, ctx->adam_X.p, M, ctx->adam_z.p + zsz * t, nullptr, nullptr,
+                 lossp, ctx->adam_g.p);
+    if (rc) break;
+    const double alpha = ctx->adam_lr * std::sqrt(1.0 - ctx->adam_b2p) / (1.0 - ctx->adam_b1p);
+    {
+      ProfScope ps(ctx, MAF_PROF_ADAM);
+      adam_clip_kernel<<<(unsigned)((nt + 255) / 256), 256, 0, ctx->stream>>>(
+          ctx->adam_X.p, ctx->adam_g.p, ctx->adam_m.p, ctx->adam_v.p, nt, q, p, d, alpha, ctx->adam_b1,
+          ctx->adam_b2, ctx->adam_eps);
+    }
+    if (cudaGetLastError() != cudaSuccess) rc = fail(ctx, "adam_clip_kernel launch failed");
+    ctx->adam_b1p *= ctx->adam_b1;
+    ctx->adam_b2p *= ctx->adam_b2;
+  }
+  if (rc == 0 && dtrace) {
+    if (cudaMemcpyAsync(out_loss_trace, dtrace, sizeof(double) * (size_t)steps * S, cudaMemcpyDeviceToHost,
+                        ctx->stream) != cudaSuccess)
+      rc = fail(ctx, "loss trace copy failed");
+  }
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess && rc == 0) rc = fail(ctx, "stream sync failed in adam loop");
+  if (dtrace) cudaFree(dtrace);
+  if (rc == 0 && steps > 0 && dtrace == nullptr) {
+    // dloss holds the last step's losses
+  }
+  return rc;
+}
+
+extern "C" int maf_adam_end(maf_ctx* ctx, double* X_out) {
+  if (!ctx) return 1;
+  if (!ctx->adam_on) return fail(ctx, "maf_adam_begin must be called first");
+  CK(cudaSetDevice(ctx->device));
+  const size_t nx = (size_t)ctx->adam_S * ctx->adam_q * ctx->mp.d;
+  if (X_out) CK(cudaMemcpyAsync(X_out, ctx->adam_X.p, nx * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->adam_on = false;
+  return 0;
+}
+
+// ---- profiling -----------------------------------------------------------------------------------
+extern "C" int maf_profile_enable(maf_ctx* ctx, int on) {
+  if (!ctx) return 1;
+  if (ctx->prof && !on) prof_collect(ctx);
+  ctx->prof = on != 0;
+  return 0;
+}
+extern "C" int maf_profile_read(maf_ctx* ctx, double* ms, int64_t* launches) {
+  if (!ctx) return 1;
+  CK(cudaSetDevice(ctx->device));
+  prof_collect(ctx);
+  for (int s = 0; s < MAF_PROF_NSLOTS; ++s) {
+    if (ms) ms[s] = ctx->slots[s].ms;
+    if (launches) launches[s] = ctx->slots[s].launches;
+  }
+  return 0;
+}
+extern "C" int maf_profile_reset(maf_ctx* ctx) {
+  if (!ctx) return 1;
+  prof_collect(ctx);
+  for (auto& ps : ctx->slots) {
+    ps.ms = 0.0;
+    ps.launches = 0;
+  }
+  return 0;
+}
+extern "C" int64_t maf_launch_count(const maf_ctx* ctx) { return ctx ? ctx->launch_count : 0; }
+
+extern "C" int maf_timer_start(maf_ctx* ctx) {
+  if (!ctx) return 1;
+  CK(cudaSetDevice(ctx->device));
+  for (auto& e : ctx->timer_ev)
+    if (!e) CK(cudaEventCreate(&e));
+  CK(cudaEventRecord(ctx->timer_ev[0], ctx->stream));
+  return 0;
+}
+extern "C" int maf_timer_stop(maf_ctx* ctx, double* ms) {
+  if (!ctx) return 1;
+  if (!ctx->timer_ev[0]) return fail(ctx, "maf_timer_start must be called first");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaEventRecord(ctx->timer_ev[1], ctx->stream));
+  CK(cudaEventSynchronize(ctx->timer_ev[1]));
+  float f = 0.f;
+  CK(cudaEventElapsedTime(&f, ctx->timer_ev[0], ctx->timer_ev[1]));
+  if (ms) *ms = (double)f;
+  return 0;
+}
+extern "C" void* maf_host_alloc(maf_ctx* ctx, size_t bytes) {
+  void* p = nullptr;
+  cudaSetDevice(ctx->device);
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+    fail(ctx, "maf_host_alloc(%zu) failed", bytes);
+    return nullptr;
+  }
+  return p;
+}
+extern "C" int maf_host_free(maf_ctx* ctx, void* p) {
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaFreeHost(p));
+  return 0;
+}
+
+// ---- raw GEMM ----------------------------------------------------------------------------------------
+extern "C" int maf_gemm_nt_dev(maf_ctx* ctx, int J, int N, int K, const double* dA, int lda, const double* dT,
+                               int ldt, double* dC, int ldc, int tri) {
+  if (!ctx) return 1;
+  CK(cudaSetDevice(ctx->device));
+  return launch_gemm(ctx, tri == 2 ? MAF_PROF_GEMM_BWD : MAF_PROF_GEMM_FWD, J, N, K, dA, lda, dT, ldt, dC, ldc, tri);
+}

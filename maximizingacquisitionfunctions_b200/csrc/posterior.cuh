@@ -1,0 +1,120 @@
+// Posterior mean / q x q covariance from V^T = K10 L0^-T, and the reverse-mode
+// propagation (mubar, Sigmabar) -> Vbar.
+// Reference: gaussian_process._predict_nd (src/models/gaussian_process.py:172-223):
+//   Means = m + Beta resid,  Covs = k(X1,X1) - Beta K01   (Beta = (K00^-1 K01)^T).
+// With V = L0^-1 K01 and gamma = L0^-1 resid this is  mu = m + V^T gamma,
+// Sigma = K11 - V^T V  (identical maths, better conditioned: sqrt(cond(K00))).
+#pragma once
+#include "common.cuh"
+
+#define POST_TK 256
+#define POST_THREADS 256
+
+// One CTA per restart.  The q x POST_TK slab of V^T is staged in shared memory once and
+// every warp accumulates the Gram rows it owns (warp w -> rows w and w+8).
+template <int Q>
+__global__ void __launch_bounds__(POST_THREADS)
+posterior_kernel(const double* __restrict__ Vt, int npad, const double* __restrict__ gamma,
+                 const double* __restrict__ X, ModelParams mp, double mean,
+                 double* __restrict__ mu, double* __restrict__ Sig) {
+  __shared__ double tile[Q][POST_TK];
+  __shared__ double gs[POST_TK];
+  __shared__ double G[Q][Q];
+  __shared__ double mus[Q];
+  const int s = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const double* V = Vt + (size_t)s * Q * npad;
+  const int i0 = warp, i1 = warp + 8;
+  double acc0[Q], acc1[Q], m0 = 0.0, m1 = 0.0;
+#pragma unroll
+  for (int j = 0; j < Q; ++j) acc0[j] = acc1[j] = 0.0;
+
+  for (int k0 = 0; k0 < npad; k0 += POST_TK) {
+    __syncthreads();
+    const int k = k0 + tid;
+#pragma unroll
+    for (int i = 0; i < Q; ++i) tile[i][tid] = (k < npad) ? V[(size_t)i * npad + k] : 0.0;
+    gs[tid] = (k < npad) ? gamma[k] : 0.0;
+    __syncthreads();
+    for (int kk = lane; kk < POST_TK; kk += 32) {
+      if (i0 < Q) {
+        double vi = tile[i0][kk];
+        m0 += vi * gs[kk];
+#pragma unroll
+        for (int j = 0; j < Q; ++j)
+          if (j <= i0) acc0[j] += vi * tile[j][kk];
+      }
+      if (Q > 8 && i1 < Q) {
+        double vi = tile[i1][kk];
+        m1 += vi * gs[kk];
+#pragma unroll
+        for (int j = 0; j < Q; ++j)
+          if (j <= i1) acc1[j] += vi * tile[j][kk];
+      }
+    }
+  }
+  if (i0 < Q) {
+    m0 = warp_sum(m0);
+#pragma unroll
+    for (int j = 0; j < Q; ++j) {
+      double v = warp_sum(acc0[j]);
+      if (lane == 0 && j <= i0) G[i0][j] = v;
+    }
+    if (lane == 0) mus[i0] = m0;
+  }
+  if (Q > 8 && i1 < Q) {
+    m1 = warp_sum(m1);
+#pragma unroll
+    for (int j = 0; j < Q; ++j) {
+      double v = warp_sum(acc1[j]);
+      if (lane == 0 && j <= i1) G[i1][j] = v;
+    }
+    if (lane == 0) mus[i1] = m1;
+  }
+  __syncthreads();
+  const double* xs = X + (size_t)s * Q * mp.d;
+  for (int t = tid; t < Q * Q; t += POST_THREADS) {
+    int i = t / Q, j = t - i * Q;
+    double r2 = 0.0;
+    if (i != j) {
+      for (int c = 0; c < mp.d; ++c) {
+        double df = xs[i * mp.d + c] * mp.inv_ls[c] - xs[j * mp.d + c] * mp.inv_ls[c];
+        r2 += df * df;
+      }
+    }
+    double g = (i >= j) ? G[i][j] : G[j][i];
+    Sig[(size_t)s * Q * Q + t] = mp.amp2 * kern_val(mp.kernel_id, r2) - g;
+  }
+  if (tid < Q) mu[(size_t)s * Q + tid] = mean + mus[tid];
+}
+
+// Vbar^T[i][k] = mubar_i gamma_k - sum_j (Sbar_ij + Sbar_ji) V^T[j][k], in place.
+template <int Q>
+__global__ void __launch_bounds__(256)
+vbar_kernel(double* __restrict__ Vt, int npad, const double* __restrict__ gamma,
+            const double* __restrict__ mubar, const double* __restrict__ Sigbar) {
+  __shared__ double W[Q][Q];
+  __shared__ double mb[Q];
+  const int s = blockIdx.x, tid = threadIdx.x;
+  const double* sb = Sigbar + (size_t)s * Q * Q;
+  for (int t = tid; t < Q * Q; t += 256) {
+    int i = t / Q, j = t - i * Q;
+    W[i][j] = sb[i * Q + j] + sb[j * Q + i];
+  }
+  if (tid < Q) mb[tid] = mubar[(size_t)s * Q + tid];
+  __syncthreads();
+  double* V = Vt + (size_t)s * Q * npad;
+  for (int k = tid; k < npad; k += 256) {
+    double v[Q];
+#pragma unroll
+    for (int i = 0; i < Q; ++i) v[i] = V[(size_t)i * npad + k];
+    const double g = gamma[k];
+#pragma unroll(Q <= 8 ? Q : 1)
+    for (int i = 0; i < Q; ++i) {
+      double o = mb[i] * g;
+#pragma unroll
+      for (int j = 0; j < Q; ++j) o -= W[i][j] * v[j];
+      V[(size_t)i * npad + k] = o;
+    }
+  }
+}

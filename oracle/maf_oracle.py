@@ -418,6 +418,10 @@ def value_and_grad(ts: TrainState, acq: Acq, X_new, z, X_pend=None,
         losses = closed_form_losses(ts, acq, pools).reshape(-1)
     else:
         losses = mc_losses(ts, acq, pools, z, weights, incumbents, shard_limit)
+    if not losses.requires_grad:
+        # hard-indicator PI is piecewise constant (negative_pi.py:67-69): TF has no gradient
+        # to offer (optimizer.minimize raises); report zeros.
+        return losses.detach().numpy(), np.zeros(tuple(Xn.shape))
     losses.sum().backward()
     return losses.detach().numpy(), Xn.grad.detach().numpy()
 

@@ -1,0 +1,260 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes), against the CPU
+oracle on identical seeded inputs and identical base samples.  Bar (BASELINE.json):
+posterior mean/cov and acquisition value/gradient within 1e-9 relative in fp64 (norm-wise:
+max-abs error / max-abs value per tensor), identical selected restart."""
+import math
+import os
+
+import numpy as np
+import pytest
+import scipy.linalg as spla
+import torch
+
+from oracle import maf_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-9
+
+
+def relerr(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from maximizingacquisitionfunctions_b200.engine import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def setup_problem(eng, n, d, q, S, M, seed=0, kernel_id="matern52", mean=0.0):
+    gp, X0, y0, X, z = orc.synthetic_problem(n, d, q, S, M, seed=seed, kernel_id=kernel_id)
+    gp.mean = mean
+    ts = orc.prepare_train(gp, X0, y0)
+    eng.set_model(kernel_id, np.full(d, math.sqrt(d) / 4), 1.0, 1e-3, mean, 1e-6)
+    eng.set_train(X0, y0)
+    return ts, X0, y0, X, z
+
+
+def prm(kind, **kw):
+    from maximizingacquisitionfunctions_b200.engine import acq_params
+    return acq_params(kind, **kw)
+
+
+# ---------------------------------------------------------------- building blocks
+@pytest.mark.parametrize("tri", [0, 1, 2])
+def test_gemm_fragment_layout_and_triangular_modes(eng, tri):
+    rng = np.random.RandomState(tri)
+    J, N = 256, 384
+    A = rng.randn(J, N)
+    T = rng.randn(N, N)
+    if tri == 1:
+        T = np.tril(T)
+    if tri == 2:
+        T = np.triu(T)
+    C = eng.gemm_nt(A, T, tri)
+    ref = A @ T.T
+    assert relerr(C, ref) < 1e-13
+
+
+def test_training_factors(eng):
+    ts, X0, y0, X, z = setup_problem(eng, n=200, d=3, q=2, S=4, M=8, seed=1)
+    L0, Linv, gamma = eng.factors()
+    Lref = ts.chol.numpy()
+    assert relerr(L0, Lref) < 1e-12
+    assert relerr(Linv @ Lref, np.eye(200)) < 1e-9
+    assert relerr(gamma, spla.solve_triangular(Lref, y0.reshape(-1), lower=True)) < 1e-10
+
+
+# ---------------------------------------------------------------- posterior
+def test_posterior_reference_golden(eng, golden_dir):
+    """The reference's own test_gp_predict numbers (tests/test_models.py:229-256): SE kernel,
+    l=0.1, a=1.2, noise=1e-3, 64 new x 128 old x 4-D.  The 64x64 joint covariance is checked
+    through its 16x16 diagonal blocks (pools of q=16) and all marginals (q=1)."""
+    g = np.load(os.path.join(golden_dir, "ref_gp_posterior.npz"))
+    for key in ("s11_rn2_ro2_mc", "s12_rn2_ro2_mc", "s11_rn2_ro2_memp", "s11_rn3_ro2_mc"):
+        X1, X0, Y0 = g[key + "_X1"], g[key + "_X0"], g[key + "_Y0"]
+        mean = None if key.endswith("emp") else 0.25
+        eng.set_model("squared_exponential", np.full(4, 0.1), 1.2, 1e-3, mean, 1e-6)
+        eng.set_train(X0, Y0)
+        X1f = X1.reshape(-1, 64, 4)
+        mref = g[key + "_mean"].reshape(-1, 64, 1)
+        cref = g[key + "_cov"].reshape(-1, 64, 64)
+        for b in range(X1f.shape[0]):
+            mu, cov = eng.posterior(X1f[b].reshape(4, 16, 4), full_cov=True)
+            assert np.abs(mu.reshape(64, 1) - mref[b]).max() < 1e-11
+            for k in range(4):
+                blk = cref[b][16 * k:16 * k + 16, 16 * k:16 * k + 16]
+                assert np.abs(cov[k] - blk).max() < 1e-11
+            mu1, var1 = eng.posterior(X1f[b].reshape(64, 1, 4), full_cov=False)
+            assert np.abs(mu1.reshape(64, 1) - mref[b]).max() < 1e-11
+            assert np.abs(var1.reshape(64) - np.diag(cref[b])).max() < 1e-11
+
+
+@pytest.mark.parametrize("kernel_id", ["matern52", "squared_exponential", "matern32"])
+@pytest.mark.parametrize("n,d,q,S", [(32, 3, 2, 64), (300, 2, 4, 100), (1024, 6, 8, 64), (130, 7, 16, 9), (257, 12, 3, 5)])
+def test_posterior_vs_oracle(eng, kernel_id, n, d, q, S):
+    ts, X0, y0, X, z = setup_problem(eng, n, d, q, S, 8, seed=3, kernel_id=kernel_id)
+    mu, cov = eng.posterior(X, full_cov=True)
+    with torch.no_grad():
+        mo, co = orc.posterior(ts, torch.as_tensor(X), full_cov=True)
+    assert relerr(mu, mo.numpy()) < TOL
+    assert relerr(cov, co.numpy()) < TOL
+    mu2, var = eng.posterior(X, full_cov=False)
+    assert relerr(var[..., 0], np.diagonal(co.numpy(), axis1=-2, axis2=-1)) < TOL
+
+
+def test_posterior_empirical_mean(eng):
+    ts, X0, y0, X, z = setup_problem(eng, 90, 3, 3, 7, 8, seed=5, mean=None)
+    mu, cov = eng.posterior(X)
+    with torch.no_grad():
+        mo, co = orc.posterior(ts, torch.as_tensor(X), full_cov=True)
+    assert relerr(mu, mo.numpy()) < TOL and relerr(cov, co.numpy()) < TOL
+
+
+# ---------------------------------------------------------------- acquisition value + gradient
+ACQS = [
+    ("ei", {}, {}),
+    ("pi", {"temperature": 0.01}, {"temperature": 0.01}),
+    ("pi", {}, {}),
+    ("sr", {}, {}),
+    ("cb", {"beta": 2.0, "lower": True}, {"beta": 2.0, "lower": True}),
+    ("cb", {"beta": 3.0, "lower": False}, {"beta": 3.0, "lower": False}),
+]
+SHAPES = [
+    # n, d, q, S, M  -- C1 (Hartmann-3 shape), C2 shape at reduced S, C3 shape at reduced S, ragged
+    (32, 3, 2, 64, 128),
+    (256, 2, 4, 128, 256),
+    (1024, 6, 8, 32, 128),
+    (100, 5, 7, 11, 100),
+    (130, 4, 16, 6, 33),
+]
+
+
+@pytest.mark.parametrize("acq,okw,gkw", ACQS)
+@pytest.mark.parametrize("n,d,q,S,M", SHAPES)
+def test_value_and_grad_vs_oracle(eng, acq, okw, gkw, n, d, q, S, M):
+    ts, X0, y0, X, z = setup_problem(eng, n, d, q, S, M, seed=7)
+    lo, go = orc.value_and_grad(ts, orc.Acq(acq, **okw), X, z)
+    lg, gg = eng.value_and_grad(prm(acq, **gkw), X, z)
+    assert relerr(lg, lo) < TOL, ("loss", relerr(lg, lo))
+    if np.abs(go).max() > 0:
+        assert relerr(gg, go) < TOL, ("grad", relerr(gg, go))
+    else:
+        assert np.abs(gg).max() == 0
+    assert int(np.argmin(lg)) == int(np.argmin(lo))
+    idx, val = eng.argmin_last()
+    assert idx == int(np.argmin(lo)) and val == lg[idx]
+    mu, cov, chol = eng.last_extras(S, q)
+    with torch.no_grad():
+        _, (mo, co, Lo) = orc.mc_losses(ts, orc.Acq(acq, **okw), torch.as_tensor(X), torch.as_tensor(z), return_extras=True)
+    assert relerr(mu, mo.numpy()) < TOL and relerr(cov, co.numpy()) < TOL and relerr(chol, Lo.numpy()) < 1e-8
+
+
+def test_pending_weights_incumbents(eng):
+    n, d, q, S, M = 64, 2, 5, 20, 40
+    ts, X0, y0, X, z = setup_problem(eng, n, d, q, S, M, seed=4)
+    rng = np.random.RandomState(0)
+    w = rng.rand(M)
+    w /= w.sum()
+    inc = float(y0.min()) + 0.3 * rng.randn(M)
+    pend, Xn = X[0, :2], X[:, 2:]
+    pools = np.ascontiguousarray(np.concatenate([np.broadcast_to(pend, (S, 2, d)), Xn], axis=1))
+    for acq in ("ei", "sr", "cb"):
+        lo, go = orc.value_and_grad(ts, orc.Acq(acq), Xn, z, X_pend=pend, weights=w, incumbents=inc)
+        lg, gg = eng.value_and_grad(prm(acq), pools, z, p_pending=2, weights=w, incumbents=inc)
+        assert gg.shape == (S, 3, d)
+        assert relerr(lg, lo) < TOL and relerr(gg, go) < TOL
+
+
+@pytest.mark.parametrize("acq,kw", [("ei", {}), ("pi", {}), ("sr", {}), ("cb", {"lower": True}), ("cb", {"lower": False, "beta": 3.0})])
+def test_closed_form_q1(eng, acq, kw):
+    ts, X0, y0, X, z = setup_problem(eng, 200, 3, 1, 300, 4, seed=6)
+    lo, go = orc.value_and_grad(ts, orc.Acq(acq, **kw), X, np.zeros((1, 1)))
+    lg, gg = eng.value_and_grad(prm(acq, **kw), X, None)
+    assert relerr(lg, lo) < TOL and relerr(gg, go) < TOL
+
+
+def test_value_only_and_explicit_level(eng):
+    ts, X0, y0, X, z = setup_problem(eng, 64, 3, 3, 10, 64, seed=9)
+    lo, _ = orc.value_and_grad(ts, orc.Acq("ei", level=-0.5), X, z)
+    lg, gg = eng.value_and_grad(prm("ei", level=-0.5), X, z, need_grad=False)
+    assert gg is None and relerr(lg, lo) < TOL
+
+
+def test_chunking_is_invisible(eng):
+    """restarts are independent (src/misc/sharded_fn.py): results must not depend on the chunking."""
+    from maximizingacquisitionfunctions_b200.engine import Engine
+    n, d, q, S, M = 160, 3, 3, 200, 64
+    ts, X0, y0, X, z = setup_problem(eng, n, d, q, S, M, seed=11)
+    l1, g1 = eng.value_and_grad(prm("ei"), X, z)
+    os.environ["MAF_CHUNK_ROWS"] = "128"
+    try:
+        e2 = Engine(0)
+    finally:
+        del os.environ["MAF_CHUNK_ROWS"]
+    e2.set_model("matern52", np.full(d, math.sqrt(d) / 4), 1.0, 1e-3, 0.0, 1e-6)
+    e2.set_train(X0, y0)
+    l2, g2 = e2.value_and_grad(prm("ei"), X, z)
+    e2.close()
+    assert np.array_equal(l1, l2) and np.array_equal(g1, g2)
+    perm = np.random.RandomState(1).permutation(S)
+    l3, g3 = eng.value_and_grad(prm("ei"), np.ascontiguousarray(X[perm]), z)
+    assert np.array_equal(l3, l1[perm]) and np.array_equal(g3, g1[perm])
+
+
+def test_adam_loop_vs_oracle(eng):
+    n, d, q, S, M, steps = 48, 3, 2, 16, 64, 5
+    ts, X0, y0, X, z = setup_problem(eng, n, d, q, S, M, seed=13)
+    zs = np.random.RandomState(99).randn(steps, M, q)
+    xo, tro = orc.adam_run(ts, orc.Acq("ei"), X, zs)
+    eng.adam_begin(prm("ei"), X)
+    trg = eng.adam_steps(zs, want_trace=True)
+    xg = eng.adam_end()
+    assert relerr(trg, tro) < 1e-7
+    assert np.abs(xg - xo).max() < 1e-7
+    assert xg.min() >= 0.0 and xg.max() <= 1.0
+
+
+def test_errors_are_loud(eng):
+    from maximizingacquisitionfunctions_b200.engine import MafError
+    setup_problem(eng, 32, 2, 2, 4, 8)
+    with pytest.raises(MafError):
+        eng.value_and_grad(prm("ei"), np.zeros((4, 2, 2)), None)          # MC path needs z
+    with pytest.raises(MafError):
+        eng.value_and_grad(prm("ei"), np.zeros((4, 17, 2)), np.zeros((8, 17)))
+    eng.set_model("squared_exponential", np.full(2, 10.0), 1.0, None, 0.0, 0.0)
+    with pytest.raises(MafError):                                          # singular K00 (duplicates, no noise/jitter)
+        eng.set_train(np.zeros((8, 2)), np.zeros(8))
+
+
+# ---------------------------------------------------------------- full-size properties
+def test_full_size_properties(eng):
+    """BASELINE sizes (n=4096, d=6, q=8): oracle on a few restarts + size-independent checks:
+    central finite differences of the GPU's own smooth loss (qSR), PSD covariance, Sigma == K11
+    minus what the training set explains (<= prior), and restart independence."""
+    n, d, q, S, M = 4096, 6, 8, 1024, 128
+    ts, X0, y0, X, z = setup_problem(eng, n, d, q, S, M, seed=0)
+    lg, gg = eng.value_and_grad(prm("ei"), X, z)
+    lo, go = orc.value_and_grad(ts, orc.Acq("ei"), X[:8], z)
+    assert relerr(lg[:8], lo) < TOL and relerr(gg[:8], go) < TOL
+    mu, cov, chol = eng.last_extras(S, q)
+    assert np.linalg.eigvalsh(0.5 * (cov + cov.transpose(0, 2, 1))).min() > -1e-9
+    assert np.diagonal(cov, axis1=1, axis2=2).max() <= 1.0 + 1e-12
+    ls, gs = eng.value_and_grad(prm("sr"), X[:64], z)
+    h = 1e-5
+    rng = np.random.RandomState(3)
+    for _ in range(4):
+        s, i, c = rng.randint(64), rng.randint(q), rng.randint(d)
+        Xp, Xm = X[:64].copy(), X[:64].copy()
+        Xp[s, i, c] += h
+        Xm[s, i, c] -= h
+        lp, _ = eng.value_and_grad(prm("sr"), Xp, z, need_grad=False)
+        lm, _ = eng.value_and_grad(prm("sr"), Xm, z, need_grad=False)
+        fd = (lp[s] - lm[s]) / (2 * h)
+        assert abs(fd - gs[s, i, c]) < 1e-5 * max(1.0, abs(fd))
+        others = np.delete(np.arange(64), s)
+        assert np.array_equal(lp[others], ls[others])

@@ -1,0 +1,91 @@
+"""CPU tests of the host-side logic: synthetic inputs, task objectives vs reference golden
+values, restart sharding and the global arg-min record selection (incl. a world_size-2 gloo run)."""
+import math
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from maximizingacquisitionfunctions_b200 import dist as mdist
+from maximizingacquisitionfunctions_b200 import synthetic, tasks
+from oracle import maf_oracle as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_tasks_match_reference_numpy(golden_dir):
+    g = np.load(os.path.join(golden_dir, "ref_tasks.npz"))
+    for name in ("hartmann3", "hartmann6", "braninhoo", "levy"):
+        got = getattr(tasks, name)(g[name + "_X"])
+        assert got.shape == g[name + "_Y"].shape
+        assert np.abs(got - g[name + "_Y"]).max() <= 1e-14 * max(1.0, np.abs(g[name + "_Y"]).max())
+        assert tasks.MINIMA[name] == float(g[name + "_min"])
+
+
+def test_synthetic_inputs_agree_with_oracle_generator():
+    gp, X0, y0, X, z = orc.synthetic_problem(40, 3, 2, 5, 16, seed=4)
+    a = synthetic.synthetic_inputs(40, 3, 2, 5, 16, seed=4)
+    for u, v in zip((X0, y0, X, z), a):
+        assert np.array_equal(u, v)
+    hp = synthetic.hyperparameters(3)
+    assert math.isclose(float(gp.lenscales()), hp["lenscales"][0])
+
+
+def test_shard_range_partitions():
+    for S in (1, 7, 64, 65536):
+        for W in (1, 2, 3, 8):
+            spans = [mdist.shard_range(S, r, W) for r in range(W)]
+            assert spans[0][0] == 0 and spans[-1][1] == S
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(W - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_pick_record_tie_break_and_nan():
+    x = np.arange(6.0).reshape(2, 3)
+    recs = np.array([
+        np.concatenate([[0.5, 10], x.ravel()]),
+        np.concatenate([[0.25, 40], (x + 1).ravel()]),
+        np.concatenate([[0.25, 20], (x + 2).ravel()]),
+        np.concatenate([[float("nan"), 5], x.ravel()]),
+        np.concatenate([[float("inf"), -1], x.ravel()]),
+    ])
+    loss, idx, xb = mdist.pick_record(recs, (2, 3))
+    assert (loss, idx) == (0.25, 20) and np.array_equal(xb, x + 2)
+    assert mdist.local_best(np.array([np.nan, 3.0, 1.0, 1.0]), 100) == (1.0, 102)
+    assert mdist.local_best(np.array([]), 5) == (float("inf"), -1)
+
+
+_GLOO_WORKER = r"""
+import os, sys
+import numpy as np
+sys.path.insert(0, {root!r})
+from maximizingacquisitionfunctions_b200 import dist as mdist
+d = mdist.init_process_group("gloo")
+rank, ws, _ = mdist.world()
+S, q, dd = 11, 2, 3
+rng = np.random.RandomState(0)
+losses = rng.randn(S); losses[7] = losses[2] = losses.min() - 1.0      # tie across ranks
+X = rng.rand(S, q, dd)
+lo, hi = mdist.shard_range(S, rank, ws)
+val, gidx = mdist.local_best(losses[lo:hi], lo)
+loss, idx, xb = mdist.select_global_best(val, gidx, X[gidx])
+assert idx == int(np.argmin(losses)) == 2, idx
+assert loss == losses[2] and np.array_equal(xb, X[2])
+assert mdist.max_over_ranks(float(rank)) == ws - 1
+mdist.barrier()
+print("rank", rank, "ok")
+"""
+
+
+def test_global_argmin_world_size_2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER.format(root=ROOT))
+    port = 29500 + (os.getpid() % 2000)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env={**os.environ, "OMP_NUM_THREADS": "1"})
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "rank 0 ok" in res.stdout and "rank 1 ok" in res.stdout
