@@ -62,6 +62,7 @@ cross_fwd_kernel(const double* __restrict__ X, int J, const double* __restrict__
     xs[jj][c] = (j < J) ? X[(size_t)j * d + c] * mp.inv_ls[c] : 0.0;
   }
   __syncthreads();
+  if (k >= npad) return;          // npad is a multiple of 128, the k-tile is 256 wide
   double x0[DD];
 #pragma unroll
   for (int c = 0; c < DD; ++c) x0[c] = (c < d) ? X0s[(size_t)c * npad + k] : 0.0;
