@@ -100,6 +100,15 @@ int maf_acq_value_grad(maf_ctx* ctx, const maf_acq_params* prm, int S, int q, in
 int maf_acq_value_grad_dev(maf_ctx* ctx, const maf_acq_params* prm, int S, int q, int p_pending,
                            const double* dX, int M, const double* dz, const double* dweights,
                            const double* dincumbents, double* dout_loss, double* dout_grad);
+/* Monte-Carlo estimator from GIVEN posterior moments: replaces the loss classes'
+ * _monte_carlo(means, cov, base_rvs=...) bodies (negative_ei.py:52-74, negative_pi.py:52-80,
+ * simple_regret.py:32-49, confidence_bound.py:48-116) incl. jitter_cholesky of cov with the
+ * model's jitter.  mu[S][q], cov[S][q][q] (lower triangle read), z[M][q]; outputs (NULL to skip)
+ * out_loss[S], out_mubar[S][q], out_covbar[S][q][q] (d sum(loss) / d mu, / d cov), out_chol. */
+int maf_mc_from_moments(maf_ctx* ctx, const maf_acq_params* prm, int S, int q, const double* mu,
+                        const double* cov, int M, const double* z, const double* weights,
+                        const double* incumbents, double* out_loss, double* out_mubar,
+                        double* out_covbar, double* out_chol);
 /* extras of the last evaluation (myopic_loss.py:179 returns (means, cov, chol)):
  * mu[S][q], cov[S][q][q], chol[S][q][q] (NULL to skip) */
 int maf_last_extras(maf_ctx* ctx, double* mu, double* cov, double* chol);
@@ -115,6 +124,7 @@ int maf_last_extras(maf_ctx* ctx, double* mu, double* cov, double* chol);
 int maf_adam_begin(maf_ctx* ctx, const maf_acq_params* prm, int S, int q, int p_pending,
                    const double* X, double lr, double beta1, double beta2, double eps);
 int maf_adam_steps(maf_ctx* ctx, int steps, int M, const double* z_steps, double* out_loss_trace);
+int maf_adam_peek(maf_ctx* ctx, double* X_out);   /* current iterate, loop stays open */
 int maf_adam_end(maf_ctx* ctx, double* X_out);
 
 /* ---- selection --------------------------------------------------------- */

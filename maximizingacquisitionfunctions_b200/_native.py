@@ -41,10 +41,13 @@ SIGNATURES = {
                                      _vp, _vp, _vp, _vp, _vp]),
     "maf_acq_value_grad_dev": (C.c_int, [_vp, C.POINTER(AcqParams), C.c_int, C.c_int, C.c_int, _vp, C.c_int,
                                          _vp, _vp, _vp, _vp, _vp]),
+    "maf_mc_from_moments": (C.c_int, [_vp, C.POINTER(AcqParams), C.c_int, C.c_int, _vp, _vp, C.c_int, _vp, _vp, _vp,
+                                      _vp, _vp, _vp, _vp]),
     "maf_last_extras": (C.c_int, [_vp, _vp, _vp, _vp]),
     "maf_adam_begin": (C.c_int, [_vp, C.POINTER(AcqParams), C.c_int, C.c_int, C.c_int, _vp,
                                  C.c_double, C.c_double, C.c_double, C.c_double]),
     "maf_adam_steps": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp]),
+    "maf_adam_peek": (C.c_int, [_vp, _vp]),
     "maf_adam_end": (C.c_int, [_vp, _vp]),
     "maf_argmin_last": (C.c_int, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
     "maf_profile_enable": (C.c_int, [_vp, C.c_int]),

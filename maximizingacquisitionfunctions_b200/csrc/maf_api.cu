@@ -653,6 +653,63 @@ extern "C" int maf_acq_value_grad(maf_ctx* ctx, const maf_acq_params* prm, int S
   return 0;
 }
 
+extern "C" int maf_mc_from_moments(maf_ctx* ctx, const maf_acq_params* prm, int S, int q, const double* mu,
+                                   const double* cov, int M, const double* z, const double* weights,
+                                   const double* incumbents, double* out_loss, double* out_mubar,
+                                   double* out_covbar, double* out_chol) {
+  if (!ctx) return 1;
+  if (!ctx->model_set) return fail(ctx, "maf_set_model must be called first");
+  if (!prm || !mu || !cov || !z) return fail(ctx, "null pointer");
+  if (S < 1 || M < 1) return fail(ctx, "S and M must be >= 1");
+  if (q < 1 || q > MAF_MAX_Q) return fail(ctx, "q=%d outside 1..%d", q, MAF_MAX_Q);
+  CK(cudaSetDevice(ctx->device));
+  AcqDev ap{};
+  if (prm->level != prm->level && !ctx->train_set && (prm->acq == MAF_ACQ_EI || prm->acq == MAF_ACQ_PI))
+    return fail(ctx, "an explicit level is required when no training set is loaded");
+  if (resolve_acq(ctx, prm, &ap)) return 1;
+  const size_t sq = (size_t)S * q, sqq = sq * q;
+  if (ensure(ctx, ctx->dmu, sq) || ensure(ctx, ctx->dmubar, sq) || ensure(ctx, ctx->dSig, sqq) ||
+      ensure(ctx, ctx->dSigbar, sqq) || ensure(ctx, ctx->dchol, sqq) || ensure(ctx, ctx->dloss, (size_t)S) ||
+      ensure(ctx, ctx->dz, (size_t)M * q))
+    return 1;
+  CK(cudaMemcpyAsync(ctx->dmu.p, mu, sizeof(double) * sq, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->dSig.p, cov, sizeof(double) * sqq, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->dz.p, z, sizeof(double) * M * q, cudaMemcpyHostToDevice, ctx->stream));
+  const double *dw = nullptr, *dinc = nullptr;
+  if (weights) {
+    if (ensure(ctx, ctx->dw, (size_t)M)) return 1;
+    CK(cudaMemcpyAsync(ctx->dw.p, weights, sizeof(double) * M, cudaMemcpyHostToDevice, ctx->stream));
+    dw = ctx->dw.p;
+  }
+  if (incumbents) {
+    if (ensure(ctx, ctx->dinc, (size_t)M)) return 1;
+    CK(cudaMemcpyAsync(ctx->dinc.p, incumbents, sizeof(double) * M, cudaMemcpyHostToDevice, ctx->stream));
+    dinc = ctx->dinc.p;
+  }
+  const int need_grad = (out_mubar != nullptr || out_covbar != nullptr) ? 1 : 0;
+  {
+    ProfScope ps(ctx, MAF_PROF_MC);
+    DISPATCH_Q(q, {
+      const size_t smem = sizeof(McSmem<Q>);
+      if (smem > 48 * 1024)
+        CK(cudaFuncSetAttribute(mc_acq_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      mc_acq_kernel<Q><<<(S + MC_WARPS - 1) / MC_WARPS, MC_WARPS * 32, smem, ctx->stream>>>(
+          S, M, ctx->dmu.p, ctx->dSig.p, ctx->dz.p, dw, dinc, ap, ctx->mp.jitter, need_grad, ctx->dloss.p,
+          ctx->dmubar.p, ctx->dSigbar.p, ctx->dchol.p);
+    });
+    CKL();
+  }
+  if (out_loss) CK(cudaMemcpyAsync(out_loss, ctx->dloss.p, sizeof(double) * S, cudaMemcpyDeviceToHost, ctx->stream));
+  if (out_mubar) CK(cudaMemcpyAsync(out_mubar, ctx->dmubar.p, sizeof(double) * sq, cudaMemcpyDeviceToHost, ctx->stream));
+  if (out_covbar) CK(cudaMemcpyAsync(out_covbar, ctx->dSigbar.p, sizeof(double) * sqq, cudaMemcpyDeviceToHost, ctx->stream));
+  if (out_chol) CK(cudaMemcpyAsync(out_chol, ctx->dchol.p, sizeof(double) * sqq, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->last_S = S;
+  ctx->last_q = q;
+  ctx->last_has_chol = true;
+  return 0;
+}
+
 extern "C" int maf_last_extras(maf_ctx* ctx, double* mu, double* cov, double* chol) {
   if (!ctx) return 1;
   if (ctx->last_S == 0) return fail(ctx, "no evaluation to report");
@@ -757,6 +814,17 @@ extern "C" int maf_adam_steps(maf_ctx* ctx, int steps, int M, const double* z_st
     // dloss holds the last step's losses
   }
   return rc;
+}
+
+extern "C" int maf_adam_peek(maf_ctx* ctx, double* X_out) {
+  if (!ctx) return 1;
+  if (!ctx->adam_on) return fail(ctx, "maf_adam_begin must be called first");
+  if (!X_out) return fail(ctx, "null pointer");
+  CK(cudaSetDevice(ctx->device));
+  const size_t nx = (size_t)ctx->adam_S * ctx->adam_q * ctx->mp.d;
+  CK(cudaMemcpyAsync(X_out, ctx->adam_X.p, nx * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
 }
 
 extern "C" int maf_adam_end(maf_ctx* ctx, double* X_out) {

@@ -194,6 +194,25 @@ class Engine:
                                                   dz.ptr if dz else None, None, None, dloss.ptr,
                                                   dgrad.ptr if dgrad else None))
 
+    def mc_from_moments(self, prm: nat.AcqParams, mu: np.ndarray, cov: np.ndarray, z: np.ndarray,
+                        weights=None, incumbents=None, need_grad: bool = False):
+        """MC estimator from given moments mu[S,q(,1)], cov[S,q,q]; returns (loss, mubar, covbar, chol)."""
+        cov = nat.as_f64(cov)
+        S, q, _ = cov.shape
+        mu = nat.as_f64(np.reshape(mu, (S, q)))
+        z = nat.as_f64(z)
+        M = int(z.shape[0])
+        assert z.shape == (M, q)
+        weights = None if weights is None else nat.as_f64(weights)
+        incumbents = None if incumbents is None else nat.as_f64(incumbents)
+        loss, chol = np.empty(S), np.empty((S, q, q))
+        mubar = np.empty((S, q)) if need_grad else None
+        covbar = np.empty((S, q, q)) if need_grad else None
+        self._ck(self._lib.maf_mc_from_moments(self._ctx, C.byref(prm), S, q, nat.ptr(mu), nat.ptr(cov), M,
+                                               nat.ptr(z), nat.ptr(weights), nat.ptr(incumbents), nat.ptr(loss),
+                                               nat.ptr(mubar), nat.ptr(covbar), nat.ptr(chol)))
+        return loss, mubar, covbar, chol
+
     def last_extras(self, S: int, q: int, want_chol: bool = True):
         mu, cov = np.empty((S, q, 1)), np.empty((S, q, q))
         chol = np.empty((S, q, q)) if want_chol else None
@@ -221,6 +240,11 @@ class Engine:
         trace = np.empty((steps, self._adam_shape[0])) if want_trace else None
         self._ck(self._lib.maf_adam_steps(self._ctx, steps, M, nat.ptr(z_steps), nat.ptr(trace)))
         return trace
+
+    def adam_peek(self) -> np.ndarray:
+        X = np.empty(self._adam_shape)
+        self._ck(self._lib.maf_adam_peek(self._ctx, nat.ptr(X)))
+        return X
 
     def adam_end(self) -> np.ndarray:
         X = np.empty(self._adam_shape)

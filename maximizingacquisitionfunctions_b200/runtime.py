@@ -1,0 +1,66 @@
+"""Process-wide engine registry and training-set cache.
+
+The reference recomputes the training Cholesky in every ``appraise_inputs`` call
+(src/agents/bayesian_optimization.py:188-198).  Here the factors live on the device; they are
+rebuilt only when the (hyper-parameters, X0, y0) fingerprint changes.
+"""
+import hashlib
+import os
+
+import numpy as np
+
+_ENGINES = {}
+_FACTORY = None
+
+
+def set_engine_factory(factory):
+    """Test hook: replace the engine constructor (``factory(device, dtype)``)."""
+    global _FACTORY
+    _FACTORY = factory
+    _ENGINES.clear()
+
+
+def default_device() -> int:
+    return int(os.environ.get("MAF_DEVICE", os.environ.get("LOCAL_RANK", 0)))
+
+
+def get_engine(device=None, dtype="float64"):
+    if device is None:
+        device = default_device()
+    key = (int(device), str(dtype))
+    if key not in _ENGINES:
+        if _FACTORY is not None:
+            eng = _FACTORY(int(device), str(dtype))
+        else:
+            from .engine import Engine
+            eng = Engine(int(device), str(dtype))
+        eng._fingerprint = None
+        _ENGINES[key] = eng
+    return _ENGINES[key]
+
+
+def release_engines():
+    for eng in _ENGINES.values():
+        try:
+            eng.close()
+        except Exception:
+            pass
+    _ENGINES.clear()
+
+
+def fingerprint(hyper: dict, X0: np.ndarray, y0: np.ndarray) -> str:
+    h = hashlib.blake2b(digest_size=16)
+    h.update(repr(sorted((k, np.asarray(v).tolist() if v is not None else None) for k, v in hyper.items())).encode())
+    h.update(np.ascontiguousarray(X0, dtype=np.float64).tobytes())
+    h.update(np.ascontiguousarray(y0, dtype=np.float64).tobytes())
+    return h.hexdigest()
+
+
+def bind(engine, hyper: dict, X0: np.ndarray, y0: np.ndarray):
+    """Make `engine` hold the model `hyper` and training set (X0, y0); no-op if it already does."""
+    fp = fingerprint(hyper, X0, y0)
+    if getattr(engine, "_fingerprint", None) != fp:
+        engine.set_model(**hyper)
+        engine.set_train(np.asarray(X0, dtype=np.float64), np.asarray(y0, dtype=np.float64).reshape(-1))
+        engine._fingerprint = fp
+    return engine

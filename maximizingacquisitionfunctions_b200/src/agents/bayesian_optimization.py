@@ -1,0 +1,444 @@
+"""Bayesian-optimisation agent: multi-start maximisation of the acquisition function
+(reference: src/agents/bayesian_optimization.py).
+
+Same method names, arguments, defaults and return shapes as the reference; evaluation is eager
+(NumPy in / NumPy out through the CUDA library) so the TensorFlow plumbing -- placeholders,
+variables, cached graph nodes, ``sess.run`` -- is replaced by a small ``pool_loss`` handle that owns
+the trainable candidate sets.  ``sess`` arguments are accepted and ignored.
+
+Supported inner optimisers: ``_optimize_inputs_sgd`` (TF-1 Adam + clip, on the device),
+``_optimize_inputs_scipy`` (joint L-BFGS-B, SciPy on the host driving device value+gradient),
+``_optimize_inputs_random``.  The derivative-free alternatives of the reference (halving, CMA-ES,
+NLopt) are outside the accelerated path.
+"""
+import logging
+
+import numpy as np
+from scipy.optimize import minimize as _scipy_minimize
+
+from ..utils import atleast_pools, join_pools
+from .search_agent import search_agent
+
+logger = logging.getLogger(__name__)
+
+
+class pool_loss(object):
+    """Stand-in for the reference's (losses_op, tf.Variable inputs_new) pair: the trainable candidate
+    sets ``value`` [S, q_new, d] plus everything needed to evaluate their losses (and gradient)."""
+
+    def __init__(self, loss_fn, model, inputs_new, inputs_old, outputs_old, inputs_pend, loss_kwargs):
+        self.loss_fn, self.model = loss_fn, model
+        self.value = np.array(atleast_pools(inputs_new), dtype=np.float64)
+        self.inputs_old, self.outputs_old, self.inputs_pend = inputs_old, outputs_old, inputs_pend
+        self.loss_kwargs = {k: v for k, v in dict(loss_kwargs or {}).items() if k != "num_fantasies"}
+
+    @property
+    def shape(self):
+        return self.value.shape
+
+    def assign(self, new_value):
+        self.value = np.array(atleast_pools(new_value), dtype=np.float64)
+
+    def pools(self, inputs_new=None):
+        return join_pools(self.value if inputs_new is None else inputs_new, self.inputs_pend)
+
+    def evaluate(self, feed_dict=None, inputs_new=None, need_grad=False):
+        """losses (reference shapes: [S] for MC, [S,1,1] closed form), extras and optionally the gradient."""
+        pools, p = self.pools(inputs_new)
+        rvs = None if feed_dict is None else feed_dict.get("fantasy_rvs", None)
+        if pools.shape[-2] == 1:
+            rvs = None                      # closed form (myopic_loss.evaluate :84-90)
+        out = self.loss_fn.evaluate(pools, self.inputs_old, self.outputs_old, fantasy_rvs=rvs, model=self.model,
+                                    num_pending=p, return_grad=need_grad, **self.loss_kwargs)
+        return out
+
+
+class bayesian_optimization(search_agent):
+    def __init__(self, loss_fn, model, num_options=2 ** 16, risk=0, configs=None, **kwargs):
+        super().__init__(**kwargs)
+        self.loss_fn = loss_fn
+        self.model = model
+        self.num_options = num_options
+        self.risk = risk
+        self.modules = dict()
+        self.configs = self.update_dict({
+            "random": {"eval_limit": 2 ** 16},
+            "sgd": {"method": "train.AdamOptimizer", "learning_rate": 25e-3, "use_averaging": False,
+                    "step_limit": 1000, "batch_size": 128},
+            "scipy": {"method": "L-BFGS-B", "maxiter": 1000, "ftol": 1e6 * np.finfo("float64").eps},
+            "nlopt": {"method": "GN_DIRECT", "maxfun": 10000},
+            "cmaes": {"method": "CMAEvolutionStrategy", "step_limit": 10000, "stop_early": False,
+                      "sigma0": 0.5, "bounds": [0, 1]},
+            "halving": {"eval_limit": 2 ** 20, "expon_step": 1, "min_samples": 128},
+        }, configs)
+
+    # ------------------------------------------------------------------------------------------
+    # suggest_inputs (:105-168)
+    # ------------------------------------------------------------------------------------------
+    def suggest_inputs(self, num_suggest, inputs_old, outputs_old, sess=None, inputs_pend=None, num_options=None,
+                       num_to_optimize=32, subroutine=None, options=None, use_sobol=False, allow_duplicates=True,
+                       time_limit=np.inf, dtype=None, **kwargs):
+        if num_options is None:
+            num_options = self.num_options
+        if dtype is None:
+            dtype = self.dtype
+        input_dim = inputs_old.shape[-1]
+        start_time = self.timer()
+        if subroutine not in [self._optimize_inputs_random, self._optimize_inputs_halving]:
+            inputs_new = self.sample_starts(num_to_optimize, num_suggest, sess, inputs_old, outputs_old,
+                                            inputs_pend, time_limit=time_limit / 10)
+        else:
+            inputs_new = self.sample_inputs([num_options, num_suggest, input_dim], options=options,
+                                            use_sobol=use_sobol, dtype=dtype)
+
+        nodes, loss_seq = self.optimize_inputs(
+            sess=sess, inputs_new=inputs_new, inputs_old=inputs_old, outputs_old=outputs_old,
+            inputs_pend=inputs_pend, time_limit=time_limit - (self.timer() - start_time),
+            subroutine=subroutine, **kwargs)
+
+        # re-evaluate the optimised sets with fresh base samples of size loss_fn.num_fantasies
+        inputs_new = np.array(nodes["inputs_new"].value)
+        losses_op, feed_dict, nodes = self.appraise_inputs(
+            sess=sess, inputs_new=inputs_new, inputs_old=inputs_old, outputs_old=outputs_old,
+            inputs_pend=inputs_pend, nodes=nodes, **{**kwargs, "inputs_as_var": False})[:3]
+        losses = np.atleast_1d(np.squeeze(losses_op))
+
+        argmin = int(np.argmin(losses))
+        suggestions = inputs_new[argmin]
+        if not allow_duplicates:
+            exclude = np.vstack([a for a in (inputs_old, inputs_pend) if a is not None])
+            replaced = 0
+            for k, suggestion in enumerate(suggestions):
+                was_dup = False
+                while np.equal(exclude, suggestion).all(axis=1).any():
+                    suggestion = self.sample_inputs([input_dim], options=options)
+                    was_dup = True
+                suggestions[k] = suggestion
+                exclude = np.vstack([exclude, suggestion[None]])
+                replaced += int(was_dup)
+            if replaced:
+                logger.info("Replaced {:d} duplicate input(s)".format(replaced))
+        return suggestions, losses[argmin]
+
+    # ------------------------------------------------------------------------------------------
+    # appraise_inputs (:171-231)
+    # ------------------------------------------------------------------------------------------
+    def appraise_inputs(self, sess, inputs_new, inputs_old, outputs_old, inputs_pend=None, feed_dict=None,
+                        model=None, loss_fn=None, nodes=None, loss_kwargs=None, predict_kwargs=None,
+                        inputs_as_var=False, **kwargs):
+        """Losses of candidate sets `inputs_new` [S, q_new, d] given observations and pending inputs.
+        Returns (losses_op, feed_dict, nodes, extras): with ``inputs_as_var`` the first item is a
+        ``pool_loss`` handle (the trainable variable + its loss), otherwise the evaluated losses."""
+        if model is None:
+            model = self.model
+        if loss_fn is None:
+            loss_fn = self.loss_fn
+        feed_dict = dict() if feed_dict is None else dict(feed_dict)
+        loss_kwargs = dict() if loss_kwargs is None else dict(loss_kwargs)
+        if np.ndim(inputs_old) == 4:
+            raise NotImplementedError("rank-4 (fantasy-padded) observation sets are not supported yet")
+        nodes = self.prepare(sess, inputs_new, inputs_old, outputs_old, inputs_pend, feed_dict, nodes,
+                             inputs_as_var)[0]
+        # the training factor is cached on the device per (hyper-parameters, X0, Y0) (runtime.bind)
+        model.bind(inputs_old, outputs_old)
+
+        num_pending = 0 if inputs_pend is None else np.shape(inputs_pend)[-2]
+        parallelism = num_pending + np.shape(inputs_new)[1]
+        placeholders, prep_feed = loss_fn.prepare(sess, inputs_old, outputs_old, parallelism, self.model, **loss_kwargs)
+        feed_dict = {**prep_feed, **feed_dict}       # user-specified terms take precedence
+
+        handle = pool_loss(loss_fn, model, nodes["inputs_new_src"], inputs_old, outputs_old, inputs_pend, loss_kwargs)
+        if inputs_as_var:
+            nodes["inputs_new"] = handle
+            return handle, feed_dict, nodes, None
+        if handle.value.shape[0] == 0:
+            nodes["inputs_new"] = handle
+            return handle, feed_dict, nodes, None     # empty probe (sample_starts builds its loss this way)
+        losses, extras = handle.evaluate(feed_dict)[:2]
+        nodes["inputs_new"] = handle
+        return losses, feed_dict, nodes, extras
+
+    # ------------------------------------------------------------------------------------------
+    # update (:234-274)
+    # ------------------------------------------------------------------------------------------
+    def update(self, sess, inputs_old, outputs_old, model=None, var_list=None, loss_fn=None, reset=True,
+               fit_kwargs=None, loss_kwargs=None, verbose=2, **kwargs):
+        if model is None:
+            model = self.model
+        if loss_fn is None:
+            loss_fn = self.loss_fn
+        tic = self.timer()
+        if reset:
+            model.reset_state()
+        model.fit(sess, inputs_old, outputs_old, **(fit_kwargs or {}))
+        var_values = [model.state[k] for k in ("mean", "log_lenscales", "log_amplitude", "log_noise")]
+        if verbose > 0:
+            logger.info("Fit model in {:.2e}s".format(self.timer() - tic))
+        loss_fn.update(sess, inputs_old, outputs_old, **{"model": model, **(loss_kwargs or {})})
+        return var_values
+
+    # ------------------------------------------------------------------------------------------
+    # optimize_inputs (:277-334)
+    # ------------------------------------------------------------------------------------------
+    def optimize_inputs(self, sess, inputs_new, inputs_old, outputs_old, inputs_pend=None, var_list=None,
+                        loss_fn=None, batch_generator=None, config=None, subroutine=None, loss_kwargs=None,
+                        time_limit=np.inf, **kwargs):
+        start_time = self.timer()
+        if loss_fn is None:
+            loss_fn = self.loss_fn
+        if loss_kwargs is None:
+            loss_kwargs = dict()
+        num_pending = 0 if inputs_pend is None else np.shape(inputs_pend)[-2]
+        parallelism = num_pending + np.shape(inputs_new)[1]
+
+        losses_op, feed_dict, nodes, extras = self.appraise_inputs(
+            sess, inputs_new, inputs_old, outputs_old, inputs_pend=inputs_pend, inputs_as_var=True,
+            loss_fn=loss_fn, loss_kwargs=loss_kwargs, **kwargs)
+
+        if batch_generator is None:
+            def batch_generator(batch_size, parallelism=parallelism):
+                batch_kwargs = {**loss_kwargs, "num_fantasies": batch_size}
+                return loss_fn.prepare(sess, inputs_old, outputs_old, parallelism, self.model, **batch_kwargs)[1]
+
+        if subroutine is None:
+            subroutine = self._optimize_inputs_scipy if parallelism == 1 else self._optimize_inputs_sgd
+
+        loss_seq = subroutine(
+            sess=sess, inputs_new=nodes["inputs_new"], losses_op=losses_op, feed_dict=feed_dict, var_list=var_list,
+            batch_generator=batch_generator, time_limit=time_limit - (self.timer() - start_time),
+            parallelism=parallelism, nodes=nodes, extras=extras, config=config, loss_fn=loss_fn)
+        return nodes, loss_seq
+
+    # ------------------------------------------------------------------------------------------
+    # random search (:337-374)
+    # ------------------------------------------------------------------------------------------
+    def _optimize_inputs_random(self, sess, inputs_new, losses_op, feed_dict=None, config=None,
+                                time_limit=np.inf, options=None, **kwargs):
+        feed_dict = dict() if feed_dict is None else dict(feed_dict)
+        config = self.update_dict(self.configs["random"], config, as_copy=True)
+        eval_limit = config["eval_limit"]
+        shard_shape = list(inputs_new.shape)
+        shard_size = shard_shape[0]
+        start_time = self.timer()
+        inputs_seq, loss_seq, counter = [], [], 0
+        while counter + shard_size <= eval_limit:
+            if self.timer() - start_time > time_limit:
+                break
+            inputs_seq.append(self.rng.rand(*shard_shape))
+            losses = losses_op.evaluate(feed_dict, inputs_new=inputs_seq[-1])[0]
+            loss_seq.append(np.ravel(losses))
+            counter += shard_size
+        loss_seq = np.hstack(loss_seq)
+        argmins = np.argpartition(loss_seq, shard_size - 1)[:shard_size]
+        inputs_new.assign(np.vstack(inputs_seq)[argmins])
+        logger.info("Random Search evaluated {:d} losses in {:.3e}s".format(len(loss_seq), self.timer() - start_time))
+        return loss_seq
+
+    # ------------------------------------------------------------------------------------------
+    # stochastic gradient descent: Adam + clip on the device (:377-482)
+    # ------------------------------------------------------------------------------------------
+    def _optimize_inputs_sgd(self, sess, inputs_new, losses_op, optimizer=None, feed_dict=None, var_list=None,
+                             batch_generator=None, config=None, time_limit=np.inf, global_step=None,
+                             scope="sgd", reuse=None, block=None, **kwargs):
+        feed_dict = dict() if feed_dict is None else dict(feed_dict)
+        if not isinstance(inputs_new, pool_loss):
+            raise TypeError("Candidates must be a trainable <pool_loss> handle")
+        config = self.update_dict(self.configs["sgd"], config, as_copy=True)
+        method = config.get("method", "train.AdamOptimizer")
+        if method.split(".")[-1] != "AdamOptimizer":
+            raise NotImplementedError("only train.AdamOptimizer runs on the device (got {})".format(method))
+        lr = config.get("learning_rate", 25e-3)
+        step_limit = config.get("step_limit", 1000)
+        batch_size = config.get("batch_size", 128)
+        use_averaging = config.get("use_averaging", False)
+
+        handle = inputs_new
+        pools, p = handle.pools()
+        S, q, d = pools.shape
+        if q == 1:
+            raise NotImplementedError("the Adam loop needs base samples (q > 1); q == 1 takes the L-BFGS-B route (:311-313)")
+        eng = handle.model.bind(handle.inputs_old, handle.outputs_old)
+        prm = handle.loss_fn.acq_params(outputs_old=handle.outputs_old, **handle.loss_kwargs)
+        eng.adam_begin(prm, pools, p_pending=p, lr=lr)     # resets slots + step (:444-451)
+
+        start_time = self.timer()
+        if block is None:
+            block = 16 if np.isinf(time_limit) else 4     # steps between looks at the clock
+        if use_averaging:
+            block = 1
+        loss_seq, mean_x, done = [], None, 0
+        while done < step_limit:
+            if self.timer() - start_time >= time_limit:
+                break
+            k = int(min(block, step_limit - done))
+            zs = []
+            for _ in range(k):
+                if callable(batch_generator):
+                    feed_dict.update(batch_generator(batch_size))
+                zs.append(np.asarray(feed_dict["fantasy_rvs"], dtype=np.float64))
+            trace = eng.adam_steps(np.stack(zs), want_trace=True)
+            loss_seq.append(trace)
+            done += k
+            if use_averaging:                               # Polyak mean of the iterates (:472-475)
+                x = eng.adam_peek()
+                mean_x = x if mean_x is None else mean_x + x
+        x = eng.adam_end()
+        if use_averaging and done:
+            x = mean_x / done
+        handle.assign(x[:, p:, :])
+        loss_seq = np.ravel(loss_seq) if loss_seq else np.empty([0])
+        logger.info("SGD evaluated {:d} losses in {:.3e}s".format(len(loss_seq), self.timer() - start_time))
+        return loss_seq
+
+    # ------------------------------------------------------------------------------------------
+    # joint L-BFGS-B (:485-555)
+    # ------------------------------------------------------------------------------------------
+    def _optimize_inputs_scipy(self, sess, inputs_new, losses_op, feed_dict=None, var_list=None, config=None,
+                               time_limit=np.inf, **kwargs):
+        feed_dict = dict() if feed_dict is None else dict(feed_dict)
+        if not isinstance(inputs_new, pool_loss):
+            raise TypeError("Candidates must be a trainable <pool_loss> handle")
+        config = self.update_dict(self.configs["scipy"], config, as_copy=True)
+        method = config.pop("method", "L-BFGS-B")
+        config.pop("var_to_bounds", None)
+        handle = inputs_new
+        shape = handle.value.shape
+        S = shape[0]
+        inputs_seq, loss_seq, start_time = [], [], self.timer()
+
+        class _Timeout(Exception):
+            pass
+
+        def fun(x):
+            xs = x.reshape(shape)
+            losses, _, grad = handle.evaluate(feed_dict, inputs_new=xs, need_grad=True)
+            losses = np.ravel(losses)
+            loss_seq.append(losses)                       # loss_callback of the reference (:505-509)
+            inputs_seq.append(xs.copy())
+            if self.timer() - start_time >= time_limit:
+                raise _Timeout("Runtime limit exhausted.")
+            return float(np.mean(losses)), np.ravel(grad) / S     # loss_op = reduce_mean(losses_op) (:512)
+
+        try:
+            _scipy_minimize(fun, np.ravel(handle.value), jac=True, method=method,
+                            bounds=[(0.0, 1.0)] * handle.value.size, options=config)
+        except _Timeout:
+            pass
+
+        # best S (iterate, restart) pairs over the whole trajectory (:541-550)
+        loss_seq = np.ravel(loss_seq)
+        inputs_seq = np.reshape(inputs_seq, (-1,) + tuple(shape[1:]))
+        argmins = np.argpartition(loss_seq, S - 1)[:S]
+        handle.assign(inputs_seq[argmins])
+        logger.info("ScipyOptimize evaluated {:d} losses in {:.3e}s".format(len(loss_seq), self.timer() - start_time))
+        return loss_seq
+
+    def _optimize_inputs_halving(self, *args, **kwargs):
+        raise NotImplementedError("successive halving is outside the accelerated path (SURVEY 2, row 1)")
+
+    def _optimize_inputs_cmaes(self, *args, **kwargs):
+        raise NotImplementedError("CMA-ES is outside the accelerated path (SURVEY 2, row 1)")
+
+    def _optimize_inputs_nlopt(self, *args, **kwargs):
+        raise NotImplementedError("NLopt is outside the accelerated path (SURVEY 2, row 1)")
+
+    # ------------------------------------------------------------------------------------------
+    # suggest_answers (:938-1048)
+    # ------------------------------------------------------------------------------------------
+    def suggest_answers(self, num_suggest, inputs_old, outputs_old, sess=None, risk=None, num_starts=2 ** 10,
+                        num_options=2 ** 16, config=None, time_limit=np.inf, in_order=False, model=None):
+        """Top-k minimisers of the (risk-penalised) posterior mean  mu - risk * sqrt(var)."""
+        from ..losses import confidence_bound, simple_regret
+        if risk is None:
+            risk = self.risk
+        if model is None:
+            model = self.model
+        start_time = self.timer()
+        config = self.update_dict(self.configs["scipy"], config, as_copy=True)
+        input_dim = inputs_old.shape[-1]
+        if risk != 0:
+            answer_loss = confidence_bound(beta=float(risk) ** 2, lower=risk > 0, model=model, seed=int(self.seed))
+        else:
+            answer_loss = simple_regret(model=model, seed=int(self.seed))
+
+        num_old = len(inputs_old)
+        src = np.vstack([inputs_old, self.sample_inputs([max(num_options - num_old, 0), input_dim], use_sobol=True)])
+        losses = np.ravel(answer_loss.evaluate(src[:, None, :], inputs_old, outputs_old, model=model)[0])
+        starts = self.sample_propto_loss(src, losses, min(num_starts, len(src)), top_k=min(32, num_options, num_starts))[0]
+
+        handle = pool_loss(answer_loss, model, starts[:, None, :], inputs_old, outputs_old, None, None)
+        self._optimize_inputs_scipy(sess, handle, handle, dict(), config=config,
+                                    time_limit=time_limit - (self.timer() - start_time))
+        answers = handle.value[:, 0, :]
+        means, sigma2s = model.predict(answers, inputs_old, outputs_old)
+        means = np.squeeze(means, axis=-1)
+        indices = np.argpartition(means, num_suggest - 1)[:num_suggest]
+        if in_order:
+            indices = indices[np.argsort(means[indices])]
+        return answers[indices], (means[indices], sigma2s[indices])
+
+    # ------------------------------------------------------------------------------------------
+    # prepare (:1051-1125)
+    # ------------------------------------------------------------------------------------------
+    def prepare(self, sess, inputs_new, inputs_old, outputs_old, inputs_pend=None, feed_dict=None, nodes=None,
+                inputs_as_var=False):
+        nodes = dict() if nodes is None else nodes
+        feed_dict = dict() if feed_dict is None else feed_dict
+        assert np.ndim(inputs_new) > 1, "Candidates must be at least 2-dimensional"
+        assert np.ndim(inputs_old) > 1, "Observations must be at least 2-dimensional"
+        assert np.ndim(inputs_old) == np.ndim(outputs_old), "Observations have mismatched rank"
+        assert np.shape(outputs_old)[-1] == 1, "Multiple objectives not yet supported"
+        nodes["inputs_old"], nodes["outputs_old"] = inputs_old, outputs_old
+        if inputs_pend is None:
+            inputs_pend = np.empty((0, np.shape(inputs_new)[-1]))
+        nodes["inputs_pend"] = inputs_pend
+        nodes["inputs_new_src"] = np.asarray(inputs_new, dtype=np.float64)
+        return nodes, feed_dict
+
+    # ------------------------------------------------------------------------------------------
+    # sample_starts (:1128-1204)
+    # ------------------------------------------------------------------------------------------
+    def sample_starts(self, num_starts, num_suggest, sess, inputs_old, outputs_old, inputs_pend=None, feed_dict=None,
+                      losses_op=None, eval_limit=2 ** 20, time_limit=np.inf, shard_size=256, shards_per_call=64,
+                      **kwargs):
+        """Starting sets drawn with probability proportional to marginal utility: closed-form (q = 1)
+        losses on uniform candidates, `shard_size` per host-RNG access exactly like the reference's loop
+        (:1167-1172); `shards_per_call` shards are sent to the device in one call."""
+        if inputs_pend is not None and len(inputs_pend):
+            means_pend = self.model.predict(inputs_pend, inputs_old, outputs_old)[0]      # fantasise at the means
+            inputs_old = np.vstack([inputs_old, inputs_pend])
+            outputs_old = np.vstack([outputs_old, means_pend])
+        input_dim = inputs_old.shape[-1]
+        if losses_op is None:
+            losses_op = self.appraise_inputs(sess=sess, inputs_new=np.empty([0, 1, input_dim]), inputs_old=inputs_old,
+                                             outputs_old=outputs_old, feed_dict=feed_dict, **kwargs)[0]
+        options, losses = [], []
+        start_time = self.timer()
+        total_shards, k = eval_limit // shard_size, 0
+        while k < total_shards:
+            if self.timer() - start_time > time_limit:
+                break
+            g = int(min(shards_per_call, total_shards - k))
+            batch = [self.rng.rand(shard_size, input_dim) for _ in range(g)]
+            options.extend(batch)
+            l = losses_op.evaluate(None, inputs_new=np.vstack(batch)[:, None, :])[0]
+            losses.append(np.atleast_1d(np.squeeze(l)))
+            k += g
+        losses = np.hstack(losses)
+        options = np.vstack(options)
+        num_options = len(options)
+        logger.info("Evaluated {:d} marginal losses in {:.3e}s".format(num_options, self.timer() - start_time))
+
+        weights = np.clip(np.max(losses) - losses, np.finfo(losses.dtype).eps, np.inf)
+        weights /= np.sum(weights)
+        indices, fillers = [], []
+        while len(indices) + len(fillers) < num_starts:
+            new = self.rng.choice(num_options, num_suggest, p=weights, replace=False)
+            if any(np.array_equal(new, old) for old in indices):
+                fillers.append(self.rng.rand(num_suggest, input_dim))
+            else:
+                indices.append(new)
+        starts = options[np.stack(indices)]
+        if len(fillers):
+            starts = np.vstack([starts, np.stack(fillers)])
+        return starts

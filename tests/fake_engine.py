@@ -1,0 +1,102 @@
+"""TEST-ONLY stand-in for engine.Engine backed by the CPU oracle, so that the host-side logic of
+the ``src`` mirror (agents / losses / models) can be exercised without a GPU.  Never imported by
+the product package."""
+import math
+
+import numpy as np
+import torch
+
+from oracle import maf_oracle as orc
+
+_KIND = {0: "ei", 1: "pi", 2: "sr", 3: "cb"}
+
+
+class FakeEngine:
+    def __init__(self, device=0, dtype="float64"):
+        self.device, self.dtype = device, dtype
+        self.launch_count = 0
+        self._last = None
+
+    def close(self):
+        pass
+
+    def set_model(self, kernel_id, lenscales, amplitude, noise, mean, jitter):
+        self.gp = orc.GP(log_lenscales=np.log(np.asarray(lenscales, dtype=np.float64)), log_amplitude=math.log(amplitude),
+                         log_noise=None if noise is None else math.log(noise), mean=mean, kernel_id=kernel_id,
+                         jitter=jitter)
+        self.d = len(np.atleast_1d(lenscales))
+
+    def set_train(self, X0, y0):
+        self.ts = orc.prepare_train(self.gp, X0, y0)
+        self.n = len(X0)
+
+    def factors(self):
+        L = self.ts.chol.numpy()
+        return L, np.linalg.inv(L), None
+
+    def _acq(self, prm):
+        t = None if math.isnan(prm.temperature) else prm.temperature
+        lvl = None if math.isnan(prm.level) else prm.level
+        return orc.Acq(_KIND[prm.acq], temperature=t, beta=prm.beta, lower=bool(prm.lower), level=lvl)
+
+    def posterior(self, X, full_cov=True):
+        with torch.no_grad():
+            m, c = orc.posterior(self.ts, torch.as_tensor(X, dtype=orc.DT), full_cov=full_cov)
+        return m.numpy(), c.numpy()
+
+    def value_and_grad(self, prm, X, z=None, p_pending=0, weights=None, incumbents=None, need_grad=True,
+                       out_loss=None, out_grad=None):
+        X = np.asarray(X, dtype=np.float64)
+        pend = X[0, :p_pending] if p_pending else None
+        zz = np.zeros((1, 1)) if z is None else z
+        losses, grad = orc.value_and_grad(self.ts, self._acq(prm), X[:, p_pending:], zz, X_pend=pend,
+                                          weights=weights, incumbents=incumbents, shard_limit=2 ** 20)
+        with torch.no_grad():
+            Xt = torch.as_tensor(X)
+            if X.shape[1] == 1 and z is None:
+                m, v = orc.posterior(self.ts, Xt, full_cov=False)
+                self._last = (m.numpy(), v.numpy(), None)
+            else:
+                m, c = orc.posterior(self.ts, Xt, full_cov=True)
+                self._last = (m.numpy(), c.numpy(), orc.jitter_cholesky(c, self.gp.jitter).numpy())
+        self._loss = losses
+        return losses, (grad if need_grad else None)
+
+    def mc_from_moments(self, prm, mu, cov, z, weights=None, incumbents=None, need_grad=False):
+        cov = torch.as_tensor(np.asarray(cov, dtype=np.float64))
+        S, q, _ = cov.shape
+        mu = torch.as_tensor(np.asarray(mu, dtype=np.float64)).reshape(S, q, 1)
+        chol = orc.jitter_cholesky(torch.tril(cov) + torch.tril(cov, -1).transpose(-1, -2), self.gp.jitter)
+        y0 = getattr(self, "ts", None)
+        y0 = y0.Y0 if y0 is not None else torch.zeros(1, 1, dtype=orc.DT)
+        w = None if weights is None else torch.as_tensor(weights)
+        inc = None if incumbents is None else torch.as_tensor(incumbents)
+        loss = orc.mc_loss(self._acq(prm), mu, chol, torch.as_tensor(np.asarray(z, dtype=np.float64)), y0, w, inc)
+        return loss.numpy(), None, None, chol.numpy()
+
+    def last_extras(self, S, q, want_chol=True):
+        return self._last
+
+    def argmin_last(self):
+        i = int(np.nanargmin(self._loss))
+        return i, float(self._loss[i])
+
+    def adam_begin(self, prm, X, p_pending=0, lr=25e-3, beta1=0.9, beta2=0.999, eps=1e-8):
+        self._ax = np.array(X, dtype=np.float64)
+        self._ap, self._aprm = p_pending, prm
+        self._ast = orc.adam_init(self._ax[:, p_pending:].shape, lr=lr, beta1=beta1, beta2=beta2, eps=eps)
+
+    def adam_steps(self, z_steps, want_trace=False):
+        trace = []
+        p = self._ap
+        for z in z_steps:
+            losses, g = self.value_and_grad(self._aprm, self._ax, z, p_pending=p)
+            trace.append(losses)
+            self._ax[:, p:] = orc.adam_step(self._ax[:, p:], g, self._ast)
+        return np.asarray(trace) if want_trace else None
+
+    def adam_peek(self):
+        return self._ax.copy()
+
+    def adam_end(self):
+        return self._ax.copy()

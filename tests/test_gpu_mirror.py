@@ -1,0 +1,93 @@
+"""GPU: the ``src`` mirror end to end on the CUDA engine vs the same host logic on the test-only
+oracle-backed engine (identical seeds => identical host-RNG streams, starts and base samples)."""
+import math
+
+import numpy as np
+import pytest
+
+from maximizingacquisitionfunctions_b200 import runtime, tasks
+from maximizingacquisitionfunctions_b200.src import agents, losses, models
+from tests.fake_engine import FakeEngine
+
+pytestmark = pytest.mark.gpu
+
+
+def build(d, n, task, seed, loss, **loss_kwargs):
+    rng = np.random.RandomState(seed)
+    X0 = rng.rand(n, d)
+    Y0 = getattr(tasks, task)(X0) + math.sqrt(1e-3) * rng.randn(n, 1)
+    model = models.gaussian_process(kernel_id="matern52", seed=seed + 1, log_lenscales=np.log(math.sqrt(d) / 4) * np.ones(d),
+                                    log_amplitude=0.0, log_noise=np.log(1e-3), mean=0.0)
+    loss_fn = getattr(losses, loss)(seed=seed + 2, **loss_kwargs)
+    return agents.bayesian_optimization(loss_fn=loss_fn, model=model, seed=seed + 3), X0, Y0
+
+
+def run_both(fn):
+    runtime.set_engine_factory(None)
+    runtime.release_engines()
+    try:
+        gpu = fn()
+    finally:
+        runtime.release_engines()
+    runtime.set_engine_factory(lambda device, dtype: FakeEngine(device, dtype))
+    try:
+        ref = fn()
+    finally:
+        runtime.set_engine_factory(None)
+    return gpu, ref
+
+
+def test_c1_hartmann3_qei_joint_sgd():
+    """BASELINE config 1: Hartmann-3, qEI q=2, n_train=32, 64 restarts, 128 MC samples per step."""
+    def flow():
+        agent, X0, Y0 = build(3, 32, "hartmann3", 0, "negative_ei")
+        agent.loss_fn.num_fantasies = 256
+        return agent.suggest_inputs(2, X0, Y0, None, num_to_optimize=64, subroutine=agent._optimize_inputs_sgd,
+                                    config={"step_limit": 25, "batch_size": 128})
+    (xg, lg), (xr, lr) = run_both(flow)
+    assert xg.shape == (2, 3)
+    assert np.abs(xg - xr).max() < 1e-6 and abs(lg - lr) < 1e-8 * max(1.0, abs(lr))
+
+
+@pytest.mark.parametrize("loss,kw", [("negative_pi", {"temperature": 0.01}), ("simple_regret", {}),
+                                     ("confidence_bound", {"beta": 2.0})])
+def test_c2_branin_q4(loss, kw):
+    def flow():
+        agent, X0, Y0 = build(2, 256, "braninhoo", 1, loss, **kw)
+        agent.loss_fn.num_fantasies = 256
+        return agent.suggest_inputs(4, X0, Y0, None, num_to_optimize=32, subroutine=agent._optimize_inputs_sgd,
+                                    config={"step_limit": 10, "batch_size": 256})
+    (xg, lg), (xr, lr) = run_both(flow)
+    assert np.abs(xg - xr).max() < 1e-6 and abs(lg - lr) < 1e-8 * max(1.0, abs(lr))
+
+
+def test_greedy_pending_and_scipy_and_answers():
+    def flow():
+        agent, X0, Y0 = build(3, 48, "hartmann3", 2, "negative_ei")
+        agent.loss_fn.num_fantasies = 128
+        pend = None
+        picks = []
+        for _ in range(3):                 # scripts/run_bayesopt.py:137-176 (pending-point greedy)
+            x, l = agent.suggest_inputs(1, X0, Y0, None, inputs_pend=pend, num_to_optimize=16,
+                                        config={"maxiter": 8, "step_limit": 8, "batch_size": 64})
+            picks.append(x)
+            pend = x if pend is None else np.vstack([pend, x])
+        ans, (m, v) = agent.suggest_answers(1, X0, Y0, None, num_starts=32, num_options=512, config={"maxiter": 10})
+        return np.vstack(picks), ans, m
+    (pg, ag, mg), (pr, ar, mr) = run_both(flow)
+    assert np.abs(pg - pr).max() < 1e-5
+    assert np.abs(ag - ar).max() < 1e-5 and np.abs(mg - mr).max() < 1e-8
+
+
+def test_loss_classes_match_oracle_engine():
+    def flow():
+        agent, X0, Y0 = build(2, 40, "braninhoo", 3, "confidence_bound", lower=False, beta=3.0)
+        pools = np.random.RandomState(4).rand(9, 3, 2)
+        z = np.random.RandomState(5).randn(64, 3)
+        l, (m, c, L) = agent.loss_fn(pools, X0, Y0, fantasy_rvs=z, model=agent.model)
+        l1, _ = agent.loss_fn(pools[:, :1], X0, Y0, model=agent.model)
+        est = agent.loss_fn._monte_carlo(m, c, base_rvs=z, model=agent.model)
+        return l, m, c, L, l1, est
+    g, r = run_both(flow)
+    for a, b in zip(g, r):
+        assert np.abs(a - b).max() < 1e-9 * max(1.0, np.abs(b).max())

@@ -1,0 +1,150 @@
+"""CPU tests of the ``src`` mirror's host logic (agents / losses / models) on a test-only,
+oracle-backed engine (tests/fake_engine.py).  The same flows run on the real engine in
+tests/test_gpu_mirror.py."""
+import math
+
+import numpy as np
+import pytest
+
+from maximizingacquisitionfunctions_b200 import runtime
+from maximizingacquisitionfunctions_b200.src import agents, losses, models
+from oracle import maf_oracle as orc
+from tests.fake_engine import FakeEngine
+
+
+@pytest.fixture(autouse=True)
+def fake_engine():
+    runtime.set_engine_factory(lambda device, dtype: FakeEngine(device, dtype))
+    yield
+    runtime.set_engine_factory(None)
+
+
+def make(d=2, n=24, seed=0, loss="negative_ei", **loss_kwargs):
+    rng = np.random.RandomState(seed)
+    X0 = rng.rand(n, d)
+    Y0 = np.sin(3 * X0.sum(-1, keepdims=True)) + 0.03 * rng.randn(n, 1)
+    model = models.gaussian_process(kernel_id="matern52", seed=seed + 1, log_lenscales=np.log(math.sqrt(d) / 4) * np.ones(d),
+                                    log_amplitude=0.0, log_noise=np.log(1e-3), mean=0.0)
+    loss_fn = getattr(losses, loss)(seed=seed + 2, **loss_kwargs)
+    agent = agents.bayesian_optimization(loss_fn=loss_fn, model=model, seed=seed + 3)
+    return agent, X0, Y0
+
+
+def test_rng_streams_and_prepare_shapes():
+    agent, X0, Y0 = make()
+    lf = agent.loss_fn
+    s0 = int(lf.seed)
+    ph, feed = lf.prepare(None, X0, Y0, parallelism=3, num_fantasies=5)
+    assert feed["fantasy_rvs"].shape == (5, 3) and int(lf.seed) == s0 + 1
+    assert np.array_equal(feed["fantasy_rvs"], np.random.RandomState(s0 + 1).randn(5, 3))
+    ph, feed = lf.prepare(None, X0, Y0, parallelism=1)
+    assert feed == {} and int(lf.seed) == s0 + 1          # q == 1 draws nothing (myopic_loss.py:307)
+
+
+def test_loss_return_shapes_match_reference():
+    agent, X0, Y0 = make()
+    pools = np.random.RandomState(5).rand(7, 3, 2)
+    z = np.random.RandomState(6).randn(16, 3)
+    losses_, (means, cov, chol) = agent.loss_fn(pools, X0, Y0, fantasy_rvs=z, model=agent.model)
+    assert losses_.shape == (7,) and means.shape == (7, 3, 1) and cov.shape == (7, 3, 3) and chol.shape == (7, 3, 3)
+    l1, (m1, v1, c1) = agent.loss_fn(pools[:, :1], X0, Y0, model=agent.model)
+    assert l1.shape == (7, 1, 1) and m1.shape == (7, 1, 1) and v1.shape == (7, 1, 1) and c1 is None
+
+
+def test_model_predict_shapes():
+    agent, X0, Y0 = make()
+    X1 = np.random.RandomState(1).rand(5, 2)
+    m, c = agent.model.predict(X1, X0, Y0, full_cov=True)
+    assert m.shape == (5, 1) and c.shape == (5, 5)
+    m, v = agent.model.predict(X1, X0, Y0)
+    assert m.shape == (5, 1) and v.shape == (5, 1)
+    m, c = agent.model.predict(X1.reshape(1, 5, 2).repeat(3, 0), X0, Y0, full_cov=True)
+    assert m.shape == (3, 5, 1) and c.shape == (3, 5, 5)
+    L = agent.model.compute_cholesky(X0, noisy=True)
+    assert L.shape == (24, 24) and np.allclose(np.triu(L, 1), 0)
+
+
+def test_sample_starts_stream_and_shape():
+    agent, X0, Y0 = make()
+    s0 = int(agent.seed)
+    starts = agent.sample_starts(6, 2, None, X0, Y0, eval_limit=1024, shard_size=256)
+    assert starts.shape == (6, 2, 2) and starts.min() >= 0 and starts.max() <= 1
+    # the k-th shard is RandomState(seed + k).rand(256, d) (module.rng semantics)
+    opts = np.vstack([np.random.RandomState(s0 + k).rand(256, 2) for k in range(1, 5)])
+    assert all(any(np.array_equal(pt, o) for o in opts) for pt in starts.reshape(-1, 2))
+
+
+@pytest.mark.parametrize("loss,kw", [("negative_ei", {}), ("negative_pi", {"temperature": 0.01}),
+                                     ("simple_regret", {}), ("confidence_bound", {"beta": 2.0})])
+def test_suggest_inputs_sgd_improves_and_returns_argmin(loss, kw):
+    agent, X0, Y0 = make(loss=loss, **kw)
+    agent.loss_fn.num_fantasies = 64
+    cfg = {"step_limit": 12, "batch_size": 32}
+    X, l = agent.suggest_inputs(2, X0, Y0, None, num_to_optimize=8, subroutine=agent._optimize_inputs_sgd, config=cfg)
+    assert X.shape == (2, 2) and X.min() >= 0 and X.max() <= 1 and np.isfinite(l)
+
+
+def test_sgd_matches_oracle_adam_trajectory():
+    agent, X0, Y0 = make()
+    starts = np.random.RandomState(9).rand(5, 2, 2)
+    s0 = int(agent.loss_fn.seed)
+    nodes, loss_seq = agent.optimize_inputs(None, starts, X0, Y0, subroutine=agent._optimize_inputs_sgd,
+                                            config={"step_limit": 4, "batch_size": 16})
+    # reference stream: appraise_inputs draws one z (num_fantasies), then one per step (batch 16)
+    zs = [np.random.RandomState(s0 + 1 + k).randn(16, 2) for k in range(1, 5)]
+    gp = orc.GP(log_lenscales=math.log(math.sqrt(2) / 4), log_amplitude=0.0, log_noise=math.log(1e-3), mean=0.0)
+    xo, tro = orc.adam_run(orc.prepare_train(gp, X0, Y0), orc.Acq("ei"), starts, zs)
+    assert np.allclose(nodes["inputs_new"].value, xo, atol=1e-12)
+    assert np.allclose(loss_seq, tro.ravel(), atol=1e-12)
+
+
+def test_greedy_pending_only_last_row_moves():
+    agent, X0, Y0 = make()
+    pend = np.random.RandomState(2).rand(2, 2)
+    X, l = agent.suggest_inputs(1, X0, Y0, None, inputs_pend=pend, num_to_optimize=4,
+                                subroutine=agent._optimize_inputs_sgd, config={"step_limit": 3, "batch_size": 8})
+    assert X.shape == (1, 2)
+
+
+def test_scipy_subroutine_q1_and_joint():
+    agent, X0, Y0 = make()
+    X, l = agent.suggest_inputs(1, X0, Y0, None, num_to_optimize=6, config={"maxiter": 5})     # q == 1 -> L-BFGS-B
+    assert X.shape == (1, 2) and np.isfinite(l)
+    agent.loss_fn.num_fantasies = 32
+    X, l = agent.suggest_inputs(2, X0, Y0, None, num_to_optimize=4, subroutine=agent._optimize_inputs_scipy,
+                                config={"maxiter": 3})
+    assert X.shape == (2, 2)
+
+
+def test_random_subroutine_keeps_top_shard():
+    agent, X0, Y0 = make()
+    agent.loss_fn.num_fantasies = 32
+    X, l = agent.suggest_inputs(2, X0, Y0, None, num_options=16, subroutine=agent._optimize_inputs_random,
+                                config={"eval_limit": 64})
+    assert X.shape == (2, 2) and np.isfinite(l)
+
+
+def test_suggest_answers_minimises_posterior_mean():
+    agent, X0, Y0 = make()
+    ans, (means, var) = agent.suggest_answers(1, X0, Y0, None, num_starts=16, num_options=256, config={"maxiter": 10})
+    assert ans.shape == (1, 2) and means.shape == (1,) and var.shape == (1, 1)
+    m_all = agent.model.predict(X0, X0, Y0)[0]
+    assert means[0] <= m_all.min() + 1e-6
+    ans2, _ = agent.suggest_answers(1, X0, Y0, None, risk=1.0, num_starts=8, num_options=128, config={"maxiter": 5})
+    assert ans2.shape == (1, 2)
+
+
+def test_monte_carlo_from_moments_folded_normal():
+    """tests/test_qUCB.py:47-53 through the loss class: q=1 MC UCB -> mu + sqrt(beta var)."""
+    qucb = losses.confidence_bound(lower=False, beta=2.0, seed=1, model=models.gaussian_process(jitter=0.0, seed=2))
+    rvs = np.random.RandomState(3).randn(200000, 1)
+    est = qucb._monte_carlo(np.array([[0.3]]), np.array([[2.0]]), base_rvs=rvs)
+    assert abs(float(est) - (0.3 + math.sqrt(2.0 * 2.0))) < 1.5e-2
+
+
+def test_unsupported_paths_raise():
+    agent, X0, Y0 = make()
+    with pytest.raises(NotImplementedError):
+        agent._optimize_inputs_cmaes()
+    with pytest.raises(NotImplementedError):
+        losses.negative_ei(use_rand_features=True)
