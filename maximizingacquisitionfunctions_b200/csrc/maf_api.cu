@@ -51,6 +51,7 @@ struct maf_ctx {
   size_t cap_train = 0;        // npad the factor buffers were sized for
   int cap_train_d = 0;
   // GEMM workspace (chunk of candidate rows)
+  int gemm_variant = 0;
   size_t chunk_rows = 65536;
   Buf K10, Vt;
   // per-restart buffers
@@ -216,13 +217,43 @@ __global__ void diag_extract_kernel(const double* __restrict__ Sig, int S, int q
     default: { constexpr int D = 0; __VA_ARGS__; } break;                          \
   }
 
+// GEMM variants (selected by MAF_GEMM_VARIANT at context creation; 0 is the default)
+template <int BM, int BN, int BK, int STAGES, int WJ, int WR, int MINB>
+static int launch_gemm_cfg(maf_ctx* ctx, int J, int N, const double* A, int lda, const double* T, int ldt, double* C,
+                           int ldc, int K, int tri) {
+  using Cfg = GemmCfg<BM, BN, BK, STAGES, WJ, WR, MINB>;
+  static bool attr = false;
+  if (!attr) {
+    CK(cudaFuncSetAttribute(gemm_nt_f64_kernel<BM, BN, BK, STAGES, WJ, WR, MINB>,
+                            cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(gemm_nt_f64_kernel<BM, BN, BK, STAGES, WJ, WR, MINB>,
+                            cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    attr = true;
+  }
+  dim3 grid(N / BN, J / BM);
+  gemm_nt_f64_kernel<BM, BN, BK, STAGES, WJ, WR, MINB><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, ctx->stream>>>(
+      A, lda, T, ldt, C, ldc, K, tri);
+  return 0;
+}
+
 static int launch_gemm(maf_ctx* ctx, int slot, int J, int N, int K, const double* A, int lda,
                        const double* T, int ldt, double* C, int ldc, int tri) {
-  if (J % GEMM_BM || N % GEMM_BN || K % GEMM_BK) return fail(ctx, "gemm dims must be multiples of 128");
+  if (J % 128 || N % 128 || K % 128) return fail(ctx, "gemm dims must be multiples of 128");
   if (tri != 0 && K != N) return fail(ctx, "triangular gemm needs K == N");
-  dim3 grid(N / GEMM_BN, J / GEMM_BM);
   ProfScope ps(ctx, slot);
-  gemm_nt_f64_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, ctx->stream>>>(A, lda, T, ldt, C, ldc, K, tri);
+  int rc;
+  switch (ctx->gemm_variant) {
+    // <BM, BN, BK, STAGES, WJ, WR, CTAs/SM>; measured on B200 (profiles/gemm_variants_r01.jsonl)
+    case 1: rc = launch_gemm_cfg<128, 128, 16, 4, 2, 4, 1>(ctx, J, N, A, lda, T, ldt, C, ldc, K, tri); break;  // v0: 32.0 TF
+    case 2: rc = launch_gemm_cfg<128, 64, 16, 3, 2, 2, 2>(ctx, J, N, A, lda, T, ldt, C, ldc, K, tri); break;   // 35.0 TF
+    case 3: rc = launch_gemm_cfg<64, 128, 16, 3, 1, 4, 2>(ctx, J, N, A, lda, T, ldt, C, ldc, K, tri); break;   // 33.2 TF
+    case 4: rc = launch_gemm_cfg<128, 64, 32, 2, 2, 2, 2>(ctx, J, N, A, lda, T, ldt, C, ldc, K, tri); break;   // 35.0 TF
+    case 5: rc = launch_gemm_cfg<64, 64, 16, 2, 2, 2, 4>(ctx, J, N, A, lda, T, ldt, C, ldc, K, tri); break;    // 4 CTAs/SM
+    case 6: rc = launch_gemm_cfg<64, 64, 32, 2, 2, 2, 3>(ctx, J, N, A, lda, T, ldt, C, ldc, K, tri); break;    // BK 32
+    case 7: rc = launch_gemm_cfg<64, 128, 16, 3, 2, 4, 2>(ctx, J, N, A, lda, T, ldt, C, ldc, K, tri); break;   // 8 warps of 32x32, 2/SM
+    default: rc = launch_gemm_cfg<64, 64, 16, 3, 2, 2, 3>(ctx, J, N, A, lda, T, ldt, C, ldc, K, tri); break;   // 35.1 TF
+  }
+  if (rc) return rc;
   CKL();
   return 0;
 }
@@ -249,7 +280,7 @@ extern "C" int maf_create(int device, int dtype, maf_ctx** out) {
   CKB(cublasSetStream(ctx->cublas, ctx->stream));
   CKB(cusolverDnCreate(&ctx->cusolver));
   CKB(cusolverDnSetStream(ctx->cusolver, ctx->stream));
-  CK(cudaFuncSetAttribute(gemm_nt_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  if (const char* gv = getenv("MAF_GEMM_VARIANT")) ctx->gemm_variant = atoi(gv);
   CK(cudaMalloc((void**)&ctx->d_argmin_val, sizeof(double)));
   CK(cudaMalloc((void**)&ctx->d_argmin_idx, sizeof(long long)));
   const char* cr = getenv("MAF_CHUNK_ROWS");

@@ -286,7 +286,7 @@ class bayesian_optimization(search_agent):
         if use_averaging and done:
             x = mean_x / done
         handle.assign(x[:, p:, :])
-        loss_seq = np.ravel(loss_seq) if loss_seq else np.empty([0])
+        loss_seq = np.concatenate([np.ravel(t) for t in loss_seq]) if loss_seq else np.empty([0])
         logger.info("SGD evaluated {:d} losses in {:.3e}s".format(len(loss_seq), self.timer() - start_time))
         return loss_seq
 
