@@ -78,6 +78,13 @@ int maf_set_train(maf_ctx* ctx, int n, const double* X0 /*[n][d]*/, const double
 /* copies of the cached factors, for tests: L0[n][n] lower, Linv[n][n] lower */
 int maf_get_factors(maf_ctx* ctx, double* L0, double* Linv, double* gamma);
 
+/* Data term of the negative log marginal likelihood of the loaded training set under the loaded
+ * model and its gradient w.r.t. (log lengthscales[d], log amplitude, log noise, mean): replaces
+ * gaussian_process.log_likelihood(as_negative=True) + tf.gradients inside gaussian_process.fit
+ * (src/models/gaussian_process.py:78-106,283-325); the hyper-priors (priors.py) are scalar
+ * functions the host adds.  grad has d + 3 entries. */
+int maf_gp_nll(maf_ctx* ctx, double* nll, double* grad);
+
 /* ---- GP posterior ------------------------------------------------------ */
 /* Replaces gaussian_process.predict/_predict_nd (src/models/gaussian_process.py:
  * 109-117,172-223) for rank-3 pools against a rank-2 training set.

@@ -36,6 +36,7 @@ SIGNATURES = {
     "maf_set_model": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_double, C.c_double, C.c_double, C.c_double]),
     "maf_set_train": (C.c_int, [_vp, C.c_int, _vp, _vp]),
     "maf_get_factors": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "maf_gp_nll": (C.c_int, [_vp, C.POINTER(C.c_double), _vp]),
     "maf_posterior": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int, _vp, _vp]),
     "maf_acq_value_grad": (C.c_int, [_vp, C.POINTER(AcqParams), C.c_int, C.c_int, C.c_int, _vp, C.c_int,
                                      _vp, _vp, _vp, _vp, _vp]),

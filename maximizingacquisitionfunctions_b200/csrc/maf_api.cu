@@ -12,6 +12,7 @@
 
 #include "common.cuh"
 #include "cov_kernels.cuh"
+#include "fit_kernels.cuh"
 #include "gemm_f64.cuh"
 #include "mc_kernels.cuh"
 #include "posterior.cuh"
@@ -248,10 +249,10 @@ static int launch_gemm(maf_ctx* ctx, int slot, int J, int N, int K, const double
     case 2: rc = launch_gemm_cfg<128, 64, 16, 3, 2, 2, 2>(ctx, J, N, A, lda, T, ldt, C, ldc, K, tri); break;   // 35.0 TF
     case 3: rc = launch_gemm_cfg<64, 128, 16, 3, 1, 4, 2>(ctx, J, N, A, lda, T, ldt, C, ldc, K, tri); break;   // 33.2 TF
     case 4: rc = launch_gemm_cfg<128, 64, 32, 2, 2, 2, 2>(ctx, J, N, A, lda, T, ldt, C, ldc, K, tri); break;   // 35.0 TF
-    case 5: rc = launch_gemm_cfg<64, 64, 16, 2, 2, 2, 4>(ctx, J, N, A, lda, T, ldt, C, ldc, K, tri); break;    // 4 CTAs/SM
+    case 5: rc = launch_gemm_cfg<64, 64, 16, 3, 2, 2, 3>(ctx, J, N, A, lda, T, ldt, C, ldc, K, tri); break;    // 35.2 TF
     case 6: rc = launch_gemm_cfg<64, 64, 32, 2, 2, 2, 3>(ctx, J, N, A, lda, T, ldt, C, ldc, K, tri); break;    // BK 32
     case 7: rc = launch_gemm_cfg<64, 128, 16, 3, 2, 4, 2>(ctx, J, N, A, lda, T, ldt, C, ldc, K, tri); break;   // 8 warps of 32x32, 2/SM
-    default: rc = launch_gemm_cfg<64, 64, 16, 3, 2, 2, 3>(ctx, J, N, A, lda, T, ldt, C, ldc, K, tri); break;   // 35.1 TF
+    default: rc = launch_gemm_cfg<64, 64, 16, 2, 2, 2, 4>(ctx, J, N, A, lda, T, ldt, C, ldc, K, tri); break;   // 4 CTAs/SM: 35.7 TF
   }
   if (rc) return rc;
   CKL();
@@ -487,6 +488,44 @@ extern "C" int maf_get_factors(maf_ctx* ctx, double* L0, double* Linv, double* g
   if (Linv) CK(cudaMemcpy2DAsync(Linv, sizeof(double) * n, ctx->Linv, sizeof(double) * npad, sizeof(double) * n, n, cudaMemcpyDeviceToHost, ctx->stream));
   if (gamma) CK(cudaMemcpyAsync(gamma, ctx->gamma, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+extern "C" int maf_gp_nll(maf_ctx* ctx, double* nll, double* grad) {
+  if (!ctx) return 1;
+  if (!ctx->train_set) return fail(ctx, "maf_set_train must be called first");
+  CK(cudaSetDevice(ctx->device));
+  const int n = ctx->n, npad = ctx->npad, d = ctx->mp.d;
+  const size_t nn = (size_t)npad * npad;
+  if (ensure(ctx, ctx->K10, nn) || ensure(ctx, ctx->dmu, (size_t)npad + MAF_MAX_D + 8)) return 1;
+  double* Kinv = ctx->K10.p;
+  double* alpha = ctx->dmu.p;
+  double* scal = ctx->dmu.p + npad;          // [0..1] scalars, [2..] gradient
+  CK(cudaMemsetAsync(scal, 0, sizeof(double) * (MAF_MAX_D + 8), ctx->stream));
+  {
+    ProfScope ps(ctx, MAF_PROF_POSTERIOR);
+    nll_scalars_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->L0, ctx->gamma, n, npad, scal);
+    CKL();
+  }
+  {
+    ProfScope ps(ctx, MAF_PROF_POSTERIOR);
+    trmv_upper_kernel<<<(npad + 7) / 8, 256, 0, ctx->stream>>>(ctx->LinvT, ctx->gamma, npad, alpha);
+    CKL();
+  }
+  // K^-1 = L^-T L^-1 = LinvT LinvT^T  (rows of LinvT are K-contiguous: the NT contraction kernel applies)
+  if (launch_gemm(ctx, MAF_PROF_GEMM_FWD, npad, npad, npad, ctx->LinvT, npad, ctx->LinvT, npad, Kinv, npad, 0)) return 1;
+  {
+    ProfScope ps(ctx, MAF_PROF_POSTERIOR);
+    dim3 grid((npad + 255) / 256, n);
+    nll_grad_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->X0s, n, npad, ctx->mp, Kinv, alpha, scal + 2);
+    CKL();
+  }
+  double h[MAF_MAX_D + 8];
+  CK(cudaMemcpyAsync(h, scal, sizeof(double) * (MAF_MAX_D + 8), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (nll) *nll = 0.5 * (h[1] + h[0] + (double)n * 1.8378770664093453);
+  if (grad)
+    for (int c = 0; c < d + 3; ++c) grad[c] = h[2 + c];
   return 0;
 }
 

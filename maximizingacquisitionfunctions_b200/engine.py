@@ -150,6 +150,13 @@ class Engine:
         self._ck(self._lib.maf_get_factors(self._ctx, nat.ptr(L0), nat.ptr(Linv), nat.ptr(gamma)))
         return L0, Linv, gamma
 
+    def gp_nll(self):
+        """(data negative log-likelihood, gradient w.r.t. [log lengthscales(d), log amplitude, log noise, mean])."""
+        nll = C.c_double(0.0)
+        grad = np.zeros(self.d + 3)
+        self._ck(self._lib.maf_gp_nll(self._ctx, C.byref(nll), nat.ptr(grad)))
+        return float(nll.value), grad
+
     # -- posterior ---------------------------------------------------------------------------------
     def posterior(self, X: np.ndarray, full_cov: bool = True):
         X = nat.as_f64(X)
