@@ -116,6 +116,20 @@ int maf_mc_from_moments(maf_ctx* ctx, const maf_acq_params* prm, int S, int q, c
                         const double* cov, int M, const double* z, const double* weights,
                         const double* incumbents, double* out_loss, double* out_mubar,
                         double* out_covbar, double* out_chol);
+/* ---- fantasy-conditioned closed form (incremental greedy) ----------------- */
+/* Replaces the rank-4 ("padded") observation-set path: scripts/run_bayesopt_incremental.py:138-218
+ * builds inputs_old[F,1,n,d] (identical copies) and outputs_old[F,1,n,1]; gaussian_process._predict_nd
+ * (:195-206) solves once with chol[0,0] and appraise_inputs (:227-229) averages the [F,S,1,1] closed-form
+ * losses over fantasies.  maf_set_fantasies keeps the factor of the loaded training inputs and loads
+ * F output vectors Y[F][n] (per-fantasy prior mean if the model mean is empirical, per-fantasy level
+ * min(Y_f) unless prm->level is given).  maf_fantasies_value_grad: loss[S] = mean_f loss(mu_sf, var_s,
+ * level_f) for single-point candidates X[S][d], out_grad[S][d] (NULL => value only).
+ * maf_fantasies_posterior: mu[F][S], var[S]. */
+int maf_set_fantasies(maf_ctx* ctx, int F, const double* Y);
+int maf_fantasies_value_grad(maf_ctx* ctx, const maf_acq_params* prm, int S, const double* X,
+                             double* out_loss, double* out_grad);
+int maf_fantasies_posterior(maf_ctx* ctx, int S, const double* X, double* mu, double* var);
+
 /* extras of the last evaluation (myopic_loss.py:179 returns (means, cov, chol)):
  * mu[S][q], cov[S][q][q], chol[S][q][q] (NULL to skip) */
 int maf_last_extras(maf_ctx* ctx, double* mu, double* cov, double* chol);

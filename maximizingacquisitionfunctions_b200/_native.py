@@ -44,6 +44,9 @@ SIGNATURES = {
                                          _vp, _vp, _vp, _vp, _vp]),
     "maf_mc_from_moments": (C.c_int, [_vp, C.POINTER(AcqParams), C.c_int, C.c_int, _vp, _vp, C.c_int, _vp, _vp, _vp,
                                       _vp, _vp, _vp, _vp]),
+    "maf_set_fantasies": (C.c_int, [_vp, C.c_int, _vp]),
+    "maf_fantasies_value_grad": (C.c_int, [_vp, C.POINTER(AcqParams), C.c_int, _vp, _vp, _vp]),
+    "maf_fantasies_posterior": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp]),
     "maf_last_extras": (C.c_int, [_vp, _vp, _vp, _vp]),
     "maf_adam_begin": (C.c_int, [_vp, C.POINTER(AcqParams), C.c_int, C.c_int, C.c_int, _vp,
                                  C.c_double, C.c_double, C.c_double, C.c_double]),

@@ -66,6 +66,9 @@ struct maf_ctx {
   maf_acq_params adam_prm{};
   int adam_S = 0, adam_q = 0, adam_p = 0;
   Buf adam_X, adam_m, adam_v, adam_g, adam_z;
+  // fantasies (rank-4 observation sets)
+  int F = 0, Fpad = 0;
+  Buf fGamma, fGammaT, fmeans, flevels, fVG, fmubar;
   double adam_lr = 0, adam_b1 = 0, adam_b2 = 0, adam_eps = 0, adam_b1p = 0, adam_b2p = 0;
   // profiling
   cudaEvent_t timer_ev[2] = {nullptr, nullptr};
@@ -162,6 +165,16 @@ __global__ void transpose_kernel(const double* __restrict__ A, double* __restric
   __syncthreads();
   int xo = blockIdx.y * 32 + threadIdx.x, yo0 = blockIdx.x * 32;
   for (int r = threadIdx.y; r < 32; r += blockDim.y) B[(size_t)(yo0 + r) * n + xo] = t[threadIdx.x][r];
+}
+
+// B[C][R] = A[R][C]^T, R and C multiples of 32
+__global__ void transpose_rect_kernel(const double* __restrict__ A, double* __restrict__ B, int R, int Cc) {
+  __shared__ double t[32][33];
+  int x = blockIdx.x * 32 + threadIdx.x, y0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) t[r][threadIdx.x] = A[(size_t)(y0 + r) * Cc + x];
+  __syncthreads();
+  int xo = blockIdx.y * 32 + threadIdx.x, yo0 = blockIdx.x * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) B[(size_t)(yo0 + r) * R + xo] = t[threadIdx.x][r];
 }
 
 // gamma_i = sum_{k<=i} Linv[i][k] rho_k ; one warp per row.
@@ -301,7 +314,8 @@ extern "C" int maf_destroy(maf_ctx* ctx) {
     if (b) cudaFree(b);
   Buf* bufs[] = {&ctx->K10, &ctx->Vt, &ctx->dX, &ctx->dz, &ctx->dw, &ctx->dinc, &ctx->dmu, &ctx->dSig, &ctx->dchol,
                  &ctx->dmubar, &ctx->dSigbar, &ctx->dloss, &ctx->dgrad, &ctx->adam_X, &ctx->adam_m, &ctx->adam_v,
-                 &ctx->adam_g, &ctx->adam_z};
+                 &ctx->adam_g, &ctx->adam_z, &ctx->fGamma, &ctx->fGammaT, &ctx->fmeans, &ctx->flevels, &ctx->fVG,
+                 &ctx->fmubar};
   for (Buf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (ctx->d_argmin_idx) cudaFree(ctx->d_argmin_idx);
@@ -477,6 +491,7 @@ extern "C" int maf_set_train(maf_ctx* ctx, int n, const double* X0, const double
   CK(cudaFree(drho));
   ctx->train_set = true;
   ctx->adam_on = false;
+  ctx->F = 0;
   return 0;
 }
 
@@ -780,6 +795,149 @@ extern "C" int maf_mc_from_moments(maf_ctx* ctx, const maf_acq_params* prm, int 
   return 0;
 }
 
+// ---- fantasies ------------------------------------------------------------------------------------
+extern "C" int maf_set_fantasies(maf_ctx* ctx, int F, const double* Y) {
+  if (!ctx) return 1;
+  if (!ctx->train_set) return fail(ctx, "maf_set_train must be called first");
+  if (F < 1 || !Y) return fail(ctx, "bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  const int n = ctx->n, npad = ctx->npad;
+  const int Fpad = round_up(F, 128);
+  std::vector<double> rho((size_t)Fpad * npad, 0.0), means(Fpad, 0.0), levels(Fpad, 0.0);
+  const bool empirical = !(ctx->mean_param == ctx->mean_param);
+  for (int f = 0; f < F; ++f) {
+    const double* y = Y + (size_t)f * n;
+    double m = ctx->mean_param, lo = y[0];
+    if (empirical) {
+      double acc = 0.0;
+      for (int i = 0; i < n; ++i) acc += y[i];
+      m = acc / n;
+    }
+    for (int i = 0; i < n; ++i) {
+      rho[(size_t)f * npad + i] = y[i] - m;
+      lo = std::min(lo, y[i]);
+    }
+    means[f] = m;
+    levels[f] = lo;
+  }
+  const size_t fn = (size_t)Fpad * npad;
+  if (ensure(ctx, ctx->fGamma, fn) || ensure(ctx, ctx->fGammaT, fn) || ensure(ctx, ctx->fmeans, Fpad) ||
+      ensure(ctx, ctx->flevels, Fpad) || ensure(ctx, ctx->Vt, fn))
+    return 1;
+  CK(cudaMemcpyAsync(ctx->Vt.p, rho.data(), sizeof(double) * fn, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->fmeans.p, means.data(), sizeof(double) * Fpad, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->flevels.p, levels.data(), sizeof(double) * Fpad, cudaMemcpyHostToDevice, ctx->stream));
+  // Gamma[f][r] = sum_c rho_f[c] Linv[r][c]
+  if (launch_gemm(ctx, MAF_PROF_GEMM_FWD, Fpad, npad, npad, ctx->Vt.p, npad, ctx->Linv, npad, ctx->fGamma.p, npad, 1)) return 1;
+  {
+    ProfScope ps(ctx, MAF_PROF_POSTERIOR);
+    dim3 grid(npad / 32, Fpad / 32), block(32, 8);
+    transpose_rect_kernel<<<grid, block, 0, ctx->stream>>>(ctx->fGamma.p, ctx->fGammaT.p, Fpad, npad);
+    CKL();
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->F = F;
+  ctx->Fpad = Fpad;
+  return 0;
+}
+
+// loss/grad (prm != null) or posterior (prm == null) over S single-point candidates, in chunks
+static int run_fantasies(maf_ctx* ctx, const maf_acq_params* prm, int S, const double* X, double* out_loss,
+                         double* out_grad, double* out_mu, double* out_var) {
+  if (ctx->F < 1) return fail(ctx, "maf_set_fantasies must be called first");
+  if (S < 1 || !X) return fail(ctx, "bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  const int d = ctx->mp.d, n = ctx->n, npad = ctx->npad, F = ctx->F, Fpad = ctx->Fpad;
+  AcqDev ap{};
+  int use_flevels = 1;
+  if (prm) {
+    if (resolve_acq(ctx, prm, &ap)) return 1;
+    use_flevels = !(prm->level == prm->level);
+  } else {
+    ap.acq = MAF_ACQ_SR;
+  }
+  const int sc_max = (int)std::min<size_t>(ctx->chunk_rows, (size_t)S);
+  const int Jmax = round_up(sc_max, 128);
+  if (ensure(ctx, ctx->dX, (size_t)S * d) || ensure(ctx, ctx->K10, (size_t)Jmax * npad) ||
+      ensure(ctx, ctx->Vt, (size_t)Jmax * npad) || ensure(ctx, ctx->fVG, (size_t)Jmax * Fpad) ||
+      ensure(ctx, ctx->fmubar, (size_t)Jmax * Fpad) || ensure(ctx, ctx->dmu, (size_t)S) ||
+      ensure(ctx, ctx->dSig, (size_t)S) || ensure(ctx, ctx->dSigbar, (size_t)S) || ensure(ctx, ctx->dloss, (size_t)S) ||
+      ensure(ctx, ctx->dgrad, (size_t)S * d))
+    return 1;
+  CK(cudaMemcpyAsync(ctx->dX.p, X, sizeof(double) * (size_t)S * d, cudaMemcpyHostToDevice, ctx->stream));
+  const int need_grad = out_grad != nullptr;
+  for (int s0 = 0; s0 < S; s0 += sc_max) {
+    const int sc = std::min(sc_max, S - s0);
+    const int Jpad = round_up(sc, 128);
+    const double* dX = ctx->dX.p + (size_t)s0 * d;
+    {
+      ProfScope ps(ctx, MAF_PROF_CROSS_FWD);
+      dim3 grid((npad + CROSS_TK - 1) / CROSS_TK, Jpad / CROSS_TJ);
+      DISPATCH_D(d, cross_fwd_kernel<D><<<grid, CROSS_TK, 0, ctx->stream>>>(dX, sc, ctx->X0s, n, npad, ctx->mp, ctx->K10.p));
+      CKL();
+    }
+    if (launch_gemm(ctx, MAF_PROF_GEMM_FWD, Jpad, npad, npad, ctx->K10.p, npad, ctx->Linv, npad, ctx->Vt.p, npad, 1)) return 1;
+    {
+      ProfScope ps(ctx, MAF_PROF_POSTERIOR);
+      posterior_kernel<1><<<sc, POST_THREADS, 0, ctx->stream>>>(ctx->Vt.p, npad, ctx->gamma, dX, ctx->mp, ctx->mean_val,
+                                                               ctx->dmu.p + s0, ctx->dSig.p + s0);
+      CKL();
+    }
+    // VG[s][f] = v_s . gamma_f
+    if (launch_gemm(ctx, MAF_PROF_GEMM_FWD, Jpad, Fpad, npad, ctx->Vt.p, npad, ctx->fGamma.p, npad, ctx->fVG.p, Fpad, 0)) return 1;
+    {
+      ProfScope ps(ctx, MAF_PROF_MC);
+      closed_form_fant_kernel<<<(sc + 3) / 4, 128, 0, ctx->stream>>>(
+          sc, F, Fpad, ctx->fVG.p, ctx->fmeans.p, ctx->flevels.p, ctx->dSig.p + s0, ap, use_flevels, need_grad,
+          ctx->dloss.p + s0, ctx->fmubar.p, ctx->dSigbar.p + s0, prm ? nullptr : ctx->fVG.p);
+      CKL();
+    }
+    if (!prm && out_mu) {
+      // fVG now holds mu[s][f]; transpose into the caller's [F][S] layout on the host
+      std::vector<double> h((size_t)sc * Fpad);
+      CK(cudaMemcpyAsync(h.data(), ctx->fVG.p, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      for (int f = 0; f < F; ++f)
+        for (int s = 0; s < sc; ++s) out_mu[(size_t)f * S + s0 + s] = h[(size_t)s * Fpad + f];
+    }
+    if (!need_grad) continue;
+    if (Jpad > sc) CK(cudaMemsetAsync(ctx->fmubar.p + (size_t)sc * Fpad, 0, sizeof(double) * (size_t)(Jpad - sc) * Fpad, ctx->stream));
+    // G = mubar Gamma  -> K10 buffer ; Vbar = G - 2 varbar V ; Kbar = Vbar Linv ; xbar
+    if (launch_gemm(ctx, MAF_PROF_GEMM_BWD, Jpad, npad, Fpad, ctx->fmubar.p, Fpad, ctx->fGammaT.p, Fpad, ctx->K10.p, npad, 0)) return 1;
+    {
+      ProfScope ps(ctx, MAF_PROF_VBAR);
+      dim3 grid((npad + 255) / 256, sc);
+      fant_vbar_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->Vt.p, ctx->K10.p, ctx->dSigbar.p + s0, sc, npad);
+      CKL();
+    }
+    if (launch_gemm(ctx, MAF_PROF_GEMM_BWD, Jpad, npad, npad, ctx->Vt.p, npad, ctx->LinvT, npad, ctx->K10.p, npad, 2)) return 1;
+    {
+      ProfScope ps(ctx, MAF_PROF_CROSS_BWD);
+      DISPATCH_D(d, cross_bwd_kernel<D><<<sc, 32, 0, ctx->stream>>>(dX, sc, 1, 0, ctx->X0s, n, npad, ctx->mp, ctx->K10.p,
+                                                                     ctx->dSigbar.p + s0, ctx->dgrad.p + (size_t)s0 * d));
+      CKL();
+    }
+  }
+  if (out_loss) CK(cudaMemcpyAsync(out_loss, ctx->dloss.p, sizeof(double) * S, cudaMemcpyDeviceToHost, ctx->stream));
+  if (out_grad) CK(cudaMemcpyAsync(out_grad, ctx->dgrad.p, sizeof(double) * (size_t)S * d, cudaMemcpyDeviceToHost, ctx->stream));
+  if (out_var) CK(cudaMemcpyAsync(out_var, ctx->dSig.p, sizeof(double) * S, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->last_S = 0;   // the per-restart extras buffers were reused
+  return 0;
+}
+
+extern "C" int maf_fantasies_value_grad(maf_ctx* ctx, const maf_acq_params* prm, int S, const double* X,
+                                        double* out_loss, double* out_grad) {
+  if (!ctx) return 1;
+  if (!prm || !out_loss) return fail(ctx, "null pointer");
+  return run_fantasies(ctx, prm, S, X, out_loss, out_grad, nullptr, nullptr);
+}
+
+extern "C" int maf_fantasies_posterior(maf_ctx* ctx, int S, const double* X, double* mu, double* var) {
+  if (!ctx) return 1;
+  return run_fantasies(ctx, nullptr, S, X, nullptr, nullptr, mu, var);
+}
+
 extern "C" int maf_last_extras(maf_ctx* ctx, double* mu, double* cov, double* chol) {
   if (!ctx) return 1;
   if (ctx->last_S == 0) return fail(ctx, "no evaluation to report");
@@ -847,20 +1005,22 @@ extern "C" int maf_adam_begin(maf_ctx* ctx, const maf_acq_params* prm, int S, in
 extern "C" int maf_adam_steps(maf_ctx* ctx, int steps, int M, const double* z_steps, double* out_loss_trace) {
   if (!ctx) return 1;
   if (!ctx->adam_on) return fail(ctx, "maf_adam_begin must be called first");
-  if (steps < 0 || M < 1 || !z_steps) return fail(ctx, "bad arguments");
+  const bool closed = (ctx->adam_q == 1 && z_steps == nullptr);      // q == 1: deterministic closed-form loss
+  if (steps < 0 || (!closed && (M < 1 || !z_steps))) return fail(ctx, "bad arguments");
   CK(cudaSetDevice(ctx->device));
   const int S = ctx->adam_S, q = ctx->adam_q, p = ctx->adam_p, d = ctx->mp.d;
   const size_t nt = (size_t)S * (q - p) * d;
-  const size_t zsz = (size_t)M * q;
-  if (ensure(ctx, ctx->adam_z, zsz * std::max(steps, 1)) || ensure(ctx, ctx->dloss, (size_t)S)) return 1;
-  CK(cudaMemcpyAsync(ctx->adam_z.p, z_steps, sizeof(double) * zsz * steps, cudaMemcpyHostToDevice, ctx->stream));
+  const size_t zsz = closed ? 0 : (size_t)M * q;
+  if (ensure(ctx, ctx->adam_z, std::max<size_t>(zsz * std::max(steps, 1), 1)) || ensure(ctx, ctx->dloss, (size_t)S)) return 1;
+  if (!closed)
+    CK(cudaMemcpyAsync(ctx->adam_z.p, z_steps, sizeof(double) * zsz * steps, cudaMemcpyHostToDevice, ctx->stream));
   double* dtrace = nullptr;
   if (out_loss_trace && steps > 0) CK(cudaMalloc((void**)&dtrace, sizeof(double) * (size_t)steps * S));
   int rc = 0;
   for (int t = 0; t < steps && rc == 0; ++t) {
     double* lossp = dtrace ? dtrace + (size_t)t * S : ctx->dloss.p;
-    rc = run_all(ctx, &ctx->adam_prm, false, S, q, p, ctx->adam_X.p, M, ctx->adam_z.p + zsz * t, nullptr, nullptr,
-                 lossp, ctx->adam_g.p);
+    rc = run_all(ctx, &ctx->adam_prm, false, S, q, p, ctx->adam_X.p, M, closed ? nullptr : ctx->adam_z.p + zsz * t,
+                 nullptr, nullptr, lossp, ctx->adam_g.p);
     if (rc) break;
     const double alpha = ctx->adam_lr * std::sqrt(1.0 - ctx->adam_b2p) / (1.0 - ctx->adam_b1p);
     {

@@ -265,13 +265,9 @@ mc_acq_kernel(int S, int M, const double* __restrict__ mu, const double* __restr
 __device__ __forceinline__ double norm_pdf(double x) { return 0.3989422804014327 * exp(-0.5 * x * x); }
 __device__ __forceinline__ double norm_cdf(double x) { return 0.5 * erfc(-0.7071067811865475 * x); }
 
-__global__ void closed_form_kernel(int S, const double* __restrict__ mu, const double* __restrict__ var,
-                                   AcqDev ap, int need_grad, double* __restrict__ loss,
-                                   double* __restrict__ mubar, double* __restrict__ varbar) {
-  int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= S) return;
-  const double m = mu[s], v = var[s];
-  double l, dm, dv;
+// loss and its derivatives w.r.t. (mean, variance) for one (candidate, level) pair
+__device__ __forceinline__ void closed_form_eval(const AcqDev& ap, double level, double m, double v,
+                                                 double& l, double& dm, double& dv) {
   if (ap.acq == MAF_ACQ_SR) {
     l = m; dm = 1.0; dv = 0.0;
   } else if (ap.acq == MAF_ACQ_CB) {
@@ -281,7 +277,7 @@ __global__ void closed_form_kernel(int S, const double* __restrict__ mu, const d
     dm = 1.0;
     dv = sgn * ap.beta / (2.0 * sb);
   } else {
-    double r = ap.level - m;
+    double r = level - m;
     double sd = sqrt(v);
     double zz = (r == 0.0 && sd == 0.0) ? 0.0 : r / sd;     // utils.safe_div
     double pdf = norm_pdf(zz), cdf = norm_cdf(zz);
@@ -295,8 +291,64 @@ __global__ void closed_form_kernel(int S, const double* __restrict__ mu, const d
       dv = pdf * zz / (2.0 * v);
     }
   }
+}
+
+__global__ void closed_form_kernel(int S, const double* __restrict__ mu, const double* __restrict__ var,
+                                   AcqDev ap, int need_grad, double* __restrict__ loss,
+                                   double* __restrict__ mubar, double* __restrict__ varbar) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  double l, dm, dv;
+  closed_form_eval(ap, ap.level, mu[s], var[s], l, dm, dv);
   loss[s] = l;
   if (need_grad) { mubar[s] = dm; varbar[s] = dv; }
+}
+
+// Fantasy-conditioned closed form (rank-4 observation sets of the incremental greedy driver,
+// scripts/run_bayesopt_incremental.py:138-218; gaussian_process._predict_nd :195-206;
+// bayesian_optimization.appraise_inputs :227-229): all F fantasies share X0 (one factor, one variance),
+// differ in outputs, hence in gamma_f, prior mean m_f and level_f;  loss_s = mean_f loss(mu_sf, var_s, level_f).
+// One warp per candidate; VG[s][f] = v_s . gamma_f.
+__global__ void closed_form_fant_kernel(int S, int F, int Fpad, const double* __restrict__ VG,
+                                        const double* __restrict__ fmeans, const double* __restrict__ flevels,
+                                        const double* __restrict__ var, AcqDev ap, int use_flevels, int need_grad,
+                                        double* __restrict__ loss, double* __restrict__ mubar /*[S][Fpad]*/,
+                                        double* __restrict__ varbar, double* __restrict__ mu_out /*[S][Fpad] or null*/) {
+  const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (s >= S) return;
+  const double v = var[s];
+  const double invF = 1.0 / (double)F;
+  double lsum = 0.0, dvsum = 0.0;
+  for (int f = lane; f < Fpad; f += 32) {
+    double dm_out = 0.0;
+    if (f < F) {
+      const double m = fmeans[f] + VG[(size_t)s * Fpad + f];
+      double l, dm, dv;
+      closed_form_eval(ap, use_flevels ? flevels[f] : ap.level, m, v, l, dm, dv);
+      lsum += l;
+      dvsum += dv;
+      dm_out = dm * invF;
+      if (mu_out) mu_out[(size_t)s * Fpad + f] = m;
+    }
+    if (need_grad) mubar[(size_t)s * Fpad + f] = dm_out;
+  }
+  lsum = warp_sum(lsum);
+  dvsum = warp_sum(dvsum);
+  if (lane == 0) {
+    loss[s] = lsum * invF;
+    if (need_grad) varbar[s] = dvsum * invF;
+  }
+}
+
+// Vbar[s][c] = G[s][c] - 2 varbar_s V[s][c]   (G = mubar Gamma), in place into V.
+__global__ void fant_vbar_kernel(double* __restrict__ Vt, const double* __restrict__ G, const double* __restrict__ varbar,
+                                 int S, int npad) {
+  const int s = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S || c >= npad) return;
+  const size_t o = (size_t)s * npad + c;
+  Vt[o] = G[o] - 2.0 * varbar[s] * Vt[o];
 }
 
 // ---- Adam + clip (TF-1 ApplyAdam kernel form, then clip_by_value(x, 0, 1)) ---------------

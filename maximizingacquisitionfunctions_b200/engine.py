@@ -220,6 +220,29 @@ class Engine:
                                                nat.ptr(mubar), nat.ptr(covbar), nat.ptr(chol)))
         return loss, mubar, covbar, chol
 
+    # -- fantasy-conditioned closed form (rank-4 observation sets) -----------------------------------
+    def set_fantasies(self, Y: np.ndarray):
+        """Y[F][n]: F output vectors over the loaded training inputs."""
+        Y = nat.as_f64(Y)
+        assert Y.ndim == 2 and Y.shape[1] == self.n
+        self.F = int(Y.shape[0])
+        self._ck(self._lib.maf_set_fantasies(self._ctx, self.F, nat.ptr(Y)))
+
+    def fantasies_value_and_grad(self, prm: nat.AcqParams, X: np.ndarray, need_grad: bool = True):
+        X = nat.as_f64(np.reshape(X, (-1, self.d)))
+        S = X.shape[0]
+        loss = np.empty(S)
+        grad = np.empty((S, self.d)) if need_grad else None
+        self._ck(self._lib.maf_fantasies_value_grad(self._ctx, C.byref(prm), S, nat.ptr(X), nat.ptr(loss), nat.ptr(grad)))
+        return loss, grad
+
+    def fantasies_posterior(self, X: np.ndarray):
+        X = nat.as_f64(np.reshape(X, (-1, self.d)))
+        S = X.shape[0]
+        mu, var = np.empty((self.F, S)), np.empty(S)
+        self._ck(self._lib.maf_fantasies_posterior(self._ctx, S, nat.ptr(X), nat.ptr(mu), nat.ptr(var)))
+        return mu, var
+
     def last_extras(self, S: int, q: int, want_chol: bool = True):
         mu, cov = np.empty((S, q, 1)), np.empty((S, q, q))
         chol = np.empty((S, q, q)) if want_chol else None
@@ -240,10 +263,15 @@ class Engine:
         self._ck(self._lib.maf_adam_begin(self._ctx, C.byref(prm), S, q, int(p_pending), nat.ptr(X),
                                           float(lr), float(beta1), float(beta2), float(eps)))
 
-    def adam_steps(self, z_steps: np.ndarray, want_trace: bool = False):
-        z_steps = nat.as_f64(z_steps)
-        steps, M, q = z_steps.shape
-        assert q == self._adam_shape[1]
+    def adam_steps(self, z_steps, want_trace: bool = False, steps: Optional[int] = None):
+        """z_steps[steps][M][q]; for q == 1 pass z_steps=None and `steps` (closed-form loss)."""
+        if z_steps is None:
+            assert self._adam_shape[1] == 1 and steps is not None
+            M = 0
+        else:
+            z_steps = nat.as_f64(z_steps)
+            steps, M, q = z_steps.shape
+            assert q == self._adam_shape[1]
         trace = np.empty((steps, self._adam_shape[0])) if want_trace else None
         self._ck(self._lib.maf_adam_steps(self._ctx, steps, M, nat.ptr(z_steps), nat.ptr(trace)))
         return trace

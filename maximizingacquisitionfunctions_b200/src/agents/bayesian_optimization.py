@@ -135,8 +135,8 @@ class bayesian_optimization(search_agent):
             loss_fn = self.loss_fn
         feed_dict = dict() if feed_dict is None else dict(feed_dict)
         loss_kwargs = dict() if loss_kwargs is None else dict(loss_kwargs)
-        if np.ndim(inputs_old) == 4:
-            raise NotImplementedError("rank-4 (fantasy-padded) observation sets are not supported yet")
+        if np.ndim(inputs_old) == 4 and inputs_pend is not None and len(inputs_pend):
+            raise NotImplementedError("pending inputs together with fantasy-padded observations")
         nodes = self.prepare(sess, inputs_new, inputs_old, outputs_old, inputs_pend, feed_dict, nodes,
                              inputs_as_var)[0]
         # the training factor is cached on the device per (hyper-parameters, X0, Y0) (runtime.bind)
@@ -255,8 +255,8 @@ class bayesian_optimization(search_agent):
         handle = inputs_new
         pools, p = handle.pools()
         S, q, d = pools.shape
-        if q == 1:
-            raise NotImplementedError("the Adam loop needs base samples (q > 1); q == 1 takes the L-BFGS-B route (:311-313)")
+        if np.ndim(handle.inputs_old) == 4:
+            raise NotImplementedError("Adam on fantasy-padded observations; use the L-BFGS-B subroutine (q == 1 default)")
         eng = handle.model.bind(handle.inputs_old, handle.outputs_old)
         prm = handle.loss_fn.acq_params(outputs_old=handle.outputs_old, **handle.loss_kwargs)
         eng.adam_begin(prm, pools, p_pending=p, lr=lr)     # resets slots + step (:444-451)
@@ -271,12 +271,15 @@ class bayesian_optimization(search_agent):
             if self.timer() - start_time >= time_limit:
                 break
             k = int(min(block, step_limit - done))
-            zs = []
-            for _ in range(k):
-                if callable(batch_generator):
-                    feed_dict.update(batch_generator(batch_size))
-                zs.append(np.asarray(feed_dict["fantasy_rvs"], dtype=np.float64))
-            trace = eng.adam_steps(np.stack(zs), want_trace=True)
+            if q == 1:                                      # deterministic closed-form loss, no base samples
+                trace = eng.adam_steps(None, want_trace=True, steps=k)
+            else:
+                zs = []
+                for _ in range(k):
+                    if callable(batch_generator):
+                        feed_dict.update(batch_generator(batch_size))
+                    zs.append(np.asarray(feed_dict["fantasy_rvs"], dtype=np.float64))
+                trace = eng.adam_steps(np.stack(zs), want_trace=True)
             loss_seq.append(trace)
             done += k
             if use_averaging:                               # Polyak mean of the iterates (:472-475)

@@ -58,6 +58,14 @@ class myopic_loss(abstract_loss):
             parallelism = q
         assert parallelism == q, "parallelism must equal the pool size"
         eng = model.bind(inputs_old, outputs_old)
+        if np.ndim(inputs_old) == 4:
+            # fantasy-padded observations: closed form averaged over the fantasies on the device
+            # (the reference returns [F,S,1,1] and appraise_inputs takes the mean over axis 0, :227-229)
+            assert q == 1, "fantasy-conditioned losses are closed-form (q == 1)"
+            prm = self.acq_params(outputs_old=None, **kwargs)
+            losses, grad = eng.fantasies_value_and_grad(prm, pools[:, 0, :], need_grad=return_grad)
+            out = (losses.reshape(S, 1, 1), None)
+            return out + (None if grad is None else grad.reshape(S, 1, d),) if return_grad else out
         prm = self.acq_params(outputs_old=outputs_old, **kwargs)
         closed = (q == 1 and fantasy_rvs is None) if subroutine is None else (subroutine == self.closed_form)
         if closed:

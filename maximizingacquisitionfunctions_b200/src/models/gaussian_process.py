@@ -97,9 +97,22 @@ class gaussian_process(abstract_model):
 
     # ---- device binding ---------------------------------------------------------------------------
     def bind(self, inputs_old, outputs_old):
-        """Engine holding this model's factors for (inputs_old, outputs_old)."""
+        """Engine holding this model's factors for (inputs_old, outputs_old).  Rank-4 ("fantasy-padded")
+        observation sets [F,1,n,d] / [F,1,n,1] share their inputs (the reference solves with chol[0,0],
+        :195-200): the factor is built once and the F output vectors are loaded as fantasies."""
         X0 = np.asarray(inputs_old, dtype=np.float64)
         Y0 = np.asarray(outputs_old, dtype=np.float64)
+        if X0.ndim == 4:
+            assert X0.shape[1] == 1 and Y0.shape[:3] == X0.shape[:3] and Y0.shape[-1] == 1
+            if not np.array_equal(X0, np.broadcast_to(X0[:1], X0.shape)):
+                raise ValueError("fantasy-padded observation sets must share their inputs")
+            eng = self.bind(X0[0, 0], Y0[0, 0])
+            Yf = np.ascontiguousarray(Y0[:, 0, :, 0])
+            key = (eng._fingerprint, Yf.tobytes())
+            if getattr(eng, "_fantasy_key", None) != key:
+                eng.set_fantasies(Yf)
+                eng._fantasy_key = key
+            return eng
         assert X0.ndim == 2 and Y0.shape[0] == X0.shape[0], "observations must be [n, d] / [n, 1]"
         assert Y0.ndim == 1 or Y0.shape[-1] == 1, "Multiple objectives not yet supported"
         eng = runtime.get_engine(self.device, self.dtype)
@@ -112,6 +125,12 @@ class gaussian_process(abstract_model):
         `chol` (the cached factor the reference threads through) is implied by the binding."""
         eng = self.bind(inputs_old, outputs_old)
         X1 = np.asarray(inputs_new, dtype=np.float64)
+        if np.ndim(inputs_old) == 4:                  # [F, S, q=1, 1] means; the variance is shared (:195-223)
+            assert not full_cov or X1.reshape(-1, X1.shape[-1]).shape[0] == 1 or X1.shape[-2] == 1
+            mu, var = eng.fantasies_posterior(X1.reshape(-1, X1.shape[-1]))
+            F, S = mu.shape
+            lead = (F,) + (X1.shape[:-1] if X1.ndim == 3 else (S,)) + (1,)
+            return mu.reshape(lead), np.broadcast_to(var.reshape(lead[1:]), lead).copy()
         rank2 = X1.ndim == 2
         if not full_cov:
             flat = X1.reshape(-1, 1, X1.shape[-1])
@@ -141,6 +160,15 @@ class gaussian_process(abstract_model):
         if X0 is None or Y0 is None:
             raise NotImplementedError("Sampling from the prior not yet supported")
         X1 = np.asarray(X1, dtype=np.float64).reshape(-1, np.shape(X0)[-1])
+        if np.ndim(X0) == 4:
+            # one shared base sample per draw across the F fantasies, as the reference's broadcasted
+            # tensordot does (:340-349): samples [F, 1, num_samples... ] -> [F, 1, 1, num_samples]
+            assert X1.shape[0] == 1, "fantasy-conditioned draws are taken at one point"
+            mu, var = self.predict(X1[None], X0, Y0)             # [F,1,1,1]
+            if base_rvs is None:
+                base_rvs = self.rng.randn(num_samples, 1)
+            sd = np.sqrt(var + self.jitter)
+            return mu + sd * np.asarray(base_rvs).reshape(1, 1, 1, -1)
         mu, cov = self.predict(X1, X0, Y0, full_cov=True)
         if base_rvs is None:
             base_rvs = self.rng.randn(num_samples, X1.shape[0])
@@ -149,7 +177,78 @@ class gaussian_process(abstract_model):
         _, _, _, chol = eng.mc_from_moments(acq_params("sr"), mu[None, :, 0], cov[None], np.asarray(base_rvs))
         return mu[:, 0][None, :] + np.asarray(base_rvs) @ chol[0].T
 
-    def fit(self, sess, inputs, outputs, **kwargs):
-        raise NotImplementedError(
-            "GP MAP fit (gaussian_process.fit, SURVEY 8f-2) is not on the accelerated path yet; "
-            "set hyper-parameters explicitly (scripts: --use_true_prior 1)")
+    # ---- MAP fit (:283-325) -------------------------------------------------------------------------
+    def _pack(self, d):
+        """Free parameters of the active state as (names, x0, bounds): every state entry that is not None."""
+        st = self.state
+        bounds_cfg = self.spo_config.get("var_to_bounds", {})
+        names, x0, bounds = [], [], []
+        if st.get("mean", None) is not None:
+            names.append(("mean", 1))
+            x0.append([float(st["mean"])])
+            bounds.append([(None, None)])
+        for key in ("log_lenscales", "log_amplitude", "log_noise"):
+            if st.get(key, None) is None:
+                continue
+            v = np.atleast_1d(np.asarray(st[key], dtype=np.float64)).ravel()
+            lo, hi = bounds_cfg.get(key, (None, None))
+            lo = None if lo is None or np.isneginf(lo) else float(lo)
+            hi = None if hi is None or np.isposinf(hi) else float(hi)
+            names.append((key, v.size))
+            x0.append(v)
+            bounds.append([(lo, hi)] * v.size)
+        return names, np.concatenate(x0), [b for bb in bounds for b in bb]
+
+    def _unpack(self, names, x):
+        st, k = self.state, 0
+        for key, size in names:
+            v = np.array(x[k:k + size])
+            k += size
+            if key == "log_lenscales":
+                st[key] = v.reshape(np.shape(st[key])) if np.ndim(st[key]) else np.asarray(v[0])
+            else:
+                st[key] = float(v[0])
+
+    def negative_log_posterior(self, inputs, outputs):
+        """-(data log-likelihood + hyper-priors) and its gradient w.r.t. the packed free parameters.
+        Data term and gradient from the device (maf_gp_nll); default priors (:55-62): log-normal on the
+        amplitude, horseshoe(0.1) on the noise variance (src/models/priors.py:42-73)."""
+        X0 = np.asarray(inputs, dtype=np.float64)
+        d = X0.shape[-1]
+        eng = self.bind(X0, outputs)
+        nll, g = eng.gp_nll()                         # [dlog_ls(d), dlog_amp, dlog_noise, dmean]
+        la = float(self.log_amplitude)
+        nll -= -0.5 * la * la - la - 0.5 * np.log(2 * np.pi)          # log_normal(scale=1)(exp(la))
+        g_amp = g[d] + (la + 1.0)
+        g_noise = g[d + 1]
+        if self.log_noise is not None:
+            ln = float(self.log_noise)
+            u = 3.0 * (0.1 ** 2) * np.exp(-2.0 * ln)
+            nll -= np.log(np.log1p(u))                                 # horseshoe(0.1)(exp(ln))
+            g_noise = g_noise - (1.0 / np.log1p(u)) * (1.0 / (1.0 + u)) * (-2.0 * u)
+        grads = {"mean": np.array([g[d + 2]]), "log_amplitude": np.array([g_amp]), "log_noise": np.array([g_noise]),
+                 "log_lenscales": g[:d] if np.size(self.log_lenscales) == d and np.ndim(self.log_lenscales) else
+                 np.array([g[:d].sum()])}
+        return float(nll), grads
+
+    def fit(self, sess, inputs, outputs, var_list=None, spo_config=None, feed_dict=None, **kwargs):
+        """MAP estimate of the active state's free parameters by L-BFGS-B with the reference's box
+        bounds (:65-75); SciPy drives, the device evaluates.  Returns the fitted values."""
+        from scipy.optimize import minimize
+        inputs = np.asarray(inputs, dtype=np.float64)
+        outputs = np.asarray(outputs, dtype=np.float64)
+        assert inputs.ndim == outputs.ndim == 2, "Tensor rank should be 2"
+        cfg = self.update_dict(self.spo_config, spo_config, as_copy=True)
+        names, x0, bounds = self._pack(inputs.shape[-1])
+        x0 = np.array([min(max(v, -np.inf if lo is None else lo), np.inf if hi is None else hi)
+                       for v, (lo, hi) in zip(x0, bounds)])
+
+        def fun(x):
+            self._unpack(names, x)
+            val, grads = self.negative_log_posterior(inputs, outputs)
+            return val, np.concatenate([np.ravel(grads[k])[:size] for k, size in names])
+
+        res = minimize(fun, x0, jac=True, method=cfg.get("method", "L-BFGS-B"), bounds=bounds,
+                       options=dict(cfg.get("options", {})))
+        self._unpack(names, res.x)
+        return [self.state[k] for k, _ in names]

@@ -200,6 +200,37 @@ class GP:
 
 
 # --------------------------------------------------------------------------
+# marginal likelihood + hyper-priors  (gaussian_process.log_likelihood :78-106,
+# priors.py:42-73; default priors gaussian_process.py:55-62)
+# --------------------------------------------------------------------------
+def log_likelihood_data(gp: GP, X0: torch.Tensor, Y0: torch.Tensor) -> torch.Tensor:
+    chol = gp.compute_cholesky(X0, noisy=True)
+    resid = Y0 - gp.mean_value(Y0)
+    gamma = torch.cholesky_solve(resid, chol, upper=False)
+    count = X0.shape[0]
+    logdet = 2.0 * torch.log(torch.diagonal(chol)).sum()
+    return -0.5 * ((resid.transpose(-1, -2) @ gamma).squeeze() + logdet + math.log(2 * math.pi) * count)
+
+
+def prior_log_normal(x: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+    return -0.5 * torch.square(torch.log(x) / scale) - torch.log(math.sqrt(2 * math.pi) * scale * x)
+
+
+def prior_horseshoe(x: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+    return torch.log(torch.log(1 + 3 * torch.square(scale / x)))
+
+
+def negative_log_posterior(gp: GP, X0, Y0) -> torch.Tensor:
+    """-(data llh + log_normal(amplitude) + horseshoe(0.1)(noise)): the objective of gaussian_process.fit."""
+    X0 = torch.as_tensor(X0, dtype=DT)
+    Y0 = torch.as_tensor(Y0, dtype=DT).reshape(-1, 1)
+    llh = log_likelihood_data(gp, X0, Y0) + prior_log_normal(gp.amplitude())
+    if gp.log_noise is not None:
+        llh = llh + prior_horseshoe(gp.noise(), 0.1)
+    return -llh
+
+
+# --------------------------------------------------------------------------
 # losses  (src/losses/*.py)
 # --------------------------------------------------------------------------
 _ISQRT2PI = 1.0 / math.sqrt(2 * math.pi)

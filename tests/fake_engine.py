@@ -34,6 +34,25 @@ class FakeEngine:
         L = self.ts.chol.numpy()
         return L, np.linalg.inv(L), None
 
+    def gp_nll(self):
+        gp = self.gp
+        d = self.d
+        ll = torch.as_tensor(np.broadcast_to(np.asarray(gp.log_lenscales, dtype=np.float64), (d,)).copy()).requires_grad_(True)
+        la = torch.tensor(float(gp.log_amplitude), dtype=orc.DT, requires_grad=True)
+        ln = None if gp.log_noise is None else torch.tensor(float(gp.log_noise), dtype=orc.DT, requires_grad=True)
+        mean_is_free = gp.mean is not None
+        mm = torch.tensor(float(gp.mean) if mean_is_free else 0.0, dtype=orc.DT, requires_grad=True)
+        g2 = orc.GP(log_lenscales=ll, log_amplitude=la, log_noise=ln, mean=mm if mean_is_free else None,
+                    kernel_id=gp.kernel_id, jitter=gp.jitter)
+        nll = -orc.log_likelihood_data(g2, self.ts.X0, self.ts.Y0)
+        nll.backward()
+        grad = np.zeros(d + 3)
+        grad[:d] = ll.grad.numpy()
+        grad[d] = la.grad.item()
+        grad[d + 1] = 0.0 if ln is None else ln.grad.item()
+        grad[d + 2] = mm.grad.item() if (mean_is_free and mm.grad is not None) else 0.0
+        return float(nll.item()), grad
+
     def _acq(self, prm):
         t = None if math.isnan(prm.temperature) else prm.temperature
         lvl = None if math.isnan(prm.level) else prm.level
@@ -74,6 +93,33 @@ class FakeEngine:
         loss = orc.mc_loss(self._acq(prm), mu, chol, torch.as_tensor(np.asarray(z, dtype=np.float64)), y0, w, inc)
         return loss.numpy(), None, None, chol.numpy()
 
+    def set_fantasies(self, Y):
+        self.F = len(Y)
+        self._fts = [orc.prepare_train(self.gp, self.ts.X0.numpy(), y) for y in np.asarray(Y)]
+
+    def fantasies_value_and_grad(self, prm, X, need_grad=True):
+        X = np.asarray(X, dtype=np.float64).reshape(-1, self.d)
+        acq = self._acq(prm)
+        Xt = torch.as_tensor(X[:, None, :]).clone().requires_grad_(True)
+        tot = 0
+        for ts in self._fts:
+            tot = tot + orc.closed_form_losses(ts, acq, Xt).reshape(-1)
+        losses = tot / self.F
+        if need_grad:
+            losses.sum().backward()
+            return losses.detach().numpy(), Xt.grad.numpy()[:, 0, :]
+        return losses.detach().numpy(), None
+
+    def fantasies_posterior(self, X):
+        X = np.asarray(X, dtype=np.float64).reshape(-1, 1, self.d)
+        mus, var = [], None
+        with torch.no_grad():
+            for ts in self._fts:
+                m, v = orc.posterior(ts, torch.as_tensor(X), full_cov=False)
+                mus.append(m.numpy().reshape(-1))
+                var = v.numpy().reshape(-1)
+        return np.asarray(mus), var
+
     def last_extras(self, S, q, want_chol=True):
         return self._last
 
@@ -86,9 +132,11 @@ class FakeEngine:
         self._ap, self._aprm = p_pending, prm
         self._ast = orc.adam_init(self._ax[:, p_pending:].shape, lr=lr, beta1=beta1, beta2=beta2, eps=eps)
 
-    def adam_steps(self, z_steps, want_trace=False):
+    def adam_steps(self, z_steps, want_trace=False, steps=None):
         trace = []
         p = self._ap
+        if z_steps is None:
+            z_steps = [None] * steps
         for z in z_steps:
             losses, g = self.value_and_grad(self._aprm, self._ax, z, p_pending=p)
             trace.append(losses)

@@ -91,3 +91,24 @@ def test_loss_classes_match_oracle_engine():
     g, r = run_both(flow)
     for a, b in zip(g, r):
         assert np.abs(a - b).max() < 1e-9 * max(1.0, np.abs(b).max())
+
+
+def test_update_fits_hyperparameters_like_the_oracle_engine():
+    def flow():
+        agent, X0, Y0 = build(2, 60, "braninhoo", 5, "negative_ei")
+        Y0 = (Y0 - Y0.mean()) / Y0.std()
+        vals = agent.update(None, X0, Y0)
+        return np.concatenate([np.ravel(v) for v in vals])
+    g, r = run_both(flow)
+    assert np.abs(g - r).max() < 1e-5
+
+
+def test_incremental_greedy_matches_oracle_engine():
+    from tests.test_src_mirror import incremental_greedy
+
+    def flow():
+        agent, X0, Y0 = build(3, 40, "hartmann3", 7, "confidence_bound", beta=2.0)
+        picks, Xf, Yf = incremental_greedy(agent, X0, Y0, 3, 16, num_to_optimize=8, config={"maxiter": 6})
+        return picks, Yf
+    (pg, yg), (pr, yr) = run_both(flow)
+    assert np.abs(pg - pr).max() < 1e-5 and np.abs(yg - yr).max() < 1e-6

@@ -258,3 +258,55 @@ def test_full_size_properties(eng):
         assert abs(fd - gs[s, i, c]) < 1e-5 * max(1.0, abs(fd))
         others = np.delete(np.arange(64), s)
         assert np.array_equal(lp[others], ls[others])
+
+
+@pytest.mark.parametrize("kernel_id", ["matern52", "squared_exponential", "matern32"])
+def test_gp_nll_and_gradient_vs_oracle_autograd(eng, kernel_id):
+    """maf_gp_nll (gaussian_process.log_likelihood + tf.gradients, :78-106) vs torch autograd."""
+    n, d = 150, 4
+    rng = np.random.RandomState(2)
+    X0, y0 = rng.rand(n, d), rng.randn(n)
+    lls, la, ln, mean = np.log([0.3, 0.5, 0.4, 0.8]), 0.1, -5.0, 0.2
+    eng.set_model(kernel_id, np.exp(lls), math.exp(la), math.exp(ln), mean, 1e-6)
+    eng.set_train(X0, y0)
+    nll, g = eng.gp_nll()
+    t = [torch.tensor(v, dtype=orc.DT, requires_grad=True) for v in (lls, la, ln, mean)]
+    gp = orc.GP(log_lenscales=t[0], log_amplitude=t[1], log_noise=t[2], mean=t[3], kernel_id=kernel_id, jitter=1e-6)
+    ref = -orc.log_likelihood_data(gp, torch.as_tensor(X0), torch.as_tensor(y0).reshape(-1, 1))
+    ref.backward()
+    gref = np.concatenate([t[0].grad.numpy(), [t[1].grad.item(), t[2].grad.item(), t[3].grad.item()]])
+    assert abs(nll - ref.item()) < 1e-10 * abs(ref.item())
+    assert relerr(g, gref) < 1e-8
+
+
+@pytest.mark.parametrize("acq,kw", [("ei", {}), ("pi", {}), ("sr", {}), ("cb", {"lower": True}), ("ei", {"level": -0.3})])
+def test_fantasy_conditioned_closed_form(eng, acq, kw):
+    """rank-4 observation sets: loss = mean over F fantasies of the per-fantasy closed form
+    (gaussian_process._predict_nd :195-206 + appraise_inputs :227-229), value and gradient."""
+    n, d, S, F = 140, 3, 70, 9
+    ts, X0, y0, X, z = setup_problem(eng, n, d, 1, S, 4, seed=21)
+    Y = y0.reshape(1, -1) + 0.2 * np.random.RandomState(1).randn(F, n)
+    eng.set_fantasies(Y)
+    lg, gg = eng.fantasies_value_and_grad(prm(acq, **kw), X[:, 0, :])
+    Xt = torch.as_tensor(X).clone().requires_grad_(True)
+    tot = 0
+    for f in range(F):
+        tsf = orc.prepare_train(ts.gp, X0, Y[f])
+        tot = tot + orc.closed_form_losses(tsf, orc.Acq(acq, **kw), Xt).reshape(-1)
+    lo = tot / F
+    lo.sum().backward()
+    assert relerr(lg, lo.detach().numpy()) < TOL
+    assert relerr(gg, Xt.grad.numpy()[:, 0, :]) < TOL
+    mu, var = eng.fantasies_posterior(X[:, 0, :])
+    with torch.no_grad():
+        m3, v3 = orc.posterior(orc.prepare_train(ts.gp, X0, Y[3]), torch.as_tensor(X), full_cov=False)
+    assert relerr(mu[3], m3.numpy().reshape(-1)) < TOL and relerr(var, v3.numpy().reshape(-1)) < TOL
+
+
+def test_adam_closed_form_q1_vs_oracle(eng):
+    ts, X0, y0, X, z = setup_problem(eng, 60, 3, 1, 12, 4, seed=17)
+    xo, tro = orc.adam_run(ts, orc.Acq("ei"), X, [np.zeros((1, 1))] * 4)
+    eng.adam_begin(prm("ei"), X)
+    trg = eng.adam_steps(None, want_trace=True, steps=4)
+    xg = eng.adam_end()
+    assert relerr(trg, tro) < 1e-8 and np.abs(xg - xo).max() < 1e-8

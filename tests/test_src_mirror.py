@@ -148,3 +148,81 @@ def test_unsupported_paths_raise():
         agent._optimize_inputs_cmaes()
     with pytest.raises(NotImplementedError):
         losses.negative_ei(use_rand_features=True)
+
+
+def test_fit_objective_and_gradient_match_oracle_autograd():
+    """negative_log_posterior (device NLL + host priors) against the oracle's torch autograd of the
+    reference objective (gaussian_process.log_likelihood + default priors)."""
+    import torch
+    agent, X0, Y0 = make(d=3, n=30)
+    m = agent.model
+    m.state["log_lenscales"] = np.log([0.3, 0.5, 0.7])
+    m.state["log_amplitude"], m.state["log_noise"], m.state["mean"] = 0.2, -4.0, 0.1
+    val, grads = m.negative_log_posterior(X0, Y0)
+    ll = torch.tensor(np.log([0.3, 0.5, 0.7]), requires_grad=True)
+    la = torch.tensor(0.2, dtype=orc.DT, requires_grad=True)
+    ln = torch.tensor(-4.0, dtype=orc.DT, requires_grad=True)
+    mm = torch.tensor(0.1, dtype=orc.DT, requires_grad=True)
+    gp = orc.GP(log_lenscales=ll, log_amplitude=la, log_noise=ln, mean=mm, kernel_id="matern52", jitter=1e-6)
+    ref = orc.negative_log_posterior(gp, X0, Y0)
+    ref.backward()
+    assert abs(val - ref.item()) < 1e-9 * abs(ref.item())
+    assert np.allclose(grads["log_lenscales"], ll.grad.numpy(), rtol=1e-8, atol=1e-10)
+    assert np.allclose(grads["log_amplitude"], la.grad.item(), rtol=1e-8)
+    assert np.allclose(grads["log_noise"], ln.grad.item(), rtol=1e-8)
+    assert np.allclose(grads["mean"], mm.grad.item(), rtol=1e-8, atol=1e-10)
+
+
+def test_fit_improves_objective_and_respects_bounds():
+    agent, X0, Y0 = make(d=2, n=40)
+    m = agent.model
+    m.state["log_lenscales"] = np.zeros(2)
+    before, _ = m.negative_log_posterior(X0, Y0)
+    vals = agent.update(None, X0, Y0, reset=False)
+    after, _ = m.negative_log_posterior(X0, Y0)
+    assert after < before
+    assert np.all(m.log_lenscales <= np.log(2.0) + 1e-12) and np.all(m.log_lenscales >= np.log(1e-2) - 1e-12)
+    assert m.log_noise <= 1e-12 and len(vals) == 4
+
+
+def incremental_greedy(agent, X0, Y0, num_suggest, num_fantasies, **kw):
+    """The reference's fantasy-conditioned greedy driver (scripts/run_bayesopt_incremental.py:138-218),
+    restated against the mirror's eager API."""
+    inputs_old, outputs_old, picks = X0, Y0, []
+    for _ in range(num_suggest):
+        x, _ = agent.suggest_inputs(1, inputs_old, outputs_old, None, **kw)
+        picks.append(np.atleast_1d(np.squeeze(x)))
+        if inputs_old.ndim == 2:
+            fant = agent.model.draw_samples(num_fantasies, x, inputs_old, outputs_old)           # [F, 1]
+            inputs_old = np.tile(np.vstack([inputs_old, x])[None, None], [num_fantasies, 1, 1, 1])
+            outputs_old = np.dstack([np.tile(outputs_old[None, None], [num_fantasies, 1, 1, 1]), fant[:, None, None]])
+        else:
+            fant = agent.model.draw_samples(1, x, inputs_old, outputs_old)                        # [F,1,1,1]
+            inputs_old = np.dstack([inputs_old, np.tile(x[None, None], [num_fantasies, 1, 1, 1])])
+            outputs_old = np.dstack([outputs_old, fant])
+    return np.asarray(picks), inputs_old, outputs_old
+
+
+@pytest.mark.parametrize("loss,kw", [("negative_ei", {}), ("confidence_bound", {"beta": 2.0})])
+def test_incremental_greedy_with_fantasies(loss, kw):
+    agent, X0, Y0 = make(d=2, n=20, loss=loss, **kw)
+    picks, Xf, Yf = incremental_greedy(agent, X0, Y0, 3, 8, num_to_optimize=6, config={"maxiter": 5})
+    assert picks.shape == (3, 2) and Xf.shape == (8, 1, 23, 2) and Yf.shape == (8, 1, 23, 1)
+    assert np.array_equal(Xf[0, 0, 20:], picks)
+    # rank-4 losses are the mean over fantasies of the per-fantasy closed forms
+    cand = np.random.RandomState(0).rand(5, 1, 2)
+    l4 = np.ravel(agent.loss_fn(cand, Xf, Yf, model=agent.model)[0])
+    l2 = np.mean([np.ravel(agent.loss_fn(cand, Xf[f, 0], Yf[f, 0], model=agent.model)[0]) for f in range(8)], axis=0)
+    assert np.allclose(l4, l2, rtol=1e-10, atol=1e-12)
+    m4, v4 = agent.model.predict(cand, Xf, Yf)
+    assert m4.shape == (8, 5, 1, 1) and v4.shape == (8, 5, 1, 1)
+
+
+def test_adam_closed_form_q1():
+    agent, X0, Y0 = make()
+    starts = np.random.RandomState(4).rand(6, 1, 2)
+    l0 = np.ravel(agent.loss_fn(starts, X0, Y0, model=agent.model)[0])
+    nodes, seq = agent.optimize_inputs(None, starts, X0, Y0, subroutine=agent._optimize_inputs_sgd,
+                                       config={"step_limit": 10})
+    l1 = np.ravel(agent.loss_fn(nodes["inputs_new"].value, X0, Y0, model=agent.model)[0])
+    assert seq.shape == (60,) and l1.mean() < l0.mean()
