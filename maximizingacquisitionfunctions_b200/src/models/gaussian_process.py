@@ -222,10 +222,14 @@ class gaussian_process(abstract_model):
         g_amp = g[d] + (la + 1.0)
         g_noise = g[d + 1]
         if self.log_noise is not None:
+            # horseshoe(0.1)(x = exp(ln)) = log(log(1 + u)), u = 3 (0.1/x)^2, in the overflow-safe form
+            # log1p(u) = logaddexp(0, t), u/(1+u) = sigmoid(t), t = log u  (the prior has no finite mode:
+            # it keeps rewarding smaller noise, so L-BFGS-B can walk far down the unbounded side)
             ln = float(self.log_noise)
-            u = 3.0 * (0.1 ** 2) * np.exp(-2.0 * ln)
-            nll -= np.log(np.log1p(u))                                 # horseshoe(0.1)(exp(ln))
-            g_noise = g_noise - (1.0 / np.log1p(u)) * (1.0 / (1.0 + u)) * (-2.0 * u)
+            t = np.log(3.0 * 0.1 ** 2) - 2.0 * ln
+            l1p = np.logaddexp(0.0, t)
+            nll -= np.log(l1p)
+            g_noise = g_noise + 2.0 * (1.0 / l1p) * (1.0 / (1.0 + np.exp(-t)))
         grads = {"mean": np.array([g[d + 2]]), "log_amplitude": np.array([g_amp]), "log_noise": np.array([g_noise]),
                  "log_lenscales": g[:d] if np.size(self.log_lenscales) == d and np.ndim(self.log_lenscales) else
                  np.array([g[:d].sum()])}

@@ -22,7 +22,7 @@ class FakeEngine:
 
     def set_model(self, kernel_id, lenscales, amplitude, noise, mean, jitter):
         self.gp = orc.GP(log_lenscales=np.log(np.asarray(lenscales, dtype=np.float64)), log_amplitude=math.log(amplitude),
-                         log_noise=None if noise is None else math.log(noise), mean=mean, kernel_id=kernel_id,
+                         log_noise=None if (noise is None or noise <= 0.0) else math.log(noise), mean=mean, kernel_id=kernel_id,
                          jitter=jitter)
         self.d = len(np.atleast_1d(lenscales))
 
