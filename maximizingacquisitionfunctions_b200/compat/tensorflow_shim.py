@@ -16,8 +16,8 @@ class Session(object):
         return False
 
     def run(self, fetches=None, feed_dict=None, **kwargs):
-        if callable(fetches):
-            return fetches(feed_dict)
+        if hasattr(fetches, "run"):          # core.lazy_op (the eager stand-in for a graph node)
+            return fetches.run(feed_dict)
         return None
 
     def close(self):

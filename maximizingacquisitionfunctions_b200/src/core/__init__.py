@@ -1,3 +1,3 @@
-from .module import module
+from .module import lazy_op, lazy_ref, module
 
-__all__ = ["module"]
+__all__ = ["module", "lazy_op", "lazy_ref"]

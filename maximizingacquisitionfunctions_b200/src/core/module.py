@@ -12,6 +12,34 @@ from copy import deepcopy
 import numpy as np
 
 
+class lazy_ref(object):
+    """Placeholder token: the eager counterpart of the reference's cached tf.placeholder
+    (module.get_or_create_ref, src/core/module.py:57-70); filled from the feed_dict by lazy_op.run."""
+
+    def __init__(self, group, shape_or_rank=None, dtype=None):
+        self.group, self.shape_or_rank, self.dtype = group, shape_or_rank, dtype
+
+    def __repr__(self):
+        return "lazy_ref({!r})".format(self.group)
+
+
+class lazy_op(object):
+    """Deferred call: the eager counterpart of a cached graph node (module.get_or_create_node, :44-54).
+    ``run(feed_dict)`` substitutes lazy_ref arguments and calls the function -- what
+    ``sess.run(op, feed_dict)`` does for scripts/run_bayesopt_incremental.py:150-163."""
+
+    def __init__(self, fn, args=None, kwargs=None):
+        self.fn, self.args, self.kwargs = fn, tuple(args or ()), dict(kwargs or {})
+
+    def run(self, feed_dict=None):
+        feed_dict = feed_dict or {}
+        sub = lambda a: feed_dict[a] if isinstance(a, lazy_ref) else a
+        kwargs = {k: sub(v) for k, v in self.kwargs.items() if k != "state_id"}
+        return self.fn(*[sub(a) for a in self.args], **kwargs)
+
+    __call__ = run
+
+
 class module(object):
     def __init__(self, dtype="float64", cache=None, seed=None, name=None):
         self._name = self.__class__.__name__ if name is None else name
@@ -21,6 +49,16 @@ class module(object):
             seed = np.random.choice(2 ** 31 - 1)
         self._seed = np.array([seed], dtype=np.int64)
         self._rng = np.random.RandomState(self._seed)
+
+    def get_or_create_ref(self, group, shape_or_rank=None, dtype=None, cache=None, **kwargs):
+        cache = self.cache if cache is None else cache
+        key = ("ref", group, str(shape_or_rank))
+        if key not in cache:
+            cache[key] = lazy_ref(group, shape_or_rank, dtype or self.dtype)
+        return cache[key]
+
+    def get_or_create_node(self, group, fn, args=None, cache=None, kwargs=None, stateful=False, **unused):
+        return lazy_op(fn, args, kwargs)
 
     def update_dict(self, src, updates=None, as_copy=False):
         """Recursive merge of `updates` into `src` (dict values merge, everything else overwrites)."""

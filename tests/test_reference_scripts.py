@@ -47,3 +47,16 @@ def test_run_bayesopt_script_unmodified(use_greedy):
     assert X.min() >= 0 and X.max() <= 1
     assert len(exp["answer"]) >= 2 and len(exp["hyperparameters"]) >= 1
     assert np.isfinite(exp["f_min"])
+
+
+def test_run_bayesopt_incremental_script_unmodified():
+    """scripts/run_bayesopt_incremental.py: fantasy-conditioned greedy batches (rank-4 observation sets),
+    incl. its direct use of get_or_create_ref / get_or_create_node / sess.run (:150-163)."""
+    from maximizingacquisitionfunctions_b200.compat import launcher
+    mod = launcher.load_script(REF, "scripts/run_bayesopt_incremental.py", name="maf_reference_incremental")
+    mod.logger = logging.getLogger("run_experiment")
+    cfg = make_config(use_greedy=1, num_fantasies=8, subroutine="scipy", loss="confidence_bound",
+                      loss_kwargs={"beta": 2.0}, parallelism=3, job_limit=10)
+    exp = mod.run_experiment(cfg)
+    X = np.asarray([exp["inputs"][k] for k in sorted(exp["inputs"])])
+    assert X.shape == (10, 3) and X.min() >= 0 and X.max() <= 1
