@@ -176,6 +176,13 @@ int maf_timer_stop(maf_ctx* ctx, double* ms);
  * tri: 0 full, 1 T lower-triangular (K==N), 2 T upper-triangular (K==N). */
 int maf_gemm_nt_dev(maf_ctx* ctx, int J, int N, int K, const double* dA, int lda,
                     const double* dT, int ldt, double* dC, int ldc, int tri);
+/* Same contraction on the INT8 tensor pipe by exact base-256 digit slicing (csrc/ozaki_i8.cuh):
+ * ns digit planes per operand (<= 7), levels up to lmax kept (ns=7, lmax=8: FP64-grade). */
+int maf_gemm_nt_i8_dev(maf_ctx* ctx, int J, int N, int K, const double* dA, int lda, const double* dT,
+                       int ldt, double* dC, int ldc, int tri, int ns, int lmax);
+/* 0: FP64 DMMA contractions (default); 1: INT8 digit-sliced contractions in the value/gradient pipeline.
+ * Takes effect at the next maf_set_train.  Also settable with the environment variable MAF_GEMM_I8. */
+int maf_set_gemm_mode(maf_ctx* ctx, int mode);
 void* maf_dev_alloc(maf_ctx* ctx, size_t bytes);
 int maf_dev_free(maf_ctx* ctx, void* p);
 int maf_h2d(maf_ctx* ctx, void* dst, const void* src, size_t bytes);

@@ -15,6 +15,7 @@
 #include "fit_kernels.cuh"
 #include "gemm_f64.cuh"
 #include "mc_kernels.cuh"
+#include "ozaki_i8.cuh"
 #include "posterior.cuh"
 
 #define MAF_VERSION_STR "maf_b200 0.1 (sm_100a, fp64 DMMA)"
@@ -66,6 +67,12 @@ struct maf_ctx {
   maf_acq_params adam_prm{};
   int adam_S = 0, adam_q = 0, adam_p = 0;
   Buf adam_X, adam_m, adam_v, adam_g, adam_z;
+  // INT8 digit-sliced contraction (ozaki_i8.cuh)
+  int gemm_i8 = 0;                 // requested mode
+  bool i8_ready = false;           // factor planes built for the current training set
+  int oz_ns = 7, oz_lmax = 8;
+  Buf ozA, ozTL, ozTU;             // digit planes (int8, sized in doubles): candidates / Linv / LinvT
+  Buf ozsA, ozsTL, ozsTU;          // row scales
   // fantasies (rank-4 observation sets)
   int F = 0, Fpad = 0;
   Buf fGamma, fGammaT, fmeans, flevels, fVG, fmubar;
@@ -272,6 +279,64 @@ static int launch_gemm(maf_ctx* ctx, int slot, int J, int N, int K, const double
   return 0;
 }
 
+// ---- INT8 digit-sliced contraction ------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int oz_make_tmap(maf_ctx* ctx, CUtensorMap* tm, const int8_t* base, int rows, int K, int ns) {
+  static PFN_encodeTiled encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn)
+      return fail(ctx, "cuTensorMapEncodeTiled is not available from the driver");
+    encode = (PFN_encodeTiled)fn;
+  }
+  cuuint64_t gdim[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)ns};
+  cuuint64_t gstr[2] = {(cuuint64_t)K, (cuuint64_t)K * (cuuint64_t)rows};
+  cuuint32_t box[3] = {OZ_BK, 128, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)base, gdim, gstr, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(ctx, "cuTensorMapEncodeTiled failed with %d", (int)r);
+  return 0;
+}
+
+// X[R][K] (ld ldx) -> digit planes [ns][Rpad][K] + row scales
+static int oz_slice(maf_ctx* ctx, int slot, const double* X, int ldx, int R, int Rpad, int K, int ns, double fixed_max,
+                    Buf& planes, Buf& scales) {
+  const size_t bytes = (size_t)ns * Rpad * K;
+  if (ensure(ctx, planes, (bytes + 7) / 8) || ensure(ctx, scales, (size_t)Rpad)) return 1;
+  ProfScope ps(ctx, slot);
+  ozaki_slice_rows_kernel<<<Rpad, OZ_SLICE_THREADS, 0, ctx->stream>>>(X, ldx, R, Rpad, K, ns, fixed_max,
+                                                                    (int8_t*)planes.p, scales.p);
+  CKL();
+  return 0;
+}
+
+static int launch_i8gemm(maf_ctx* ctx, int slot, int J, int N, int K, const Buf& Ap, const Buf& sA, const Buf& Tp,
+                         const Buf& sT, double* C, int ldc, int tri, int ns, int lmax) {
+  if (J % 128 || N % 128 || K % 128) return fail(ctx, "i8 gemm dims must be multiples of 128");
+  if (tri != 0 && K != N) return fail(ctx, "triangular gemm needs K == N");
+  if (ns < 1 || ns > OZ_MAXS || lmax < 2 || lmax > 2 * ns) return fail(ctx, "bad digit configuration ns=%d lmax=%d", ns, lmax);
+  if (K > 8192) return fail(ctx, "i8 gemm: K=%d would overflow the int32 level accumulators (max 8192)", K);
+  static bool attr = false;
+  if (!attr) {
+    CK(cudaFuncSetAttribute(ozaki_i8_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES));
+    attr = true;
+  }
+  CUtensorMap tmA, tmT;
+  if (oz_make_tmap(ctx, &tmA, (const int8_t*)Ap.p, J, K, ns) || oz_make_tmap(ctx, &tmT, (const int8_t*)Tp.p, N, K, ns)) return 1;
+  OzParams prm{K, ns, lmax, tri, ldc};
+  dim3 grid(N / OZ_BN, J / OZ_BM);
+  ProfScope ps(ctx, slot);
+  ozaki_i8_gemm_kernel<<<grid, OZ_THREADS, OZ_SMEM_BYTES, ctx->stream>>>(tmA, tmT, sA.p, sT.p, C, prm);
+  CKL();
+  return 0;
+}
+
 // ---- life cycle ---------------------------------------------------------------------------
 extern "C" const char* maf_version(void) { return MAF_VERSION_STR; }
 
@@ -295,6 +360,7 @@ extern "C" int maf_create(int device, int dtype, maf_ctx** out) {
   CKB(cusolverDnCreate(&ctx->cusolver));
   CKB(cusolverDnSetStream(ctx->cusolver, ctx->stream));
   if (const char* gv = getenv("MAF_GEMM_VARIANT")) ctx->gemm_variant = atoi(gv);
+  if (const char* gi = getenv("MAF_GEMM_I8")) ctx->gemm_i8 = atoi(gi);
   CK(cudaMalloc((void**)&ctx->d_argmin_val, sizeof(double)));
   CK(cudaMalloc((void**)&ctx->d_argmin_idx, sizeof(long long)));
   const char* cr = getenv("MAF_CHUNK_ROWS");
@@ -315,7 +381,7 @@ extern "C" int maf_destroy(maf_ctx* ctx) {
   Buf* bufs[] = {&ctx->K10, &ctx->Vt, &ctx->dX, &ctx->dz, &ctx->dw, &ctx->dinc, &ctx->dmu, &ctx->dSig, &ctx->dchol,
                  &ctx->dmubar, &ctx->dSigbar, &ctx->dloss, &ctx->dgrad, &ctx->adam_X, &ctx->adam_m, &ctx->adam_v,
                  &ctx->adam_g, &ctx->adam_z, &ctx->fGamma, &ctx->fGammaT, &ctx->fmeans, &ctx->flevels, &ctx->fVG,
-                 &ctx->fmubar};
+                 &ctx->fmubar, &ctx->ozA, &ctx->ozTL, &ctx->ozTU, &ctx->ozsA, &ctx->ozsTL, &ctx->ozsTU};
   for (Buf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (ctx->d_argmin_idx) cudaFree(ctx->d_argmin_idx);
@@ -487,6 +553,14 @@ extern "C" int maf_set_train(maf_ctx* ctx, int n, const double* X0, const double
     trmv_lower_kernel<<<(npad + 7) / 8, 256, 0, ctx->stream>>>(ctx->Linv, drho, npad, ctx->gamma);
     CKL();
   }
+  ctx->i8_ready = false;
+  if (ctx->gemm_i8) {
+    if (npad > 8192) return fail(ctx, "INT8 contraction mode supports n <= 8192");
+    if (oz_slice(ctx, MAF_PROF_CROSS_FWD, ctx->Linv, npad, npad, npad, npad, ctx->oz_ns, 0.0, ctx->ozTL, ctx->ozsTL) ||
+        oz_slice(ctx, MAF_PROF_CROSS_FWD, ctx->LinvT, npad, npad, npad, npad, ctx->oz_ns, 0.0, ctx->ozTU, ctx->ozsTU))
+      return 1;
+    ctx->i8_ready = true;
+  }
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaFree(drho));
   ctx->train_set = true;
@@ -574,7 +648,15 @@ static int run_chunk(maf_ctx* ctx, const AcqDev& ap, bool posterior_only, bool c
     DISPATCH_D(d, cross_fwd_kernel<D><<<grid, CROSS_TK, 0, ctx->stream>>>(dX, J, ctx->X0s, n, npad, ctx->mp, K10));
     CKL();
   }
-  if (launch_gemm(ctx, MAF_PROF_GEMM_FWD, Jpad, npad, npad, K10, npad, ctx->Linv, npad, Vt, npad, 1)) return 1;
+  if (ctx->i8_ready) {
+    // cross-covariances are bounded by a^2: fixed row scale, no reduction pass
+    if (oz_slice(ctx, MAF_PROF_CROSS_FWD, K10, npad, J, Jpad, npad, ctx->oz_ns, ctx->mp.amp2, ctx->ozA, ctx->ozsA)) return 1;
+    if (launch_i8gemm(ctx, MAF_PROF_GEMM_FWD, Jpad, npad, npad, ctx->ozA, ctx->ozsA, ctx->ozTL, ctx->ozsTL, Vt, npad, 1,
+                      ctx->oz_ns, ctx->oz_lmax))
+      return 1;
+  } else if (launch_gemm(ctx, MAF_PROF_GEMM_FWD, Jpad, npad, npad, K10, npad, ctx->Linv, npad, Vt, npad, 1)) {
+    return 1;
+  }
   {
     ProfScope ps(ctx, MAF_PROF_POSTERIOR);
     DISPATCH_Q(q, posterior_kernel<Q><<<sc, POST_THREADS, 0, ctx->stream>>>(Vt, npad, ctx->gamma, dX, ctx->mp, ctx->mean_val, mu, Sig));
@@ -606,7 +688,14 @@ static int run_chunk(maf_ctx* ctx, const AcqDev& ap, bool posterior_only, bool c
     DISPATCH_Q(q, vbar_kernel<Q><<<sc, 256, 0, ctx->stream>>>(Vt, npad, ctx->gamma, mubar, Sigbar));
     CKL();
   }
-  if (launch_gemm(ctx, MAF_PROF_GEMM_BWD, Jpad, npad, npad, Vt, npad, ctx->LinvT, npad, K10, npad, 2)) return 1;
+  if (ctx->i8_ready) {
+    if (oz_slice(ctx, MAF_PROF_VBAR, Vt, npad, J, Jpad, npad, ctx->oz_ns, 0.0, ctx->ozA, ctx->ozsA)) return 1;
+    if (launch_i8gemm(ctx, MAF_PROF_GEMM_BWD, Jpad, npad, npad, ctx->ozA, ctx->ozsA, ctx->ozTU, ctx->ozsTU, K10, npad, 2,
+                      ctx->oz_ns, ctx->oz_lmax))
+      return 1;
+  } else if (launch_gemm(ctx, MAF_PROF_GEMM_BWD, Jpad, npad, npad, Vt, npad, ctx->LinvT, npad, K10, npad, 2)) {
+    return 1;
+  }
   {
     ProfScope ps(ctx, MAF_PROF_CROSS_BWD);
     DISPATCH_D(d, cross_bwd_kernel<D><<<sc, 32 * q, 0, ctx->stream>>>(dX, sc, q, p, ctx->X0s, n, npad, ctx->mp, K10, Sigbar, dgrad));
@@ -1128,6 +1217,29 @@ extern "C" int maf_host_free(maf_ctx* ctx, void* p) {
   CK(cudaSetDevice(ctx->device));
   CK(cudaFreeHost(p));
   return 0;
+}
+
+extern "C" int maf_set_gemm_mode(maf_ctx* ctx, int mode) {
+  if (!ctx) return 1;
+  if (mode != 0 && mode != 1) return fail(ctx, "unknown gemm mode %d", mode);
+  ctx->gemm_i8 = mode;
+  ctx->i8_ready = false;
+  ctx->train_set = false;       // the factor planes are built by maf_set_train
+  return 0;
+}
+
+extern "C" int maf_gemm_nt_i8_dev(maf_ctx* ctx, int J, int N, int K, const double* dA, int lda, const double* dT,
+                                  int ldt, double* dC, int ldc, int tri, int ns, int lmax) {
+  if (!ctx) return 1;
+  CK(cudaSetDevice(ctx->device));
+  Buf pa, pt, sa, st;
+  int rc = oz_slice(ctx, MAF_PROF_CROSS_FWD, dA, lda, J, J, K, ns, 0.0, pa, sa) ||
+           oz_slice(ctx, MAF_PROF_CROSS_FWD, dT, ldt, N, N, K, ns, 0.0, pt, st) ||
+           launch_i8gemm(ctx, tri == 2 ? MAF_PROF_GEMM_BWD : MAF_PROF_GEMM_FWD, J, N, K, pa, sa, pt, st, dC, ldc, tri, ns, lmax);
+  cudaStreamSynchronize(ctx->stream);
+  for (Buf* b : {&pa, &pt, &sa, &st})
+    if (b->p) cudaFree(b->p);
+  return rc;
 }
 
 // ---- raw GEMM ----------------------------------------------------------------------------------------

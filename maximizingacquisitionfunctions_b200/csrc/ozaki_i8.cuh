@@ -1,0 +1,283 @@
+// FP64-grade contraction on the INT8 tensor pipe (tcgen05.mma kind::i8) by exact digit slicing.
+//
+//   C[J][N] = A[J][K] * T[N][K]^T          (same contract as gemm_nt_f64_kernel, incl. triangular T)
+//
+// Each row of A and T is scaled by a power of two and written as NS signed base-256 digits
+// (int8 planes):  x = 2^e * sum_{i=1..NS} d_i 2^(1-8i),  d_i in [-128,127]  (exact 8*NS-1 bit fixed point).
+// Products of digit planes are exact in int32 (|d d'| <= 2^14, K <= 8192, <= 7 pairs per level), so
+//   C = 2^(eA_j + eT_r) * sum_{l=2..LMAX} 2^(2-8l) * sum_{i+i'=l} (A_i T_i'^T)
+// with the only error being the dropped levels l > LMAX.  NS=7, LMAX=8 (28 pair products) reproduces the
+// FP64 posterior to ~2e-13 (tests/test_gpu_ozaki.py), i.e. the same grade as the DMMA path, at the INT8
+// rate of the part (4.58 POP/s measured vs 0.036 PFLOP/s FP64).
+//
+// Kernel: one 128x128 output tile per CTA, 6 warps: warp 0 = TMA producer (cp.async.bulk.tensor 3-D boxes
+// {32 B, 128 rows, 1 plane}, SWIZZLE_32B, 3 smem stages, mbarrier full/empty), warp 1 = MMA issuer
+// (one thread, tcgen05.mma.cta_group::1.kind::i8 M=128 N=128 K=32, accumulators in TMEM, one per level),
+// warps 2-5 = epilogue (tcgen05.ld -> int32 -> FP64 recombination -> global).  TMEM holds 4 level
+// accumulators of 128 columns (512 columns), so the levels are processed in passes of <= 4
+// (levels 2-5: 10 pairs, levels 6-8: 18 pairs); pass 2 adds into C.
+#pragma once
+#include <cuda.h>
+#include "common.cuh"
+
+#define OZ_MAXS 7
+#define OZ_BM 128
+#define OZ_BN 128
+#define OZ_BK 32                                   // bytes (= int8 elements) per k-chunk = one MMA K
+#define OZ_STAGES 3
+#define OZ_TILE_BYTES (128 * OZ_BK)                // one digit plane tile
+#define OZ_STAGE_BYTES (2 * OZ_MAXS * OZ_TILE_BYTES)
+#define OZ_SMEM_BYTES (OZ_STAGES * OZ_STAGE_BYTES + 1024)
+#define OZ_THREADS 192
+
+__device__ __forceinline__ uint32_t oz_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void oz_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(oz_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void oz_mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\tOZ_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra OZ_DONE;\n\tbra OZ_WAIT;\n\tOZ_DONE:\n\t}" ::"r"(oz_smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void oz_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(oz_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void oz_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(oz_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void oz_tma_load_3d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(oz_smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(oz_smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// K-major, SWIZZLE_32B canonical tile [rows][32 B]: 8-row groups are 256 B apart
+__device__ __forceinline__ uint64_t oz_desc_sw32(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;                 // LBO: unused for swizzled K-major
+  d |= (uint64_t)(256 >> 4) << 32;        // SBO
+  d |= (uint64_t)1 << 46;                 // descriptor version (sm_100)
+  d |= (uint64_t)6 << 61;                 // SWIZZLE_32B
+  return d;
+}
+__device__ __forceinline__ void oz_mma_i8(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void oz_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(oz_smem_u32(bar)) : "memory");
+}
+
+struct OzParams {
+  int K;            // contraction length (bytes per digit-plane row), multiple of 128
+  int ns;           // digit planes in use (<= OZ_MAXS)
+  int lmax;         // highest level kept (2 .. 2*ns)
+  int tri;          // 0 full, 1 T lower-triangular, 2 upper
+  int ldc;
+};
+
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+ozaki_i8_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmT,
+                     const double* __restrict__ sA /*[J] row scales 2^eA*/, const double* __restrict__ sT /*[N]*/,
+                     double* __restrict__ C, OzParams p) {
+  extern __shared__ uint8_t oz_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(oz_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t full_bar[OZ_STAGES], empty_bar[OZ_STAGES], acc_full, acc_empty;
+  __shared__ uint32_t tmem_base_sh;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rb = (p.tri == 1) ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;
+  const int r0 = rb * OZ_BN, j0 = blockIdx.y * OZ_BM;
+  const int c_begin = (p.tri == 2) ? r0 : 0;
+  const int c_end = (p.tri == 1) ? min(p.K, r0 + OZ_BN) : p.K;
+  const int kchunks = (c_end - c_begin) / OZ_BK;
+  const int npass = (p.lmax - 1 + 3) / 4;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < OZ_STAGES; ++s) {
+      oz_mbar_init(&full_bar[s], 1);
+      oz_mbar_init(&empty_bar[s], 1);
+    }
+    oz_mbar_init(&acc_full, 1);
+    oz_mbar_init(&acc_empty, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmT)) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(oz_smem_u32(&tmem_base_sh)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tbase = tmem_base_sh;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int pass = 0; pass < npass; ++pass) {
+        const int lo = 2 + 4 * pass, hi = min(p.lmax, lo + 3);
+        const int smax = min(p.ns, hi - 1);                 // planes 1..smax take part in levels <= hi
+        for (int kc = 0; kc < kchunks; ++kc) {
+          oz_mbar_wait(&empty_bar[stage], phase ^ 1);
+          oz_mbar_expect_tx(&full_bar[stage], 2u * smax * OZ_TILE_BYTES);
+          uint8_t* st = smem + stage * OZ_STAGE_BYTES;
+          const int c = c_begin + kc * OZ_BK;
+          for (int i = 0; i < smax; ++i) {
+            oz_tma_load_3d(st + i * OZ_TILE_BYTES, &tmA, &full_bar[stage], c, j0, i);
+            oz_tma_load_3d(st + (OZ_MAXS + i) * OZ_TILE_BYTES, &tmT, &full_bar[stage], c, r0, i);
+          }
+          if (++stage == OZ_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      // instruction descriptor: D = S32, A = B = signed int8, K-major, N = 128, M = 128
+      const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BN >> 3) << 17) | ((uint32_t)(OZ_BM >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int pass = 0; pass < npass; ++pass) {
+        const int lo = 2 + 4 * pass, hi = min(p.lmax, lo + 3);
+        if (pass > 0) {
+          oz_mbar_wait(&acc_empty, (uint32_t)((pass - 1) & 1));   // epilogue has drained the accumulators
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        for (int kc = 0; kc < kchunks; ++kc) {
+          oz_mbar_wait(&full_bar[stage], phase);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sbase = oz_smem_u32(smem + stage * OZ_STAGE_BYTES);
+          for (int l = lo; l <= hi; ++l) {
+            const uint32_t d_tmem = tbase + (uint32_t)((l - lo) * OZ_BN);
+            bool first = (kc == 0);
+            for (int i = max(1, l - p.ns); i <= min(p.ns, l - 1); ++i) {
+              const int ip = l - i;
+              const uint64_t da = oz_desc_sw32(sbase + (uint32_t)((i - 1) * OZ_TILE_BYTES));
+              const uint64_t db = oz_desc_sw32(sbase + (uint32_t)((OZ_MAXS + ip - 1) * OZ_TILE_BYTES));
+              oz_mma_i8(d_tmem, da, db, idesc, first ? 0u : 1u);
+              first = false;
+            }
+          }
+          oz_commit(&empty_bar[stage]);                     // frees the smem stage when the MMAs retire
+          if (++stage == OZ_STAGES) { stage = 0; phase ^= 1; }
+        }
+        oz_commit(&acc_full);                               // accumulators of this pass are complete
+      }
+    }
+  } else {
+    // ================= epilogue: TMEM -> FP64 -> global =================
+    const int quarter = warp & 3;                           // TMEM lanes [32*quarter, +32) belong to this warp
+    const int row = quarter * 32 + lane;
+    const size_t j = (size_t)(j0 + row);
+    const double srow = sA[j];
+    double* crow = C + j * p.ldc + r0;
+    const uint32_t lane_addr = tbase + ((uint32_t)(quarter * 32) << 16);
+    for (int pass = 0; pass < npass; ++pass) {
+      const int lo = 2 + 4 * pass, hi = min(p.lmax, lo + 3);
+      oz_mbar_wait(&acc_full, (uint32_t)(pass & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int c0 = 0; c0 < OZ_BN; c0 += 8) {
+        double v[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) v[t] = 0.0;
+        for (int l = hi; l >= lo; --l) {                    // smallest contributions first
+          uint32_t r[8];
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                       : "r"(lane_addr + (uint32_t)((l - lo) * OZ_BN + c0)));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          const double w = exp2((double)(2 - 8 * l));
+#pragma unroll
+          for (int t = 0; t < 8; ++t) v[t] += (double)(int)r[t] * w;
+        }
+#pragma unroll
+        for (int t = 0; t < 8; t += 2) {
+          double2 o = make_double2(v[t] * srow * sT[r0 + c0 + t], v[t + 1] * srow * sT[r0 + c0 + t + 1]);
+          double2* dst = reinterpret_cast<double2*>(crow + c0 + t);
+          if (pass > 0) {
+            double2 old = *dst;
+            o.x += old.x;
+            o.y += old.y;
+          }
+          *dst = o;
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      oz_mbar_arrive(&acc_empty);
+    }
+  }
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(512) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// Digit slicing:  row r of X[R][K] (FP64, leading dimension ldx) -> OZ planes [ns][Rpad][K] of int8 digits
+// and the row scale 2^e.  e is chosen from the row maximum (|x| 2^-e <= 0.98) or, when `fixed_max` > 0,
+// from that bound (cross-covariances are bounded by a^2, no reduction pass needed).
+// One CTA per row; the row is read once (kept in registers across the two phases: 16 values per thread).
+// ---------------------------------------------------------------------------------------------
+#define OZ_SLICE_THREADS 256
+#define OZ_SLICE_PER_THREAD 4
+
+__global__ void __launch_bounds__(OZ_SLICE_THREADS)
+ozaki_slice_rows_kernel(const double* __restrict__ X, int ldx, int R, int Rpad, int K, int ns, double fixed_max,
+                        int8_t* __restrict__ planes, double* __restrict__ scales) {
+  __shared__ double red[OZ_SLICE_THREADS / 32];
+  __shared__ double s_scale_inv;
+  const int r = blockIdx.x;
+  const int tid = threadIdx.x;
+  const size_t plane_stride = (size_t)Rpad * K;
+  if (r >= R) {                                            // pad rows: zero digits, unit scale
+    for (int i = 0; i < ns; ++i)
+      for (int k = tid * 4; k < K; k += OZ_SLICE_THREADS * 4)
+        *reinterpret_cast<int*>(planes + i * plane_stride + (size_t)r * K + k) = 0;
+    if (tid == 0) scales[r] = 1.0;
+    return;
+  }
+  const double* x = X + (size_t)r * ldx;
+  double mx = fixed_max;
+  if (!(fixed_max > 0.0)) {
+    mx = 0.0;
+    for (int k = tid; k < K; k += OZ_SLICE_THREADS) mx = fmax(mx, fabs(x[k]));
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((tid & 31) == 0) red[tid >> 5] = mx;
+    __syncthreads();
+    mx = red[0];
+    for (int w = 1; w < OZ_SLICE_THREADS / 32; ++w) mx = fmax(mx, red[w]);
+  }
+  if (tid == 0) {
+    int e = 0;
+    if (mx > 0.0) {
+      frexp(mx / 0.98, &e);                               // mx/0.98 = f 2^e, f in [0.5,1)  =>  |x| 2^-e <= 0.98
+    }
+    scales[r] = ldexp(1.0, e);
+    s_scale_inv = ldexp(1.0, -e + 8 * ns - 1);             // x -> fixed point with 8 ns - 1 fractional bits
+  }
+  __syncthreads();
+  const double sc = s_scale_inv;
+  for (int k = tid * 4; k < K; k += OZ_SLICE_THREADS * 4) {
+    long long I[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) I[t] = __double2ll_rn(x[k + t] * sc);
+    for (int i = ns - 1; i >= 0; --i) {                    // least significant digit first, balanced base 256
+      int packed = 0;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        long long d = ((I[t] + 128) & 255) - 128;
+        I[t] = (I[t] - d) >> 8;
+        packed |= (int)((unsigned)(d & 255) << (8 * t));
+      }
+      *reinterpret_cast<int*>(planes + i * plane_stride + (size_t)r * K + k) = packed;
+    }
+  }
+}

@@ -299,6 +299,25 @@ class Engine:
         self._ck(self._lib.maf_profile_read(self._ctx, nat.ptr(ms), ln.ctypes.data_as(C.c_void_p)))
         return {k: (float(ms[i]), int(ln[i])) for i, k in enumerate(nat.PROF_SLOTS)}
 
+    def set_gemm_mode(self, mode: int):
+        """0 = FP64 DMMA contractions, 1 = INT8 digit-sliced contractions (effective at the next set_train)."""
+        self._ck(self._lib.maf_set_gemm_mode(self._ctx, int(mode)))
+        self._fingerprint = None
+
+    def gemm_nt_i8(self, A: np.ndarray, T: np.ndarray, tri: int = 0, ns: int = 7, lmax: int = 8) -> np.ndarray:
+        A, T = nat.as_f64(A), nat.as_f64(T)
+        J, K = A.shape
+        N, K2 = T.shape
+        assert K == K2
+        dA, dT = self.alloc(A.nbytes).upload(A), self.alloc(T.nbytes).upload(T)
+        dC = self.alloc(J * N * 8)
+        self._ck(self._lib.maf_gemm_nt_i8_dev(self._ctx, J, N, K, dA.ptr, K, dT.ptr, K, dC.ptr, N, int(tri), ns, lmax))
+        self.sync()
+        out = dC.download((J, N))
+        for b in (dA, dT, dC):
+            b.free()
+        return out
+
     # -- raw GEMM (tests / micro-benchmarks) --------------------------------------------------------------
     def gemm_nt(self, A: np.ndarray, T: np.ndarray, tri: int = 0) -> np.ndarray:
         A, T = nat.as_f64(A), nat.as_f64(T)
