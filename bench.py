@@ -52,6 +52,34 @@ def load_fp64_peak():
     return 37.0, "nominal B200 fp64 (no measurement found)"
 
 
+OZ_PAIRS = 28          # digit-plane pair products of the FP64-grade configuration (ns=7, lmax=8)
+DEFAULT_GEMM = "f64"
+
+
+def load_i8_peak():
+    """INT8 tensor-pipe denominator: 2 x the driver-measured cuBLAS bf16 figure of MEASURED_PEAKS.json (kind::i8
+    runs at twice the bf16 rate on tcgen05; sustained figure, the kernel is timed inside a long step), plus this
+    repo's own raw tcgen05 kind::i8 issue measurement (scripts/microbench_tcgen05.cu) for context."""
+    issue = None
+    try:
+        issue = float(json.load(open(os.path.join(ROOT, "profiles", "i8_peaks.json")))["tcgen05_i8_issue_tops"])
+    except Exception:
+        pass
+    try:
+        d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return 2.0 * float(d["bf16_tflops_sustained"]), "2 x bf16_tflops_sustained of MEASURED_PEAKS.json (of measured)", issue
+    except Exception:
+        return 2.0 * 1400.0, "2 x 1.4 PFLOP/s sustained bf16 (of fallback)", issue
+
+
+def load_traffic(kind):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/), or None."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[kind]
+    except Exception:
+        return None
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clocks and throttle reasons during the timed region (nvidia-smi, 200 ms)."""
 
@@ -160,6 +188,8 @@ def main():
     ap.add_argument("--impl", type=str, default="b200", choices=["b200", "reference"])
     ap.add_argument("--restarts", type=int, default=WORKLOAD["S_per_gpu"], help="restarts per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gemm", type=str, default=os.environ.get("MAF_BENCH_GEMM", DEFAULT_GEMM), choices=["f64", "i8"],
+                    help="contraction engine: f64 = DMMA, i8 = exact INT8 digit slicing on tcgen05 (FP64-grade)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -180,6 +210,7 @@ def main():
     X0, y0, _, z = make_inputs(1, w)
     X = np.random.RandomState(w["seed"] + 2 + 1000 * rank).rand(S, q, d)
     eng = Engine(local)
+    eng.set_gemm_mode(1 if args.gemm == "i8" else 0)
     eng.set_model(w["kernel"], np.full(d, math.sqrt(d) / 4), 1.0, 1e-3, 0.0, 1e-6)
     t0 = time.perf_counter()
     eng.set_train(X0, y0)
@@ -226,12 +257,24 @@ def main():
     gemm_launches = prof["gemm_fwd"][1] + prof["gemm_bwd"][1]
     npad = (n + 127) // 128 * 128
     flops_per_step = 2.0 * npad * npad * q * S            # n^2 q per triangular GEMM, two GEMMs
-    peak, peak_src = load_fp64_peak()
-    achieved = flops_per_step * args.steps / (gemm_ms * 1e-3) * 1e-12 if gemm_ms > 0 else 0.0
-    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "gemm_nt_f64_kernel (DMMA.8x8x4)", "peak_source": peak_src,
-                "kernel_ms_per_launch": gemm_ms / max(gemm_launches, 1), "kernel_share_of_step": gemm_ms / ms,
-                "per_kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()}}
+    peak64, peak64_src = load_fp64_peak()
+    fp64_equiv = flops_per_step * args.steps / (gemm_ms * 1e-3) * 1e-12 if gemm_ms > 0 else 0.0
+    common = {"kernel_ms_per_launch": gemm_ms / max(gemm_launches, 1), "kernel_share_of_step": gemm_ms / ms,
+              "per_kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()}}
+    if args.gemm == "i8":
+        # every algorithmic FP64 flop is OZ_PAIRS exact int8 digit-plane products on the tcgen05 i8 pipe
+        peak8, peak8_src, peak8_issue = load_i8_peak()
+        achieved = fp64_equiv * OZ_PAIRS
+        roofline = {"bound": "tensor", "achieved": achieved, "peak": peak8, "unit": "TOP/s", "frac": achieved / peak8,
+                    "traffic": load_traffic("i8"), "kernel": "ozaki_i8_gemm_kernel (tcgen05.mma kind::i8, TMA, TMEM)",
+                    "peak_source": peak8_src, "frac_of_own_tcgen05_i8_issue_peak": achieved / peak8_issue if peak8_issue else None,
+                    "algorithmic": "n^2 q FP64 flops per restart per launch x %d digit-plane products (ns=7, levels<=8)" % OZ_PAIRS,
+                    "fp64_equivalent_tflops": fp64_equiv, "fp64_dgemm_peak_tflops": peak64,
+                    "fp64_equivalent_over_dgemm_peak": fp64_equiv / peak64}
+    else:
+        roofline = {"bound": "tensor", "achieved": fp64_equiv, "peak": peak64, "unit": "TFLOP/s", "frac": fp64_equiv / peak64,
+                    "traffic": load_traffic("f64"), "kernel": "gemm_nt_f64_kernel (DMMA.8x8x4)", "peak_source": peak64_src}
+    roofline.update(common)
 
     # ---- e2e: host buffers through the C ABI -----------------------------------------------------
     hX = eng.pinned_empty((S, q, d))
@@ -267,8 +310,10 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
+            "dtype": "f64" if args.gemm == "f64" else "f64 (contractions: exact int8 digit planes, int32 accumulate, FP64 recombination)",
+            "data": "synthetic",
             "config": {"workload": "qEI value+grad, n=%d d=%d q=%d M=%d matern52, S=%d restarts per GPU" % (n, d, q, M, S),
+                       "contraction": args.gemm,
                        "parallelism": "restarts sharded x%d, replicated training factor, one all-gather per step" % ws,
                        "l2_policy": "working set per chunk (K10 + V^T = %.1f GB) >> 126 MB L2; no flush needed" % (2 * min(S * q, 65536) * npad * 8 / 1e9),
                        "setup_s_not_timed": setup_s},

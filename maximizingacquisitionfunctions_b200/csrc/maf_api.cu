@@ -16,6 +16,7 @@
 #include "gemm_f64.cuh"
 #include "mc_kernels.cuh"
 #include "ozaki_i8.cuh"
+#include "ozaki_i8_v3.cuh"
 #include "posterior.cuh"
 
 #define MAF_VERSION_STR "maf_b200 0.1 (sm_100a, fp64 DMMA)"
@@ -71,6 +72,8 @@ struct maf_ctx {
   int gemm_i8 = 0;                 // requested mode
   bool i8_ready = false;           // factor planes built for the current training set
   int oz_ns = 7, oz_lmax = 8;
+  int oz_dbg = 0;                  // MAF_OZ_DBG diagnostics (results invalid)
+  int oz_variant = 3;              // 1: whole-chunk stages of 32-byte boxes; 2: plane-tile ring of 128-byte lines
   Buf ozA, ozTL, ozTU;             // digit planes (int8, sized in doubles): candidates / Linv / LinvT
   Buf ozsA, ozsTL, ozsTU;          // row scales
   // fantasies (rank-4 observation sets)
@@ -284,7 +287,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int oz_make_tmap(maf_ctx* ctx, CUtensorMap* tm, const int8_t* base, int rows, int K, int ns) {
+static int oz_make_tmap(maf_ctx* ctx, CUtensorMap* tm, const int8_t* base, int rows, int K, int ns, int bk) {
   static PFN_encodeTiled encode = nullptr;
   if (!encode) {
     void* fn = nullptr;
@@ -295,10 +298,11 @@ static int oz_make_tmap(maf_ctx* ctx, CUtensorMap* tm, const int8_t* base, int r
   }
   cuuint64_t gdim[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)ns};
   cuuint64_t gstr[2] = {(cuuint64_t)K, (cuuint64_t)K * (cuuint64_t)rows};
-  cuuint32_t box[3] = {OZ_BK, 128, 1};
+  cuuint32_t box[3] = {(cuuint32_t)bk, 128, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)base, gdim, gstr, box, estr,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(ctx, "cuTensorMapEncodeTiled failed with %d", (int)r);
   return 0;
@@ -325,14 +329,40 @@ static int launch_i8gemm(maf_ctx* ctx, int slot, int J, int N, int K, const Buf&
   static bool attr = false;
   if (!attr) {
     CK(cudaFuncSetAttribute(ozaki_i8_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(ozaki_i8_gemm_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ2_SMEM_BYTES));
+#define OZ3_ATTR(NS_, LM_) \
+  CK(cudaFuncSetAttribute(ozaki_i8_gemm_v3_kernel<NS_, LM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, Oz3<NS_, LM_>::SMEM_BYTES))
+    OZ3_ATTR(7, 8); OZ3_ATTR(6, 7); OZ3_ATTR(5, 6); OZ3_ATTR(4, 5); OZ3_ATTR(3, 4);
+#undef OZ3_ATTR
     attr = true;
   }
+  const bool v3ok = lmax == ns + 1 && ns >= 3 && ns <= 7;
+  const int variant = (ctx->oz_variant == 3 && !v3ok) ? 1 : ctx->oz_variant;
+  const int bk = variant == 1 ? OZ_BK : OZ2_BK;
   CUtensorMap tmA, tmT;
-  if (oz_make_tmap(ctx, &tmA, (const int8_t*)Ap.p, J, K, ns) || oz_make_tmap(ctx, &tmT, (const int8_t*)Tp.p, N, K, ns)) return 1;
-  OzParams prm{K, ns, lmax, tri, ldc};
+  if (oz_make_tmap(ctx, &tmA, (const int8_t*)Ap.p, J, K, ns, bk) || oz_make_tmap(ctx, &tmT, (const int8_t*)Tp.p, N, K, ns, bk))
+    return 1;
+  OzParams prm{K, ns, lmax, tri, ldc, ctx->oz_dbg};
   dim3 grid(N / OZ_BN, J / OZ_BM);
   ProfScope ps(ctx, slot);
-  ozaki_i8_gemm_kernel<<<grid, OZ_THREADS, OZ_SMEM_BYTES, ctx->stream>>>(tmA, tmT, sA.p, sT.p, C, prm);
+  if (variant == 1) {
+    ozaki_i8_gemm_kernel<<<grid, OZ_THREADS, OZ_SMEM_BYTES, ctx->stream>>>(tmA, tmT, sA.p, sT.p, C, prm);
+  } else if (variant == 2) {
+    ozaki_i8_gemm_v2_kernel<<<grid, OZ_THREADS, OZ2_SMEM_BYTES, ctx->stream>>>(tmA, tmT, sA.p, sT.p, C, prm);
+  } else {
+#define OZ3_GO(NS_, LM_)                                                                                                     \
+  case NS_:                                                                                                                  \
+    ozaki_i8_gemm_v3_kernel<NS_, LM_><<<grid, OZ3_THREADS, Oz3<NS_, LM_>::SMEM_BYTES, ctx->stream>>>(tmA, tmT, sA.p, sT.p, C, prm); \
+    break
+    switch (ns) {
+      OZ3_GO(7, 8);
+      OZ3_GO(6, 7);
+      OZ3_GO(5, 6);
+      OZ3_GO(4, 5);
+      OZ3_GO(3, 4);
+    }
+#undef OZ3_GO
+  }
   CKL();
   return 0;
 }
@@ -361,6 +391,8 @@ extern "C" int maf_create(int device, int dtype, maf_ctx** out) {
   CKB(cusolverDnSetStream(ctx->cusolver, ctx->stream));
   if (const char* gv = getenv("MAF_GEMM_VARIANT")) ctx->gemm_variant = atoi(gv);
   if (const char* gi = getenv("MAF_GEMM_I8")) ctx->gemm_i8 = atoi(gi);
+  if (const char* ov = getenv("MAF_OZ_VARIANT")) ctx->oz_variant = atoi(ov);
+  if (const char* od = getenv("MAF_OZ_DBG")) ctx->oz_dbg = atoi(od);
   CK(cudaMalloc((void**)&ctx->d_argmin_val, sizeof(double)));
   CK(cudaMalloc((void**)&ctx->d_argmin_idx, sizeof(long long)));
   const char* cr = getenv("MAF_CHUNK_ROWS");

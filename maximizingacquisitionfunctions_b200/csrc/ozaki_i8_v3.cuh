@@ -1,0 +1,301 @@
+// INT8 digit-sliced contraction, statically scheduled (v3).
+//
+// Measured on B200 (gpurun_out/gemm_i8_dbg.jsonl, microbench_tcgen05_v2.jsonl): a tcgen05.mma of shape
+// 128x128x32 (kind::i8) occupies the tensor pipe for 64 clocks, and ONE thread issues every MMA of the CTA, so
+// the issue loop may spend ~10 instructions per MMA.  The generic kernel (ozaki_i8.cuh) spends ~25 (descriptor
+// construction, run-time loop bounds, divergent-code ELECT loops) and runs at 145 clocks per MMA with loads and
+// epilogue switched off.  This version removes all of that:
+//
+//   * <NS, LMAX> are template parameters; the (A plane, T plane) pair schedule of a k-chunk is unrolled at
+//     compile time, every plane tile has a FIXED shared-memory slot (16 KB, [128 rows][128 B], SWIZZLE_128B)
+//     with its own full/empty mbarrier, so a descriptor is `base + constant` and a phase is one bit of a mask;
+//   * producer and issuer warps stay converged (barrier waits by all lanes, elect.sync for the asynchronous
+//     instructions), so UTCIMMA / UTMALDG are issued straight from uniform registers;
+//   * within a k-chunk the pairs are walked by A plane i = 1..smax; the T planes A_i meets form a window
+//     [lo-i, hi-i] that slides down, each tile is released (tcgen05.commit) right after its last MMA and is
+//     refilled for the next k-chunk while the remaining pairs run.  In the first pass (levels 2..5) the window
+//     is anchored at T_1, so its T tiles are double-buffered by chunk parity in the slots the pass leaves idle;
+//   * the epilogue recombines the <= 4 level accumulators exactly in int64 (one I2F per element instead of
+//     four), on 8 warps instead of 4.
+#pragma once
+#include "ozaki_i8.cuh"
+
+#define OZ3_BK 128
+#define OZ3_TILE_BYTES (128 * OZ3_BK)
+#define OZ3_THREADS 320                       // warp 0: TMA producer, warp 1: MMA issuer, warps 2-9: epilogue
+#define OZ3_DESC_HI 0x40004040u               // SBO = 1024 B, descriptor version 1, SWIZZLE_128B
+
+template <int NS, int LMAX>
+struct Oz3 {
+  static constexpr int NPASS = (LMAX - 1 + 3) / 4;
+  static constexpr int NSLOT = (2 * NS > 12) ? 2 * NS : 12;
+  static constexpr int SMEM_BYTES = NSLOT * OZ3_TILE_BYTES + 1024;
+  __host__ __device__ static constexpr int lo(int pass) { return 2 + 4 * pass; }
+  __host__ __device__ static constexpr int hi(int pass) { return (lo(pass) + 3 < LMAX) ? lo(pass) + 3 : LMAX; }
+  __host__ __device__ static constexpr int smax(int pass) { return (NS < hi(pass) - 1) ? NS : hi(pass) - 1; }
+  __host__ __device__ static constexpr int wlo(int pass, int i) { return (lo(pass) - i > 1) ? lo(pass) - i : 1; }
+  __host__ __device__ static constexpr int whi(int pass, int i) { return (hi(pass) - i < NS) ? hi(pass) - i : NS; }
+  __host__ __device__ static constexpr int slotA(int i) { return i - 1; }
+  // second buffer of T plane ip in pass 0: taken from the slots pass 0 leaves idle
+  __host__ __device__ static constexpr int alt(int ip) {
+    const int s0 = smax(0), nfree = NS - s0;
+    int idx = ip - 1;
+    if (idx < nfree) return s0 + idx;
+    idx -= nfree;
+    if (idx < nfree) return NS + s0 + idx;
+    idx -= nfree;
+    return 2 * NS + idx;
+  }
+  __host__ __device__ static constexpr int slotT(int pass, int ip, int par) {
+    return (pass == 0 && par == 1) ? alt(ip) : NS + ip - 1;
+  }
+};
+
+__device__ __forceinline__ bool oz_elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void oz3_mma(uint32_t d_tmem, uint32_t alo, uint32_t blo, uint32_t idesc, uint32_t acc) {
+  const uint64_t da = ((uint64_t)OZ3_DESC_HI << 32) | alo, db = ((uint64_t)OZ3_DESC_HI << 32) | blo;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void oz3_commit(uint32_t bar_addr) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr) : "memory");
+}
+__device__ __forceinline__ void oz3_wait(uint32_t bar_addr, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\tOZ3_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra OZ3_DONE;\n\tbra OZ3_WAIT;\n\tOZ3_DONE:\n\t}" ::"r"(bar_addr), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void oz3_load(uint32_t dst, const CUtensorMap* tm, uint32_t bar_addr, int c0, int c1, int c2) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(OZ3_TILE_BYTES) : "memory");
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar_addr), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+// ---- one k-chunk of one pass: producer side -----------------------------------------------------
+template <int NS, int LMAX, int PASS, int PAR>
+__device__ __forceinline__ void oz3_produce_chunk(const CUtensorMap* tmA, const CUtensorMap* tmT, uint32_t smem0,
+                                                  uint32_t full0, uint32_t empty0, uint32_t& ph_empty, int c, int j0,
+                                                  int r0) {
+  using Z = Oz3<NS, LMAX>;
+#pragma unroll
+  for (int i = 1; i <= Z::smax(PASS); ++i) {
+    // T planes entering the window at this step (all of it at i == 1), then A_i
+#pragma unroll
+    for (int ip = Z::whi(PASS, i); ip >= Z::wlo(PASS, i); --ip) {
+      if (i == 1 || ip < Z::wlo(PASS, i - 1)) {
+        const int s = Z::slotT(PASS, ip, PAR);
+        oz3_wait(empty0 + 8u * s, (ph_empty >> s) & 1u);
+        ph_empty ^= 1u << s;
+        if (oz_elect_one()) oz3_load(smem0 + (uint32_t)s * OZ3_TILE_BYTES, tmT, full0 + 8u * s, c, r0, ip - 1);
+        __syncwarp();
+      }
+    }
+    {
+      const int s = Z::slotA(i);
+      oz3_wait(empty0 + 8u * s, (ph_empty >> s) & 1u);
+      ph_empty ^= 1u << s;
+      if (oz_elect_one()) oz3_load(smem0 + (uint32_t)s * OZ3_TILE_BYTES, tmA, full0 + 8u * s, c, j0, i - 1);
+      __syncwarp();
+    }
+  }
+}
+
+// ---- one k-chunk of one pass: MMA issuer side -----------------------------------------------------
+template <int NS, int LMAX, int PASS, int PAR>
+__device__ __forceinline__ void oz3_issue_chunk(uint32_t desc0 /* (smem0 >> 4) | LBO */, uint32_t full0, uint32_t empty0,
+                                                uint32_t& ph_full, uint32_t tbase, uint32_t idesc, uint32_t not_first) {
+  using Z = Oz3<NS, LMAX>;
+#pragma unroll
+  for (int i = 1; i <= Z::smax(PASS); ++i) {
+#pragma unroll
+    for (int ip = Z::whi(PASS, i); ip >= Z::wlo(PASS, i); --ip) {
+      if (i == 1 || ip < Z::wlo(PASS, i - 1)) {
+        const int s = Z::slotT(PASS, ip, PAR);
+        oz3_wait(full0 + 8u * s, (ph_full >> s) & 1u);
+        ph_full ^= 1u << s;
+      }
+    }
+    {
+      const int s = Z::slotA(i);
+      oz3_wait(full0 + 8u * s, (ph_full >> s) & 1u);
+      ph_full ^= 1u << s;
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (oz_elect_one()) {
+      const uint32_t alo = desc0 + (uint32_t)(Z::slotA(i) * (OZ3_TILE_BYTES >> 4));
+#pragma unroll
+      for (int ip = Z::wlo(PASS, i); ip <= Z::whi(PASS, i); ++ip) {
+        const int l = i + ip;
+        const uint32_t d_tmem = tbase + (uint32_t)((l - Z::lo(PASS)) * OZ_BN);
+        const uint32_t blo = desc0 + (uint32_t)(Z::slotT(PASS, ip, PAR) * (OZ3_TILE_BYTES >> 4));
+        const bool level_start = (i == ((l - NS > 1) ? l - NS : 1));
+#pragma unroll
+        for (int k = 0; k < OZ3_BK / 32; ++k)
+          oz3_mma(d_tmem, alo + 2u * k, blo + 2u * k, idesc, (level_start && k == 0) ? not_first : 1u);
+      }
+      oz3_commit(empty0 + 8u * Z::slotA(i));
+      if (i < Z::smax(PASS)) {
+        if (Z::hi(PASS) - i <= NS) oz3_commit(empty0 + 8u * Z::slotT(PASS, Z::hi(PASS) - i, PAR));
+      } else {
+#pragma unroll
+        for (int ip = Z::wlo(PASS, i); ip <= Z::whi(PASS, i); ++ip) oz3_commit(empty0 + 8u * Z::slotT(PASS, ip, PAR));
+      }
+    }
+    __syncwarp();
+  }
+}
+
+template <int NS, int LMAX, int PASS>
+__device__ __forceinline__ void oz3_produce_pass(const CUtensorMap* tmA, const CUtensorMap* tmT, uint32_t smem0,
+                                                 uint32_t full0, uint32_t empty0, uint32_t& ph_empty, int c_begin,
+                                                 int kchunks, int j0, int r0) {
+  for (int kc = 0; kc < kchunks; kc += 2) {
+    oz3_produce_chunk<NS, LMAX, PASS, 0>(tmA, tmT, smem0, full0, empty0, ph_empty, c_begin + kc * OZ3_BK, j0, r0);
+    if (kc + 1 < kchunks)
+      oz3_produce_chunk<NS, LMAX, PASS, 1>(tmA, tmT, smem0, full0, empty0, ph_empty, c_begin + (kc + 1) * OZ3_BK, j0, r0);
+  }
+}
+template <int NS, int LMAX, int PASS>
+__device__ __forceinline__ void oz3_issue_pass(uint32_t desc0, uint32_t full0, uint32_t empty0, uint32_t& ph_full,
+                                               uint32_t tbase, uint32_t idesc, int kchunks) {
+  for (int kc = 0; kc < kchunks; kc += 2) {
+    oz3_issue_chunk<NS, LMAX, PASS, 0>(desc0, full0, empty0, ph_full, tbase, idesc, kc > 0 ? 1u : 0u);
+    if (kc + 1 < kchunks) oz3_issue_chunk<NS, LMAX, PASS, 1>(desc0, full0, empty0, ph_full, tbase, idesc, 1u);
+  }
+}
+
+template <int NS, int LMAX>
+__global__ void __launch_bounds__(OZ3_THREADS, 1)
+ozaki_i8_gemm_v3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmT,
+                        const double* __restrict__ sA, const double* __restrict__ sT, double* __restrict__ C, OzParams p) {
+  using Z = Oz3<NS, LMAX>;
+  extern __shared__ uint8_t oz_raw[];
+  __shared__ uint64_t full_bar[Z::NSLOT], empty_bar[Z::NSLOT], acc_full, acc_empty;
+  __shared__ uint32_t tmem_base_sh;
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);      // provably warp-uniform
+  const int lane = threadIdx.x & 31;
+  const uint32_t smem0 = (oz_smem_u32(oz_raw) + 1023u) & ~1023u;
+  const int rb = (p.tri == 1) ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;
+  const int r0 = rb * OZ_BN, j0 = blockIdx.y * OZ_BM;
+  const int c_begin = (p.tri == 2) ? r0 : 0;
+  const int c_end = (p.tri == 1) ? min(p.K, r0 + OZ_BN) : p.K;
+  const int kchunks = (c_end - c_begin) / OZ3_BK;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < Z::NSLOT; ++s) {
+      oz_mbar_init(&full_bar[s], 1);
+      oz_mbar_init(&empty_bar[s], 1);
+    }
+    oz_mbar_init(&acc_full, 1);
+    oz_mbar_init(&acc_empty, OZ3_THREADS - 64);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmT)) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(oz_smem_u32(&tmem_base_sh)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tbase = tmem_base_sh;
+  const uint32_t full0 = oz_smem_u32(&full_bar[0]), empty0 = oz_smem_u32(&empty_bar[0]);
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    uint32_t ph_empty = 0xffffffffu;                          // first wait on every slot passes
+    oz3_produce_pass<NS, LMAX, 0>(&tmA, &tmT, smem0, full0, empty0, ph_empty, c_begin, kchunks, j0, r0);
+    if constexpr (Z::NPASS > 1)
+      oz3_produce_pass<NS, LMAX, 1>(&tmA, &tmT, smem0, full0, empty0, ph_empty, c_begin, kchunks, j0, r0);
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BN >> 3) << 17) | ((uint32_t)(OZ_BM >> 4) << 24);
+    const uint32_t desc0 = ((smem0 & 0x3FFFFu) >> 4) | (1u << 16);
+    uint32_t ph_full = 0u;
+    oz3_issue_pass<NS, LMAX, 0>(desc0, full0, empty0, ph_full, tbase, idesc, kchunks);
+    if (oz_elect_one()) oz3_commit(oz_smem_u32(&acc_full));
+    __syncwarp();
+    if constexpr (Z::NPASS > 1) {
+      oz3_wait(oz_smem_u32(&acc_empty), 0u);                  // epilogue has drained the accumulators
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      oz3_issue_pass<NS, LMAX, 1>(desc0, full0, empty0, ph_full, tbase, idesc, kchunks);
+      if (oz_elect_one()) oz3_commit(oz_smem_u32(&acc_full));
+      __syncwarp();
+    }
+  } else {
+    // ================= epilogue: TMEM -> int64 recombination -> FP64 -> global =================
+    const int quarter = warp & 3;                             // TMEM lanes [32 quarter, +32) belong to this warp
+    const int half = (warp - 2) >> 2;                         // columns [64 half, +64)
+    const size_t j = (size_t)(j0 + quarter * 32 + lane);
+    const double srow = sA[j];
+    double* crow = C + j * p.ldc + r0 + half * 64;
+    const double* st = sT + r0 + half * 64;
+    const uint32_t taddr = tbase + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * 64);
+#pragma unroll
+    for (int pass = 0; pass < Z::NPASS; ++pass) {
+      const int lo = Z::lo(pass), nl = Z::hi(pass) - Z::lo(pass) + 1;
+      // sum_t r_t 2^(2 - 8 (lo + t)) = 2^(2 - 8 (lo + nl - 1)) * sum_t r_t 2^(8 (nl - 1 - t))
+      const double w = exp2((double)(2 - 8 * (lo + nl - 1))) * srow;
+      oz3_wait(oz_smem_u32(&acc_full), (uint32_t)(pass & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+      for (int c0 = 0; c0 < 64; c0 += 8) {
+        uint32_t r[4][8];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          if (t < nl) {
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(r[t][0]), "=r"(r[t][1]), "=r"(r[t][2]), "=r"(r[t][3]), "=r"(r[t][4]), "=r"(r[t][5]),
+                           "=r"(r[t][6]), "=r"(r[t][7])
+                         : "r"(taddr + (uint32_t)(t * OZ_BN + c0)));
+          }
+        }
+        double sc[8];
+#pragma unroll
+        for (int u = 0; u < 8; u += 2) {
+          const double2 s2 = __ldg(reinterpret_cast<const double2*>(st + c0 + u));
+          sc[u] = s2.x * w;
+          sc[u + 1] = s2.y * w;
+        }
+        double old[8];
+        if (pass > 0) {
+#pragma unroll
+          for (int u = 0; u < 8; u += 2) {
+            const double2 o2 = *reinterpret_cast<const double2*>(crow + c0 + u);
+            old[u] = o2.x;
+            old[u + 1] = o2.y;
+          }
+        }
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          long long acc = (long long)(int)r[0][u];
+#pragma unroll
+          for (int t = 1; t < 4; ++t)
+            if (t < nl) acc = acc * 256 + (long long)(int)r[t][u];
+          v[u] = (double)acc * sc[u];
+          if (pass > 0) v[u] += old[u];
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u += 2) *reinterpret_cast<double2*>(crow + c0 + u) = make_double2(v[u], v[u + 1]);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      oz_mbar_arrive(&acc_empty);
+    }
+  }
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(512) : "memory");
+}

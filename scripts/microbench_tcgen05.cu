@@ -32,9 +32,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 
 // kind: 0 = i8 (K = 32 bytes per MMA), 1 = tf32 (K = 8 elements = 32 bytes per MMA)
 template <int KIND, int N>
-__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int iters, int mmas_per_iter, uint32_t* out) {
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int iters, int mmas_per_iter, uint32_t* out, int rot, int commit_every, int layout) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t bar;
+  __shared__ uint64_t bar, bar2;
   __shared__ uint32_t tmem_base;
   const int warp = threadIdx.x >> 5;
   if (warp == 0) {
@@ -43,6 +43,7 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int iters, int mmas_pe
   }
   if (threadIdx.x == 32) {
     mbar_init(&bar, 1);
+    mbar_init(&bar2, 1);
     asm volatile("fence.mbarrier_init.release.cluster;");
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
@@ -59,9 +60,9 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int iters, int mmas_pe
     for (int it = 0; it < iters; ++it) {
       for (int m = 0; m < mmas_per_iter; ++m) {
         const int ks = m & 3;                                 // 4 k-steps of 32 B inside the 128-byte swizzle atom
-        const uint64_t da = make_desc(a_addr, 1024, 2) + (uint64_t)(ks * 2);
-        const uint64_t db = make_desc(b_addr, 1024, 2) + (uint64_t)(ks * 2);
-        const uint32_t d_tmem = tbase + (uint32_t)((m % (512 / N)) * N);   // rotate over the accumulators that fit
+        const uint64_t da = layout == 2 ? make_desc(a_addr, 1024, 2) + (uint64_t)(ks * 2) : make_desc(a_addr + ks * 4096, 256, 6);
+        const uint64_t db = layout == 2 ? make_desc(b_addr, 1024, 2) + (uint64_t)(ks * 2) : make_desc(b_addr + ks * 8192, 256, 6);
+        const uint32_t d_tmem = tbase + (uint32_t)((m % rot) * N);   // rotate over `rot` accumulators
         const uint32_t acc = (it | m) ? 1u : 0u;
         if (KIND == 0)
           asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -69,6 +70,8 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int iters, int mmas_pe
         else
           asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc));
+        if (commit_every && (m + 1) % commit_every == 0)
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar2)));
       }
     }
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)));
@@ -85,7 +88,7 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int iters, int mmas_pe
 }
 
 template <int KIND, int N>
-int run(const char* name, int sms, uint32_t* out) {
+int run(const char* name, int sms, uint32_t* out, int rot = 512 / N, int commit_every = 0, int layout = 2) {
   const int smem = 128 * 128 + 256 * 128 + 1024;
   CK(cudaFuncSetAttribute(mma_rate_kernel<KIND, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   cudaEvent_t e0, e1;
@@ -94,7 +97,7 @@ int run(const char* name, int sms, uint32_t* out) {
   const int iters = 2000, per = 28;
   for (int rep = 0; rep < 3; ++rep) {
     cudaEventRecord(e0);
-    mma_rate_kernel<KIND, N><<<sms, 128, smem>>>(iters, per, out);
+    mma_rate_kernel<KIND, N><<<sms, 128, smem>>>(iters, per, out, rot, commit_every, layout);
     cudaEventRecord(e1);
     CK(cudaEventSynchronize(e1));
   }
@@ -103,7 +106,7 @@ int run(const char* name, int sms, uint32_t* out) {
   cudaEventElapsedTime(&ms, e0, e1);
   const double kdim = KIND == 0 ? 32.0 : 8.0;
   double ops = 2.0 * 128 * N * kdim * (double)iters * per * sms;
-  printf("{\"bench\": \"tcgen05_%s\", \"M\": 128, \"N\": %d, \"ms\": %.3f, \"tops\": %.1f}\n", name, N, ms, ops / ms * 1e-9);
+  printf("{\"bench\": \"tcgen05_%s\", \"M\": 128, \"N\": %d, \"rot\": %d, \"commit_every\": %d, \"layout\": %d, \"ms\": %.3f, \"tops\": %.1f}\n", name, N, rot, commit_every, layout, ms, ops / ms * 1e-9);
   return 0;
 }
 
@@ -115,6 +118,15 @@ int main() {
   CK(cudaMalloc(&out, sizeof(uint32_t) * sms));
   if (run<0, 64>("i8", sms, out)) return 1;
   if (run<0, 128>("i8", sms, out)) return 1;
+  for (int rot = 1; rot <= 4; rot *= 2) run<0, 128>("i8", sms, out, rot, 0, 2);
+  run<0, 128>("i8", sms, out, 4, 7, 2);
+  run<0, 128>("i8", sms, out, 4, 1, 2);
+  run<0, 128>("i8", sms, out, 1, 7, 2);
+  run<0, 128>("i8", sms, out, 4, 0, 6);
+  run<0, 128>("i8", sms, out, 1, 0, 6);
+  run<0, 128>("i8", sms, out, 1, 7, 6);
+  run<0, 256>("i8", sms, out, 1, 0, 2);
+  run<0, 256>("i8", sms, out, 2, 0, 2);
   if (run<0, 256>("i8", sms, out)) return 1;
   if (run<1, 64>("tf32", sms, out)) return 1;
   if (run<1, 128>("tf32", sms, out)) return 1;
