@@ -45,6 +45,8 @@ def build(force=False, verbose=False):
     cmd = [_nvcc()] + NVCC_FLAGS + ["-o", LIB, os.path.join(CSRC, "maf_api.cu"),
                                      "-L" + cuda_lib, "-Xlinker", "-rpath," + cuda_lib,
                                      "-lcublas", "-lcusolver"]
+    if os.environ.get("MAF_OZ_DIAG"):
+        cmd.insert(1, "-DMAF_OZ_DIAG")      # extra diagnostic instantiations of the INT8 kernel (MAF_OZ_DBG)
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

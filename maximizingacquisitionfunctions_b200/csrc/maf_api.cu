@@ -334,6 +334,11 @@ static int launch_i8gemm(maf_ctx* ctx, int slot, int J, int N, int K, const Buf&
   CK(cudaFuncSetAttribute(ozaki_i8_gemm_v3_kernel<NS_, LM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, Oz3<NS_, LM_>::SMEM_BYTES))
     OZ3_ATTR(7, 8); OZ3_ATTR(6, 7); OZ3_ATTR(5, 6); OZ3_ATTR(4, 5); OZ3_ATTR(3, 4);
 #undef OZ3_ATTR
+#ifdef MAF_OZ_DIAG
+#define OZ3_DATTR(D_) CK(cudaFuncSetAttribute(ozaki_i8_gemm_v3_kernel<7, 8, D_>, cudaFuncAttributeMaxDynamicSharedMemorySize, Oz3<7, 8>::SMEM_BYTES))
+    OZ3_DATTR(1); OZ3_DATTR(2); OZ3_DATTR(3); OZ3_DATTR(4); OZ3_DATTR(5); OZ3_DATTR(6); OZ3_DATTR(7);
+#undef OZ3_DATTR
+#endif
     attr = true;
   }
   const bool v3ok = lmax == ns + 1 && ns >= 3 && ns <= 7;
@@ -344,15 +349,25 @@ static int launch_i8gemm(maf_ctx* ctx, int slot, int J, int N, int K, const Buf&
     return 1;
   OzParams prm{K, ns, lmax, tri, ldc, ctx->oz_dbg};
   dim3 grid(N / OZ_BN, J / OZ_BM);
+  static int num_sms = 0;
+  if (!num_sms) CK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, ctx->device));
+  const long long ntiles = (long long)(N / OZ_BN) * (J / OZ_BM);
+  dim3 pgrid((unsigned)(ntiles < num_sms ? ntiles : num_sms));   // persistent: one CTA per SM
   ProfScope ps(ctx, slot);
   if (variant == 1) {
     ozaki_i8_gemm_kernel<<<grid, OZ_THREADS, OZ_SMEM_BYTES, ctx->stream>>>(tmA, tmT, sA.p, sT.p, C, prm);
   } else if (variant == 2) {
     ozaki_i8_gemm_v2_kernel<<<grid, OZ_THREADS, OZ2_SMEM_BYTES, ctx->stream>>>(tmA, tmT, sA.p, sT.p, C, prm);
+#ifdef MAF_OZ_DIAG
+  } else if (ns == 7 && ctx->oz_dbg) {
+#define OZ3_DGO(D_) case D_: ozaki_i8_gemm_v3_kernel<7, 8, D_><<<pgrid, OZ3_THREADS, Oz3<7, 8>::SMEM_BYTES, ctx->stream>>>(tmA, tmT, sA.p, sT.p, C, prm, N / OZ_BN, J / OZ_BM); break
+    switch (ctx->oz_dbg) { OZ3_DGO(1); OZ3_DGO(2); OZ3_DGO(3); OZ3_DGO(4); OZ3_DGO(5); OZ3_DGO(6); OZ3_DGO(7); }
+#undef OZ3_DGO
+#endif
   } else {
 #define OZ3_GO(NS_, LM_)                                                                                                     \
   case NS_:                                                                                                                  \
-    ozaki_i8_gemm_v3_kernel<NS_, LM_><<<grid, OZ3_THREADS, Oz3<NS_, LM_>::SMEM_BYTES, ctx->stream>>>(tmA, tmT, sA.p, sT.p, C, prm); \
+    ozaki_i8_gemm_v3_kernel<NS_, LM_><<<pgrid, OZ3_THREADS, Oz3<NS_, LM_>::SMEM_BYTES, ctx->stream>>>(tmA, tmT, sA.p, sT.p, C, prm, N / OZ_BN, J / OZ_BM); \
     break
     switch (ns) {
       OZ3_GO(7, 8);

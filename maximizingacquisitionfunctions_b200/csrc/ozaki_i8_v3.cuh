@@ -16,13 +16,15 @@
 //     refilled for the next k-chunk while the remaining pairs run.  In the first pass (levels 2..5) the window
 //     is anchored at T_1, so its T tiles are double-buffered by chunk parity in the slots the pass leaves idle;
 //   * the epilogue recombines the <= 4 level accumulators exactly in int64 (one I2F per element instead of
-//     four), on 8 warps instead of 4.
+//     four), on 16 warps instead of 4;
+//   * the grid is persistent (one CTA per SM, static round-robin over a supertiled, heaviest-first tile list):
+//     the producer prefetches the next pass / tile while the epilogue drains TMEM.
 #pragma once
 #include "ozaki_i8.cuh"
 
 #define OZ3_BK 128
 #define OZ3_TILE_BYTES (128 * OZ3_BK)
-#define OZ3_THREADS 320                       // warp 0: TMA producer, warp 1: MMA issuer, warps 2-9: epilogue
+#define OZ3_THREADS 576                       // warp 0: TMA producer, warp 1: MMA issuer, warps 2-17: epilogue
 #define OZ3_DESC_HI 0x40004040u               // SBO = 1024 B, descriptor version 1, SWIZZLE_128B
 
 template <int NS, int LMAX>
@@ -73,6 +75,9 @@ __device__ __forceinline__ void oz3_wait(uint32_t bar_addr, uint32_t parity) {
       "@P1 bra OZ3_DONE;\n\tbra OZ3_WAIT;\n\tOZ3_DONE:\n\t}" ::"r"(bar_addr), "r"(parity)
       : "memory");
 }
+__device__ __forceinline__ void oz3_arrive(uint32_t bar_addr) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_addr) : "memory");
+}
 __device__ __forceinline__ void oz3_load(uint32_t dst, const CUtensorMap* tm, uint32_t bar_addr, int c0, int c1, int c2) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(OZ3_TILE_BYTES) : "memory");
   asm volatile(
@@ -82,7 +87,7 @@ __device__ __forceinline__ void oz3_load(uint32_t dst, const CUtensorMap* tm, ui
 }
 
 // ---- one k-chunk of one pass: producer side -----------------------------------------------------
-template <int NS, int LMAX, int PASS, int PAR>
+template <int NS, int LMAX, int PASS, int PAR, int DBG>
 __device__ __forceinline__ void oz3_produce_chunk(const CUtensorMap* tmA, const CUtensorMap* tmT, uint32_t smem0,
                                                   uint32_t full0, uint32_t empty0, uint32_t& ph_empty, int c, int j0,
                                                   int r0) {
@@ -96,7 +101,10 @@ __device__ __forceinline__ void oz3_produce_chunk(const CUtensorMap* tmA, const 
         const int s = Z::slotT(PASS, ip, PAR);
         oz3_wait(empty0 + 8u * s, (ph_empty >> s) & 1u);
         ph_empty ^= 1u << s;
-        if (oz_elect_one()) oz3_load(smem0 + (uint32_t)s * OZ3_TILE_BYTES, tmT, full0 + 8u * s, c, r0, ip - 1);
+        if (oz_elect_one()) {
+          if (DBG & 2) oz3_arrive(full0 + 8u * s);
+          else oz3_load(smem0 + (uint32_t)s * OZ3_TILE_BYTES, tmT, full0 + 8u * s, c, r0, ip - 1);
+        }
         __syncwarp();
       }
     }
@@ -104,14 +112,17 @@ __device__ __forceinline__ void oz3_produce_chunk(const CUtensorMap* tmA, const 
       const int s = Z::slotA(i);
       oz3_wait(empty0 + 8u * s, (ph_empty >> s) & 1u);
       ph_empty ^= 1u << s;
-      if (oz_elect_one()) oz3_load(smem0 + (uint32_t)s * OZ3_TILE_BYTES, tmA, full0 + 8u * s, c, j0, i - 1);
+      if (oz_elect_one()) {
+        if (DBG & 2) oz3_arrive(full0 + 8u * s);
+        else oz3_load(smem0 + (uint32_t)s * OZ3_TILE_BYTES, tmA, full0 + 8u * s, c, j0, i - 1);
+      }
       __syncwarp();
     }
   }
 }
 
 // ---- one k-chunk of one pass: MMA issuer side -----------------------------------------------------
-template <int NS, int LMAX, int PASS, int PAR>
+template <int NS, int LMAX, int PASS, int PAR, int DBG>
 __device__ __forceinline__ void oz3_issue_chunk(uint32_t desc0 /* (smem0 >> 4) | LBO */, uint32_t full0, uint32_t empty0,
                                                 uint32_t& ph_full, uint32_t tbase, uint32_t idesc, uint32_t not_first) {
   using Z = Oz3<NS, LMAX>;
@@ -141,7 +152,7 @@ __device__ __forceinline__ void oz3_issue_chunk(uint32_t desc0 /* (smem0 >> 4) |
         const bool level_start = (i == ((l - NS > 1) ? l - NS : 1));
 #pragma unroll
         for (int k = 0; k < OZ3_BK / 32; ++k)
-          oz3_mma(d_tmem, alo + 2u * k, blo + 2u * k, idesc, (level_start && k == 0) ? not_first : 1u);
+          if (!(DBG & 1)) oz3_mma(d_tmem, alo + 2u * k, blo + 2u * k, idesc, (level_start && k == 0) ? not_first : 1u);
       }
       oz3_commit(empty0 + 8u * Z::slotA(i));
       if (i < Z::smax(PASS)) {
@@ -155,29 +166,54 @@ __device__ __forceinline__ void oz3_issue_chunk(uint32_t desc0 /* (smem0 >> 4) |
   }
 }
 
-template <int NS, int LMAX, int PASS>
+template <int NS, int LMAX, int PASS, int DBG>
 __device__ __forceinline__ void oz3_produce_pass(const CUtensorMap* tmA, const CUtensorMap* tmT, uint32_t smem0,
                                                  uint32_t full0, uint32_t empty0, uint32_t& ph_empty, int c_begin,
                                                  int kchunks, int j0, int r0) {
   for (int kc = 0; kc < kchunks; kc += 2) {
-    oz3_produce_chunk<NS, LMAX, PASS, 0>(tmA, tmT, smem0, full0, empty0, ph_empty, c_begin + kc * OZ3_BK, j0, r0);
+    oz3_produce_chunk<NS, LMAX, PASS, 0, DBG>(tmA, tmT, smem0, full0, empty0, ph_empty, c_begin + kc * OZ3_BK, j0, r0);
     if (kc + 1 < kchunks)
-      oz3_produce_chunk<NS, LMAX, PASS, 1>(tmA, tmT, smem0, full0, empty0, ph_empty, c_begin + (kc + 1) * OZ3_BK, j0, r0);
+      oz3_produce_chunk<NS, LMAX, PASS, 1, DBG>(tmA, tmT, smem0, full0, empty0, ph_empty, c_begin + (kc + 1) * OZ3_BK, j0, r0);
   }
 }
-template <int NS, int LMAX, int PASS>
+template <int NS, int LMAX, int PASS, int DBG>
 __device__ __forceinline__ void oz3_issue_pass(uint32_t desc0, uint32_t full0, uint32_t empty0, uint32_t& ph_full,
                                                uint32_t tbase, uint32_t idesc, int kchunks) {
   for (int kc = 0; kc < kchunks; kc += 2) {
-    oz3_issue_chunk<NS, LMAX, PASS, 0>(desc0, full0, empty0, ph_full, tbase, idesc, kc > 0 ? 1u : 0u);
-    if (kc + 1 < kchunks) oz3_issue_chunk<NS, LMAX, PASS, 1>(desc0, full0, empty0, ph_full, tbase, idesc, 1u);
+    oz3_issue_chunk<NS, LMAX, PASS, 0, DBG>(desc0, full0, empty0, ph_full, tbase, idesc, kc > 0 ? 1u : 0u);
+    if (kc + 1 < kchunks) oz3_issue_chunk<NS, LMAX, PASS, 1, DBG>(desc0, full0, empty0, ph_full, tbase, idesc, 1u);
   }
 }
 
-template <int NS, int LMAX>
+// Tile order of the persistent grid.  Tiles are grouped in super-rows of OZ3_SJ row blocks (the A planes of a
+// super-row, 16 x 128 x K x NS bytes, stay in L2 while every column block passes over them); inside a super-row
+// the column blocks go heaviest first (triangular T: the K range of a column block is proportional to its
+// index) with the row block as the fast index, so CTAs running together share T tiles and the static round-robin
+// t = blockIdx.x + i gridDim.x hands every CTA the same mix of heavy and light tiles.
+#define OZ3_SJ 16
+struct Oz3Tile {
+  int r0, j0, c_begin, kchunks;
+};
+__device__ __forceinline__ Oz3Tile oz3_tile(int t, int nN, int nJ, const OzParams& p) {
+  const int per = OZ3_SJ * nN;
+  const int st = t / per, rem = t - st * per;
+  const int jcount = min(OZ3_SJ, nJ - st * OZ3_SJ);
+  const int rbi = rem / jcount, jb = st * OZ3_SJ + (rem - rbi * jcount);
+  const int rb = (p.tri == 1) ? (nN - 1 - rbi) : rbi;
+  Oz3Tile x;
+  x.r0 = rb * OZ_BN;
+  x.j0 = jb * OZ_BM;
+  x.c_begin = (p.tri == 2) ? x.r0 : 0;
+  const int c_end = (p.tri == 1) ? min(p.K, x.r0 + OZ_BN) : p.K;
+  x.kchunks = (c_end - x.c_begin) / OZ3_BK;
+  return x;
+}
+
+template <int NS, int LMAX, int DBG = 0>
 __global__ void __launch_bounds__(OZ3_THREADS, 1)
 ozaki_i8_gemm_v3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmT,
-                        const double* __restrict__ sA, const double* __restrict__ sT, double* __restrict__ C, OzParams p) {
+                        const double* __restrict__ sA, const double* __restrict__ sT, double* __restrict__ C, OzParams p,
+                        int nN, int nJ) {
   using Z = Oz3<NS, LMAX>;
   extern __shared__ uint8_t oz_raw[];
   __shared__ uint64_t full_bar[Z::NSLOT], empty_bar[Z::NSLOT], acc_full, acc_empty;
@@ -186,11 +222,7 @@ ozaki_i8_gemm_v3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);      // provably warp-uniform
   const int lane = threadIdx.x & 31;
   const uint32_t smem0 = (oz_smem_u32(oz_raw) + 1023u) & ~1023u;
-  const int rb = (p.tri == 1) ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;
-  const int r0 = rb * OZ_BN, j0 = blockIdx.y * OZ_BM;
-  const int c_begin = (p.tri == 2) ? r0 : 0;
-  const int c_end = (p.tri == 1) ? min(p.K, r0 + OZ_BN) : p.K;
-  const int kchunks = (c_end - c_begin) / OZ3_BK;
+  const int ntiles = nN * nJ;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < Z::NSLOT; ++s) {
@@ -214,86 +246,117 @@ ozaki_i8_gemm_v3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   const uint32_t full0 = oz_smem_u32(&full_bar[0]), empty0 = oz_smem_u32(&empty_bar[0]);
 
   if (warp == 0) {
-    // ================= TMA producer =================
+    // ================= TMA producer: runs ahead across passes and tiles =================
     uint32_t ph_empty = 0xffffffffu;                          // first wait on every slot passes
-    oz3_produce_pass<NS, LMAX, 0>(&tmA, &tmT, smem0, full0, empty0, ph_empty, c_begin, kchunks, j0, r0);
-    if constexpr (Z::NPASS > 1)
-      oz3_produce_pass<NS, LMAX, 1>(&tmA, &tmT, smem0, full0, empty0, ph_empty, c_begin, kchunks, j0, r0);
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      const Oz3Tile x = oz3_tile(t, nN, nJ, p);
+      oz3_produce_pass<NS, LMAX, 0, DBG>(&tmA, &tmT, smem0, full0, empty0, ph_empty, x.c_begin, x.kchunks, x.j0, x.r0);
+      if constexpr (Z::NPASS > 1)
+        oz3_produce_pass<NS, LMAX, 1, DBG>(&tmA, &tmT, smem0, full0, empty0, ph_empty, x.c_begin, x.kchunks, x.j0, x.r0);
+    }
   } else if (warp == 1) {
     // ================= MMA issuer =================
     const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BN >> 3) << 17) | ((uint32_t)(OZ_BM >> 4) << 24);
     const uint32_t desc0 = ((smem0 & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t accf = oz_smem_u32(&acc_full), acce = oz_smem_u32(&acc_empty);
     uint32_t ph_full = 0u;
-    oz3_issue_pass<NS, LMAX, 0>(desc0, full0, empty0, ph_full, tbase, idesc, kchunks);
-    if (oz_elect_one()) oz3_commit(oz_smem_u32(&acc_full));
-    __syncwarp();
-    if constexpr (Z::NPASS > 1) {
-      oz3_wait(oz_smem_u32(&acc_empty), 0u);                  // epilogue has drained the accumulators
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      oz3_issue_pass<NS, LMAX, 1>(desc0, full0, empty0, ph_full, tbase, idesc, kchunks);
-      if (oz_elect_one()) oz3_commit(oz_smem_u32(&acc_full));
+    uint32_t g = 0;                                           // passes issued so far (accumulator hand-overs)
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      const Oz3Tile x = oz3_tile(t, nN, nJ, p);
+      if (g > 0) {
+        oz3_wait(acce, (g - 1) & 1u);                         // epilogue has drained the accumulators
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      }
+      oz3_issue_pass<NS, LMAX, 0, DBG>(desc0, full0, empty0, ph_full, tbase, idesc, x.kchunks);
+      if (oz_elect_one()) oz3_commit(accf);
       __syncwarp();
+      ++g;
+      if constexpr (Z::NPASS > 1) {
+        oz3_wait(acce, (g - 1) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        oz3_issue_pass<NS, LMAX, 1, DBG>(desc0, full0, empty0, ph_full, tbase, idesc, x.kchunks);
+        if (oz_elect_one()) oz3_commit(accf);
+        __syncwarp();
+        ++g;
+      }
     }
   } else {
     // ================= epilogue: TMEM -> int64 recombination -> FP64 -> global =================
+    // tcgen05.ld.16x256b hands a warp 16 accumulator rows x 8 columns per repetition in the mma C-fragment
+    // layout (lane t: row t/4 and t/4+8, columns 2 (t%4) + {0,1}), so four neighbouring lanes write 64
+    // contiguous bytes of one C row and a warp-wide 16-byte store touches 8 lines instead of the 32 that the
+    // row-per-lane shape (32x32b) costs; the L1 tag stage, one line per clock, was the epilogue's limiter.
+    constexpr int EW = (OZ3_THREADS - 64) / 128;              // warps per TMEM lane quarter
+    constexpr int CW = OZ_BN / EW;                            // columns per warp
+    static_assert(CW % 16 == 0, "epilogue column split");
     const int quarter = warp & 3;                             // TMEM lanes [32 quarter, +32) belong to this warp
-    const int half = (warp - 2) >> 2;                         // columns [64 half, +64)
-    const size_t j = (size_t)(j0 + quarter * 32 + lane);
-    const double srow = sA[j];
-    double* crow = C + j * p.ldc + r0 + half * 64;
-    const double* st = sT + r0 + half * 64;
-    const uint32_t taddr = tbase + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * 64);
+    const int part = (warp - 2) >> 2;                         // columns [CW part, +CW)
+    const int fr = lane >> 2, fc = (lane & 3) * 2;            // fragment row / column of this lane
+    const uint32_t accf = oz_smem_u32(&acc_full);
+    uint32_t g = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      const Oz3Tile x = oz3_tile(t, nN, nJ, p);
 #pragma unroll
-    for (int pass = 0; pass < Z::NPASS; ++pass) {
-      const int lo = Z::lo(pass), nl = Z::hi(pass) - Z::lo(pass) + 1;
-      // sum_t r_t 2^(2 - 8 (lo + t)) = 2^(2 - 8 (lo + nl - 1)) * sum_t r_t 2^(8 (nl - 1 - t))
-      const double w = exp2((double)(2 - 8 * (lo + nl - 1))) * srow;
-      oz3_wait(oz_smem_u32(&acc_full), (uint32_t)(pass & 1));
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int pass = 0; pass < Z::NPASS; ++pass) {
+        const int lo = Z::lo(pass), nl = Z::hi(pass) - Z::lo(pass) + 1;
+        // sum_t r_t 2^(2 - 8 (lo + t)) = 2^(2 - 8 (lo + nl - 1)) * sum_t r_t 2^(8 (nl - 1 - t))
+        const double w = exp2((double)(2 - 8 * (lo + nl - 1)));
+        oz3_wait(accf, g & 1u);
+        ++g;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-      for (int c0 = 0; c0 < 64; c0 += 8) {
-        uint32_t r[4][8];
+        for (int it = 0; it < ((DBG & 4) ? 0 : 2 * (CW / 16)); ++it) {
+          const int h = it & 1, cb = part * CW + (it >> 1) * 16;          // 16-row half, first column
+          const uint32_t taddr = tbase + ((uint32_t)(quarter * 32 + h * 16) << 16) + (uint32_t)cb;
+          uint32_t r[4][8];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          if (t < nl) {
-            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                         : "=r"(r[t][0]), "=r"(r[t][1]), "=r"(r[t][2]), "=r"(r[t][3]), "=r"(r[t][4]), "=r"(r[t][5]),
-                           "=r"(r[t][6]), "=r"(r[t][7])
-                         : "r"(taddr + (uint32_t)(t * OZ_BN + c0)));
+          for (int tt = 0; tt < 4; ++tt) {
+            if (tt < nl) {
+              asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                           : "=r"(r[tt][0]), "=r"(r[tt][1]), "=r"(r[tt][2]), "=r"(r[tt][3]), "=r"(r[tt][4]), "=r"(r[tt][5]),
+                             "=r"(r[tt][6]), "=r"(r[tt][7])
+                           : "r"(taddr + (uint32_t)(tt * OZ_BN)));
+            }
+          }
+          const size_t ja = (size_t)(x.j0 + quarter * 32 + h * 16 + fr), jb = ja + 8;
+          const double wa = sA[ja] * w, wb = sA[jb] * w;
+          double* ca = C + ja * p.ldc + x.r0 + cb + fc;
+          double* cbp = C + jb * p.ldc + x.r0 + cb + fc;
+          const double* st = sT + x.r0 + cb + fc;
+          double2 sc[2], olda[2], oldb[2];
+#pragma unroll
+          for (int n = 0; n < 2; ++n) {
+            sc[n] = __ldg(reinterpret_cast<const double2*>(st + 8 * n));
+            if (pass > 0) {
+              olda[n] = *reinterpret_cast<const double2*>(ca + 8 * n);
+              oldb[n] = *reinterpret_cast<const double2*>(cbp + 8 * n);
+            }
+          }
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int n = 0; n < 2; ++n) {
+            double v[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              long long acc = (long long)(int)r[0][4 * n + e];
+#pragma unroll
+              for (int tt = 1; tt < 4; ++tt)
+                if (tt < nl) acc = acc * 256 + (long long)(int)r[tt][4 * n + e];
+              v[e] = (double)acc * ((e & 1) ? sc[n].y : sc[n].x) * ((e & 2) ? wb : wa);
+            }
+            if (pass > 0) {
+              v[0] += olda[n].x;
+              v[1] += olda[n].y;
+              v[2] += oldb[n].x;
+              v[3] += oldb[n].y;
+            }
+            *reinterpret_cast<double2*>(ca + 8 * n) = make_double2(v[0], v[1]);
+            *reinterpret_cast<double2*>(cbp + 8 * n) = make_double2(v[2], v[3]);
           }
         }
-        double sc[8];
-#pragma unroll
-        for (int u = 0; u < 8; u += 2) {
-          const double2 s2 = __ldg(reinterpret_cast<const double2*>(st + c0 + u));
-          sc[u] = s2.x * w;
-          sc[u + 1] = s2.y * w;
-        }
-        double old[8];
-        if (pass > 0) {
-#pragma unroll
-          for (int u = 0; u < 8; u += 2) {
-            const double2 o2 = *reinterpret_cast<const double2*>(crow + c0 + u);
-            old[u] = o2.x;
-            old[u + 1] = o2.y;
-          }
-        }
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        double v[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          long long acc = (long long)(int)r[0][u];
-#pragma unroll
-          for (int t = 1; t < 4; ++t)
-            if (t < nl) acc = acc * 256 + (long long)(int)r[t][u];
-          v[u] = (double)acc * sc[u];
-          if (pass > 0) v[u] += old[u];
-        }
-#pragma unroll
-        for (int u = 0; u < 8; u += 2) *reinterpret_cast<double2*>(crow + c0 + u) = make_double2(v[u], v[u + 1]);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        oz_mbar_arrive(&acc_empty);
       }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      oz_mbar_arrive(&acc_empty);
     }
   }
   __syncthreads();
