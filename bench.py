@@ -53,7 +53,7 @@ def load_fp64_peak():
 
 
 OZ_PAIRS = 28          # digit-plane pair products of the FP64-grade configuration (ns=7, lmax=8)
-DEFAULT_GEMM = "f64"
+DEFAULT_GEMM = "i8"
 
 
 def load_i8_peak():
@@ -266,7 +266,7 @@ def main():
         peak8, peak8_src, peak8_issue = load_i8_peak()
         achieved = fp64_equiv * OZ_PAIRS
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peak8, "unit": "TOP/s", "frac": achieved / peak8,
-                    "traffic": load_traffic("i8"), "kernel": "ozaki_i8_gemm_kernel (tcgen05.mma kind::i8, TMA, TMEM)",
+                    "traffic": load_traffic("i8"), "kernel": "ozaki_i8_gemm_v3_kernel<7,8> (tcgen05.mma kind::i8, TMA, TMEM; persistent)",
                     "peak_source": peak8_src, "frac_of_own_tcgen05_i8_issue_peak": achieved / peak8_issue if peak8_issue else None,
                     "algorithmic": "n^2 q FP64 flops per restart per launch x %d digit-plane products (ns=7, levels<=8)" % OZ_PAIRS,
                     "fp64_equivalent_tflops": fp64_equiv, "fp64_dgemm_peak_tflops": peak64,

@@ -180,8 +180,8 @@ int maf_gemm_nt_dev(maf_ctx* ctx, int J, int N, int K, const double* dA, int lda
  * ns digit planes per operand (<= 7), levels up to lmax kept (ns=7, lmax=8: FP64-grade). */
 int maf_gemm_nt_i8_dev(maf_ctx* ctx, int J, int N, int K, const double* dA, int lda, const double* dT,
                        int ldt, double* dC, int ldc, int tri, int ns, int lmax);
-/* 0: FP64 DMMA contractions (default); 1: INT8 digit-sliced contractions in the value/gradient pipeline.
- * Takes effect at the next maf_set_train.  Also settable with the environment variable MAF_GEMM_I8. */
+/* 1 (default): FP64-grade contractions by exact INT8 digit slicing on tcgen05 (n <= 8192; larger n uses DMMA);
+ * 0: FP64 DMMA contractions.  Takes effect at the next maf_set_train.  Environment override: MAF_GEMM_I8. */
 int maf_set_gemm_mode(maf_ctx* ctx, int mode);
 void* maf_dev_alloc(maf_ctx* ctx, size_t bytes);
 int maf_dev_free(maf_ctx* ctx, void* p);

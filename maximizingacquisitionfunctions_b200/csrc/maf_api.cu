@@ -69,9 +69,11 @@ struct maf_ctx {
   int adam_S = 0, adam_q = 0, adam_p = 0;
   Buf adam_X, adam_m, adam_v, adam_g, adam_z;
   // INT8 digit-sliced contraction (ozaki_i8.cuh)
-  int gemm_i8 = 0;                 // requested mode
+  int gemm_i8 = 1;                 // requested mode (default: INT8 digit slicing; DMMA when n > 8192)
   bool i8_ready = false;           // factor planes built for the current training set
   int oz_ns = 7, oz_lmax = 8;
+  int oz_fuse = 1;                 // bit 0: cross-covariance, bit 1: Vbar written straight to digit planes (MAF_OZ_FUSE)
+  int oz_sj = 8;                   // super-row height of the persistent tile order (MAF_OZ_SJ)
   int oz_dbg = 0;                  // MAF_OZ_DBG diagnostics (results invalid)
   int oz_variant = 3;              // 1: whole-chunk stages of 32-byte boxes; 2: plane-tile ring of 128-byte lines
   Buf ozA, ozTL, ozTU;             // digit planes (int8, sized in doubles): candidates / Linv / LinvT
@@ -347,7 +349,7 @@ static int launch_i8gemm(maf_ctx* ctx, int slot, int J, int N, int K, const Buf&
   CUtensorMap tmA, tmT;
   if (oz_make_tmap(ctx, &tmA, (const int8_t*)Ap.p, J, K, ns, bk) || oz_make_tmap(ctx, &tmT, (const int8_t*)Tp.p, N, K, ns, bk))
     return 1;
-  OzParams prm{K, ns, lmax, tri, ldc, ctx->oz_dbg};
+  OzParams prm{K, ns, lmax, tri, ldc, ctx->oz_sj, ctx->oz_dbg};
   dim3 grid(N / OZ_BN, J / OZ_BM);
   static int num_sms = 0;
   if (!num_sms) CK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, ctx->device));
@@ -408,6 +410,8 @@ extern "C" int maf_create(int device, int dtype, maf_ctx** out) {
   if (const char* gi = getenv("MAF_GEMM_I8")) ctx->gemm_i8 = atoi(gi);
   if (const char* ov = getenv("MAF_OZ_VARIANT")) ctx->oz_variant = atoi(ov);
   if (const char* od = getenv("MAF_OZ_DBG")) ctx->oz_dbg = atoi(od);
+  if (const char* of = getenv("MAF_OZ_FUSE")) ctx->oz_fuse = atoi(of);
+  if (const char* sj = getenv("MAF_OZ_SJ")) ctx->oz_sj = atoi(sj) > 0 ? atoi(sj) : 1;
   CK(cudaMalloc((void**)&ctx->d_argmin_val, sizeof(double)));
   CK(cudaMalloc((void**)&ctx->d_argmin_idx, sizeof(long long)));
   const char* cr = getenv("MAF_CHUNK_ROWS");
@@ -601,8 +605,7 @@ extern "C" int maf_set_train(maf_ctx* ctx, int n, const double* X0, const double
     CKL();
   }
   ctx->i8_ready = false;
-  if (ctx->gemm_i8) {
-    if (npad > 8192) return fail(ctx, "INT8 contraction mode supports n <= 8192");
+  if (ctx->gemm_i8 && npad <= 8192) {   // int32 level accumulators hold K <= 8192; larger n keeps the DMMA contraction
     if (oz_slice(ctx, MAF_PROF_CROSS_FWD, ctx->Linv, npad, npad, npad, npad, ctx->oz_ns, 0.0, ctx->ozTL, ctx->ozsTL) ||
         oz_slice(ctx, MAF_PROF_CROSS_FWD, ctx->LinvT, npad, npad, npad, npad, ctx->oz_ns, 0.0, ctx->ozTU, ctx->ozsTU))
       return 1;
@@ -689,20 +692,37 @@ static int run_chunk(maf_ctx* ctx, const AcqDev& ap, bool posterior_only, bool c
   const int J = sc * q, Jpad = round_up(J, 128);
   double* K10 = ctx->K10.p;
   double* Vt = ctx->Vt.p;
-  {
-    ProfScope ps(ctx, MAF_PROF_CROSS_FWD);
-    dim3 grid((npad + CROSS_TK - 1) / CROSS_TK, Jpad / CROSS_TJ);
-    DISPATCH_D(d, cross_fwd_kernel<D><<<grid, CROSS_TK, 0, ctx->stream>>>(dX, J, ctx->X0s, n, npad, ctx->mp, K10));
-    CKL();
-  }
-  if (ctx->i8_ready) {
-    // cross-covariances are bounded by a^2: fixed row scale, no reduction pass
-    if (oz_slice(ctx, MAF_PROF_CROSS_FWD, K10, npad, J, Jpad, npad, ctx->oz_ns, ctx->mp.amp2, ctx->ozA, ctx->ozsA)) return 1;
+  const bool fused = ctx->i8_ready && (ctx->oz_fuse & 1), fused_bwd = ctx->i8_ready && (ctx->oz_fuse & 2);
+  if (fused) {
+    // K10 goes straight to digit planes (bounded by a^2: fixed row scale), FP64 K10 is never materialised
+    const size_t bytes = (size_t)ctx->oz_ns * Jpad * npad;
+    if (ensure(ctx, ctx->ozA, (bytes + 7) / 8) || ensure(ctx, ctx->ozsA, (size_t)Jpad)) return 1;
+    {
+      ProfScope ps(ctx, MAF_PROF_CROSS_FWD);
+      dim3 grid((npad + OZC_THREADS * 4 - 1) / (OZC_THREADS * 4), Jpad / OZC_TJ);
+      DISPATCH_D(d, cross_fwd_planes_kernel<D><<<grid, OZC_THREADS, 0, ctx->stream>>>(dX, J, Jpad, ctx->X0s, n, npad, ctx->mp, ctx->oz_ns,
+                                                                                  (int8_t*)ctx->ozA.p, ctx->ozsA.p));
+      CKL();
+    }
     if (launch_i8gemm(ctx, MAF_PROF_GEMM_FWD, Jpad, npad, npad, ctx->ozA, ctx->ozsA, ctx->ozTL, ctx->ozsTL, Vt, npad, 1,
                       ctx->oz_ns, ctx->oz_lmax))
       return 1;
-  } else if (launch_gemm(ctx, MAF_PROF_GEMM_FWD, Jpad, npad, npad, K10, npad, ctx->Linv, npad, Vt, npad, 1)) {
-    return 1;
+  } else {
+    {
+      ProfScope ps(ctx, MAF_PROF_CROSS_FWD);
+      dim3 grid((npad + CROSS_TK - 1) / CROSS_TK, Jpad / CROSS_TJ);
+      DISPATCH_D(d, cross_fwd_kernel<D><<<grid, CROSS_TK, 0, ctx->stream>>>(dX, J, ctx->X0s, n, npad, ctx->mp, K10));
+      CKL();
+    }
+    if (ctx->i8_ready) {
+      // cross-covariances are bounded by a^2: fixed row scale, no reduction pass
+      if (oz_slice(ctx, MAF_PROF_CROSS_FWD, K10, npad, J, Jpad, npad, ctx->oz_ns, ctx->mp.amp2, ctx->ozA, ctx->ozsA)) return 1;
+      if (launch_i8gemm(ctx, MAF_PROF_GEMM_FWD, Jpad, npad, npad, ctx->ozA, ctx->ozsA, ctx->ozTL, ctx->ozsTL, Vt, npad, 1,
+                        ctx->oz_ns, ctx->oz_lmax))
+        return 1;
+    } else if (launch_gemm(ctx, MAF_PROF_GEMM_FWD, Jpad, npad, npad, K10, npad, ctx->Linv, npad, Vt, npad, 1)) {
+      return 1;
+    }
   }
   {
     ProfScope ps(ctx, MAF_PROF_POSTERIOR);
@@ -730,18 +750,32 @@ static int run_chunk(maf_ctx* ctx, const AcqDev& ap, bool posterior_only, bool c
     CKL();
   }
   if (!need_grad) return 0;
-  {
-    ProfScope ps(ctx, MAF_PROF_VBAR);
-    DISPATCH_Q(q, vbar_kernel<Q><<<sc, 256, 0, ctx->stream>>>(Vt, npad, ctx->gamma, mubar, Sigbar));
-    CKL();
-  }
-  if (ctx->i8_ready) {
-    if (oz_slice(ctx, MAF_PROF_VBAR, Vt, npad, J, Jpad, npad, ctx->oz_ns, 0.0, ctx->ozA, ctx->ozsA)) return 1;
+  if (fused_bwd) {
+    const size_t bytes = (size_t)ctx->oz_ns * Jpad * npad;
+    if (ensure(ctx, ctx->ozA, (bytes + 7) / 8) || ensure(ctx, ctx->ozsA, (size_t)Jpad)) return 1;
+    {
+      ProfScope ps(ctx, MAF_PROF_VBAR);
+      DISPATCH_Q(q, vbar_planes_kernel<Q><<<sc + (Jpad - J), 256, 0, ctx->stream>>>(Vt, npad, sc, Jpad, ctx->gamma, mubar, Sigbar, ctx->oz_ns,
+                                                                                   (int8_t*)ctx->ozA.p, ctx->ozsA.p));
+      CKL();
+    }
     if (launch_i8gemm(ctx, MAF_PROF_GEMM_BWD, Jpad, npad, npad, ctx->ozA, ctx->ozsA, ctx->ozTU, ctx->ozsTU, K10, npad, 2,
                       ctx->oz_ns, ctx->oz_lmax))
       return 1;
-  } else if (launch_gemm(ctx, MAF_PROF_GEMM_BWD, Jpad, npad, npad, Vt, npad, ctx->LinvT, npad, K10, npad, 2)) {
-    return 1;
+  } else {
+    {
+      ProfScope ps(ctx, MAF_PROF_VBAR);
+      DISPATCH_Q(q, vbar_kernel<Q><<<sc, 256, 0, ctx->stream>>>(Vt, npad, ctx->gamma, mubar, Sigbar));
+      CKL();
+    }
+    if (ctx->i8_ready) {
+      if (oz_slice(ctx, MAF_PROF_VBAR, Vt, npad, J, Jpad, npad, ctx->oz_ns, 0.0, ctx->ozA, ctx->ozsA)) return 1;
+      if (launch_i8gemm(ctx, MAF_PROF_GEMM_BWD, Jpad, npad, npad, ctx->ozA, ctx->ozsA, ctx->ozTU, ctx->ozsTU, K10, npad, 2,
+                        ctx->oz_ns, ctx->oz_lmax))
+        return 1;
+    } else if (launch_gemm(ctx, MAF_PROF_GEMM_BWD, Jpad, npad, npad, Vt, npad, ctx->LinvT, npad, K10, npad, 2)) {
+      return 1;
+    }
   }
   {
     ProfScope ps(ctx, MAF_PROF_CROSS_BWD);

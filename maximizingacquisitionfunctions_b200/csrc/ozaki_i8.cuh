@@ -80,6 +80,7 @@ struct OzParams {
   int lmax;         // highest level kept (2 .. 2*ns)
   int tri;          // 0 full, 1 T lower-triangular, 2 upper
   int ldc;
+  int sj;           // persistent kernel: row blocks per super-row of the tile order
   int dbg;          // diagnostics only (results invalid): 1 = issue no MMAs, 2 = issue no TMA loads, 4 = skip the epilogue body
 };
 
@@ -443,6 +444,37 @@ ozaki_i8_gemm_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 // from that bound (cross-covariances are bounded by a^2, no reduction pass needed).
 // One CTA per row; the row is read once (kept in registers across the two phases: 16 values per thread).
 // ---------------------------------------------------------------------------------------------
+// Balanced base-256 digits of 4 fixed-point values -> one packed int per plane.
+// I = sum_i d_i 256^i with d_i in [-128,127]  <=>  I + sum_i 128 256^i = sum_i (d_i + 128) 256^i, the ordinary
+// unsigned bytes; so one 64-bit add and an XOR with 0x80 per byte give all digits at once, and three PRMTs per
+// plane gather byte b of the four values.  The value is left-aligned to 7 digits so that plane i is byte 6 - i.
+__device__ __forceinline__ void oz_emit_digits4(const long long (&I)[4], int ns, int8_t* __restrict__ dst, size_t plane_stride) {
+  const unsigned long long bias = 0x0080808080808080ull >> (8 * (OZ_MAXS - ns));
+  const int sh = 8 * (OZ_MAXS - ns);
+  unsigned lo[4], hi[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const unsigned long long u = (((unsigned long long)I[t] + bias) << sh) ^ 0x0080808080808080ull;
+    lo[t] = (unsigned)u;
+    hi[t] = (unsigned)(u >> 32);
+  }
+#pragma unroll
+  for (int i = 0; i < OZ_MAXS; ++i) {
+    if (i < ns) {
+      const int b = 6 - i;                                   // byte of the left-aligned value
+      const unsigned sel = (unsigned)((b & 3) | (((b & 3) + 4) << 4));
+      const unsigned p01 = (b < 4) ? __byte_perm(lo[0], lo[1], sel) : __byte_perm(hi[0], hi[1], sel);
+      const unsigned p23 = (b < 4) ? __byte_perm(lo[2], lo[3], sel) : __byte_perm(hi[2], hi[3], sel);
+      *reinterpret_cast<unsigned*>(dst + i * plane_stride) = __byte_perm(p01, p23, 0x5410);
+    }
+  }
+}
+__host__ __device__ __forceinline__ int oz_exponent_for(double mx) {
+  int e = 0;
+  if (mx > 0.0) frexp(mx / 0.98, &e);                        // mx/0.98 = f 2^e, f in [0.5,1)  =>  |x| 2^-e <= 0.98
+  return e;
+}
+
 #define OZ_SLICE_THREADS 256
 #define OZ_SLICE_PER_THREAD 4
 
@@ -486,15 +518,149 @@ ozaki_slice_rows_kernel(const double* __restrict__ X, int ldx, int R, int Rpad, 
     long long I[4];
 #pragma unroll
     for (int t = 0; t < 4; ++t) I[t] = __double2ll_rn(x[k + t] * sc);
-    for (int i = ns - 1; i >= 0; --i) {                    // least significant digit first, balanced base 256
-      int packed = 0;
+    oz_emit_digits4(I, ns, planes + (size_t)r * K + k, plane_stride);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused producers of digit planes (INT8 mode): the FP64 operand of a contraction is never written to HBM.
+// Both emit exactly the digits ozaki_slice_rows_kernel would produce from the FP64 matrix.
+// ---------------------------------------------------------------------------------------------
+// Cross-covariance rows K10[j][:] = a^2 kappa(|xs_j - x0s_k|^2) straight to digit planes (cross_fwd_kernel +
+// ozaki_slice_rows_kernel with the fixed bound a^2).  One thread owns 4 consecutive training points (their
+// scaled coordinates stay in registers), OZC_TJ candidate rows per CTA from shared memory; each store is one
+// packed int per plane, 128 contiguous bytes per warp.
+#define OZC_TJ 32
+#define OZC_THREADS 256
+template <int D>
+__global__ void __launch_bounds__(OZC_THREADS)
+cross_fwd_planes_kernel(const double* __restrict__ X, int J, int Jpad, const double* __restrict__ X0s, int n, int npad,
+                        ModelParams mp, int ns, int8_t* __restrict__ planes, double* __restrict__ scales) {
+  constexpr int DD = D > 0 ? D : MAF_MAX_D;
+  const int d = D > 0 ? D : mp.d;
+  __shared__ double xs[OZC_TJ][DD];
+  const int k = (blockIdx.x * OZC_THREADS + threadIdx.x) * 4;
+  const int j0 = blockIdx.y * OZC_TJ;
+  for (int t = threadIdx.x; t < OZC_TJ * d; t += OZC_THREADS) {
+    int jj = t / d, c = t - jj * d;
+    int j = j0 + jj;
+    xs[jj][c] = (j < J) ? X[(size_t)j * d + c] * mp.inv_ls[c] : 0.0;
+  }
+  const int e = oz_exponent_for(mp.amp2);
+  if (blockIdx.x == 0 && threadIdx.x < OZC_TJ) scales[j0 + threadIdx.x] = (j0 + (int)threadIdx.x < J) ? ldexp(1.0, e) : 1.0;
+  __syncthreads();
+  if (k >= npad) return;
+  const double sc = ldexp(1.0, -e + 8 * ns - 1);
+  double x0[4][DD];
+#pragma unroll
+  for (int t = 0; t < 4; ++t)
+#pragma unroll
+    for (int c = 0; c < DD; ++c) x0[t][c] = (c < d) ? X0s[(size_t)c * npad + k + t] : 0.0;
+  const size_t plane_stride = (size_t)Jpad * npad;
+#pragma unroll 2
+  for (int jj = 0; jj < OZC_TJ; ++jj) {
+    long long I[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      double r2 = 0.0;
+#pragma unroll
+      for (int c = 0; c < DD; ++c) {
+        if (c < d) {
+          double df = xs[jj][c] - x0[t][c];
+          r2 += df * df;
+        }
+      }
+      const double v = ((k + t) < n && (j0 + jj) < J) ? mp.amp2 * kern_val(mp.kernel_id, r2) : 0.0;
+      I[t] = __double2ll_rn(v * sc);
+    }
+    oz_emit_digits4(I, ns, planes + (size_t)(j0 + jj) * npad + k, plane_stride);
+  }
+}
+
+// Vbar^T[i][k] = mubar_i gamma_k - sum_j (Sbar_ij + Sbar_ji) V^T[j][k]  (vbar_kernel) straight to digit planes.
+// One CTA per restart.  Sweep 1 finds the row maxima of Vbar^T, sweep 2 recomputes the same values (the q x n
+// slab of V^T is re-read from L2) and emits the digits with the exact row scale, so the planes are identical to
+// slicing the FP64 matrix.  Rows >= J of the last 128-row block are zeroed by the CTAs with s >= S.
+template <int Q>
+__global__ void __launch_bounds__(256, Q <= 8 ? 2 : 1)
+vbar_planes_kernel(const double* __restrict__ Vt, int npad, int S, int Jpad, const double* __restrict__ gamma,
+                   const double* __restrict__ mubar, const double* __restrict__ Sigbar, int ns,
+                   int8_t* __restrict__ planes, double* __restrict__ scales) {
+  __shared__ double W[Q][Q];
+  __shared__ double mb[Q];
+  __shared__ double red[8][Q];
+  __shared__ double sinv[Q];
+  const int s = blockIdx.x, tid = threadIdx.x;
+  const size_t plane_stride = (size_t)Jpad * npad;
+  if (s >= S) {                                             // pad rows [S Q, Jpad): zero digits, unit scale
+    const int r = S * Q + (s - S);
+    if (r >= Jpad) return;
+    for (int i = 0; i < ns; ++i)
+      for (int k = tid * 4; k < npad; k += 256 * 4) *reinterpret_cast<int*>(planes + i * plane_stride + (size_t)r * npad + k) = 0;
+    if (tid == 0) scales[r] = 1.0;
+    return;
+  }
+  const double* sb = Sigbar + (size_t)s * Q * Q;
+  for (int t = tid; t < Q * Q; t += 256) {
+    int i = t / Q, j = t - i * Q;
+    W[i][j] = sb[i * Q + j] + sb[j * Q + i];
+  }
+  if (tid < Q) mb[tid] = mubar[(size_t)s * Q + tid];
+  __syncthreads();
+  const double* V = Vt + (size_t)s * Q * npad;
+  double mx[Q];
+#pragma unroll
+  for (int i = 0; i < Q; ++i) mx[i] = 0.0;
+  for (int k = tid; k < npad; k += 256) {
+    double v[Q];
+#pragma unroll
+    for (int i = 0; i < Q; ++i) v[i] = V[(size_t)i * npad + k];
+    const double g = gamma[k];
+#pragma unroll(Q <= 8 ? Q : 1)
+    for (int i = 0; i < Q; ++i) {
+      double o = mb[i] * g;
+#pragma unroll
+      for (int j = 0; j < Q; ++j) o -= W[i][j] * v[j];
+      mx[i] = fmax(mx[i], fabs(o));
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < Q; ++i) {
+    double m = mx[i];
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((tid & 31) == 0) red[tid >> 5][i] = m;
+  }
+  __syncthreads();
+  if (tid < Q) {
+    double m = red[0][tid];
+    for (int w = 1; w < 8; ++w) m = fmax(m, red[w][tid]);
+    const int e = oz_exponent_for(m);
+    scales[(size_t)s * Q + tid] = ldexp(1.0, e);
+    sinv[tid] = ldexp(1.0, -e + 8 * ns - 1);
+  }
+  __syncthreads();
+  for (int k = tid * 4; k < npad; k += 256 * 4) {
+    double v[Q][4];
+#pragma unroll
+    for (int i = 0; i < Q; ++i) {
+      const double2 a = *reinterpret_cast<const double2*>(V + (size_t)i * npad + k);
+      const double2 b = *reinterpret_cast<const double2*>(V + (size_t)i * npad + k + 2);
+      v[i][0] = a.x; v[i][1] = a.y; v[i][2] = b.x; v[i][3] = b.y;
+    }
+    double g[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) g[t] = gamma[k + t];
+#pragma unroll 1
+    for (int i = 0; i < Q; ++i) {
+      long long I[4];
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
-        long long d = ((I[t] + 128) & 255) - 128;
-        I[t] = (I[t] - d) >> 8;
-        packed |= (int)((unsigned)(d & 255) << (8 * t));
+        double o = mb[i] * g[t];
+#pragma unroll
+        for (int j = 0; j < Q; ++j) o -= W[i][j] * v[j][t];
+        I[t] = __double2ll_rn(o * sinv[i]);
       }
-      *reinterpret_cast<int*>(planes + i * plane_stride + (size_t)r * K + k) = packed;
+      oz_emit_digits4(I, ns, planes + ((size_t)s * Q + i) * npad + k, plane_stride);
     }
   }
 }

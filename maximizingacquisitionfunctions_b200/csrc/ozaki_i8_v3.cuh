@@ -185,16 +185,16 @@ __device__ __forceinline__ void oz3_issue_pass(uint32_t desc0, uint32_t full0, u
   }
 }
 
-// Tile order of the persistent grid.  Tiles are grouped in super-rows of OZ3_SJ row blocks (the A planes of a
-// super-row, 16 x 128 x K x NS bytes, stay in L2 while every column block passes over them); inside a super-row
+// Tile order of the persistent grid.  Tiles are grouped in super-rows of p.sj row blocks (the A planes of a
+// super-row, sj x 128 x K x NS bytes, stay in L2 while every column block passes over them); inside a super-row
 // the column blocks go heaviest first (triangular T: the K range of a column block is proportional to its
 // index) with the row block as the fast index, so CTAs running together share T tiles and the static round-robin
 // t = blockIdx.x + i gridDim.x hands every CTA the same mix of heavy and light tiles.
-#define OZ3_SJ 16
 struct Oz3Tile {
   int r0, j0, c_begin, kchunks;
 };
 __device__ __forceinline__ Oz3Tile oz3_tile(int t, int nN, int nJ, const OzParams& p) {
+  const int OZ3_SJ = p.sj;
   const int per = OZ3_SJ * nN;
   const int st = t / per, rem = t - st * per;
   const int jcount = min(OZ3_SJ, nJ - st * OZ3_SJ);

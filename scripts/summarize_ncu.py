@@ -16,6 +16,10 @@ KEYS = [
     "sm__throughput.avg.pct_of_peak_sustained_elapsed",
     "sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active",
     "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "gpc__cycles_elapsed.avg.per_second",
+    "l1tex__m_xbar2l1tex_read_bytes.sum", "l1tex__m_l1tex2xbar_req_cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "lts__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__inst_executed_op_tma_ld.sum",
     "sm__inst_executed_pipe_tensor.avg.pct_of_peak_sustained_active",
     "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
     "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",

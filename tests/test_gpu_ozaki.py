@@ -45,15 +45,65 @@ def sliced_product(A, T, ns, lmax):
     return C * sa * st.T
 
 
-@pytest.mark.parametrize("ns,lmax", [(1, 2), (2, 3), (2, 4), (4, 5), (5, 7), (7, 8), (7, 14)])
-def test_digit_planes_are_multiplied_exactly(eng, ns, lmax):
+@pytest.mark.parametrize("variant", [3, 1])
+@pytest.mark.parametrize("ns,lmax", [(1, 2), (2, 3), (2, 4), (3, 4), (4, 5), (5, 6), (6, 7), (5, 7), (7, 8), (7, 14)])
+def test_digit_planes_are_multiplied_exactly(ns, lmax, variant):
+    """variant 3 = statically scheduled persistent kernel (lmax == ns + 1, 3 <= ns <= 7; other configurations
+    take the generic kernel), variant 1 = generic kernel."""
+    import os
+    from maximizingacquisitionfunctions_b200.engine import Engine
+    os.environ["MAF_OZ_VARIANT"] = str(variant)
+    try:
+        eng = Engine(0)
+    finally:
+        del os.environ["MAF_OZ_VARIANT"]
+    try:
+        _check_digit_product(eng, ns, lmax)
+    finally:
+        eng.close()
+
+
+def _check_digit_product(eng, ns, lmax):
     rng = np.random.RandomState(ns * 10 + lmax)
-    J, N, K = 256, 128, 384
+    J, N, K = 384, 256, 640        # 3 x 2 tiles, odd number of 128-byte k-chunks (both chunk parities + tail)
     A = rng.randn(J, K) * np.exp(rng.randn(J, 1))
     T = rng.randn(N, K) * np.exp(rng.randn(N, 1))
     C = eng.gemm_nt_i8(A, T, 0, ns=ns, lmax=lmax)
     ref = sliced_product(A, T, ns, lmax)
     assert np.abs(C - ref).max() <= 1e-13 * np.abs(ref).max()
+
+
+def test_persistent_grid_many_tiles_per_cta(eng):
+    """More tiles than SMs: every CTA of the persistent grid walks several tiles (supertile order, barrier phases
+    carried across tiles); triangular T, so the tiles have different k ranges."""
+    rng = np.random.RandomState(5)
+    J, N = 128 * 40, 128 * 8                       # 320 tiles > 148 SMs; 3 supertiles of 16 row blocks (last one short)
+    A = rng.rand(J, N)
+    T = np.tril(rng.randn(N, N))
+    for tri, Tm in ((1, T), (2, T.T.copy()), (0, T)):
+        C = eng.gemm_nt_i8(A, Tm, tri)
+        ref = A @ Tm.T
+        scale = np.abs(A).max(1, keepdims=True) * np.abs(Tm).max(1, keepdims=True).T * math.sqrt(N)
+        assert (np.abs(C - ref) / scale).max() < 1e-13
+
+
+def test_large_n_keeps_dmma(eng):
+    """n > 8192 would overflow the int32 level accumulators: the default mode keeps the FP64 DMMA contraction."""
+    from maximizingacquisitionfunctions_b200.engine import Engine
+    n, d, q, S = 8300, 4, 2, 6
+    gp, X0, y0, X, z = orc.synthetic_problem(n, d, q, S, 16, seed=9)
+    ts = orc.prepare_train(gp, X0, y0)
+    e = Engine(0)
+    try:
+        e.set_model("matern52", np.full(d, math.sqrt(d) / 4), 1.0, 1e-3, 0.0, 1e-6)
+        e.set_train(X0, y0)
+        mu, cov = e.posterior(X)
+    finally:
+        e.close()
+    import torch
+    with torch.no_grad():
+        mu_o, cov_o = orc.posterior(ts, torch.as_tensor(X), full_cov=True)
+    assert relerr(mu, mu_o.numpy().reshape(mu.shape)) < 1e-9 and relerr(cov, cov_o.numpy()) < 1e-9
 
 
 @pytest.mark.parametrize("tri", [0, 1, 2])

@@ -22,10 +22,14 @@ def relerr(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
 
 
-@pytest.fixture(scope="module")
-def eng():
+@pytest.fixture(scope="module", params=["i8", "f64"])
+def eng(request):
+    """Every parity test runs on both contraction engines: exact INT8 digit slicing on tcgen05 (the default)
+    and the FP64 DMMA kernel."""
     from maximizingacquisitionfunctions_b200.engine import Engine
     e = Engine(0)
+    e.set_gemm_mode(1 if request.param == "i8" else 0)
+    e.test_gemm_mode = 1 if request.param == "i8" else 0
     yield e
     e.close()
 
@@ -196,6 +200,7 @@ def test_chunking_is_invisible(eng):
         e2 = Engine(0)
     finally:
         del os.environ["MAF_CHUNK_ROWS"]
+    e2.set_gemm_mode(eng.test_gemm_mode)
     e2.set_model("matern52", np.full(d, math.sqrt(d) / 4), 1.0, 1e-3, 0.0, 1e-6)
     e2.set_train(X0, y0)
     l2, g2 = e2.value_and_grad(prm("ei"), X, z)
