@@ -190,6 +190,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gemm", type=str, default=os.environ.get("MAF_BENCH_GEMM", DEFAULT_GEMM), choices=["f64", "i8"],
                     help="contraction engine: f64 = DMMA, i8 = exact INT8 digit slicing on tcgen05 (FP64-grade)")
+    ap.add_argument("--dtype", type=str, default="float64", choices=["float64", "float32"],
+                    help="float32 = the reference's dtype='float32' mode (jitter 1e-4, 1e-4 bar): 15 digit-plane products")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -209,9 +211,11 @@ def main():
     # every rank owns S restarts (weak scaling); its shard of the global restart index space
     X0, y0, _, z = make_inputs(1, w)
     X = np.random.RandomState(w["seed"] + 2 + 1000 * rank).rand(S, q, d)
-    eng = Engine(local)
+    eng = Engine(local, args.dtype)
     eng.set_gemm_mode(1 if args.gemm == "i8" else 0)
-    eng.set_model(w["kernel"], np.full(d, math.sqrt(d) / 4), 1.0, 1e-3, 0.0, 1e-6)
+    f32 = args.dtype == "float32"
+    pairs = 15 if f32 else OZ_PAIRS
+    eng.set_model(w["kernel"], np.full(d, math.sqrt(d) / 4), 1.0, 1e-3, 0.0, 1e-4 if f32 else 1e-6)
     t0 = time.perf_counter()
     eng.set_train(X0, y0)
     setup_s = time.perf_counter() - t0
@@ -264,11 +268,11 @@ def main():
     if args.gemm == "i8":
         # every algorithmic FP64 flop is OZ_PAIRS exact int8 digit-plane products on the tcgen05 i8 pipe
         peak8, peak8_src, peak8_issue = load_i8_peak()
-        achieved = fp64_equiv * OZ_PAIRS
+        achieved = fp64_equiv * pairs
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peak8, "unit": "TOP/s", "frac": achieved / peak8,
-                    "traffic": load_traffic("i8"), "kernel": "ozaki_i8_gemm_v3_kernel<7,8> (tcgen05.mma kind::i8, TMA, TMEM; persistent)",
+                    "traffic": load_traffic("i8"), "kernel": "ozaki_i8_gemm_v3_kernel<%s> (tcgen05.mma kind::i8, TMA, TMEM; persistent)" % ("5,6" if f32 else "7,8"),
                     "peak_source": peak8_src, "frac_of_own_tcgen05_i8_issue_peak": achieved / peak8_issue if peak8_issue else None,
-                    "algorithmic": "n^2 q FP64 flops per restart per launch x %d digit-plane products (ns=7, levels<=8)" % OZ_PAIRS,
+                    "algorithmic": "n^2 q flops per restart per launch x %d digit-plane products (%s)" % (pairs, "ns=5, levels<=6" if f32 else "ns=7, levels<=8"),
                     "fp64_equivalent_tflops": fp64_equiv, "fp64_dgemm_peak_tflops": peak64,
                     "fp64_equivalent_over_dgemm_peak": fp64_equiv / peak64}
     else:
@@ -310,7 +314,8 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64" if args.gemm == "f64" else "f64 (contractions: exact int8 digit planes, int32 accumulate, FP64 recombination)",
+            "dtype": ("f32-grade (contractions: 5 int8 digit planes per operand = 39-bit fixed point; everything else f64)" if f32 else
+                      "f64" if args.gemm == "f64" else "f64 (contractions: exact int8 digit planes, int32 accumulate, FP64 recombination)"),
             "data": "synthetic",
             "config": {"workload": "qEI value+grad, n=%d d=%d q=%d M=%d matern52, S=%d restarts per GPU" % (n, d, q, M, S),
                        "contraction": args.gemm,

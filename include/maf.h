@@ -38,6 +38,10 @@ extern "C" {
 
 typedef struct maf_ctx maf_ctx;
 
+/* MAF_F64: the reference's default dtype (src/core/module.py:29), 1e-9 bar.  MAF_F32: its dtype='float32' mode
+ * (jitter 1e-4, src/models/gaussian_process.py:42-44; 1e-4 bar): the two contractions keep 5 digit planes per
+ * operand (39-bit fixed point, 15 exact INT8 products instead of 28); all other arithmetic and every buffer of
+ * this ABI stay double. */
 enum maf_dtype { MAF_F64 = 0, MAF_F32 = 1 };
 /* src/models/kernels.py:32-49 */
 enum maf_kernel { MAF_KERNEL_SE = 0, MAF_KERNEL_MATERN52 = 1, MAF_KERNEL_MATERN32 = 2 };

@@ -149,3 +149,29 @@ def test_pipeline_in_int8_mode_matches_oracle(acq, n, d, q, S, M):
     assert relerr(mu, mo.numpy()) < 1e-9 and relerr(cov, co.numpy()) < 1e-9
     assert relerr(lg, lo) < 1e-9 and relerr(gg, go) < 1e-9
     assert int(np.argmin(lg)) == int(np.argmin(lo))
+
+
+@pytest.mark.parametrize("acq,n,d,q,S,M", [("ei", 1024, 6, 8, 40, 128), ("cb", 300, 3, 4, 50, 64), ("sr", 4096, 6, 8, 24, 128)])
+def test_float32_mode_within_1e_4(acq, n, d, q, S, M):
+    """dtype='float32' (src/models/gaussian_process.py:42-44: jitter 1e-4): contractions on 5 digit planes.
+    Bar of BASELINE.json for this mode: 1e-4 relative; the 39-bit fixed-point planes give ~1e-7."""
+    from maximizingacquisitionfunctions_b200.engine import Engine, acq_params
+    gp, X0, y0, X, z = orc.synthetic_problem(n, d, q, S, M, seed=4)
+    gp.jitter = 1e-4
+    ts = orc.prepare_train(gp, X0, y0)
+    e = Engine(0, "float32")
+    try:
+        e.set_model("matern52", np.full(d, math.sqrt(d) / 4), 1.0, 1e-3, 0.0, 1e-4)
+        e.set_train(X0, y0)
+        lg, gg = e.value_and_grad(acq_params(acq), X, z)
+        mu, cov, chol = e.last_extras(S, q)
+    finally:
+        e.close()
+    import torch
+    lo, go = orc.value_and_grad(ts, orc.Acq(acq), X, z)
+    with torch.no_grad():
+        mo, co = orc.posterior(ts, torch.as_tensor(X), full_cov=True)
+    errs = (relerr(lg, lo), relerr(gg, go), relerr(mu, mo.numpy().reshape(mu.shape)), relerr(cov, co.numpy()))
+    assert max(errs) < 1e-4, errs
+    assert max(errs) < 1e-6, errs            # what the digit configuration actually delivers
+    assert int(np.argmin(lg)) == int(np.argmin(lo))
