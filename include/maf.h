@@ -148,6 +148,12 @@ int maf_last_extras(maf_ctx* ctx, double* mu, double* cov, double* chol);
  * maf_adam_end downloads the iterate. */
 int maf_adam_begin(maf_ctx* ctx, const maf_acq_params* prm, int S, int q, int p_pending,
                    const double* X, double lr, double beta1, double beta2, double eps);
+/* Optimizer of the loop, between maf_adam_begin and the first step (default Adam).  MAF_OPT_GD / MAF_OPT_MOMENTUM are
+ * the reference's tf.train.GradientDescentOptimizer / MomentumOptimizer(., momentum) branches (:405-412): learning
+ * rate lr * (global_step + 1)^-0.7 (lr of maf_adam_begin, global_step from 0), accum = momentum*accum + g,
+ * x -= lr_t*accum, then the same clip. */
+enum maf_optimizer { MAF_OPT_ADAM = 0, MAF_OPT_GD = 1, MAF_OPT_MOMENTUM = 2 };
+int maf_adam_set_method(maf_ctx* ctx, int method, double momentum);
 int maf_adam_steps(maf_ctx* ctx, int steps, int M, const double* z_steps, double* out_loss_trace);
 int maf_adam_peek(maf_ctx* ctx, double* X_out);   /* current iterate, loop stays open */
 int maf_adam_end(maf_ctx* ctx, double* X_out);

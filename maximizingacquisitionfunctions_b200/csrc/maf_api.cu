@@ -67,6 +67,9 @@ struct maf_ctx {
   bool adam_on = false;
   maf_acq_params adam_prm{};
   int adam_S = 0, adam_q = 0, adam_p = 0;
+  int opt_method = 0;              // MAF_OPT_*
+  double opt_momentum = 0.0;
+  long long opt_t = 0;             // global_step since maf_adam_begin
   Buf adam_X, adam_m, adam_v, adam_g, adam_z;
   // INT8 digit-sliced contraction (ozaki_i8.cuh)
   int gemm_i8 = 1;                 // requested mode (default: INT8 digit slicing; DMMA when n > 8192)
@@ -74,6 +77,7 @@ struct maf_ctx {
   int oz_ns = 7, oz_lmax = 8;
   int oz_fuse = 1;                 // bit 0: cross-covariance, bit 1: Vbar written straight to digit planes (MAF_OZ_FUSE)
   int oz_sj = 8;                   // super-row height of the persistent tile order (MAF_OZ_SJ)
+  int oz_hint_a = 0, oz_hint_t = 0; // L2 policy of the A / T plane loads: 0 normal, 1 evict-first, 2 evict-last (MAF_OZ_HINTS=at)
   int oz_dbg = 0;                  // MAF_OZ_DBG diagnostics (results invalid)
   int oz_variant = 3;              // 1: whole-chunk stages of 32-byte boxes; 2: plane-tile ring of 128-byte lines
   Buf ozA, ozTL, ozTU;             // digit planes (int8, sized in doubles): candidates / Linv / LinvT
@@ -349,7 +353,8 @@ static int launch_i8gemm(maf_ctx* ctx, int slot, int J, int N, int K, const Buf&
   CUtensorMap tmA, tmT;
   if (oz_make_tmap(ctx, &tmA, (const int8_t*)Ap.p, J, K, ns, bk) || oz_make_tmap(ctx, &tmT, (const int8_t*)Tp.p, N, K, ns, bk))
     return 1;
-  OzParams prm{K, ns, lmax, tri, ldc, ctx->oz_sj, ctx->oz_dbg};
+  static const unsigned long long pol[3] = {OZ3_L2_NORMAL, OZ3_L2_EVICT_FIRST, OZ3_L2_EVICT_LAST};
+  OzParams prm{K, ns, lmax, tri, ldc, ctx->oz_sj, pol[ctx->oz_hint_a % 3], pol[ctx->oz_hint_t % 3], ctx->oz_dbg};
   dim3 grid(N / OZ_BN, J / OZ_BM);
   static int num_sms = 0;
   if (!num_sms) CK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, ctx->device));
@@ -418,6 +423,10 @@ extern "C" int maf_create(int device, int dtype, maf_ctx** out) {
   if (const char* ov = getenv("MAF_OZ_VARIANT")) ctx->oz_variant = atoi(ov);
   if (const char* od = getenv("MAF_OZ_DBG")) ctx->oz_dbg = atoi(od);
   if (const char* of = getenv("MAF_OZ_FUSE")) ctx->oz_fuse = atoi(of);
+  if (const char* h = getenv("MAF_OZ_HINTS")) {
+    if (h[0]) ctx->oz_hint_a = h[0] - '0';
+    if (h[0] && h[1]) ctx->oz_hint_t = h[1] - '0';
+  }
   if (const char* sj = getenv("MAF_OZ_SJ")) ctx->oz_sj = atoi(sj) > 0 ? atoi(sj) : 1;
   CK(cudaMalloc((void**)&ctx->d_argmin_val, sizeof(double)));
   CK(cudaMalloc((void**)&ctx->d_argmin_idx, sizeof(long long)));
@@ -1176,6 +1185,19 @@ extern "C" int maf_adam_begin(maf_ctx* ctx, const maf_acq_params* prm, int S, in
   ctx->adam_b1p = beta1;
   ctx->adam_b2p = beta2;
   ctx->adam_on = true;
+  ctx->opt_method = MAF_OPT_ADAM;
+  ctx->opt_momentum = 0.0;
+  ctx->opt_t = 0;
+  return 0;
+}
+
+extern "C" int maf_adam_set_method(maf_ctx* ctx, int method, double momentum) {
+  if (!ctx) return 1;
+  if (!ctx->adam_on) return fail(ctx, "maf_adam_begin must be called first");
+  if (method != MAF_OPT_ADAM && method != MAF_OPT_GD && method != MAF_OPT_MOMENTUM) return fail(ctx, "unknown optimizer %d", method);
+  if (ctx->opt_t != 0) return fail(ctx, "the optimizer cannot change after the first step");
+  ctx->opt_method = method;
+  ctx->opt_momentum = method == MAF_OPT_MOMENTUM ? momentum : 0.0;
   return 0;
 }
 
@@ -1199,16 +1221,22 @@ extern "C" int maf_adam_steps(maf_ctx* ctx, int steps, int M, const double* z_st
     rc = run_all(ctx, &ctx->adam_prm, false, S, q, p, ctx->adam_X.p, M, closed ? nullptr : ctx->adam_z.p + zsz * t,
                  nullptr, nullptr, lossp, ctx->adam_g.p);
     if (rc) break;
-    const double alpha = ctx->adam_lr * std::sqrt(1.0 - ctx->adam_b2p) / (1.0 - ctx->adam_b1p);
-    {
+    if (ctx->opt_method == MAF_OPT_ADAM) {
+      const double alpha = ctx->adam_lr * std::sqrt(1.0 - ctx->adam_b2p) / (1.0 - ctx->adam_b1p);
       ProfScope ps(ctx, MAF_PROF_ADAM);
       adam_clip_kernel<<<(unsigned)((nt + 255) / 256), 256, 0, ctx->stream>>>(
           ctx->adam_X.p, ctx->adam_g.p, ctx->adam_m.p, ctx->adam_v.p, nt, q, p, d, alpha, ctx->adam_b1,
           ctx->adam_b2, ctx->adam_eps);
+    } else {
+      const double lr_t = ctx->adam_lr * std::pow((double)(ctx->opt_t + 1), -0.7);   // decay of :405-412
+      ProfScope ps(ctx, MAF_PROF_ADAM);
+      sgd_clip_kernel<<<(unsigned)((nt + 255) / 256), 256, 0, ctx->stream>>>(ctx->adam_X.p, ctx->adam_g.p, ctx->adam_m.p, nt, q, p,
+                                                                              d, lr_t, ctx->opt_momentum);
     }
-    if (cudaGetLastError() != cudaSuccess) rc = fail(ctx, "adam_clip_kernel launch failed");
+    if (cudaGetLastError() != cudaSuccess) rc = fail(ctx, "optimizer update kernel launch failed");
     ctx->adam_b1p *= ctx->adam_b1;
     ctx->adam_b2p *= ctx->adam_b2;
+    ctx->opt_t += 1;
   }
   if (rc == 0 && dtrace) {
     if (cudaMemcpyAsync(out_loss_trace, dtrace, sizeof(double) * (size_t)steps * S, cudaMemcpyDeviceToHost,

@@ -372,6 +372,21 @@ __global__ void adam_clip_kernel(double* __restrict__ X, const double* __restric
   X[xi] = fmin(fmax(x, 0.0), 1.0);
 }
 
+// ---- GradientDescent / Momentum + clip (bayesian_optimization.py:405-412; TF ApplyMomentum without Nesterov:
+// accum = momentum * accum + g, x -= lr_t * accum; momentum == 0 is plain gradient descent) ----
+__global__ void sgd_clip_kernel(double* __restrict__ X, const double* __restrict__ g, double* __restrict__ accum,
+                                size_t ntrain, int q, int p, int d, double lr_t, double momentum) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ntrain) return;
+  const int qn = q - p;
+  size_t s = t / ((size_t)qn * d);
+  size_t rem = t - s * (size_t)qn * d;
+  size_t xi = s * (size_t)q * d + (size_t)p * d + rem;
+  const double a = momentum * accum[t] + g[t];
+  accum[t] = a;
+  X[xi] = fmin(fmax(X[xi] - lr_t * a, 0.0), 1.0);
+}
+
 // ---- first-minimum argmin over the loss vector (np.argmin; NaNs never win) ----------------
 __global__ void argmin_kernel(const double* __restrict__ loss, int S, double* out_val, long long* out_idx) {
   __shared__ double sv[32];

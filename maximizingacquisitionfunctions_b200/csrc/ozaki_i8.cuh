@@ -81,6 +81,7 @@ struct OzParams {
   int tri;          // 0 full, 1 T lower-triangular, 2 upper
   int ldc;
   int sj;           // persistent kernel: row blocks per super-row of the tile order
+  unsigned long long hintA, hintT;   // L2 eviction policies of the A / T plane loads (persistent kernel)
   int dbg;          // diagnostics only (results invalid): 1 = issue no MMAs, 2 = issue no TMA loads, 4 = skip the epilogue body
 };
 

@@ -78,11 +78,16 @@ __device__ __forceinline__ void oz3_wait(uint32_t bar_addr, uint32_t parity) {
 __device__ __forceinline__ void oz3_arrive(uint32_t bar_addr) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_addr) : "memory");
 }
-__device__ __forceinline__ void oz3_load(uint32_t dst, const CUtensorMap* tm, uint32_t bar_addr, int c0, int c1, int c2) {
+// L2 eviction-priority policies for TMA loads (the encodings createpolicy.fractional.L2::evict_* produces)
+#define OZ3_L2_NORMAL 0x1000000000000000ull
+#define OZ3_L2_EVICT_FIRST 0x12F0000000000000ull
+#define OZ3_L2_EVICT_LAST 0x14F0000000000000ull
+__device__ __forceinline__ void oz3_load(uint32_t dst, const CUtensorMap* tm, uint32_t bar_addr, int c0, int c1, int c2,
+                                         uint64_t hint) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(OZ3_TILE_BYTES) : "memory");
   asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar_addr), "r"(c0), "r"(c1), "r"(c2)
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar_addr), "r"(c0), "r"(c1), "r"(c2), "l"(hint)
       : "memory");
 }
 
@@ -90,7 +95,7 @@ __device__ __forceinline__ void oz3_load(uint32_t dst, const CUtensorMap* tm, ui
 template <int NS, int LMAX, int PASS, int PAR, int DBG>
 __device__ __forceinline__ void oz3_produce_chunk(const CUtensorMap* tmA, const CUtensorMap* tmT, uint32_t smem0,
                                                   uint32_t full0, uint32_t empty0, uint32_t& ph_empty, int c, int j0,
-                                                  int r0) {
+                                                  int r0, uint64_t hintA, uint64_t hintT) {
   using Z = Oz3<NS, LMAX>;
 #pragma unroll
   for (int i = 1; i <= Z::smax(PASS); ++i) {
@@ -103,7 +108,7 @@ __device__ __forceinline__ void oz3_produce_chunk(const CUtensorMap* tmA, const 
         ph_empty ^= 1u << s;
         if (oz_elect_one()) {
           if (DBG & 2) oz3_arrive(full0 + 8u * s);
-          else oz3_load(smem0 + (uint32_t)s * OZ3_TILE_BYTES, tmT, full0 + 8u * s, c, r0, ip - 1);
+          else oz3_load(smem0 + (uint32_t)s * OZ3_TILE_BYTES, tmT, full0 + 8u * s, c, r0, ip - 1, hintT);
         }
         __syncwarp();
       }
@@ -114,7 +119,7 @@ __device__ __forceinline__ void oz3_produce_chunk(const CUtensorMap* tmA, const 
       ph_empty ^= 1u << s;
       if (oz_elect_one()) {
         if (DBG & 2) oz3_arrive(full0 + 8u * s);
-        else oz3_load(smem0 + (uint32_t)s * OZ3_TILE_BYTES, tmA, full0 + 8u * s, c, j0, i - 1);
+        else oz3_load(smem0 + (uint32_t)s * OZ3_TILE_BYTES, tmA, full0 + 8u * s, c, j0, i - 1, hintA);
       }
       __syncwarp();
     }
@@ -169,11 +174,11 @@ __device__ __forceinline__ void oz3_issue_chunk(uint32_t desc0 /* (smem0 >> 4) |
 template <int NS, int LMAX, int PASS, int DBG>
 __device__ __forceinline__ void oz3_produce_pass(const CUtensorMap* tmA, const CUtensorMap* tmT, uint32_t smem0,
                                                  uint32_t full0, uint32_t empty0, uint32_t& ph_empty, int c_begin,
-                                                 int kchunks, int j0, int r0) {
+                                                 int kchunks, int j0, int r0, uint64_t hintA, uint64_t hintT) {
   for (int kc = 0; kc < kchunks; kc += 2) {
-    oz3_produce_chunk<NS, LMAX, PASS, 0, DBG>(tmA, tmT, smem0, full0, empty0, ph_empty, c_begin + kc * OZ3_BK, j0, r0);
+    oz3_produce_chunk<NS, LMAX, PASS, 0, DBG>(tmA, tmT, smem0, full0, empty0, ph_empty, c_begin + kc * OZ3_BK, j0, r0, hintA, hintT);
     if (kc + 1 < kchunks)
-      oz3_produce_chunk<NS, LMAX, PASS, 1, DBG>(tmA, tmT, smem0, full0, empty0, ph_empty, c_begin + (kc + 1) * OZ3_BK, j0, r0);
+      oz3_produce_chunk<NS, LMAX, PASS, 1, DBG>(tmA, tmT, smem0, full0, empty0, ph_empty, c_begin + (kc + 1) * OZ3_BK, j0, r0, hintA, hintT);
   }
 }
 template <int NS, int LMAX, int PASS, int DBG>
@@ -250,9 +255,9 @@ ozaki_i8_gemm_v3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     uint32_t ph_empty = 0xffffffffu;                          // first wait on every slot passes
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
       const Oz3Tile x = oz3_tile(t, nN, nJ, p);
-      oz3_produce_pass<NS, LMAX, 0, DBG>(&tmA, &tmT, smem0, full0, empty0, ph_empty, x.c_begin, x.kchunks, x.j0, x.r0);
+      oz3_produce_pass<NS, LMAX, 0, DBG>(&tmA, &tmT, smem0, full0, empty0, ph_empty, x.c_begin, x.kchunks, x.j0, x.r0, p.hintA, p.hintT);
       if constexpr (Z::NPASS > 1)
-        oz3_produce_pass<NS, LMAX, 1, DBG>(&tmA, &tmT, smem0, full0, empty0, ph_empty, x.c_begin, x.kchunks, x.j0, x.r0);
+        oz3_produce_pass<NS, LMAX, 1, DBG>(&tmA, &tmT, smem0, full0, empty0, ph_empty, x.c_begin, x.kchunks, x.j0, x.r0, p.hintA, p.hintT);
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================

@@ -255,13 +255,19 @@ class Engine:
         return int(idx.value), float(val.value)
 
     # -- Adam loop -----------------------------------------------------------------------------------
+    OPTIMIZERS = {"adam": 0, "gd": 1, "momentum": 2}
+
     def adam_begin(self, prm: nat.AcqParams, X: np.ndarray, p_pending: int = 0, lr: float = 25e-3,
-                   beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8):
+                   beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8, method: str = "adam",
+                   momentum: float = 0.9):
+        """method: 'adam' (default), 'gd' or 'momentum' (lr * (t+1)^-0.7 decay, bayesian_optimization.py:405-412)."""
         X = nat.as_f64(X)
         S, q, d = X.shape
         self._adam_shape = (S, q, d)
         self._ck(self._lib.maf_adam_begin(self._ctx, C.byref(prm), S, q, int(p_pending), nat.ptr(X),
                                           float(lr), float(beta1), float(beta2), float(eps)))
+        if method != "adam":
+            self._ck(self._lib.maf_adam_set_method(self._ctx, self.OPTIMIZERS[method], float(momentum)))
 
     def adam_steps(self, z_steps, want_trace: bool = False, steps: Optional[int] = None):
         """z_steps[steps][M][q]; for q == 1 pass z_steps=None and `steps` (closed-form loss)."""

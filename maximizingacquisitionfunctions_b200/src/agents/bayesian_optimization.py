@@ -8,7 +8,7 @@ the trainable candidate sets.  ``sess`` arguments are accepted and ignored.
 
 Supported inner optimisers: ``_optimize_inputs_sgd`` (TF-1 Adam + clip, on the device),
 ``_optimize_inputs_scipy`` (joint L-BFGS-B, SciPy on the host driving device value+gradient),
-``_optimize_inputs_random``.  The derivative-free alternatives of the reference (halving, CMA-ES,
+``_optimize_inputs_random``, ``_optimize_inputs_halving``.  The other derivative-free alternatives of the reference (CMA-ES,
 NLopt) are outside the accelerated path.
 """
 import logging
@@ -245,9 +245,12 @@ class bayesian_optimization(search_agent):
             raise TypeError("Candidates must be a trainable <pool_loss> handle")
         config = self.update_dict(self.configs["sgd"], config, as_copy=True)
         method = config.get("method", "train.AdamOptimizer")
-        if method.split(".")[-1] != "AdamOptimizer":
-            raise NotImplementedError("only train.AdamOptimizer runs on the device (got {})".format(method))
-        lr = config.get("learning_rate", 25e-3)
+        kinds = {"AdamOptimizer": "adam", "GradientDescentOptimizer": "gd", "MomentumOptimizer": "momentum"}
+        if method.split(".")[-1] not in kinds:
+            raise NotImplementedError("optimizers on the device: {} (got {})".format(sorted(kinds), method))
+        kind = kinds[method.split(".")[-1]]
+        # Adam: lr 25e-3; GradientDescent / Momentum(0.9): lr 1.0 decayed by (global_step + 1)^-0.7 (:405-415)
+        lr = config.get("learning_rate", 25e-3 if kind == "adam" else 1.0)
         step_limit = config.get("step_limit", 1000)
         batch_size = config.get("batch_size", 128)
         use_averaging = config.get("use_averaging", False)
@@ -259,7 +262,7 @@ class bayesian_optimization(search_agent):
             raise NotImplementedError("Adam on fantasy-padded observations; use the L-BFGS-B subroutine (q == 1 default)")
         eng = handle.model.bind(handle.inputs_old, handle.outputs_old)
         prm = handle.loss_fn.acq_params(outputs_old=handle.outputs_old, **handle.loss_kwargs)
-        eng.adam_begin(prm, pools, p_pending=p, lr=lr)     # resets slots + step (:444-451)
+        eng.adam_begin(prm, pools, p_pending=p, lr=lr, method=kind, momentum=0.9)     # resets slots + step (:444-451)
 
         start_time = self.timer()
         if block is None:
@@ -336,8 +339,115 @@ class bayesian_optimization(search_agent):
         logger.info("ScipyOptimize evaluated {:d} losses in {:.3e}s".format(len(loss_seq), self.timer() - start_time))
         return loss_seq
 
-    def _optimize_inputs_halving(self, *args, **kwargs):
-        raise NotImplementedError("successive halving is outside the accelerated path (SURVEY 2, row 1)")
+    # ------------------------------------------------------------------------------------------
+    # successive halving (:697-935), non-random-feature path
+    # ------------------------------------------------------------------------------------------
+    def _optimize_inputs_halving(self, sess, inputs_new, losses_op, feed_dict=None, config=None, time_limit=np.inf,
+                                 options=None, batch_generator=None, parallelism=None, nodes=None, extras=None,
+                                 loss_fn=None, cost_history=None, **kwargs):
+        """Random options are scored with a growing number of base samples (128, 256, ... num_fantasies); after every
+        round the better half survives.  Round 0 runs the full path (posterior + Monte-Carlo) on the device and
+        keeps the posterior moments of every option; later rounds re-use them (``maf_mc_from_moments``: Cholesky
+        + sampling only, the reference's ``loss_kwargs={'posteriors': ...}`` graph, :835-848) with the NEW base
+        samples only and fold the estimates together weighted by their sample counts (:872-883)."""
+        if not isinstance(inputs_new, pool_loss):
+            raise TypeError("Candidates must be a trainable <pool_loss> handle")
+        if loss_fn is None:
+            loss_fn = self.loss_fn
+        if getattr(loss_fn, "use_rand_features", False):
+            raise NotImplementedError("random-feature sample paths are outside the accelerated path (SURVEY 2)")
+        if cost_history is None:
+            if not hasattr(self, "halving_costs"):
+                self.halving_costs = dict()
+            cost_history = self.halving_costs
+        feed_dict = dict() if feed_dict is None else dict(feed_dict)
+        config = self.update_dict(self.configs["halving"], config, as_copy=True)
+        handle = inputs_new
+        shard_shape = list(handle.shape)
+        shard_size = shard_shape[0]
+        num_pending = 0 if handle.inputs_pend is None else len(handle.inputs_pend)
+        num_suggest = shard_shape[-2]
+        if parallelism is None:
+            parallelism = num_pending + num_suggest
+
+        max_samples = config.get("max_samples", self.loss_fn.num_fantasies)
+        expon_step = config.get("expon_step", 1)
+        if parallelism > 1:
+            lower, upper = int(np.log2(config.get("min_samples", 128))), int(np.log2(max_samples))
+            if expon_step < 0:
+                expon_step = upper - lower
+            log_sizes = list(range(lower, upper + 1, max(int(expon_step), 1)))
+            log_sizes[-1] = upper
+            batch_sizes = [int(2 ** ls) for ls in log_sizes]
+        else:
+            batch_sizes = [max_samples]                     # closed form: a single round
+
+        try:                                               # allocate_time (:764-783)
+            allocs = [cost_history[(num_pending, num_suggest, b)] / b for b in batch_sizes]
+        except KeyError:
+            allocs = np.ones(len(batch_sizes))
+        time_allocs = np.multiply(time_limit / np.sum(allocs), allocs)
+
+        eng = handle.model.bind(handle.inputs_old, handle.outputs_old)
+        prm = handle.loss_fn.acq_params(outputs_old=handle.outputs_old, **handle.loss_kwargs)
+
+        def run_random_search(time_limit, eval_limit, options, posteriors, rvs):
+            inputs_seq, loss_seq, kept, costs = [], [], [], []
+            counter, run_start = 0, self.timer()
+            while counter + shard_size <= eval_limit:
+                tic = self.timer()
+                if self.timer() - run_start > time_limit:
+                    break
+                if options is None:
+                    inputs_seq.append(self.rng.rand(*shard_shape))
+                    out = handle.evaluate({"fantasy_rvs": rvs}, inputs_new=inputs_seq[-1])
+                    losses_k, ex = out[0], out[1]
+                    kept.append(ex)
+                else:
+                    sl = slice(counter, counter + shard_size)
+                    inputs_seq.append(options[sl])
+                    mu, cov = posteriors[0][sl], posteriors[1][sl]
+                    losses_k, _, _, chol = eng.mc_from_moments(prm, mu, cov, np.asarray(rvs, dtype=np.float64))
+                    kept.append((mu, cov, chol))
+                loss_seq.append(np.ravel(losses_k))
+                counter += shard_size
+                costs.append(self.timer() - tic)
+            post = None
+            if kept and kept[0] is not None and kept[0][0] is not None:
+                post = [np.vstack([np.asarray(k[i]) for k in kept]) if kept[0][i] is not None else None for i in range(3)]
+            return np.vstack(inputs_seq), np.hstack(loss_seq), costs, post
+
+        losses, posteriors, counters, bsize_prev = None, None, [], 0
+        start_time = self.timer()
+        for k, (batch_size, time_alloc) in enumerate(zip(batch_sizes, time_allocs)):
+            feed_dict.update(batch_generator(batch_size - bsize_prev))
+            rvs = feed_dict.get("fantasy_rvs", None)
+            eval_limit = config["eval_limit"] if options is None else len(options)
+            options, losses_new, costs, posteriors = run_random_search(time_alloc, eval_limit, options, posteriors, rvs)
+            cost_history[(num_pending, num_suggest, batch_size)] = float(np.mean(costs)) if costs else 0.0
+            if losses is None:
+                losses = losses_new
+            else:
+                num = len(losses_new)
+                w_old, w_new = bsize_prev, batch_size - bsize_prev
+                losses = (w_old * losses[:num] + w_new * losses_new) / (w_old + w_new)
+            bsize_prev = batch_size
+            num_options = len(options)
+            counters.append(num_options)
+            if k + 1 < len(batch_sizes):
+                if time_limit == np.inf and num_options > shard_size:
+                    top_k = max(shard_size, num_options // (2 ** int(expon_step)))
+                    leaders = np.argpartition(losses, top_k - 1)[:top_k]
+                    indices = leaders[np.argsort(losses[leaders])]
+                else:
+                    indices = np.argsort(losses)
+                options, losses = options[indices], losses[indices]
+                posteriors = [None if t is None else t[indices] for t in posteriors]
+
+        argmins = np.argpartition(losses, shard_size - 1)[:shard_size]
+        handle.assign(options[argmins])
+        logger.info("Successive Halving evaluated {:d} options in {:.3e}s".format(counters[0], self.timer() - start_time))
+        return losses
 
     def _optimize_inputs_cmaes(self, *args, **kwargs):
         raise NotImplementedError("CMA-ES is outside the accelerated path (SURVEY 2, row 1)")

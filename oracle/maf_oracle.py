@@ -492,6 +492,22 @@ def adam_step(x: np.ndarray, g: np.ndarray, st: AdamState) -> np.ndarray:
     return np.clip(x, 0.0, 1.0)
 
 
+def sgd_run(ts: TrainState, acq: Acq, X_new: np.ndarray, z_steps, X_pend=None, lr=1.0, momentum=0.0):
+    """tf.train.GradientDescentOptimizer / MomentumOptimizer(., 0.9) branches of _optimize_inputs_sgd
+    (src/agents/bayesian_optimization.py:405-412): learning rate lr * (global_step + 1)^-0.7 with global_step
+    counting from 0; Momentum: accum = momentum * accum + g, x -= lr_t * accum; then clip_by_value(x, 0, 1)."""
+    x = np.array(X_new, dtype=np.float64)
+    accum = np.zeros_like(x)
+    trace = []
+    for t, z in enumerate(z_steps):
+        losses, g = value_and_grad(ts, acq, x, z, X_pend)
+        trace.append(losses)
+        lr_t = lr * float(t + 1) ** -0.7
+        accum = momentum * accum + g
+        x = np.clip(x - lr_t * accum, 0.0, 1.0)
+    return x, np.asarray(trace)
+
+
 def adam_run(ts: TrainState, acq: Acq, X_new: np.ndarray, z_steps, X_pend=None,
              lr=25e-3):
     """HOT LOOP B (:462-469): fresh z per step, value+grad, Adam, clip."""

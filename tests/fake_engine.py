@@ -127,10 +127,12 @@ class FakeEngine:
         i = int(np.nanargmin(self._loss))
         return i, float(self._loss[i])
 
-    def adam_begin(self, prm, X, p_pending=0, lr=25e-3, beta1=0.9, beta2=0.999, eps=1e-8):
+    def adam_begin(self, prm, X, p_pending=0, lr=25e-3, beta1=0.9, beta2=0.999, eps=1e-8, method="adam", momentum=0.9):
         self._ax = np.array(X, dtype=np.float64)
         self._ap, self._aprm = p_pending, prm
         self._ast = orc.adam_init(self._ax[:, p_pending:].shape, lr=lr, beta1=beta1, beta2=beta2, eps=eps)
+        self._amethod, self._amom, self._alr, self._at = method, (momentum if method == "momentum" else 0.0), lr, 0
+        self._aacc = np.zeros_like(self._ax[:, p_pending:])
 
     def adam_steps(self, z_steps, want_trace=False, steps=None):
         trace = []
@@ -140,7 +142,12 @@ class FakeEngine:
         for z in z_steps:
             losses, g = self.value_and_grad(self._aprm, self._ax, z, p_pending=p)
             trace.append(losses)
-            self._ax[:, p:] = orc.adam_step(self._ax[:, p:], g, self._ast)
+            if self._amethod == "adam":
+                self._ax[:, p:] = orc.adam_step(self._ax[:, p:], g, self._ast)
+            else:                                         # same update as oracle.sgd_run
+                self._aacc = self._amom * self._aacc + g
+                self._ax[:, p:] = np.clip(self._ax[:, p:] - self._alr * float(self._at + 1) ** -0.7 * self._aacc, 0.0, 1.0)
+            self._at += 1
         return np.asarray(trace) if want_trace else None
 
     def adam_peek(self):

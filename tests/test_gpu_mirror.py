@@ -115,3 +115,20 @@ def test_incremental_greedy_matches_oracle_engine():
         return picks, Yf
     (pg, yg), (pr, yr) = run_both(flow)
     assert np.abs(pg - pr).max() < 1e-5 and np.abs(yg - yr).max() < 1e-6
+
+
+def test_successive_halving_and_gd_variants():
+    """_optimize_inputs_halving (cached posterior moments + maf_mc_from_moments) and the GradientDescent / Momentum
+    branches of _optimize_inputs_sgd, CUDA engine vs the oracle-backed engine on identical host-RNG streams."""
+    def flow():
+        agent, X0, Y0 = build(3, 40, "hartmann3", 5, "simple_regret")
+        agent.loss_fn.num_fantasies = 64
+        xh, lh = agent.suggest_inputs(2, X0, Y0, None, num_options=16, subroutine=agent._optimize_inputs_halving,
+                                      config={"eval_limit": 128, "min_samples": 16})
+        xm, lm = agent.suggest_inputs(2, X0, Y0, None, num_to_optimize=8, subroutine=agent._optimize_inputs_sgd,
+                                      config={"step_limit": 6, "batch_size": 32, "method": "train.MomentumOptimizer",
+                                              "learning_rate": 0.05})
+        return xh, lh, xm, lm
+    (xhg, lhg, xmg, lmg), (xhr, lhr, xmr, lmr) = run_both(flow)
+    assert np.abs(xhg - xhr).max() < 1e-9 and abs(lhg - lhr) < 1e-8 * max(1.0, abs(lhr))
+    assert np.abs(xmg - xmr).max() < 1e-6 and abs(lmg - lmr) < 1e-8 * max(1.0, abs(lmr))

@@ -224,6 +224,22 @@ def test_adam_loop_vs_oracle(eng):
     assert xg.min() >= 0.0 and xg.max() <= 1.0
 
 
+@pytest.mark.parametrize("method,momentum", [("gd", 0.0), ("momentum", 0.9)])
+def test_gd_and_momentum_loops_vs_oracle(eng, method, momentum):
+    """GradientDescent / Momentum(0.9) branches of _optimize_inputs_sgd (:405-412), lr (t+1)^-0.7 decay."""
+    n, d, q, S, M, steps = 48, 3, 2, 16, 64, 6
+    ts, X0, y0, X, z = setup_problem(eng, n, d, q, S, M, seed=14)
+    zs = np.random.RandomState(98).randn(steps, M, q)
+    xo, tro = orc.sgd_run(ts, orc.Acq("sr"), X, zs, lr=0.05, momentum=momentum)
+    eng.adam_begin(prm("sr"), X, lr=0.05, method=method, momentum=momentum)
+    trg = eng.adam_steps(zs[:2], want_trace=True)
+    trg = np.concatenate([trg, eng.adam_steps(zs[2:], want_trace=True)])     # global_step carries over calls
+    xg = eng.adam_end()
+    assert relerr(trg, tro) < 1e-7
+    assert np.abs(xg - xo).max() < 1e-7
+    assert xg.min() >= 0.0 and xg.max() <= 1.0
+
+
 def test_errors_are_loud(eng):
     from maximizingacquisitionfunctions_b200.engine import MafError
     setup_problem(eng, 32, 2, 2, 4, 8)

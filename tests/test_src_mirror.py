@@ -98,6 +98,54 @@ def test_sgd_matches_oracle_adam_trajectory():
     assert np.allclose(loss_seq, tro.ravel(), atol=1e-12)
 
 
+@pytest.mark.parametrize("method,momentum", [("train.GradientDescentOptimizer", 0.0), ("train.MomentumOptimizer", 0.9)])
+def test_sgd_gd_and_momentum_variants(method, momentum):
+    """config['method'] other than Adam: lr * (global_step + 1)^-0.7 (bayesian_optimization.py:405-412)."""
+    agent, X0, Y0 = make()
+    starts = np.random.RandomState(9).rand(5, 2, 2)
+    s0 = int(agent.loss_fn.seed)
+    nodes, loss_seq = agent.optimize_inputs(None, starts, X0, Y0, subroutine=agent._optimize_inputs_sgd,
+                                            config={"step_limit": 4, "batch_size": 16, "method": method, "learning_rate": 0.1})
+    zs = [np.random.RandomState(s0 + 1 + k).randn(16, 2) for k in range(1, 5)]
+    gp = orc.GP(log_lenscales=math.log(math.sqrt(2) / 4), log_amplitude=0.0, log_noise=math.log(1e-3), mean=0.0)
+    xo, tro = orc.sgd_run(orc.prepare_train(gp, X0, Y0), orc.Acq("ei"), starts, zs, lr=0.1, momentum=momentum)
+    assert np.allclose(nodes["inputs_new"].value, xo, atol=1e-12)
+    assert np.allclose(loss_seq, tro.ravel(), atol=1e-12)
+
+
+def test_successive_halving_rounds_fold_sample_sets():
+    """_optimize_inputs_halving (:697-935): round k scores the survivors with the NEW base samples only, re-using the
+    cached posterior moments, and folds the estimates weighted by their sample counts -- so a survivor's final
+    loss is the plain MC estimate over all base samples drawn so far."""
+    agent, X0, Y0 = make(num_fantasies=32)
+    drawn = []
+
+    def batch_generator(batch_size):
+        z = np.random.RandomState(100 + len(drawn)).randn(batch_size, 2)
+        drawn.append(z)
+        return {"fantasy_rvs": z}
+
+    starts = np.random.RandomState(4).rand(8, 2, 2)                       # shard of 8 options, q = 2
+    nodes, losses_ = agent.optimize_inputs(None, starts, X0, Y0, subroutine=agent._optimize_inputs_halving,
+                                           batch_generator=batch_generator,
+                                           config={"eval_limit": 64, "min_samples": 8, "expon_step": 1})
+    assert [len(z) for z in drawn] == [8, 8, 16]                          # 8 -> 16 -> 32 samples in total
+    best = nodes["inputs_new"].value
+    assert best.shape == (8, 2, 2) and best.min() >= 0 and best.max() <= 1
+    assert len(losses_) == 16                                             # 64 -> 32 -> 16 survivors
+    # the 8 selected options carry the 8 smallest folded losses, each equal to the estimate over all 32 samples
+    direct = agent.loss_fn(best, X0, Y0, fantasy_rvs=np.vstack(drawn), model=agent.model)[0]
+    assert np.allclose(np.sort(direct), np.sort(losses_)[:8], atol=1e-12)
+    assert (0, 2, 8) in agent.halving_costs and (0, 2, 32) in agent.halving_costs
+
+
+def test_successive_halving_closed_form_single_round():
+    agent, X0, Y0 = make()
+    X, l = agent.suggest_inputs(1, X0, Y0, None, num_options=16, subroutine=agent._optimize_inputs_halving,
+                                config={"eval_limit": 64})
+    assert X.shape == (1, 2) and np.isfinite(l)
+
+
 def test_greedy_pending_only_last_row_moves():
     agent, X0, Y0 = make()
     pend = np.random.RandomState(2).rand(2, 2)
