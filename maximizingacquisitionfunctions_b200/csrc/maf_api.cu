@@ -76,8 +76,9 @@ struct maf_ctx {
   bool i8_ready = false;           // factor planes built for the current training set
   int oz_ns = 7, oz_lmax = 8;
   int oz_fuse = 1;                 // bit 0: cross-covariance, bit 1: Vbar written straight to digit planes (MAF_OZ_FUSE)
-  int oz_sj = 8;                   // super-row height of the persistent tile order (MAF_OZ_SJ)
+  int oz_sj = 4;                   // super-row height of the persistent tile order (MAF_OZ_SJ)
   int oz_hint_a = 0, oz_hint_t = 0; // L2 policy of the A / T plane loads: 0 normal, 1 evict-first, 2 evict-last (MAF_OZ_HINTS=at)
+  int oz_pf = 0;                   // L2 prefetch of plane tiles two k-chunks ahead (MAF_OZ_PF)
   int oz_dbg = 0;                  // MAF_OZ_DBG diagnostics (results invalid)
   int oz_variant = 3;              // 1: whole-chunk stages of 32-byte boxes; 2: plane-tile ring of 128-byte lines
   Buf ozA, ozTL, ozTU;             // digit planes (int8, sized in doubles): candidates / Linv / LinvT
@@ -354,7 +355,7 @@ static int launch_i8gemm(maf_ctx* ctx, int slot, int J, int N, int K, const Buf&
   if (oz_make_tmap(ctx, &tmA, (const int8_t*)Ap.p, J, K, ns, bk) || oz_make_tmap(ctx, &tmT, (const int8_t*)Tp.p, N, K, ns, bk))
     return 1;
   static const unsigned long long pol[3] = {OZ3_L2_NORMAL, OZ3_L2_EVICT_FIRST, OZ3_L2_EVICT_LAST};
-  OzParams prm{K, ns, lmax, tri, ldc, ctx->oz_sj, pol[ctx->oz_hint_a % 3], pol[ctx->oz_hint_t % 3], ctx->oz_dbg};
+  OzParams prm{K, ns, lmax, tri, ldc, ctx->oz_sj, pol[ctx->oz_hint_a % 3], pol[ctx->oz_hint_t % 3], ctx->oz_pf, ctx->oz_dbg};
   dim3 grid(N / OZ_BN, J / OZ_BM);
   static int num_sms = 0;
   if (!num_sms) CK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, ctx->device));
@@ -427,6 +428,7 @@ extern "C" int maf_create(int device, int dtype, maf_ctx** out) {
     if (h[0]) ctx->oz_hint_a = h[0] - '0';
     if (h[0] && h[1]) ctx->oz_hint_t = h[1] - '0';
   }
+  if (const char* pf = getenv("MAF_OZ_PF")) ctx->oz_pf = atoi(pf);
   if (const char* sj = getenv("MAF_OZ_SJ")) ctx->oz_sj = atoi(sj) > 0 ? atoi(sj) : 1;
   CK(cudaMalloc((void**)&ctx->d_argmin_val, sizeof(double)));
   CK(cudaMalloc((void**)&ctx->d_argmin_idx, sizeof(long long)));

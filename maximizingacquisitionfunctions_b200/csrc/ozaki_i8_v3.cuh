@@ -68,11 +68,13 @@ __device__ __forceinline__ void oz3_mma(uint32_t d_tmem, uint32_t alo, uint32_t 
 __device__ __forceinline__ void oz3_commit(uint32_t bar_addr) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr) : "memory");
 }
+// try_wait with a suspend-time hint (as CUTLASS' ClusterBarrier::wait): a waiting thread sleeps in hardware until the
+// phase completes instead of re-polling shared memory; 512 epilogue threads otherwise poll acc_full for a whole pass.
 __device__ __forceinline__ void oz3_wait(uint32_t bar_addr, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred P1;\n\tOZ3_WAIT:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-      "@P1 bra OZ3_DONE;\n\tbra OZ3_WAIT;\n\tOZ3_DONE:\n\t}" ::"r"(bar_addr), "r"(parity)
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
+      "@P1 bra OZ3_DONE;\n\tbra OZ3_WAIT;\n\tOZ3_DONE:\n\t}" ::"r"(bar_addr), "r"(parity), "r"(0x989680u)
       : "memory");
 }
 __device__ __forceinline__ void oz3_arrive(uint32_t bar_addr) {
@@ -91,12 +93,29 @@ __device__ __forceinline__ void oz3_load(uint32_t dst, const CUtensorMap* tm, ui
       : "memory");
 }
 
+// TMA prefetch of one plane tile into L2 (no shared memory, no barrier): issued OZ3_PF k-chunks ahead of the load so
+// that first-touch (DRAM) latency is not exposed when a k-chunk of the first pass lasts only 1.3 us.
+#define OZ3_PF 2
+__device__ __forceinline__ void oz3_prefetch(const CUtensorMap* tm, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(c0),
+               "r"(c1), "r"(c2)
+               : "memory");
+}
+
 // ---- one k-chunk of one pass: producer side -----------------------------------------------------
 template <int NS, int LMAX, int PASS, int PAR, int DBG>
 __device__ __forceinline__ void oz3_produce_chunk(const CUtensorMap* tmA, const CUtensorMap* tmT, uint32_t smem0,
                                                   uint32_t full0, uint32_t empty0, uint32_t& ph_empty, int c, int j0,
-                                                  int r0, uint64_t hintA, uint64_t hintT) {
+                                                  int r0, uint64_t hintA, uint64_t hintT, int c_pf) {
   using Z = Oz3<NS, LMAX>;
+  if (c_pf >= 0 && oz_elect_one()) {
+#pragma unroll
+    for (int i = 1; i <= Z::smax(PASS); ++i) {
+      oz3_prefetch(tmA, c_pf, j0, i - 1);
+      oz3_prefetch(tmT, c_pf, r0, i - 1);
+    }
+  }
+  __syncwarp();
 #pragma unroll
   for (int i = 1; i <= Z::smax(PASS); ++i) {
     // T planes entering the window at this step (all of it at i == 1), then A_i
@@ -174,11 +193,13 @@ __device__ __forceinline__ void oz3_issue_chunk(uint32_t desc0 /* (smem0 >> 4) |
 template <int NS, int LMAX, int PASS, int DBG>
 __device__ __forceinline__ void oz3_produce_pass(const CUtensorMap* tmA, const CUtensorMap* tmT, uint32_t smem0,
                                                  uint32_t full0, uint32_t empty0, uint32_t& ph_empty, int c_begin,
-                                                 int kchunks, int j0, int r0, uint64_t hintA, uint64_t hintT) {
+                                                 int kchunks, int j0, int r0, uint64_t hintA, uint64_t hintT, int pf) {
   for (int kc = 0; kc < kchunks; kc += 2) {
-    oz3_produce_chunk<NS, LMAX, PASS, 0, DBG>(tmA, tmT, smem0, full0, empty0, ph_empty, c_begin + kc * OZ3_BK, j0, r0, hintA, hintT);
+    oz3_produce_chunk<NS, LMAX, PASS, 0, DBG>(tmA, tmT, smem0, full0, empty0, ph_empty, c_begin + kc * OZ3_BK, j0, r0, hintA, hintT,
+                                           (pf && kc + OZ3_PF < kchunks) ? c_begin + (kc + OZ3_PF) * OZ3_BK : -1);
     if (kc + 1 < kchunks)
-      oz3_produce_chunk<NS, LMAX, PASS, 1, DBG>(tmA, tmT, smem0, full0, empty0, ph_empty, c_begin + (kc + 1) * OZ3_BK, j0, r0, hintA, hintT);
+      oz3_produce_chunk<NS, LMAX, PASS, 1, DBG>(tmA, tmT, smem0, full0, empty0, ph_empty, c_begin + (kc + 1) * OZ3_BK, j0, r0,
+                                             hintA, hintT, (pf && kc + 1 + OZ3_PF < kchunks) ? c_begin + (kc + 1 + OZ3_PF) * OZ3_BK : -1);
   }
 }
 template <int NS, int LMAX, int PASS, int DBG>
@@ -255,9 +276,9 @@ ozaki_i8_gemm_v3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     uint32_t ph_empty = 0xffffffffu;                          // first wait on every slot passes
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
       const Oz3Tile x = oz3_tile(t, nN, nJ, p);
-      oz3_produce_pass<NS, LMAX, 0, DBG>(&tmA, &tmT, smem0, full0, empty0, ph_empty, x.c_begin, x.kchunks, x.j0, x.r0, p.hintA, p.hintT);
+      oz3_produce_pass<NS, LMAX, 0, DBG>(&tmA, &tmT, smem0, full0, empty0, ph_empty, x.c_begin, x.kchunks, x.j0, x.r0, p.hintA, p.hintT, p.pf);
       if constexpr (Z::NPASS > 1)
-        oz3_produce_pass<NS, LMAX, 1, DBG>(&tmA, &tmT, smem0, full0, empty0, ph_empty, x.c_begin, x.kchunks, x.j0, x.r0, p.hintA, p.hintT);
+        oz3_produce_pass<NS, LMAX, 1, DBG>(&tmA, &tmT, smem0, full0, empty0, ph_empty, x.c_begin, x.kchunks, x.j0, x.r0, p.hintA, p.hintT, p.pf);
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
