@@ -302,6 +302,21 @@ def main():
     e2e = {"value": ws * S * q * M * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(hX.nbytes + hz.nbytes),
            "d2h_bytes_per_step": int(hloss.nbytes + hgrad.nbytes), "steps": e2e_steps}
 
+    # ---- Adam loop on the device (steps x S x q x M / time), fresh z per step, same S --------------
+    adam_steps = 2
+    zs = np.random.RandomState(w["seed"] + 7).randn(adam_steps, M, q)
+    eng.adam_begin(prm, X)
+    eng.adam_steps(zs[:1])                                  # warm-up step (buffers)
+    mdist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    eng.adam_steps(zs)
+    torch.cuda.synchronize()
+    adam_s = mdist.max_over_ranks(time.perf_counter() - t0)
+    eng.adam_end()
+    adam_loop = {"value": ws * S * q * M * adam_steps / adam_s, "unit": UNIT, "steps": adam_steps,
+                 "note": "maf_adam_steps: value+gradient, Adam update and clip per step on the device; z uploaded once per call"}
+
     # ---- CPU baseline (rank 0, N=1) ------------------------------------------------------------------
     cpu = None
     if rank == 0 and ws == 1 and not args.no_cpu_baseline:
@@ -322,7 +337,7 @@ def main():
                        "parallelism": "restarts sharded x%d, replicated training factor, one all-gather per step" % ws,
                        "l2_policy": "working set per chunk (K10 + V^T = %.1f GB) >> 126 MB L2; no flush needed" % (2 * min(S * q, 65536) * npad * 8 / 1e9),
                        "setup_s_not_timed": setup_s},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "adam_loop": adam_loop, "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     eng.close()
