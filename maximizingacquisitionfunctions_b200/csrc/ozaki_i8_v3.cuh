@@ -13,8 +13,8 @@
 //     instructions), so UTCIMMA / UTMALDG are issued straight from uniform registers;
 //   * within a k-chunk the pairs are walked by A plane i = 1..smax; the T planes A_i meets form a window
 //     [lo-i, hi-i] that slides down, each tile is released (tcgen05.commit) right after its last MMA and is
-//     refilled for the next k-chunk while the remaining pairs run.  In the first pass (levels 2..5) the window
-//     is anchored at T_1, so its T tiles are double-buffered by chunk parity in the slots the pass leaves idle;
+//     refilled for the next k-chunk while the remaining pairs run.  The short first pass (levels 2..4) is
+//     double-buffered by chunk parity (its k-chunk is shorter than a TMA round trip);
 //   * the epilogue recombines the <= 4 level accumulators exactly in int64 (one I2F per element instead of
 //     four), on 16 warps instead of 4;
 //   * the grid is persistent (one CTA per SM, static round-robin over a supertiled, heaviest-first tile list):
@@ -29,16 +29,22 @@
 
 template <int NS, int LMAX>
 struct Oz3 {
-  static constexpr int NPASS = (LMAX - 1 + 3) / 4;
+  // LMAX - 1 levels, 4 TMEM accumulators: the LAST pass takes 4 levels, the first one the remainder (FP64-grade:
+  // levels 2-4 = 6 products on planes 1-3, then levels 5-8 = 22 products on planes 1-7).  A k-chunk of the short
+  // first pass lasts only ~0.8 us, less than a TMA round trip, so ALL its tiles are double-buffered by chunk
+  // parity (4 smax(0) <= NSLOT); when that does not fit (single-pass configurations) only the T tiles are.
+  static constexpr int NLEV = LMAX - 1;
+  static constexpr int NPASS = (NLEV + 3) / 4;
+  static constexpr int N0 = NLEV - 4 * (NPASS - 1);           // levels of the first pass
   static constexpr int NSLOT = (2 * NS > 12) ? 2 * NS : 12;
   static constexpr int SMEM_BYTES = NSLOT * OZ3_TILE_BYTES + 1024;
-  __host__ __device__ static constexpr int lo(int pass) { return 2 + 4 * pass; }
-  __host__ __device__ static constexpr int hi(int pass) { return (lo(pass) + 3 < LMAX) ? lo(pass) + 3 : LMAX; }
+  __host__ __device__ static constexpr int lo(int pass) { return pass == 0 ? 2 : 2 + N0 + 4 * (pass - 1); }
+  __host__ __device__ static constexpr int hi(int pass) { return pass == 0 ? 2 + N0 - 1 : lo(pass) + 3; }
   __host__ __device__ static constexpr int smax(int pass) { return (NS < hi(pass) - 1) ? NS : hi(pass) - 1; }
   __host__ __device__ static constexpr int wlo(int pass, int i) { return (lo(pass) - i > 1) ? lo(pass) - i : 1; }
   __host__ __device__ static constexpr int whi(int pass, int i) { return (hi(pass) - i < NS) ? hi(pass) - i : NS; }
-  __host__ __device__ static constexpr int slotA(int i) { return i - 1; }
-  // second buffer of T plane ip in pass 0: taken from the slots pass 0 leaves idle
+  static constexpr bool DBL_ALL = (4 * smax(0) <= NSLOT);     // first pass: every tile has two buffers
+  // second buffer of T plane ip in pass 0 when only the T tiles are doubled: taken from the slots pass 0 leaves idle
   __host__ __device__ static constexpr int alt(int ip) {
     const int s0 = smax(0), nfree = NS - s0;
     int idx = ip - 1;
@@ -48,7 +54,11 @@ struct Oz3 {
     idx -= nfree;
     return 2 * NS + idx;
   }
+  __host__ __device__ static constexpr int slotA(int pass, int i, int par) {
+    return (pass == 0 && DBL_ALL) ? par * 2 * smax(0) + (i - 1) : i - 1;
+  }
   __host__ __device__ static constexpr int slotT(int pass, int ip, int par) {
+    if (pass == 0 && DBL_ALL) return par * 2 * smax(0) + smax(0) + (ip - 1);
     return (pass == 0 && par == 1) ? alt(ip) : NS + ip - 1;
   }
 };
@@ -133,7 +143,7 @@ __device__ __forceinline__ void oz3_produce_chunk(const CUtensorMap* tmA, const 
       }
     }
     {
-      const int s = Z::slotA(i);
+      const int s = Z::slotA(PASS, i, PAR);
       oz3_wait(empty0 + 8u * s, (ph_empty >> s) & 1u);
       ph_empty ^= 1u << s;
       if (oz_elect_one()) {
@@ -161,13 +171,13 @@ __device__ __forceinline__ void oz3_issue_chunk(uint32_t desc0 /* (smem0 >> 4) |
       }
     }
     {
-      const int s = Z::slotA(i);
+      const int s = Z::slotA(PASS, i, PAR);
       oz3_wait(full0 + 8u * s, (ph_full >> s) & 1u);
       ph_full ^= 1u << s;
     }
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     if (oz_elect_one()) {
-      const uint32_t alo = desc0 + (uint32_t)(Z::slotA(i) * (OZ3_TILE_BYTES >> 4));
+      const uint32_t alo = desc0 + (uint32_t)(Z::slotA(PASS, i, PAR) * (OZ3_TILE_BYTES >> 4));
 #pragma unroll
       for (int ip = Z::wlo(PASS, i); ip <= Z::whi(PASS, i); ++ip) {
         const int l = i + ip;
@@ -178,7 +188,7 @@ __device__ __forceinline__ void oz3_issue_chunk(uint32_t desc0 /* (smem0 >> 4) |
         for (int k = 0; k < OZ3_BK / 32; ++k)
           if (!(DBG & 1)) oz3_mma(d_tmem, alo + 2u * k, blo + 2u * k, idesc, (level_start && k == 0) ? not_first : 1u);
       }
-      oz3_commit(empty0 + 8u * Z::slotA(i));
+      oz3_commit(empty0 + 8u * Z::slotA(PASS, i, PAR));
       if (i < Z::smax(PASS)) {
         if (Z::hi(PASS) - i <= NS) oz3_commit(empty0 + 8u * Z::slotT(PASS, Z::hi(PASS) - i, PAR));
       } else {
@@ -209,6 +219,16 @@ __device__ __forceinline__ void oz3_issue_pass(uint32_t desc0, uint32_t full0, u
     oz3_issue_chunk<NS, LMAX, PASS, 0, DBG>(desc0, full0, empty0, ph_full, tbase, idesc, kc > 0 ? 1u : 0u);
     if (kc + 1 < kchunks) oz3_issue_chunk<NS, LMAX, PASS, 1, DBG>(desc0, full0, empty0, ph_full, tbase, idesc, 1u);
   }
+}
+
+// int64 -> double (round to nearest, as I2F.F64.S64) from the two 32-bit halves with the 2^52 exponent trick: two
+// LOPs, two DADDs and one DFMA on the full-rate FP64 pipe instead of one slow 64-bit conversion per element.
+__device__ __forceinline__ double oz3_ll2double(long long a) {
+  const unsigned lo = (unsigned)a;
+  const int hi = (int)(a >> 32);
+  const double dlo = __hiloint2double(0x43300000, (int)lo) - 4503599627370496.0;                        // 2^52 + lo
+  const double dhi = __hiloint2double(0x43300000, hi ^ (int)0x80000000) - 4503601774854144.0;           // 2^52 + 2^31 + hi
+  return fma(dhi, 4294967296.0, dlo);
 }
 
 // Tile order of the persistent grid.  Tiles are grouped in super-rows of p.sj row blocks (the A planes of a
@@ -256,7 +276,7 @@ ozaki_i8_gemm_v3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       oz_mbar_init(&empty_bar[s], 1);
     }
     oz_mbar_init(&acc_full, 1);
-    oz_mbar_init(&acc_empty, OZ3_THREADS - 64);
+    oz_mbar_init(&acc_empty, (OZ3_THREADS - 64) / 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmT)) : "memory");
@@ -319,9 +339,27 @@ ozaki_i8_gemm_v3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     const int part = (warp - 2) >> 2;                         // columns [CW part, +CW)
     const int fr = lane >> 2, fc = (lane & 3) * 2;            // fragment row / column of this lane
     const uint32_t accf = oz_smem_u32(&acc_full);
+    constexpr int NG = CW / 16;                               // 16-column groups per warp
     uint32_t g = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
       const Oz3Tile x = oz3_tile(t, nN, nJ, p);
+      // row / column scales of this lane's fragment positions: fetched while the MMAs of the tile run
+      double sa[2][2];
+      double2 sc[NG][2];
+      double* crow[2][2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const size_t j = (size_t)(x.j0 + quarter * 32 + h * 16 + fr + 8 * e);
+          sa[h][e] = __ldg(sA + j);
+          crow[h][e] = C + j * p.ldc + x.r0 + part * CW + fc;
+        }
+#pragma unroll
+      for (int gq = 0; gq < NG; ++gq)
+#pragma unroll
+        for (int n = 0; n < 2; ++n)
+          sc[gq][n] = __ldg(reinterpret_cast<const double2*>(sT + x.r0 + part * CW + gq * 16 + fc + 8 * n));
 #pragma unroll
       for (int pass = 0; pass < Z::NPASS; ++pass) {
         const int lo = Z::lo(pass), nl = Z::hi(pass) - Z::lo(pass) + 1;
@@ -330,58 +368,59 @@ ozaki_i8_gemm_v3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         oz3_wait(accf, g & 1u);
         ++g;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
-        for (int it = 0; it < ((DBG & 4) ? 0 : 2 * (CW / 16)); ++it) {
-          const int h = it & 1, cb = part * CW + (it >> 1) * 16;          // 16-row half, first column
-          const uint32_t taddr = tbase + ((uint32_t)(quarter * 32 + h * 16) << 16) + (uint32_t)cb;
-          uint32_t r[4][8];
+        if (!(DBG & 4)) {
 #pragma unroll
-          for (int tt = 0; tt < 4; ++tt) {
-            if (tt < nl) {
-              asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                           : "=r"(r[tt][0]), "=r"(r[tt][1]), "=r"(r[tt][2]), "=r"(r[tt][3]), "=r"(r[tt][4]), "=r"(r[tt][5]),
-                             "=r"(r[tt][6]), "=r"(r[tt][7])
-                           : "r"(taddr + (uint32_t)(tt * OZ_BN)));
-            }
-          }
-          const size_t ja = (size_t)(x.j0 + quarter * 32 + h * 16 + fr), jb = ja + 8;
-          const double wa = sA[ja] * w, wb = sA[jb] * w;
-          double* ca = C + ja * p.ldc + x.r0 + cb + fc;
-          double* cbp = C + jb * p.ldc + x.r0 + cb + fc;
-          const double* st = sT + x.r0 + cb + fc;
-          double2 sc[2], olda[2], oldb[2];
-#pragma unroll
-          for (int n = 0; n < 2; ++n) {
-            sc[n] = __ldg(reinterpret_cast<const double2*>(st + 8 * n));
+          for (int gq = 0; gq < NG; ++gq) {
+            // this 16-column group: both 16-row halves; the read-modify-write operands of pass > 0 are requested first
+            double2 old[2][2][2];
             if (pass > 0) {
-              olda[n] = *reinterpret_cast<const double2*>(ca + 8 * n);
-              oldb[n] = *reinterpret_cast<const double2*>(cbp + 8 * n);
-            }
-          }
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-          for (int n = 0; n < 2; ++n) {
-            double v[4];
+              for (int h = 0; h < 2; ++h)
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              long long acc = (long long)(int)r[0][4 * n + e];
+                for (int e = 0; e < 2; ++e)
 #pragma unroll
-              for (int tt = 1; tt < 4; ++tt)
-                if (tt < nl) acc = acc * 256 + (long long)(int)r[tt][4 * n + e];
-              v[e] = (double)acc * ((e & 1) ? sc[n].y : sc[n].x) * ((e & 2) ? wb : wa);
+                  for (int n = 0; n < 2; ++n) old[h][e][n] = *reinterpret_cast<const double2*>(crow[h][e] + gq * 16 + 8 * n);
             }
-            if (pass > 0) {
-              v[0] += olda[n].x;
-              v[1] += olda[n].y;
-              v[2] += oldb[n].x;
-              v[3] += oldb[n].y;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const uint32_t taddr = tbase + ((uint32_t)(quarter * 32 + h * 16) << 16) + (uint32_t)(part * CW + gq * 16);
+              uint32_t r[4][8];
+#pragma unroll
+              for (int tt = 0; tt < 4; ++tt) {
+                if (tt < nl) {
+                  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                               : "=r"(r[tt][0]), "=r"(r[tt][1]), "=r"(r[tt][2]), "=r"(r[tt][3]), "=r"(r[tt][4]),
+                                 "=r"(r[tt][5]), "=r"(r[tt][6]), "=r"(r[tt][7])
+                               : "r"(taddr + (uint32_t)(tt * OZ_BN)));
+                }
+              }
+              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+              for (int n = 0; n < 2; ++n) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {               // e: row fr (0) / fr + 8 (1); registers 4n + 2e + {0,1}
+                  double v[2];
+#pragma unroll
+                  for (int c = 0; c < 2; ++c) {
+                    long long acc = (long long)(int)r[0][4 * n + 2 * e + c];
+#pragma unroll
+                    for (int tt = 1; tt < 4; ++tt)
+                      if (tt < nl) acc = acc * 256 + (long long)(int)r[tt][4 * n + 2 * e + c];
+                    v[c] = oz3_ll2double(acc) * (c ? sc[gq][n].y : sc[gq][n].x) * (sa[h][e] * w);
+                  }
+                  if (pass > 0) {
+                    v[0] += old[h][e][n].x;
+                    v[1] += old[h][e][n].y;
+                  }
+                  *reinterpret_cast<double2*>(crow[h][e] + gq * 16 + 8 * n) = make_double2(v[0], v[1]);
+                }
+              }
             }
-            *reinterpret_cast<double2*>(ca + 8 * n) = make_double2(v[0], v[1]);
-            *reinterpret_cast<double2*>(cbp + 8 * n) = make_double2(v[2], v[3]);
           }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        oz_mbar_arrive(&acc_empty);
+        __syncwarp();
+        if (lane == 0) oz_mbar_arrive(&acc_empty);            // one arrival per epilogue warp
       }
     }
   }
