@@ -17,6 +17,7 @@
 #include "mc_kernels.cuh"
 #include "ozaki_i8.cuh"
 #include "ozaki_i8_v3.cuh"
+#include "ozaki_i8_v4.cuh"
 #include "posterior.cuh"
 
 #define MAF_VERSION_STR "maf_b200 0.1 (sm_100a, fp64 DMMA)"
@@ -80,7 +81,7 @@ struct maf_ctx {
   int oz_hint_a = 0, oz_hint_t = 0; // L2 policy of the A / T plane loads: 0 normal, 1 evict-first, 2 evict-last (MAF_OZ_HINTS=at)
   int oz_pf = 0;                   // L2 prefetch of plane tiles two k-chunks ahead (MAF_OZ_PF)
   int oz_dbg = 0;                  // MAF_OZ_DBG diagnostics (results invalid)
-  int oz_variant = 3;              // 1: whole-chunk stages of 32-byte boxes; 2: plane-tile ring of 128-byte lines
+  int oz_variant = 4;              // 1: generic kernel; 2: plane-tile ring; 3: static schedule, persistent; 4: 3 on CTA pairs (cta_group::2)
   Buf ozA, ozTL, ozTU;             // digit planes (int8, sized in doubles): candidates / Linv / LinvT
   Buf ozsA, ozsTL, ozsTU;          // row scales
   // fantasies (rank-4 observation sets)
@@ -294,7 +295,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int oz_make_tmap(maf_ctx* ctx, CUtensorMap* tm, const int8_t* base, int rows, int K, int ns, int bk) {
+static int oz_make_tmap(maf_ctx* ctx, CUtensorMap* tm, const int8_t* base, int rows, int K, int ns, int bk, int box_rows = 128) {
   static PFN_encodeTiled encode = nullptr;
   if (!encode) {
     void* fn = nullptr;
@@ -305,7 +306,7 @@ static int oz_make_tmap(maf_ctx* ctx, CUtensorMap* tm, const int8_t* base, int r
   }
   cuuint64_t gdim[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)ns};
   cuuint64_t gstr[2] = {(cuuint64_t)K, (cuuint64_t)K * (cuuint64_t)rows};
-  cuuint32_t box[3] = {(cuuint32_t)bk, 128, 1};
+  cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)base, gdim, gstr, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B,
@@ -341,6 +342,10 @@ static int launch_i8gemm(maf_ctx* ctx, int slot, int J, int N, int K, const Buf&
   CK(cudaFuncSetAttribute(ozaki_i8_gemm_v3_kernel<NS_, LM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, Oz3<NS_, LM_>::SMEM_BYTES))
     OZ3_ATTR(7, 8); OZ3_ATTR(6, 7); OZ3_ATTR(5, 6); OZ3_ATTR(4, 5); OZ3_ATTR(3, 4);
 #undef OZ3_ATTR
+#define OZ4_ATTR(NS_, LM_) \
+  CK(cudaFuncSetAttribute(ozaki_i8_gemm_v4_kernel<NS_, LM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, Oz4<NS_, LM_>::SMEM_BYTES))
+    OZ4_ATTR(7, 8); OZ4_ATTR(6, 7); OZ4_ATTR(5, 6); OZ4_ATTR(4, 5); OZ4_ATTR(3, 4);
+#undef OZ4_ATTR
 #ifdef MAF_OZ_DIAG
 #define OZ3_DATTR(D_) CK(cudaFuncSetAttribute(ozaki_i8_gemm_v3_kernel<7, 8, D_>, cudaFuncAttributeMaxDynamicSharedMemorySize, Oz3<7, 8>::SMEM_BYTES))
     OZ3_DATTR(1); OZ3_DATTR(2); OZ3_DATTR(3); OZ3_DATTR(4); OZ3_DATTR(5); OZ3_DATTR(6); OZ3_DATTR(7);
@@ -349,10 +354,13 @@ static int launch_i8gemm(maf_ctx* ctx, int slot, int J, int N, int K, const Buf&
     attr = true;
   }
   const bool v3ok = lmax == ns + 1 && ns >= 3 && ns <= 7;
-  const int variant = (ctx->oz_variant == 3 && !v3ok) ? 1 : ctx->oz_variant;
+  int variant = ctx->oz_variant;
+  if (variant == 4 && (!v3ok || J % 256 != 0)) variant = 3;       // CTA pairs need 256-row blocks
+  if (variant == 3 && !v3ok) variant = 1;
   const int bk = variant == 1 ? OZ_BK : OZ2_BK;
   CUtensorMap tmA, tmT;
-  if (oz_make_tmap(ctx, &tmA, (const int8_t*)Ap.p, J, K, ns, bk) || oz_make_tmap(ctx, &tmT, (const int8_t*)Tp.p, N, K, ns, bk))
+  if (oz_make_tmap(ctx, &tmA, (const int8_t*)Ap.p, J, K, ns, bk) ||
+      oz_make_tmap(ctx, &tmT, (const int8_t*)Tp.p, N, K, ns, bk, variant == 4 ? 64 : 128))
     return 1;
   static const unsigned long long pol[3] = {OZ3_L2_NORMAL, OZ3_L2_EVICT_FIRST, OZ3_L2_EVICT_LAST};
   OzParams prm{K, ns, lmax, tri, ldc, ctx->oz_sj, pol[ctx->oz_hint_a % 3], pol[ctx->oz_hint_t % 3], ctx->oz_pf, ctx->oz_dbg};
@@ -372,6 +380,22 @@ static int launch_i8gemm(maf_ctx* ctx, int slot, int J, int N, int K, const Buf&
     switch (ctx->oz_dbg) { OZ3_DGO(1); OZ3_DGO(2); OZ3_DGO(3); OZ3_DGO(4); OZ3_DGO(5); OZ3_DGO(6); OZ3_DGO(7); }
 #undef OZ3_DGO
 #endif
+  } else if (variant == 4) {
+    const long long ntiles2 = (long long)(N / OZ_BN) * (J / 256);
+    const long long pairs = std::min<long long>(ntiles2, num_sms / 2);
+    dim3 cgrid((unsigned)(2 * pairs));                           // persistent: one CTA pair per TPC
+#define OZ4_GO(NS_, LM_)                                                                                                     \
+  case NS_:                                                                                                                  \
+    ozaki_i8_gemm_v4_kernel<NS_, LM_><<<cgrid, OZ4_THREADS, Oz4<NS_, LM_>::SMEM_BYTES, ctx->stream>>>(tmA, tmT, sA.p, sT.p, C, prm, N / OZ_BN, J / 256); \
+    break
+    switch (ns) {
+      OZ4_GO(7, 8);
+      OZ4_GO(6, 7);
+      OZ4_GO(5, 6);
+      OZ4_GO(4, 5);
+      OZ4_GO(3, 4);
+    }
+#undef OZ4_GO
   } else {
 #define OZ3_GO(NS_, LM_)                                                                                                     \
   case NS_:                                                                                                                  \
@@ -707,7 +731,7 @@ static int run_chunk(maf_ctx* ctx, const AcqDev& ap, bool posterior_only, bool c
                      const double* dX, int M, const double* dz, const double* dw, const double* dinc, double* mu,
                      double* Sig, double* chol, double* mubar, double* Sigbar, double* dloss, double* dgrad) {
   const int d = ctx->mp.d, n = ctx->n, npad = ctx->npad;
-  const int J = sc * q, Jpad = round_up(J, 128);
+  const int J = sc * q, Jpad = round_up(J, 256);     // 256: one row block per CTA pair of the INT8 contraction
   double* K10 = ctx->K10.p;
   double* Vt = ctx->Vt.p;
   const bool fused = ctx->i8_ready && (ctx->oz_fuse & 1), fused_bwd = ctx->i8_ready && (ctx->oz_fuse & 2);
@@ -832,7 +856,7 @@ static int run_all(maf_ctx* ctx, const maf_acq_params* prm, bool posterior_only,
     return 1;
   int sc_max = (int)std::max<size_t>(1, ctx->chunk_rows / q);
   sc_max = std::min(sc_max, S);
-  const size_t need = (size_t)round_up(sc_max * q, 128) * npad;
+  const size_t need = (size_t)round_up(sc_max * q, 256) * npad;
   if (ensure(ctx, ctx->K10, need) || ensure(ctx, ctx->Vt, need)) return 1;
   for (int s0 = 0; s0 < S; s0 += sc_max) {
     const int sc = std::min(sc_max, S - s0);

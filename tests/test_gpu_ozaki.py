@@ -45,11 +45,12 @@ def sliced_product(A, T, ns, lmax):
     return C * sa * st.T
 
 
-@pytest.mark.parametrize("variant", [3, 1])
+@pytest.mark.parametrize("variant", [4, 3, 1])
 @pytest.mark.parametrize("ns,lmax", [(1, 2), (2, 3), (2, 4), (3, 4), (4, 5), (5, 6), (6, 7), (5, 7), (7, 8), (7, 14)])
 def test_digit_planes_are_multiplied_exactly(ns, lmax, variant):
-    """variant 3 = statically scheduled persistent kernel (lmax == ns + 1, 3 <= ns <= 7; other configurations
-    take the generic kernel), variant 1 = generic kernel."""
+    """variant 4 = statically scheduled persistent kernel on CTA pairs (tcgen05 cta_group::2; lmax == ns + 1,
+    3 <= ns <= 7, rows a multiple of 256), variant 3 = the same on single CTAs, variant 1 = generic kernel; a
+    variant that does not cover a configuration hands over to the next one."""
     import os
     from maximizingacquisitionfunctions_b200.engine import Engine
     os.environ["MAF_OZ_VARIANT"] = str(variant)
@@ -65,7 +66,7 @@ def test_digit_planes_are_multiplied_exactly(ns, lmax, variant):
 
 def _check_digit_product(eng, ns, lmax):
     rng = np.random.RandomState(ns * 10 + lmax)
-    J, N, K = 384, 256, 640        # 3 x 2 tiles, odd number of 128-byte k-chunks (both chunk parities + tail)
+    J, N, K = 512, 256, 640        # 4 x 2 tiles (2 x 2 pair tiles), odd number of 128-byte k-chunks (both parities + tail)
     A = rng.randn(J, K) * np.exp(rng.randn(J, 1))
     T = rng.randn(N, K) * np.exp(rng.randn(N, 1))
     C = eng.gemm_nt_i8(A, T, 0, ns=ns, lmax=lmax)
