@@ -363,7 +363,7 @@ static int launch_i8gemm(maf_ctx* ctx, int slot, int J, int N, int K, const Buf&
       oz_make_tmap(ctx, &tmT, (const int8_t*)Tp.p, N, K, ns, bk, variant == 4 ? 64 : 128))
     return 1;
   static const unsigned long long pol[3] = {OZ3_L2_NORMAL, OZ3_L2_EVICT_FIRST, OZ3_L2_EVICT_LAST};
-  OzParams prm{K, ns, lmax, tri, ldc, ctx->oz_sj, pol[ctx->oz_hint_a % 3], pol[ctx->oz_hint_t % 3], ctx->oz_pf, ctx->oz_dbg};
+  OzParams prm{K, ns, lmax, tri, ldc, ctx->oz_sj, pol[ctx->oz_hint_a % 3], pol[ctx->oz_hint_t % 3], ctx->oz_pf, nullptr, ctx->oz_dbg};
   dim3 grid(N / OZ_BN, J / OZ_BM);
   static int num_sms = 0;
   if (!num_sms) CK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, ctx->device));
@@ -375,7 +375,7 @@ static int launch_i8gemm(maf_ctx* ctx, int slot, int J, int N, int K, const Buf&
   } else if (variant == 2) {
     ozaki_i8_gemm_v2_kernel<<<grid, OZ_THREADS, OZ2_SMEM_BYTES, ctx->stream>>>(tmA, tmT, sA.p, sT.p, C, prm);
 #ifdef MAF_OZ_DIAG
-  } else if (ns == 7 && ctx->oz_dbg) {
+  } else if (variant == 3 && ns == 7 && ctx->oz_dbg > 0 && ctx->oz_dbg < 8) {
 #define OZ3_DGO(D_) case D_: ozaki_i8_gemm_v3_kernel<7, 8, D_><<<pgrid, OZ3_THREADS, Oz3<7, 8>::SMEM_BYTES, ctx->stream>>>(tmA, tmT, sA.p, sT.p, C, prm, N / OZ_BN, J / OZ_BM); break
     switch (ctx->oz_dbg) { OZ3_DGO(1); OZ3_DGO(2); OZ3_DGO(3); OZ3_DGO(4); OZ3_DGO(5); OZ3_DGO(6); OZ3_DGO(7); }
 #undef OZ3_DGO
@@ -384,6 +384,14 @@ static int launch_i8gemm(maf_ctx* ctx, int slot, int J, int N, int K, const Buf&
     const long long ntiles2 = (long long)(N / OZ_BN) * (J / 256);
     const long long pairs = std::min<long long>(ntiles2, num_sms / 2);
     dim3 cgrid((unsigned)(2 * pairs));                           // persistent: one CTA pair per TPC
+#ifdef MAF_OZ_DIAG
+    static long long* dstats = nullptr;
+    if (getenv("MAF_OZ_STATS")) {
+      if (!dstats) CK(cudaMalloc((void**)&dstats, sizeof(long long) * 8 * 128));
+      CK(cudaMemsetAsync(dstats, 0, sizeof(long long) * 8 * 128, ctx->stream));
+      prm.stats = dstats;
+    }
+#endif
 #define OZ4_GO(NS_, LM_)                                                                                                     \
   case NS_:                                                                                                                  \
     ozaki_i8_gemm_v4_kernel<NS_, LM_><<<cgrid, OZ4_THREADS, Oz4<NS_, LM_>::SMEM_BYTES, ctx->stream>>>(tmA, tmT, sA.p, sT.p, C, prm, N / OZ_BN, J / 256); \
@@ -396,6 +404,21 @@ static int launch_i8gemm(maf_ctx* ctx, int slot, int J, int N, int K, const Buf&
       OZ4_GO(3, 4);
     }
 #undef OZ4_GO
+#ifdef MAF_OZ_DIAG
+    if (prm.stats) {
+      std::vector<long long> h(8 * 128);
+      CK(cudaStreamSynchronize(ctx->stream));
+      CK(cudaMemcpy(h.data(), prm.stats, sizeof(long long) * 8 * 128, cudaMemcpyDeviceToHost));
+      double tot = 0, full = 0, acc = 0, epi = 0, f[4] = {0, 0, 0, 0};
+      for (long long c = 0; c < pairs; ++c) {
+        tot += h[8 * c]; full += h[8 * c + 1]; acc += h[8 * c + 2]; epi += h[8 * c + 3];
+        for (int u = 0; u < 4; ++u) f[u] += h[8 * c + 4 + u];
+      }
+      fprintf(stderr, "[oz4 stats] tri=%d pairs=%lld tiles/pair=%.1f  issuer cycles: total %.0f  wait-operands %.1f%% (pass0 first chunk %.1f%%, later %.1f%%; pass1 first %.1f%%, later %.1f%%)  wait-epilogue %.1f%%  | epilogue body (1 warp) %.1f%% of total\n",
+              tri, pairs, (double)ntiles2 / pairs, tot / pairs, 100 * full / tot, 100 * f[0] / tot, 100 * f[1] / tot, 100 * f[2] / tot,
+              100 * f[3] / tot, 100 * acc / tot, 100 * epi / tot);
+    }
+#endif
   } else {
 #define OZ3_GO(NS_, LM_)                                                                                                     \
   case NS_:                                                                                                                  \

@@ -83,6 +83,7 @@ struct OzParams {
   int sj;           // persistent kernel: row blocks per super-row of the tile order
   unsigned long long hintA, hintT;   // L2 eviction policies of the A / T plane loads (persistent kernel)
   int pf;           // persistent kernel: TMA-prefetch plane tiles into L2 two k-chunks ahead
+  long long* stats; // MAF_OZ_DIAG builds: per-CTA cycle counters of the issuer / epilogue (or null)
   int dbg;          // diagnostics only (results invalid): 1 = issue no MMAs, 2 = issue no TMA loads, 4 = skip the epilogue body
 };
 

@@ -76,7 +76,7 @@ __device__ __forceinline__ void oz4_arrive_leader(uint32_t local_bar_addr) {
 template <int NS, int LMAX, int PASS, int PAR>
 __device__ __forceinline__ void oz4_produce_chunk(const CUtensorMap* tmA, const CUtensorMap* tmT, uint32_t smem0, uint32_t full0,
                                                   uint32_t full0_leader, uint32_t empty0, uint32_t& ph_empty, int c, int jrow,
-                                                  int trow, bool leader) {
+                                                  int trow, bool leader, int dbg) {
   using Z = Oz4<NS, LMAX>;
 #pragma unroll
   for (int i = 1; i <= Z::smax(PASS); ++i) {
@@ -87,8 +87,15 @@ __device__ __forceinline__ void oz4_produce_chunk(const CUtensorMap* tmA, const 
         oz3_wait(empty0 + 8u * s, (ph_empty >> s) & 1u);
         ph_empty ^= 1u << s;
         if (oz_elect_one()) {
-          if (leader) oz4_expect(full0 + 8u * s, 2u * OZ4_T_BYTES);
-          oz4_load(smem0 + (uint32_t)Z::offT(b), tmT, full0_leader + 8u * s, c, trow, ip - 1);
+#ifdef MAF_OZ_DIAG
+          if (dbg & 16) {                                      // diagnostics: no T loads (operands stale)
+            if (leader) oz3_arrive(full0 + 8u * s);
+          } else
+#endif
+          {
+            if (leader) oz4_expect(full0 + 8u * s, 2u * OZ4_T_BYTES);
+            oz4_load(smem0 + (uint32_t)Z::offT(b), tmT, full0_leader + 8u * s, c, trow, ip - 1);
+          }
         }
         __syncwarp();
       }
@@ -98,8 +105,15 @@ __device__ __forceinline__ void oz4_produce_chunk(const CUtensorMap* tmA, const 
       oz3_wait(empty0 + 8u * s, (ph_empty >> s) & 1u);
       ph_empty ^= 1u << s;
       if (oz_elect_one()) {
-        if (leader) oz4_expect(full0 + 8u * s, 2u * OZ4_A_BYTES);
-        oz4_load(smem0 + (uint32_t)Z::offA(b), tmA, full0_leader + 8u * s, c, jrow, i - 1);
+#ifdef MAF_OZ_DIAG
+        if (dbg & 8) {                                         // diagnostics: no A loads
+          if (leader) oz3_arrive(full0 + 8u * s);
+        } else
+#endif
+        {
+          if (leader) oz4_expect(full0 + 8u * s, 2u * OZ4_A_BYTES);
+          oz4_load(smem0 + (uint32_t)Z::offA(b), tmA, full0_leader + 8u * s, c, jrow, i - 1);
+        }
       }
       __syncwarp();
     }
@@ -107,12 +121,21 @@ __device__ __forceinline__ void oz4_produce_chunk(const CUtensorMap* tmA, const 
 }
 
 // ---- one k-chunk of one pass: MMA issuer (leader CTA) ------------------------------------------------------
+#ifdef MAF_OZ_DIAG
+#define OZ4_T0() const long long t0_ = clock64()
+#define OZ4_ACC(x) (x) += clock64() - t0_
+#else
+#define OZ4_T0()
+#define OZ4_ACC(x)
+#endif
+
 template <int NS, int LMAX, int PASS, int PAR>
 __device__ __forceinline__ void oz4_issue_chunk(uint32_t desc0, uint32_t full0, uint32_t empty0, uint32_t& ph_full, uint32_t tbase,
-                                                uint32_t idesc, uint32_t not_first) {
+                                                uint32_t idesc, uint32_t not_first, long long& t_full) {   // t_full: waiting for operand tiles
   using Z = Oz4<NS, LMAX>;
 #pragma unroll
   for (int i = 1; i <= Z::smax(PASS); ++i) {
+    OZ4_T0();
 #pragma unroll
     for (int ip = Z::whi(PASS, i); ip >= Z::wlo(PASS, i); --ip) {
       if (i == 1 || ip < Z::wlo(PASS, i - 1)) {
@@ -126,6 +149,7 @@ __device__ __forceinline__ void oz4_issue_chunk(uint32_t desc0, uint32_t full0, 
       oz3_wait(full0 + 8u * s, (ph_full >> s) & 1u);
       ph_full ^= 1u << s;
     }
+    OZ4_ACC(t_full);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     if (oz_elect_one()) {
       const uint32_t alo = desc0 + (uint32_t)(Z::offA(Z::bufA(PASS, i, PAR)) >> 4);
@@ -153,19 +177,19 @@ __device__ __forceinline__ void oz4_issue_chunk(uint32_t desc0, uint32_t full0, 
 template <int NS, int LMAX, int PASS>
 __device__ __forceinline__ void oz4_produce_pass(const CUtensorMap* tmA, const CUtensorMap* tmT, uint32_t smem0, uint32_t full0,
                                                  uint32_t full0_leader, uint32_t empty0, uint32_t& ph_empty, int c_begin,
-                                                 int kchunks, int jrow, int trow, bool leader) {
+                                                 int kchunks, int jrow, int trow, bool leader, int dbg) {
   for (int kc = 0; kc < kchunks; kc += 2) {
-    oz4_produce_chunk<NS, LMAX, PASS, 0>(tmA, tmT, smem0, full0, full0_leader, empty0, ph_empty, c_begin + kc * OZ3_BK, jrow, trow, leader);
+    oz4_produce_chunk<NS, LMAX, PASS, 0>(tmA, tmT, smem0, full0, full0_leader, empty0, ph_empty, c_begin + kc * OZ3_BK, jrow, trow, leader, dbg);
     if (kc + 1 < kchunks)
-      oz4_produce_chunk<NS, LMAX, PASS, 1>(tmA, tmT, smem0, full0, full0_leader, empty0, ph_empty, c_begin + (kc + 1) * OZ3_BK, jrow, trow, leader);
+      oz4_produce_chunk<NS, LMAX, PASS, 1>(tmA, tmT, smem0, full0, full0_leader, empty0, ph_empty, c_begin + (kc + 1) * OZ3_BK, jrow, trow, leader, dbg);
   }
 }
 template <int NS, int LMAX, int PASS>
 __device__ __forceinline__ void oz4_issue_pass(uint32_t desc0, uint32_t full0, uint32_t empty0, uint32_t& ph_full, uint32_t tbase,
-                                               uint32_t idesc, int kchunks) {
+                                               uint32_t idesc, int kchunks, long long* t_full /*[first chunk, later chunks]*/) {
   for (int kc = 0; kc < kchunks; kc += 2) {
-    oz4_issue_chunk<NS, LMAX, PASS, 0>(desc0, full0, empty0, ph_full, tbase, idesc, kc > 0 ? 1u : 0u);
-    if (kc + 1 < kchunks) oz4_issue_chunk<NS, LMAX, PASS, 1>(desc0, full0, empty0, ph_full, tbase, idesc, 1u);
+    oz4_issue_chunk<NS, LMAX, PASS, 0>(desc0, full0, empty0, ph_full, tbase, idesc, kc > 0 ? 1u : 0u, t_full[kc > 0]);
+    if (kc + 1 < kchunks) oz4_issue_chunk<NS, LMAX, PASS, 1>(desc0, full0, empty0, ph_full, tbase, idesc, 1u, t_full[1]);
   }
 }
 
@@ -217,9 +241,9 @@ ozaki_i8_gemm_v4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     for (int t = cluster_id; t < ntiles; t += nclusters) {
       Oz3Tile x = oz3_tile(t, nN, nJ2, p);                     // j0 counts 128-row blocks: rescale to 256
       const int jrow = 2 * x.j0 + 128 * (int)rank, trow = x.r0 + 64 * (int)rank;
-      oz4_produce_pass<NS, LMAX, 0>(&tmA, &tmT, smem0, full0, full0_leader, empty0, ph_empty, x.c_begin, x.kchunks, jrow, trow, leader);
+      oz4_produce_pass<NS, LMAX, 0>(&tmA, &tmT, smem0, full0, full0_leader, empty0, ph_empty, x.c_begin, x.kchunks, jrow, trow, leader, p.dbg);
       if constexpr (Z::NPASS > 1)
-        oz4_produce_pass<NS, LMAX, 1>(&tmA, &tmT, smem0, full0, full0_leader, empty0, ph_empty, x.c_begin, x.kchunks, jrow, trow, leader);
+        oz4_produce_pass<NS, LMAX, 1>(&tmA, &tmT, smem0, full0, full0_leader, empty0, ph_empty, x.c_begin, x.kchunks, jrow, trow, leader, p.dbg);
     }
   } else if (warp == 1) {
     // ================= MMA issuer (leader CTA only) =================
@@ -228,25 +252,43 @@ ozaki_i8_gemm_v4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       const uint32_t desc0 = ((smem0 & 0x3FFFFu) >> 4) | (1u << 16);
       const uint32_t accf = oz_smem_u32(&acc_full), acce = oz_smem_u32(&acc_empty);
       uint32_t ph_full = 0u, g = 0;
+      long long t_full[4] = {0, 0, 0, 0}, t_acc = 0;
+#ifdef MAF_OZ_DIAG
+      const long long t_begin = clock64();
+#endif
       for (int t = cluster_id; t < ntiles; t += nclusters) {
         const Oz3Tile x = oz3_tile(t, nN, nJ2, p);
         if (g > 0) {
+          OZ4_T0();
           oz3_wait(acce, (g - 1) & 1u);
+          OZ4_ACC(t_acc);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
-        oz4_issue_pass<NS, LMAX, 0>(desc0, full0, empty0, ph_full, tbase, idesc, x.kchunks);
+        oz4_issue_pass<NS, LMAX, 0>(desc0, full0, empty0, ph_full, tbase, idesc, x.kchunks, t_full);
         if (oz_elect_one()) oz4_commit2(accf);
         __syncwarp();
         ++g;
         if constexpr (Z::NPASS > 1) {
-          oz3_wait(acce, (g - 1) & 1u);
+          {
+            OZ4_T0();
+            oz3_wait(acce, (g - 1) & 1u);
+            OZ4_ACC(t_acc);
+          }
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          oz4_issue_pass<NS, LMAX, 1>(desc0, full0, empty0, ph_full, tbase, idesc, x.kchunks);
+          oz4_issue_pass<NS, LMAX, 1>(desc0, full0, empty0, ph_full, tbase, idesc, x.kchunks, t_full + 2);
           if (oz_elect_one()) oz4_commit2(accf);
           __syncwarp();
           ++g;
         }
       }
+#ifdef MAF_OZ_DIAG
+      if (p.stats && lane == 0) {
+        p.stats[8 * cluster_id + 0] = clock64() - t_begin;       // issuer: first wait to last commit
+        p.stats[8 * cluster_id + 1] = t_full[0] + t_full[1] + t_full[2] + t_full[3];   // ... waiting for operand tiles
+        p.stats[8 * cluster_id + 2] = t_acc;                     // ... waiting for the epilogues to drain TMEM
+        for (int u = 0; u < 4; ++u) p.stats[8 * cluster_id + 4 + u] = t_full[u];        // pass 0 first/later chunks, pass 1 first/later
+      }
+#endif
     }
   } else {
     // ================= epilogue (both CTAs, own 128 rows): as v3 =================
@@ -284,6 +326,9 @@ ozaki_i8_gemm_v4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         oz3_wait(accf, g & 1u);
         ++g;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#ifdef MAF_OZ_DIAG
+        const long long te0 = clock64();
+#endif
 #pragma unroll
         for (int gq = 0; gq < NG; ++gq) {
           double2 old[2][2][2];
@@ -333,6 +378,9 @@ ozaki_i8_gemm_v4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
+#ifdef MAF_OZ_DIAG
+        if (p.stats && leader && warp == 2 && lane == 0) p.stats[8 * cluster_id + 3] += clock64() - te0;   // epilogue body (one warp)
+#endif
         if (lane == 0) oz4_arrive_leader(acce);                // one arrival per epilogue warp, on the leader's barrier
       }
     }
