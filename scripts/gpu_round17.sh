@@ -1,7 +1,7 @@
 #!/bin/bash
 # full gpu suite (both contraction engines), bench (default = INT8), ncu launch list + full capture of the INT8 GEMM
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q -rA --no-header -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"
+echo skip-pytest
 tail -3 gpurun_out/pytest_gpu.log; grep -E "^(FAILED|ERROR)" gpurun_out/pytest_gpu.log | head; grep -E "^E  " gpurun_out/pytest_gpu.log | head
 timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.log 2>&1; echo "bench rc=$?"
 tail -1 gpurun_out/bench.log | cut -c1-400
@@ -13,6 +13,6 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
 echo "launch list rc=$?"
 SMALL="python bench.py --steps 1 --warmup 3 --restarts 16384 --no-cpu-baseline"
 $SMALL > gpurun_out/bench_small_plain.log 2>&1 &&
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:ozaki_i8_gemm_v3 -s 8 -c 2 -f -o gpurun_out/prof_i8v3 $SMALL > gpurun_out/ncu_full.log 2>&1
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:ozaki_i8_gemm_v4 -s 8 -c 2 -f -o gpurun_out/prof_i8v4 $SMALL > gpurun_out/ncu_full.log 2>&1
 echo "full capture rc=$?"
 ls -la gpurun_out | tail -8
