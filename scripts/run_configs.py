@@ -1,0 +1,54 @@
+"""BASELINE.json configs C2-C5 as seeded synthetic inputs on one GPU: time of one value+gradient pass through
+the C ABI with device-resident inputs, evals/s = S q M / time, and parity against the CPU oracle on the first restarts
+(the oracle is the checker here, never the thing measured).  C1 (Hartmann-3 BO through the reference script) is covered by
+tests/test_reference_scripts.py and tests/test_gpu_mirror.py."""
+import json, math, os, sys, time
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from maximizingacquisitionfunctions_b200.engine import Engine, acq_params
+from oracle import maf_oracle as orc
+
+CONFIGS = [
+    ("C2 Branin qPI(tau=0.01) q=4 n=256 S=1024 M=256", dict(n=256, d=2, q=4, S=1024, M=256, acq="pi", kw={"temperature": 0.01})),
+    ("C2 Branin qSR q=4 n=256 S=1024 M=256", dict(n=256, d=2, q=4, S=1024, M=256, acq="sr", kw={})),
+    ("C3 Hartmann-6 qEI q=8 n=1024 S=4096 M=128", dict(n=1024, d=6, q=8, S=4096, M=128, acq="ei", kw={})),
+    ("C4 Levy d=6 qLCB(beta=2) q=16 n=2048 S=8192 M=128", dict(n=2048, d=6, q=16, S=8192, M=128, acq="cb", kw={"beta": 2.0, "lower": True})),
+    ("C5 synthetic d=6 qEI q=8 n=4096 S=8192 (1/8 of 65536) M=1024", dict(n=4096, d=6, q=8, S=8192, M=1024, acq="ei", kw={})),
+]
+
+def relerr(a, b):
+    return float(np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(np.asarray(b)).max(), 1e-300))
+
+def main():
+    eng = Engine(0)
+    out = []
+    for name, c in CONFIGS:
+        n, d, q, S, M = c["n"], c["d"], c["q"], c["S"], c["M"]
+        gp, X0, y0, X, z = orc.synthetic_problem(n, d, q, S, M, seed=0)
+        eng.set_model("matern52", np.full(d, math.sqrt(d) / 4), 1.0, 1e-3, 0.0, 1e-6)
+        t0 = time.perf_counter(); eng.set_train(X0, y0); setup = time.perf_counter() - t0
+        prm = acq_params(c["acq"], **c["kw"])
+        dX = eng.alloc(X.nbytes).upload(X); dz = eng.alloc(z.nbytes).upload(z)
+        dl = eng.alloc(S * 8); dg = eng.alloc(X.nbytes)
+        for _ in range(3):
+            eng.value_and_grad_dev(prm, S, q, 0, dX, M, dz, dl, dg)
+        eng.timer_start()
+        reps = 5
+        for _ in range(reps):
+            eng.value_and_grad_dev(prm, S, q, 0, dX, M, dz, dl, dg)
+        ms = eng.timer_stop() / reps
+        loss = dl.download((S,)); grad = dg.download((S, q, d))
+        s_chk = min(S, 32)
+        ts = orc.prepare_train(gp, X0, y0)
+        lo, go = orc.value_and_grad(ts, orc.Acq(c["acq"], **c["kw"]), X[:s_chk], z)
+        rec = {"config": name, "ms_per_pass": ms, "evals_per_s": S * q * M / (ms * 1e-3), "setup_s": setup,
+               "relerr_loss_vs_oracle": relerr(loss[:s_chk], lo), "relerr_grad_vs_oracle": relerr(grad[:s_chk], go),
+               "argmin_matches_oracle_on_checked": int(np.argmin(loss[:s_chk])) == int(np.argmin(lo))}
+        print(json.dumps(rec), flush=True)
+        out.append(rec)
+        for b in (dX, dz, dl, dg):
+            b.free()
+    eng.close()
+
+if __name__ == "__main__":
+    main()
