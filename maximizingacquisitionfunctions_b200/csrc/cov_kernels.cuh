@@ -89,7 +89,8 @@ cross_fwd_kernel(const double* __restrict__ X, int J, const double* __restrict__
 // coalesced reads of Kbar10 and of the SoA training set; warp-shuffle reduction.
 // ---------------------------------------------------------------------------
 template <int D>
-__global__ void cross_bwd_kernel(const double* __restrict__ X, int S, int q, int p,
+__global__ void __launch_bounds__(512, (D > 0 && D <= 8) ? 2 : 1)      // <= 64 registers: 32 warps per SM
+cross_bwd_kernel(const double* __restrict__ X, int S, int q, int p,
                                  const double* __restrict__ X0s, int n, int npad, ModelParams mp,
                                  const double* __restrict__ Kbar /*[S*q][npad]*/,
                                  const double* __restrict__ Sigbar /*[S][q][q]*/,

@@ -750,6 +750,15 @@ static int resolve_acq(maf_ctx* ctx, const maf_acq_params* prm, AcqDev* out) {
 }
 
 // forward (+ optional backward) over one chunk of restarts
+// posterior mean / covariance of one chunk: register-accumulating kernel for Q <= 8, shared-memory slab beyond
+template <int Q>
+static void launch_posterior(maf_ctx* ctx, int sc, const double* Vt, int npad, const double* dX, double* mu, double* Sig) {
+  if constexpr (Q <= 8)
+    posterior_reg_kernel<Q><<<sc, POST_THREADS, 0, ctx->stream>>>(Vt, npad, ctx->gamma, dX, ctx->mp, ctx->mean_val, mu, Sig);
+  else
+    posterior_kernel<Q><<<sc, POST_THREADS, 0, ctx->stream>>>(Vt, npad, ctx->gamma, dX, ctx->mp, ctx->mean_val, mu, Sig);
+}
+
 static int run_chunk(maf_ctx* ctx, const AcqDev& ap, bool posterior_only, bool closed_form, int sc, int q, int p,
                      const double* dX, int M, const double* dz, const double* dw, const double* dinc, double* mu,
                      double* Sig, double* chol, double* mubar, double* Sigbar, double* dloss, double* dgrad) {
@@ -791,7 +800,7 @@ static int run_chunk(maf_ctx* ctx, const AcqDev& ap, bool posterior_only, bool c
   }
   {
     ProfScope ps(ctx, MAF_PROF_POSTERIOR);
-    DISPATCH_Q(q, posterior_kernel<Q><<<sc, POST_THREADS, 0, ctx->stream>>>(Vt, npad, ctx->gamma, dX, ctx->mp, ctx->mean_val, mu, Sig));
+    DISPATCH_Q(q, launch_posterior<Q>(ctx, sc, Vt, npad, dX, mu, Sig));
     CKL();
   }
   if (posterior_only) return 0;

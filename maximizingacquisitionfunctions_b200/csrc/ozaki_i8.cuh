@@ -536,7 +536,7 @@ ozaki_slice_rows_kernel(const double* __restrict__ X, int ldx, int R, int Rpad, 
 #define OZC_TJ 32
 #define OZC_THREADS 256
 template <int D>
-__global__ void __launch_bounds__(OZC_THREADS)
+__global__ void __launch_bounds__(OZC_THREADS, (D > 0 && D <= 8) ? 3 : 1)
 cross_fwd_planes_kernel(const double* __restrict__ X, int J, int Jpad, const double* __restrict__ X0s, int n, int npad,
                         ModelParams mp, int ns, int8_t* __restrict__ planes, double* __restrict__ scales) {
   constexpr int DD = D > 0 ? D : MAF_MAX_D;

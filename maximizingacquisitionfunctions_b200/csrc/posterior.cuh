@@ -88,6 +88,77 @@ posterior_kernel(const double* __restrict__ Vt, int npad, const double* __restri
   if (tid < Q) mu[(size_t)s * Q + tid] = mean + mus[tid];
 }
 
+// Same result for Q <= 8 without the shared-memory slab (ncu: posterior_kernel runs at 94 % of the L1/shared
+// pipe): one thread owns a strided set of training columns, keeps its Q values of V^T in registers and accumulates the
+// Q (Q+1)/2 Gram entries and the Q mean terms there; one block reduction at the end.  Streams V^T once (HBM-bound).
+template <int Q>
+__global__ void __launch_bounds__(POST_THREADS)
+posterior_reg_kernel(const double* __restrict__ Vt, int npad, const double* __restrict__ gamma,
+                     const double* __restrict__ X, ModelParams mp, double mean,
+                     double* __restrict__ mu, double* __restrict__ Sig) {
+  constexpr int NG = Q * (Q + 1) / 2;
+  __shared__ double red[POST_THREADS / 32][NG + Q];
+  __shared__ double G[Q][Q];
+  __shared__ double mus[Q];
+  const int s = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const double* V = Vt + (size_t)s * Q * npad;
+  double acc[NG], m[Q];
+#pragma unroll
+  for (int t = 0; t < NG; ++t) acc[t] = 0.0;
+#pragma unroll
+  for (int i = 0; i < Q; ++i) m[i] = 0.0;
+  for (int k = tid; k < npad; k += POST_THREADS) {
+    double v[Q];
+#pragma unroll
+    for (int i = 0; i < Q; ++i) v[i] = V[(size_t)i * npad + k];
+    const double g = gamma[k];
+#pragma unroll
+    for (int i = 0; i < Q; ++i) {
+      m[i] += v[i] * g;
+#pragma unroll
+      for (int j = 0; j <= i; ++j) acc[i * (i + 1) / 2 + j] += v[i] * v[j];
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < NG; ++t) {
+    const double v = warp_sum(acc[t]);
+    if (lane == 0) red[warp][t] = v;
+  }
+#pragma unroll
+  for (int i = 0; i < Q; ++i) {
+    const double v = warp_sum(m[i]);
+    if (lane == 0) red[warp][NG + i] = v;
+  }
+  __syncthreads();
+  for (int t = tid; t < NG + Q; t += POST_THREADS) {
+    double v = 0.0;
+    for (int w = 0; w < POST_THREADS / 32; ++w) v += red[w][t];
+    if (t < NG) {
+      int i = 0;
+      while ((i + 1) * (i + 2) / 2 <= t) ++i;
+      G[i][t - i * (i + 1) / 2] = v;
+    } else {
+      mus[t - NG] = v;
+    }
+  }
+  __syncthreads();
+  const double* xs = X + (size_t)s * Q * mp.d;
+  for (int t = tid; t < Q * Q; t += POST_THREADS) {
+    int i = t / Q, j = t - i * Q;
+    double r2 = 0.0;
+    if (i != j) {
+      for (int c = 0; c < mp.d; ++c) {
+        double df = xs[i * mp.d + c] * mp.inv_ls[c] - xs[j * mp.d + c] * mp.inv_ls[c];
+        r2 += df * df;
+      }
+    }
+    double g = (i >= j) ? G[i][j] : G[j][i];
+    Sig[(size_t)s * Q * Q + t] = mp.amp2 * kern_val(mp.kernel_id, r2) - g;
+  }
+  if (tid < Q) mu[(size_t)s * Q + tid] = mean + mus[tid];
+}
+
 // Vbar^T[i][k] = mubar_i gamma_k - sum_j (Sbar_ij + Sbar_ji) V^T[j][k], in place.
 template <int Q>
 __global__ void __launch_bounds__(256)
@@ -109,7 +180,9 @@ vbar_kernel(double* __restrict__ Vt, int npad, const double* __restrict__ gamma,
 #pragma unroll
     for (int i = 0; i < Q; ++i) v[i] = V[(size_t)i * npad + k];
     const double g = gamma[k];
-#pragma unroll(Q <= 8 ? Q : 1)
+    // the row loop stays rolled (W, mb from shared memory): fully unrolled it costs 226 registers and leaves one
+    // CTA of 8 warps per SM on a kernel whose only job is to stream V^T through HBM
+#pragma unroll 1
     for (int i = 0; i < Q; ++i) {
       double o = mb[i] * g;
 #pragma unroll
