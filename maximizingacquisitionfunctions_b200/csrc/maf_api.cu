@@ -76,7 +76,7 @@ struct maf_ctx {
   int gemm_i8 = 1;                 // requested mode (default: INT8 digit slicing; DMMA when n > 8192)
   bool i8_ready = false;           // factor planes built for the current training set
   int oz_ns = 7, oz_lmax = 8;
-  int oz_fuse = 1;                 // bit 0: cross-covariance, bit 1: Vbar written straight to digit planes (MAF_OZ_FUSE)
+  int oz_fuse = 3;                 // bit 0: cross-covariance, bit 1: Vbar written straight to digit planes (MAF_OZ_FUSE)
   int oz_sj = 4;                   // super-row height of the persistent tile order (MAF_OZ_SJ)
   int oz_hint_a = 0, oz_hint_t = 0; // L2 policy of the A / T plane loads: 0 normal, 1 evict-first, 2 evict-last (MAF_OZ_HINTS=at)
   int oz_pf = 0;                   // L2 prefetch of plane tiles two k-chunks ahead (MAF_OZ_PF)

@@ -472,6 +472,27 @@ __device__ __forceinline__ void oz_emit_digits4(const long long (&I)[4], int ns,
     }
   }
 }
+// two values -> one packed 16-bit store per plane (same digits as oz_emit_digits4)
+__device__ __forceinline__ void oz_emit_digits2(const long long (&I)[2], int ns, int8_t* __restrict__ dst, size_t plane_stride) {
+  const unsigned long long bias = 0x0080808080808080ull >> (8 * (OZ_MAXS - ns));
+  const int sh = 8 * (OZ_MAXS - ns);
+  unsigned lo[2], hi[2];
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const unsigned long long u = (((unsigned long long)I[t] + bias) << sh) ^ 0x0080808080808080ull;
+    lo[t] = (unsigned)u;
+    hi[t] = (unsigned)(u >> 32);
+  }
+#pragma unroll
+  for (int i = 0; i < OZ_MAXS; ++i) {
+    if (i < ns) {
+      const int b = 6 - i;
+      const unsigned sel = (unsigned)((b & 3) | (((b & 3) + 4) << 4));
+      const unsigned p01 = (b < 4) ? __byte_perm(lo[0], lo[1], sel) : __byte_perm(hi[0], hi[1], sel);
+      *reinterpret_cast<unsigned short*>(dst + i * plane_stride) = (unsigned short)(p01 & 0xffffu);
+    }
+  }
+}
 __host__ __device__ __forceinline__ int oz_exponent_for(double mx) {
   int e = 0;
   if (mx > 0.0) frexp(mx / 0.98, &e);                        // mx/0.98 = f 2^e, f in [0.5,1)  =>  |x| 2^-e <= 0.98
@@ -581,17 +602,18 @@ cross_fwd_planes_kernel(const double* __restrict__ X, int J, int Jpad, const dou
 }
 
 // Vbar^T[i][k] = mubar_i gamma_k - sum_j (Sbar_ij + Sbar_ji) V^T[j][k]  (vbar_kernel) straight to digit planes.
-// One CTA per restart.  Sweep 1 finds the row maxima of Vbar^T, sweep 2 recomputes the same values (the q x n
-// slab of V^T is re-read from L2) and emits the digits with the exact row scale, so the planes are identical to
-// slicing the FP64 matrix.  Rows >= J of the last 128-row block are zeroed by the CTAs with s >= S.
+// One CTA per restart.  Sweep 1 bounds the row maxima of Vbar^T from the row maxima of V^T, sweep 2 (the q x n slab
+// of V^T re-read from L2) computes Vbar^T two columns per thread and emits its digits.  Rows >= J of the last
+// row block are zeroed by the CTAs with s >= S.
 template <int Q>
-__global__ void __launch_bounds__(256, Q <= 8 ? 2 : 1)
+__global__ void __launch_bounds__(256, Q <= 8 ? 3 : 1)
 vbar_planes_kernel(const double* __restrict__ Vt, int npad, int S, int Jpad, const double* __restrict__ gamma,
                    const double* __restrict__ mubar, const double* __restrict__ Sigbar, int ns,
                    int8_t* __restrict__ planes, double* __restrict__ scales) {
   __shared__ double W[Q][Q];
   __shared__ double mb[Q];
   __shared__ double red[8][Q];
+  __shared__ double redg[8];
   __shared__ double sinv[Q];
   const int s = blockIdx.x, tid = threadIdx.x;
   const size_t plane_stride = (size_t)Jpad * npad;
@@ -611,21 +633,16 @@ vbar_planes_kernel(const double* __restrict__ Vt, int npad, int S, int Jpad, con
   if (tid < Q) mb[tid] = mubar[(size_t)s * Q + tid];
   __syncthreads();
   const double* V = Vt + (size_t)s * Q * npad;
-  double mx[Q];
+  // Sweep 1: row maxima of V^T and of gamma only (no q x q work, q + 1 registers); the row scale of Vbar^T comes from
+  // the bound |Vbar_ik| <= |mubar_i| max|gamma| + sum_j |W_ij| max_k |V_jk|, at most a factor q + 1 (3.2 bits of the
+  // 55) above the true maximum.
+  double mx[Q], gx = 0.0;
 #pragma unroll
   for (int i = 0; i < Q; ++i) mx[i] = 0.0;
   for (int k = tid; k < npad; k += 256) {
-    double v[Q];
 #pragma unroll
-    for (int i = 0; i < Q; ++i) v[i] = V[(size_t)i * npad + k];
-    const double g = gamma[k];
-#pragma unroll(Q <= 8 ? Q : 1)
-    for (int i = 0; i < Q; ++i) {
-      double o = mb[i] * g;
-#pragma unroll
-      for (int j = 0; j < Q; ++j) o -= W[i][j] * v[j];
-      mx[i] = fmax(mx[i], fabs(o));
-    }
+    for (int i = 0; i < Q; ++i) mx[i] = fmax(mx[i], fabs(V[(size_t)i * npad + k]));
+    gx = fmax(gx, fabs(gamma[k]));
   }
 #pragma unroll
   for (int i = 0; i < Q; ++i) {
@@ -633,37 +650,38 @@ vbar_planes_kernel(const double* __restrict__ Vt, int npad, int S, int Jpad, con
     for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
     if ((tid & 31) == 0) red[tid >> 5][i] = m;
   }
+  for (int o = 16; o > 0; o >>= 1) gx = fmax(gx, __shfl_xor_sync(0xffffffffu, gx, o));
+  if ((tid & 31) == 0) redg[tid >> 5] = gx;
   __syncthreads();
   if (tid < Q) {
-    double m = red[0][tid];
-    for (int w = 1; w < 8; ++w) m = fmax(m, red[w][tid]);
-    const int e = oz_exponent_for(m);
+    double gm = redg[0];
+    for (int w = 1; w < 8; ++w) gm = fmax(gm, redg[w]);
+    double bound = fabs(mb[tid]) * gm;
+    for (int j = 0; j < Q; ++j) {
+      double vm = red[0][j];
+      for (int w = 1; w < 8; ++w) vm = fmax(vm, red[w][j]);
+      bound += fabs(W[tid][j]) * vm;
+    }
+    const int e = oz_exponent_for(bound);
     scales[(size_t)s * Q + tid] = ldexp(1.0, e);
     sinv[tid] = ldexp(1.0, -e + 8 * ns - 1);
   }
   __syncthreads();
-  for (int k = tid * 4; k < npad; k += 256 * 4) {
-    double v[Q][4];
+  for (int k = tid * 2; k < npad; k += 256 * 2) {          // two columns per thread: q values of V^T each stay in registers
+    double2 v[Q];
 #pragma unroll
-    for (int i = 0; i < Q; ++i) {
-      const double2 a = *reinterpret_cast<const double2*>(V + (size_t)i * npad + k);
-      const double2 b = *reinterpret_cast<const double2*>(V + (size_t)i * npad + k + 2);
-      v[i][0] = a.x; v[i][1] = a.y; v[i][2] = b.x; v[i][3] = b.y;
-    }
-    double g[4];
-#pragma unroll
-    for (int t = 0; t < 4; ++t) g[t] = gamma[k + t];
+    for (int i = 0; i < Q; ++i) v[i] = *reinterpret_cast<const double2*>(V + (size_t)i * npad + k);
+    const double2 g = *reinterpret_cast<const double2*>(gamma + k);
 #pragma unroll 1
     for (int i = 0; i < Q; ++i) {
-      long long I[4];
+      double o0 = mb[i] * g.x, o1 = mb[i] * g.y;
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        double o = mb[i] * g[t];
-#pragma unroll
-        for (int j = 0; j < Q; ++j) o -= W[i][j] * v[j][t];
-        I[t] = __double2ll_rn(o * sinv[i]);
+      for (int j = 0; j < Q; ++j) {
+        o0 -= W[i][j] * v[j].x;
+        o1 -= W[i][j] * v[j].y;
       }
-      oz_emit_digits4(I, ns, planes + ((size_t)s * Q + i) * npad + k, plane_stride);
+      const long long I[2] = {__double2ll_rn(o0 * sinv[i]), __double2ll_rn(o1 * sinv[i])};
+      oz_emit_digits2(I, ns, planes + ((size_t)s * Q + i) * npad + k, plane_stride);
     }
   }
 }
