@@ -1101,7 +1101,7 @@ static int run_fantasies(maf_ctx* ctx, const maf_acq_params* prm, int S, const d
     ap.acq = MAF_ACQ_SR;
   }
   const int sc_max = (int)std::min<size_t>(ctx->chunk_rows, (size_t)S);
-  const int Jmax = round_up(sc_max, 128);
+  const int Jmax = round_up(sc_max, 256);
   if (ensure(ctx, ctx->dX, (size_t)S * d) || ensure(ctx, ctx->K10, (size_t)Jmax * npad) ||
       ensure(ctx, ctx->Vt, (size_t)Jmax * npad) || ensure(ctx, ctx->fVG, (size_t)Jmax * Fpad) ||
       ensure(ctx, ctx->fmubar, (size_t)Jmax * Fpad) || ensure(ctx, ctx->dmu, (size_t)S) ||
@@ -1112,15 +1112,31 @@ static int run_fantasies(maf_ctx* ctx, const maf_acq_params* prm, int S, const d
   const int need_grad = out_grad != nullptr;
   for (int s0 = 0; s0 < S; s0 += sc_max) {
     const int sc = std::min(sc_max, S - s0);
-    const int Jpad = round_up(sc, 128);
+    const int Jpad = round_up(sc, 256);
     const double* dX = ctx->dX.p + (size_t)s0 * d;
-    {
-      ProfScope ps(ctx, MAF_PROF_CROSS_FWD);
-      dim3 grid((npad + CROSS_TK - 1) / CROSS_TK, Jpad / CROSS_TJ);
-      DISPATCH_D(d, cross_fwd_kernel<D><<<grid, CROSS_TK, 0, ctx->stream>>>(dX, sc, ctx->X0s, n, npad, ctx->mp, ctx->K10.p));
-      CKL();
+    if (ctx->i8_ready) {
+      // same contraction engine as the Monte-Carlo path: K10 straight to digit planes, INT8 products
+      const size_t bytes = (size_t)ctx->oz_ns * Jpad * npad;
+      if (ensure(ctx, ctx->ozA, (bytes + 7) / 8) || ensure(ctx, ctx->ozsA, (size_t)Jpad)) return 1;
+      {
+        ProfScope ps(ctx, MAF_PROF_CROSS_FWD);
+        dim3 grid((npad + OZC_THREADS * 4 - 1) / (OZC_THREADS * 4), Jpad / OZC_TJ);
+        DISPATCH_D(d, cross_fwd_planes_kernel<D><<<grid, OZC_THREADS, 0, ctx->stream>>>(dX, sc, Jpad, ctx->X0s, n, npad, ctx->mp, ctx->oz_ns,
+                                                                                    (int8_t*)ctx->ozA.p, ctx->ozsA.p));
+        CKL();
+      }
+      if (launch_i8gemm(ctx, MAF_PROF_GEMM_FWD, Jpad, npad, npad, ctx->ozA, ctx->ozsA, ctx->ozTL, ctx->ozsTL, ctx->Vt.p, npad, 1,
+                        ctx->oz_ns, ctx->oz_lmax))
+        return 1;
+    } else {
+      {
+        ProfScope ps(ctx, MAF_PROF_CROSS_FWD);
+        dim3 grid((npad + CROSS_TK - 1) / CROSS_TK, Jpad / CROSS_TJ);
+        DISPATCH_D(d, cross_fwd_kernel<D><<<grid, CROSS_TK, 0, ctx->stream>>>(dX, sc, ctx->X0s, n, npad, ctx->mp, ctx->K10.p));
+        CKL();
+      }
+      if (launch_gemm(ctx, MAF_PROF_GEMM_FWD, Jpad, npad, npad, ctx->K10.p, npad, ctx->Linv, npad, ctx->Vt.p, npad, 1)) return 1;
     }
-    if (launch_gemm(ctx, MAF_PROF_GEMM_FWD, Jpad, npad, npad, ctx->K10.p, npad, ctx->Linv, npad, ctx->Vt.p, npad, 1)) return 1;
     {
       ProfScope ps(ctx, MAF_PROF_POSTERIOR);
       posterior_kernel<1><<<sc, POST_THREADS, 0, ctx->stream>>>(ctx->Vt.p, npad, ctx->gamma, dX, ctx->mp, ctx->mean_val,
@@ -1154,7 +1170,14 @@ static int run_fantasies(maf_ctx* ctx, const maf_acq_params* prm, int S, const d
       fant_vbar_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->Vt.p, ctx->K10.p, ctx->dSigbar.p + s0, sc, npad);
       CKL();
     }
-    if (launch_gemm(ctx, MAF_PROF_GEMM_BWD, Jpad, npad, npad, ctx->Vt.p, npad, ctx->LinvT, npad, ctx->K10.p, npad, 2)) return 1;
+    if (ctx->i8_ready) {
+      if (oz_slice(ctx, MAF_PROF_VBAR, ctx->Vt.p, npad, sc, Jpad, npad, ctx->oz_ns, 0.0, ctx->ozA, ctx->ozsA)) return 1;
+      if (launch_i8gemm(ctx, MAF_PROF_GEMM_BWD, Jpad, npad, npad, ctx->ozA, ctx->ozsA, ctx->ozTU, ctx->ozsTU, ctx->K10.p, npad, 2,
+                        ctx->oz_ns, ctx->oz_lmax))
+        return 1;
+    } else if (launch_gemm(ctx, MAF_PROF_GEMM_BWD, Jpad, npad, npad, ctx->Vt.p, npad, ctx->LinvT, npad, ctx->K10.p, npad, 2)) {
+      return 1;
+    }
     {
       ProfScope ps(ctx, MAF_PROF_CROSS_BWD);
       DISPATCH_D(d, cross_bwd_kernel<D><<<sc, 32, 0, ctx->stream>>>(dX, sc, 1, 0, ctx->X0s, n, npad, ctx->mp, ctx->K10.p,
