@@ -1,123 +1,141 @@
-"""Base search agent: timer, input sampling, loss-proportional sub-sampling
-(reference: src/agents/search_agent.py).  Host-side NumPy; not a GPU target."""
+"""Host-side base class of the agents: wall-clock timer, candidate sampling in the unit cube (uniform, Sobol, or
+distinct subsets of a finite option list) and loss-weighted sub-sampling of options.  Interface and host-RNG
+consumption follow src/agents/search_agent.py of the reference (one ``self.rng`` access per draw, same arguments),
+so seeded runs pick the same candidates; nothing here runs on the GPU."""
 import itertools
 import logging
 from timeit import default_timer
 
 import numpy as np
-from scipy.special import comb as nCr
+from scipy.special import comb
 
 from ..core import module
 
 logger = logging.getLogger(__name__)
 
+SOBOL_MAX_DIM = 40           # the reference's generator stops at 40 dimensions (:103-106)
+
+
+def _split_shape(shape):
+    """[..., set_size, input_dim] -> (number of sets, flattened size of one set) the way :96-101 counts them."""
+    shape = list(shape)
+    if len(shape) > 2:
+        count = int(np.prod(shape[:-2]))
+        return count, int(np.prod(shape)) // count
+    return int(shape[0]), int(shape[1])
+
 
 class search_agent(module):
     def __init__(self, *args, timer=None, grids=None, **kwargs):
         super().__init__(*args, **kwargs)
-        self.timer = default_timer if timer is None else timer
-        self.grids = dict() if grids is None else grids
+        self.timer = timer or default_timer
+        self.grids = {} if grids is None else grids           # cache of sampled grids, keyed by request
 
+    # -- interface ---------------------------------------------------------------------------------------
     def suggest_inputs(self, num_suggest, inputs_old, outputs_old, *args, **kwargs):
         raise NotImplementedError("Search agents must implement suggest_inputs()")
 
     def suggest_answers(self, num_suggest, inputs_old, outputs_old, in_order=False):
-        """Top-k best seen inputs (:49-58)."""
-        idx = np.argpartition(np.ravel(outputs_old), num_suggest - 1)[:num_suggest]
+        """The num_suggest best observations (:49-58)."""
+        flat = np.ravel(outputs_old)
+        best = np.argpartition(flat, num_suggest - 1)[:num_suggest]
         if in_order:
-            idx = idx[np.argsort(np.ravel(outputs_old)[idx])]
-        return inputs_old[idx], outputs_old[idx]
+            best = best[np.argsort(flat[best])]
+        return inputs_old[best], outputs_old[best]
 
+    # -- candidate sampling ------------------------------------------------------------------------------
     def sample_inputs(self, shape, options=None, use_sobol=False, use_cache=False, dtype=None):
-        if dtype is None:
-            dtype = self.dtype
-        if use_cache and options is None:
-            key = (use_sobol, np.dtype(dtype).name, tuple(shape))
-            if self.grids.get(key, None) is None:
-                self.grids[key] = self._sample_inputs(shape, options, use_sobol, dtype)
-            return self.grids[key]
-        return self._sample_inputs(shape, options, use_sobol, dtype)
+        dtype = self.dtype if dtype is None else dtype
+        if not (use_cache and options is None):
+            return self._sample_inputs(shape, options, use_sobol, dtype)
+        key = (use_sobol, np.dtype(dtype).name, tuple(shape))
+        cached = self.grids.get(key)
+        if cached is None:
+            cached = self.grids[key] = self._sample_inputs(shape, options, use_sobol, dtype)
+        return cached
 
     def _sample_inputs(self, shape, options=None, use_sobol=False, dtype=None):
-        """Input sets in [0,1]^d (uniform or Sobol) or distinct combinations of given options (:81-133).
-        The reference's Sobol points come from its vendored Burkardt generator with a random skip;
-        here scipy's unscrambled Sobol sequence with the same random skip is used."""
-        if dtype is None:
-            dtype = self.dtype
+        dtype = self.dtype if dtype is None else dtype
         shape = list(shape)
-        if options is None:
-            if use_sobol:
-                num_sets = int(np.prod(shape[:-2])) if len(shape) > 2 else shape[0]
-                set_size = int(np.prod(shape)) // num_sets
-                if set_size > 40:
-                    logger.warning("Sobol sequence not available for >40d spaces; using uniform random values instead")
-                    inputs = self.rng.rand(*shape)
-                else:
-                    from scipy.stats import qmc
-                    skip = int(self.rng.randint(2 ** 13 - 1))
-                    eng = qmc.Sobol(d=set_size, scramble=False)
-                    if skip:
-                        eng.fast_forward(skip)
-                    inputs = np.reshape(eng.random(num_sets), shape)
-            else:
-                inputs = self.rng.rand(*shape)
+        if options is not None:
+            points = self._distinct_subsets(np.asarray(options), shape)
+        elif use_sobol:
+            points = self._sobol(shape)
         else:
-            assert options.shape[-1] == shape[-1], "Input dimensionality mismatch"
-            num_options = len(options)
-            num_sets, set_size = int(np.prod(shape[:-2])), shape[-2]
-            num_combs = nCr(num_options, set_size, exact=True)
-            if num_combs > num_sets:
-                indices = np.empty([num_sets, set_size], dtype="int")
-                counter = 0
-                while counter < num_sets:
-                    new = self.rng.choice(num_options, set_size, replace=False)
-                    if not any(np.equal(indices[:counter], new).all(axis=1)):
-                        indices[counter] = new
-                        counter += 1
-                inputs = options[indices]
-            else:
-                if num_combs != num_sets:
-                    logger.warning("Requested more unique sets than options allow")
-                inputs = np.array(tuple(itertools.combinations(options, set_size)))
-        return np.asarray(inputs, dtype=dtype)
+            points = self.rng.rand(*shape)
+        return np.asarray(points, dtype=dtype)
 
+    def _sobol(self, shape):
+        """Low-discrepancy sets with a random skip (:96-112).  The reference calls its vendored Burkardt generator;
+        SciPy's unscrambled Sobol sequence fast-forwarded by the same random skip stands in for it."""
+        count, width = _split_shape(shape)
+        if width > SOBOL_MAX_DIM:
+            logger.warning("Sobol sequence not available for >40d spaces; using uniform random values instead")
+            return self.rng.rand(*shape)
+        from scipy.stats import qmc
+        skip = int(self.rng.randint(2 ** 13 - 1))
+        sequence = qmc.Sobol(d=width, scramble=False)
+        if skip:
+            sequence.fast_forward(skip)
+        return np.reshape(sequence.random(count), shape)
+
+    def _distinct_subsets(self, options, shape):
+        """`count` different size-`k` subsets of the option rows (:114-132): rejection sampling while there are more
+        subsets than requested, otherwise all of them."""
+        assert options.shape[-1] == shape[-1], "Input dimensionality mismatch"
+        count, k = int(np.prod(shape[:-2])), shape[-2]
+        available = comb(len(options), k, exact=True)
+        if available <= count:
+            if available != count:
+                logger.warning("Requested more unique sets than options allow")
+            return np.array(tuple(itertools.combinations(options, k)))
+        picked = np.empty([count, k], dtype="int")
+        filled = 0
+        while filled < count:
+            draw = self.rng.choice(len(options), k, replace=False)
+            if not (picked[:filled] == draw).all(axis=1).any():
+                picked[filled] = draw
+                filled += 1
+        return options[picked]
+
+    # -- loss-weighted sub-sampling (:136-183) -------------------------------------------------------------
     def sample_propto_loss(self, options, losses, num_samples, top_k=1, eps=None):
-        """Sub-sample options with probability proportional to (max loss - loss), the top-k always in
-        (:136-183).  Returns (options[indices], indices)."""
+        """num_samples options: the top_k lowest losses always, the rest drawn without replacement with probability
+        proportional to (worst loss - loss); options no better than the worst only fill up when needed.
+        Returns (options[chosen], chosen)."""
         losses = np.asarray(losses)
-        if eps is None:
-            eps = np.finfo(losses.dtype).eps
-        num_options = len(options)
-        assert num_options >= len(losses), "Insufficient options provided"
-        weights = np.max(losses) - losses
-        mask = np.greater_equal(weights, eps)
-        nnz = int(np.sum(mask))
-        if top_k > 0 and nnz > 0:
-            num_top = min(top_k, nnz)
-            num_samples = num_samples - num_top
-            top = np.argpartition(losses, num_top - 1)[:num_top]
-            nnz -= num_top
-            weights[top] = 0
-            mask[top] = 0
-        else:
-            top = None
+        eps = np.finfo(losses.dtype).eps if eps is None else eps
+        assert len(options) >= len(losses), "Insufficient options provided"
+        gap = losses.max() - losses                       # sampling weight before normalisation
+        useful = gap >= eps
+        remaining = int(useful.sum())
+
+        leaders = None
+        if top_k > 0 and remaining > 0:
+            lead = min(top_k, remaining)
+            leaders = np.argpartition(losses, lead - 1)[:lead]
+            gap[leaders] = 0
+            useful[leaders] = False
+            remaining -= lead
+            num_samples -= lead
+
         if num_samples == 0:
-            idx = np.empty([0], dtype="int")
-        elif nnz == num_samples:
-            idx = np.where(mask)[0]
-        elif nnz < num_samples:
-            nz = np.where(mask)[0]
-            rest = self.rng.choice(np.where(np.logical_not(mask))[0], num_samples - nnz, replace=False)
-            idx = np.hstack([nz, rest])
+            drawn = np.empty([0], dtype="int")
+        elif remaining == num_samples:
+            drawn = np.flatnonzero(useful)
+        elif remaining < num_samples:
+            fillers = self.rng.choice(np.flatnonzero(~useful), num_samples - remaining, replace=False)
+            drawn = np.concatenate([np.flatnonzero(useful), fillers])
         else:
-            total = np.sum(weights)
-            if total > eps:
-                weights /= np.sum(weights)
-                weights[mask] = np.maximum(weights[mask], eps)
-                weights /= np.sum(weights)      # numpy >= 1.x insists on an exactly normalised p
-            else:
-                weights = mask / np.sum(mask)
-            idx = self.rng.choice(num_options, num_samples, p=weights, replace=False)
-        if top is not None:
-            idx = np.hstack([top, idx])
-        return options[idx], idx
+            drawn = self.rng.choice(len(options), num_samples, p=self._probabilities(gap, useful, eps), replace=False)
+        chosen = drawn if leaders is None else np.concatenate([leaders, drawn])
+        return options[chosen], chosen
+
+    @staticmethod
+    def _probabilities(gap, useful, eps):
+        total = gap.sum()
+        if total <= eps:
+            return useful / useful.sum()
+        p = gap / total
+        p[useful] = np.maximum(p[useful], eps)
+        return p / p.sum()                                # current NumPy wants p normalised to the last bit
