@@ -41,10 +41,8 @@ def is_stale():
 def build(force=False, verbose=False):
     if not force and not is_stale():
         return LIB
-    cuda_lib = os.path.join(os.path.dirname(os.path.dirname(_nvcc())), "lib64")
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-o", LIB, os.path.join(CSRC, "maf_api.cu"),
-                                     "-L" + cuda_lib, "-Xlinker", "-rpath," + cuda_lib,
-                                     "-lcublas", "-lcusolver"]
+    # no CUDA math libraries: every kernel, including the training-set factorisation, is in csrc/
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-o", LIB, os.path.join(CSRC, "maf_api.cu")]
     if os.environ.get("MAF_OZ_DIAG"):
         cmd.insert(1, "-DMAF_OZ_DIAG")      # extra diagnostic instantiations of the INT8 kernel (MAF_OZ_DBG)
     if verbose:

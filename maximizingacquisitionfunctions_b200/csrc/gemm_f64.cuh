@@ -45,10 +45,12 @@ struct GemmCfg {
 };
 
 // tri: 0 = full T, 1 = T lower-triangular (T[r][c] = 0 for c > r), 2 = upper (c < r).
+// epi: 0 = store C, 1 = C -= A T^T on the tiles that touch the lower triangle of a square C (symmetric rank-k update
+//      of the blocked Cholesky, factor.cuh), 2 = store -A T^T.
 template <int BM, int BN, int BK, int STAGES, int WJ, int WR, int MINB>
 __global__ void __launch_bounds__(WJ * WR * 32, MINB)
 gemm_nt_f64_kernel(const double* __restrict__ A, int lda, const double* __restrict__ T, int ldt,
-                   double* __restrict__ C, int ldc, int K, int tri) {
+                   double* __restrict__ C, int ldc, int K, int tri, int epi) {
   using Cfg = GemmCfg<BM, BN, BK, STAGES, WJ, WR, MINB>;
   constexpr int LD = Cfg::LD, THREADS = Cfg::THREADS, MT = Cfg::MT, NT = Cfg::NT;
   extern __shared__ __align__(16) double gsm[];
@@ -59,6 +61,7 @@ gemm_nt_f64_kernel(const double* __restrict__ A, int lda, const double* __restri
   const int rb = (tri == 1) ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;
   const int r0 = rb * BN;
   const int j0 = blockIdx.y * BM;
+  if (epi == 1 && r0 >= j0 + BM) return;                      // tile strictly above the diagonal
   const int c_begin = (tri == 2) ? r0 : 0;
   const int c_end = (tri == 1) ? min(K, r0 + BN) : K;
   const int ktiles = (c_end - c_begin) / BK;
@@ -143,6 +146,12 @@ gemm_nt_f64_kernel(const double* __restrict__ A, int lda, const double* __restri
 #pragma unroll
     for (int ni = 0; ni < NT; ++ni) {
       double2 v = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+      if (epi == 1) {
+        const double2 old = *reinterpret_cast<const double2*>(crow + ni * 8);
+        v = make_double2(old.x - v.x, old.y - v.y);
+      } else if (epi == 2) {
+        v = make_double2(-v.x, -v.y);
+      }
       *reinterpret_cast<double2*>(crow + ni * 8) = v;
     }
   }

@@ -1,7 +1,5 @@
 // C ABI of the B200-native acquisition-maximisation path (see include/maf.h).
 // Host orchestration only: every number is produced by the kernels in the .cuh files.
-#include <cublas_v2.h>
-#include <cusolverDn.h>
 
 #include <algorithm>
 #include <cstdarg>
@@ -12,6 +10,7 @@
 
 #include "common.cuh"
 #include "cov_kernels.cuh"
+#include "factor.cuh"
 #include "fit_kernels.cuh"
 #include "gemm_f64.cuh"
 #include "mc_kernels.cuh"
@@ -38,8 +37,6 @@ struct maf_ctx {
   int device = 0;
   int dtype = MAF_F64;
   cudaStream_t stream = nullptr;
-  cublasHandle_t cublas = nullptr;
-  cusolverDnHandle_t cusolver = nullptr;
   std::string err;
   int64_t launch_count = 0;
 
@@ -252,7 +249,7 @@ __global__ void diag_extract_kernel(const double* __restrict__ Sig, int S, int q
 // GEMM variants (selected by MAF_GEMM_VARIANT at context creation; 0 is the default)
 template <int BM, int BN, int BK, int STAGES, int WJ, int WR, int MINB>
 static int launch_gemm_cfg(maf_ctx* ctx, int J, int N, const double* A, int lda, const double* T, int ldt, double* C,
-                           int ldc, int K, int tri) {
+                           int ldc, int K, int tri, int epi) {
   using Cfg = GemmCfg<BM, BN, BK, STAGES, WJ, WR, MINB>;
   static bool attr = false;
   if (!attr) {
@@ -264,26 +261,26 @@ static int launch_gemm_cfg(maf_ctx* ctx, int J, int N, const double* A, int lda,
   }
   dim3 grid(N / BN, J / BM);
   gemm_nt_f64_kernel<BM, BN, BK, STAGES, WJ, WR, MINB><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, ctx->stream>>>(
-      A, lda, T, ldt, C, ldc, K, tri);
+      A, lda, T, ldt, C, ldc, K, tri, epi);
   return 0;
 }
 
 static int launch_gemm(maf_ctx* ctx, int slot, int J, int N, int K, const double* A, int lda,
-                       const double* T, int ldt, double* C, int ldc, int tri) {
+                       const double* T, int ldt, double* C, int ldc, int tri, int epi = 0) {
   if (J % 128 || N % 128 || K % 128) return fail(ctx, "gemm dims must be multiples of 128");
   if (tri != 0 && K != N) return fail(ctx, "triangular gemm needs K == N");
   ProfScope ps(ctx, slot);
   int rc;
   switch (ctx->gemm_variant) {
     // <BM, BN, BK, STAGES, WJ, WR, CTAs/SM>; measured on B200 (profiles/gemm_variants_r01.jsonl)
-    case 1: rc = launch_gemm_cfg<128, 128, 16, 4, 2, 4, 1>(ctx, J, N, A, lda, T, ldt, C, ldc, K, tri); break;  // v0: 32.0 TF
-    case 2: rc = launch_gemm_cfg<128, 64, 16, 3, 2, 2, 2>(ctx, J, N, A, lda, T, ldt, C, ldc, K, tri); break;   // 35.0 TF
-    case 3: rc = launch_gemm_cfg<64, 128, 16, 3, 1, 4, 2>(ctx, J, N, A, lda, T, ldt, C, ldc, K, tri); break;   // 33.2 TF
-    case 4: rc = launch_gemm_cfg<128, 64, 32, 2, 2, 2, 2>(ctx, J, N, A, lda, T, ldt, C, ldc, K, tri); break;   // 35.0 TF
-    case 5: rc = launch_gemm_cfg<64, 64, 16, 3, 2, 2, 3>(ctx, J, N, A, lda, T, ldt, C, ldc, K, tri); break;    // 35.2 TF
-    case 6: rc = launch_gemm_cfg<64, 64, 32, 2, 2, 2, 3>(ctx, J, N, A, lda, T, ldt, C, ldc, K, tri); break;    // BK 32
-    case 7: rc = launch_gemm_cfg<64, 128, 16, 3, 2, 4, 2>(ctx, J, N, A, lda, T, ldt, C, ldc, K, tri); break;   // 8 warps of 32x32, 2/SM
-    default: rc = launch_gemm_cfg<64, 64, 16, 2, 2, 2, 4>(ctx, J, N, A, lda, T, ldt, C, ldc, K, tri); break;   // 4 CTAs/SM: 35.7 TF
+    case 1: rc = launch_gemm_cfg<128, 128, 16, 4, 2, 4, 1>(ctx, J, N, A, lda, T, ldt, C, ldc, K, tri, epi); break;  // v0: 32.0 TF
+    case 2: rc = launch_gemm_cfg<128, 64, 16, 3, 2, 2, 2>(ctx, J, N, A, lda, T, ldt, C, ldc, K, tri, epi); break;   // 35.0 TF
+    case 3: rc = launch_gemm_cfg<64, 128, 16, 3, 1, 4, 2>(ctx, J, N, A, lda, T, ldt, C, ldc, K, tri, epi); break;   // 33.2 TF
+    case 4: rc = launch_gemm_cfg<128, 64, 32, 2, 2, 2, 2>(ctx, J, N, A, lda, T, ldt, C, ldc, K, tri, epi); break;   // 35.0 TF
+    case 5: rc = launch_gemm_cfg<64, 64, 16, 3, 2, 2, 3>(ctx, J, N, A, lda, T, ldt, C, ldc, K, tri, epi); break;    // 35.2 TF
+    case 6: rc = launch_gemm_cfg<64, 64, 32, 2, 2, 2, 3>(ctx, J, N, A, lda, T, ldt, C, ldc, K, tri, epi); break;    // BK 32
+    case 7: rc = launch_gemm_cfg<64, 128, 16, 3, 2, 4, 2>(ctx, J, N, A, lda, T, ldt, C, ldc, K, tri, epi); break;   // 8 warps of 32x32, 2/SM
+    default: rc = launch_gemm_cfg<64, 64, 16, 2, 2, 2, 4>(ctx, J, N, A, lda, T, ldt, C, ldc, K, tri, epi); break;   // 4 CTAs/SM: 35.7 TF
   }
   if (rc) return rc;
   CKL();
@@ -437,6 +434,88 @@ static int launch_i8gemm(maf_ctx* ctx, int slot, int J, int N, int K, const Buf&
   return 0;
 }
 
+// ---- training-set factorisation (factor.cuh): blocked Cholesky + triangular inverse by block doubling ------------
+static int factorize(maf_ctx* ctx) {
+  const int npad = ctx->npad, nb = npad / FAC_NB;
+  static bool attr = false;
+  if (!attr) {
+    CK(cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FAC_SMEM_BYTES));
+    attr = true;
+  }
+  double *dinv = nullptr, *panel = nullptr, *scratch = nullptr;
+  int* dinfo = nullptr;
+  const size_t half = (size_t)((nb + 1) / 2) * FAC_NB;            // largest block of the doubling recursion
+  CK(cudaMalloc((void**)&dinv, sizeof(double) * (size_t)nb * FAC_NB * FAC_NB));
+  CK(cudaMalloc((void**)&panel, sizeof(double) * (size_t)npad * FAC_NB));
+  CK(cudaMalloc((void**)&scratch, sizeof(double) * half * half));
+  CK(cudaMalloc((void**)&dinfo, sizeof(int)));
+  CK(cudaMemsetAsync(dinfo, 0, sizeof(int), ctx->stream));
+  double* L = ctx->L0;
+  int rc = 0;
+  for (int k = 0; k < nb && rc == 0; ++k) {
+    const int k0 = k * FAC_NB, rows = npad - k0 - FAC_NB;
+    double* diag = L + (size_t)k0 * npad + k0;
+    double* dk = dinv + (size_t)k * FAC_NB * FAC_NB;
+    {
+      ProfScope ps(ctx, MAF_PROF_CROSS_FWD);
+      chol_diag_kernel<<<1, 256, FAC_SMEM_BYTES, ctx->stream>>>(diag, npad, dk, dinfo, k0);
+      if (cudaGetLastError() != cudaSuccess) rc = fail(ctx, "chol_diag_kernel launch failed");
+    }
+    if (rows <= 0 || rc) continue;
+    double* below = L + (size_t)(k0 + FAC_NB) * npad + k0;       // A_ik, i > k
+    // panel = A_ik D_k^-T  (T = D_k^-1 lower-triangular), then back into place
+    rc = launch_gemm(ctx, MAF_PROF_GEMM_FWD, rows, FAC_NB, FAC_NB, below, npad, dk, FAC_NB, panel, FAC_NB, 1);
+    if (rc) break;
+    {
+      ProfScope ps(ctx, MAF_PROF_CROSS_FWD);
+      dim3 grid((FAC_NB + 127) / 128, rows);
+      copy_block_kernel<<<grid, 128, 0, ctx->stream>>>(panel, FAC_NB, below, npad, rows, FAC_NB);
+    }
+    // trailing update A_ij -= L_ik L_jk^T (lower tiles)
+    rc = launch_gemm(ctx, MAF_PROF_GEMM_FWD, rows, rows, FAC_NB, below, npad, below, npad,
+                     L + (size_t)(k0 + FAC_NB) * npad + k0 + FAC_NB, npad, 0, 1);
+  }
+  int info = 0;
+  if (rc == 0) {
+    if (cudaMemcpyAsync(&info, dinfo, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+        cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+      rc = fail(ctx, "Cholesky factorisation failed on the device: %s", cudaGetErrorString(cudaGetLastError()));
+    else if (info != 0)
+      rc = fail(ctx, "Cholesky decomposition was not successful (leading minor %d of K00 is not positive definite)", info);
+  }
+  if (rc == 0) {
+    {
+      ProfScope ps(ctx, MAF_PROF_CROSS_FWD);
+      dim3 grid((npad + 255) / 256, npad);
+      inverse_init_kernel<<<grid, 256, 0, ctx->stream>>>(dinv, L, ctx->Linv, ctx->LinvT, npad);
+    }
+    for (int b = FAC_NB; b < npad && rc == 0; b *= 2) {
+      for (int o = 0; o + b < npad && rc == 0; o += 2 * b) {
+        const int b2 = std::min(b, npad - (o + b));
+        const double* L21 = L + (size_t)(o + b) * npad + o;
+        const double* Y11 = ctx->LinvT + (size_t)o * npad + o;
+        double* X22 = ctx->Linv + (size_t)(o + b) * npad + (o + b);
+        double* X21 = ctx->Linv + (size_t)(o + b) * npad + o;
+        // scratch[b][b2] = (L21 X11)^T = Y11 L21^T ;  X21 = -X22 (L21 X11)
+        rc = launch_gemm(ctx, MAF_PROF_GEMM_FWD, b, b2, b, Y11, npad, L21, npad, scratch, b2, 0);
+        if (rc) break;
+        rc = launch_gemm(ctx, MAF_PROF_GEMM_FWD, b2, b, b2, X22, npad, scratch, b2, X21, npad, 0, 2);
+        if (rc) break;
+        ProfScope ps(ctx, MAF_PROF_CROSS_FWD);
+        dim3 grid(b / 32, b2 / 32), block(32, 8);
+        transpose_block_kernel<<<grid, block, 0, ctx->stream>>>(X21, npad, ctx->LinvT + (size_t)o * npad + (o + b), npad);
+      }
+    }
+    if (rc == 0 && cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+      rc = fail(ctx, "triangular inverse failed on the device: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  cudaFree(dinv);
+  cudaFree(panel);
+  cudaFree(scratch);
+  cudaFree(dinfo);
+  return rc;
+}
+
 // ---- life cycle ---------------------------------------------------------------------------
 extern "C" const char* maf_version(void) { return MAF_VERSION_STR; }
 
@@ -462,10 +541,6 @@ extern "C" int maf_create(int device, int dtype, maf_ctx** out) {
   CK(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10) return fail(ctx, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
   CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-  CKB(cublasCreate(&ctx->cublas));
-  CKB(cublasSetStream(ctx->cublas, ctx->stream));
-  CKB(cusolverDnCreate(&ctx->cusolver));
-  CKB(cusolverDnSetStream(ctx->cusolver, ctx->stream));
   if (const char* gv = getenv("MAF_GEMM_VARIANT")) ctx->gemm_variant = atoi(gv);
   if (const char* gi = getenv("MAF_GEMM_I8")) ctx->gemm_i8 = atoi(gi);
   if (const char* ov = getenv("MAF_OZ_VARIANT")) ctx->oz_variant = atoi(ov);
@@ -505,8 +580,6 @@ extern "C" int maf_destroy(maf_ctx* ctx) {
     for (auto e : ps.ev) cudaEventDestroy(e);
   for (auto e : ctx->timer_ev)
     if (e) cudaEventDestroy(e);
-  if (ctx->cusolver) cusolverDnDestroy(ctx->cusolver);
-  if (ctx->cublas) cublasDestroy(ctx->cublas);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return 0;
@@ -626,40 +699,8 @@ extern "C" int maf_set_train(maf_ctx* ctx, int n, const double* X0, const double
     k00_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->X0s, n, npad, ctx->mp, ctx->L0);
     CKL();
   }
-  // Cholesky: the row-major buffer viewed column-major is K00 itself (symmetric);
-  // FILL_MODE_UPPER there == lower triangle of the row-major view.
-  int lwork = 0;
-  CKB(cusolverDnDpotrf_bufferSize(ctx->cusolver, CUBLAS_FILL_MODE_UPPER, npad, ctx->L0, npad, &lwork));
-  double* work = nullptr;
-  int* dinfo = nullptr;
-  CK(cudaMalloc((void**)&work, sizeof(double) * std::max(lwork, 1)));
-  CK(cudaMalloc((void**)&dinfo, sizeof(int)));
-  int st = (int)cusolverDnDpotrf(ctx->cusolver, CUBLAS_FILL_MODE_UPPER, npad, ctx->L0, npad, work, lwork, dinfo);
-  int info = 0;
-  cudaMemcpyAsync(&info, dinfo, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
-  cudaStreamSynchronize(ctx->stream);
-  cudaFree(work);
-  cudaFree(dinfo);
-  ctx->launch_count++;
-  if (st != 0) return fail(ctx, "cusolverDnDpotrf failed with status %d", st);
-  if (info != 0) return fail(ctx, "Cholesky decomposition was not successful (leading minor %d of K00 is not positive definite)", info);
-  {
-    ProfScope ps(ctx, MAF_PROF_CROSS_FWD);
-    dim3 grid((npad + 255) / 256, npad);
-    tril_identity_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->L0, ctx->Linv, npad);
-    CKL();
-  }
-  // Linv: column-major view of L0 is U = L^T; solve U X = I  =>  X = U^-1 whose row-major view is L^-1.
-  const double one = 1.0;
-  CKB(cublasDtrsm(ctx->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, npad,
-                  npad, &one, ctx->L0, npad, ctx->Linv, npad));
-  ctx->launch_count++;
-  {
-    ProfScope ps(ctx, MAF_PROF_CROSS_FWD);
-    dim3 grid(npad / 32, npad / 32), block(32, 8);
-    transpose_kernel<<<grid, block, 0, ctx->stream>>>(ctx->Linv, ctx->LinvT, npad);
-    CKL();
-  }
+  // L0 (holding K00) -> its lower Cholesky factor, Linv = L0^-1, LinvT = L0^-T: own blocked kernels (factor.cuh)
+  if (factorize(ctx)) return 1;
   // gamma = Linv rho  (rho staged in the GEMM-independent dSig-free scratch: reuse X0s? no -> temp)
   double* drho = nullptr;
   CK(cudaMalloc((void**)&drho, sizeof(double) * npad));

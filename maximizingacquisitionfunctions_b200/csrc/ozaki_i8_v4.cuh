@@ -253,6 +253,7 @@ ozaki_i8_gemm_v4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       const uint32_t accf = oz_smem_u32(&acc_full), acce = oz_smem_u32(&acc_empty);
       uint32_t ph_full = 0u, g = 0;
       long long t_full[4] = {0, 0, 0, 0}, t_acc = 0;
+      (void)t_acc;
 #ifdef MAF_OZ_DIAG
       const long long t_begin = clock64();
 #endif
