@@ -13,9 +13,12 @@ the global best.  Prints ONE JSON line (rank 0).
   value : inputs (X, z) resident in HBM, timed with CUDA events on the library's stream.
   e2e   : the same through the host-pointer C-ABI call (maf_acq_value_grad) with pinned host
           buffers: H2D of X and z, D2H of losses and gradient inside the timed region.
-  roofline : the FP64 tensor-pipe (DMMA) contraction V^T = K10 L0^-T / Kbar = Vbar^T L0^-1;
-          algorithmic flops 2 n^2 q per restart per value+grad, durations from
-          CUDA events around every launch of that kernel.
+  roofline : the dominant kernel, the contraction V^T = K10 L0^-T / Kbar = Vbar^T L0^-1.  Default engine: exact INT8
+          digit slicing on tcgen05 (ozaki_i8_gemm_v4_kernel, 28 int8 digit-plane products per FP64 product) against
+          2 x the measured cuBLAS bf16 figure of MEASURED_PEAKS.json; --gemm f64: the FP64 DMMA kernel against the
+          repo's own cuBLAS DGEMM measurement.  Algorithmic flops 2 n^2 q per restart per value+grad,
+          durations from CUDA events around every launch of that kernel on the library's stream.
+  adam_loop : the same metric through maf_adam_steps (value+gradient, Adam update and clip on the device).
   cpu_baseline : the torch-CPU float64 restatement of the reference op sequence (oracle/), timed
           on this box's host cores on a bounded sample (rank 0, N=1 only).
 """
