@@ -65,6 +65,14 @@ __device__ __forceinline__ void oz4_load(uint32_t dst, const CUtensorMap* tm, ui
 __device__ __forceinline__ void oz4_expect(uint32_t bar_addr, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(bytes) : "memory");
 }
+// wait with cluster-scope acquire: the arrivals on acc_empty come from the peer CTA as well (release.cluster)
+__device__ __forceinline__ void oz4_wait_cluster(uint32_t bar_addr, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\tOZ4_WAIT:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1, %2;\n\t"
+      "@P1 bra OZ4_DONE;\n\tbra OZ4_WAIT;\n\tOZ4_DONE:\n\t}" ::"r"(bar_addr), "r"(parity), "r"(0x989680u)
+      : "memory");
+}
 __device__ __forceinline__ void oz4_arrive_leader(uint32_t local_bar_addr) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, 0;\n\t"
@@ -261,7 +269,7 @@ ozaki_i8_gemm_v4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         const Oz3Tile x = oz3_tile(t, nN, nJ2, p);
         if (g > 0) {
           OZ4_T0();
-          oz3_wait(acce, (g - 1) & 1u);
+          oz4_wait_cluster(acce, (g - 1) & 1u);
           OZ4_ACC(t_acc);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
@@ -272,7 +280,7 @@ ozaki_i8_gemm_v4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         if constexpr (Z::NPASS > 1) {
           {
             OZ4_T0();
-            oz3_wait(acce, (g - 1) & 1u);
+            oz4_wait_cluster(acce, (g - 1) & 1u);
             OZ4_ACC(t_acc);
           }
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
