@@ -78,7 +78,7 @@ struct maf_ctx {
   int oz_hint_a = 0, oz_hint_t = 0; // L2 policy of the A / T plane loads: 0 normal, 1 evict-first, 2 evict-last (MAF_OZ_HINTS=at)
   int oz_pf = 0;                   // L2 prefetch of plane tiles two k-chunks ahead (MAF_OZ_PF)
   int oz_dbg = 0;                  // MAF_OZ_DBG diagnostics (results invalid)
-  int oz_variant = 4;              // 1: generic kernel; 2: plane-tile ring; 3: static schedule, persistent; 4: 3 on CTA pairs (cta_group::2)
+  int oz_variant = 4;              // 1: generic kernel; 3: static schedule, persistent; 4: 3 on CTA pairs (cta_group::2)
   Buf ozA, ozTL, ozTU;             // digit planes (int8, sized in doubles): candidates / Linv / LinvT
   Buf ozsA, ozsTL, ozsTU;          // row scales
   // fantasies (rank-4 observation sets)
@@ -334,7 +334,6 @@ static int launch_i8gemm(maf_ctx* ctx, int slot, int J, int N, int K, const Buf&
   static bool attr = false;
   if (!attr) {
     CK(cudaFuncSetAttribute(ozaki_i8_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES));
-    CK(cudaFuncSetAttribute(ozaki_i8_gemm_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ2_SMEM_BYTES));
 #define OZ3_ATTR(NS_, LM_) \
   CK(cudaFuncSetAttribute(ozaki_i8_gemm_v3_kernel<NS_, LM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, Oz3<NS_, LM_>::SMEM_BYTES))
     OZ3_ATTR(7, 8); OZ3_ATTR(6, 7); OZ3_ATTR(5, 6); OZ3_ATTR(4, 5); OZ3_ATTR(3, 4);
@@ -353,8 +352,9 @@ static int launch_i8gemm(maf_ctx* ctx, int slot, int J, int N, int K, const Buf&
   const bool v3ok = lmax == ns + 1 && ns >= 3 && ns <= 7;
   int variant = ctx->oz_variant;
   if (variant == 4 && (!v3ok || J % 256 != 0)) variant = 3;       // CTA pairs need 256-row blocks
+  if (variant != 4 && variant != 3) variant = 1;
   if (variant == 3 && !v3ok) variant = 1;
-  const int bk = variant == 1 ? OZ_BK : OZ2_BK;
+  const int bk = variant == 1 ? OZ_BK : OZ3_BK;
   CUtensorMap tmA, tmT;
   if (oz_make_tmap(ctx, &tmA, (const int8_t*)Ap.p, J, K, ns, bk) ||
       oz_make_tmap(ctx, &tmT, (const int8_t*)Tp.p, N, K, ns, bk, variant == 4 ? 64 : 128))
@@ -369,8 +369,6 @@ static int launch_i8gemm(maf_ctx* ctx, int slot, int J, int N, int K, const Buf&
   ProfScope ps(ctx, slot);
   if (variant == 1) {
     ozaki_i8_gemm_kernel<<<grid, OZ_THREADS, OZ_SMEM_BYTES, ctx->stream>>>(tmA, tmT, sA.p, sT.p, C, prm);
-  } else if (variant == 2) {
-    ozaki_i8_gemm_v2_kernel<<<grid, OZ_THREADS, OZ2_SMEM_BYTES, ctx->stream>>>(tmA, tmT, sA.p, sT.p, C, prm);
 #ifdef MAF_OZ_DIAG
   } else if (variant == 3 && ns == 7 && ctx->oz_dbg > 0 && ctx->oz_dbg < 8) {
 #define OZ3_DGO(D_) case D_: ozaki_i8_gemm_v3_kernel<7, 8, D_><<<pgrid, OZ3_THREADS, Oz3<7, 8>::SMEM_BYTES, ctx->stream>>>(tmA, tmT, sA.p, sT.p, C, prm, N / OZ_BN, J / OZ_BM); break

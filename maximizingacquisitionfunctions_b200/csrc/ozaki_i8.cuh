@@ -10,7 +10,12 @@
 // FP64 posterior to ~2e-13 (tests/test_gpu_ozaki.py), i.e. the same grade as the DMMA path, at the INT8
 // rate of the part (4.58 POP/s measured vs 0.036 PFLOP/s FP64).
 //
-// Kernel: one 128x128 output tile per CTA, 6 warps: warp 0 = TMA producer (cp.async.bulk.tensor 3-D boxes
+// This file: the digit-plane producers (slicing of an FP64 matrix, fused cross-covariance and Vbar producers) and the
+// GENERIC contraction kernel, which accepts any (ns, lmax) at run time.  The configurations the pipeline uses
+// (lmax = ns + 1, 3 <= ns <= 7) run on the statically scheduled kernels of ozaki_i8_v3.cuh (single CTA) and
+// ozaki_i8_v4.cuh (CTA pairs, default), which are 2x faster; this one is their fallback and their reference in the tests.
+//
+// Generic kernel: one 128x128 output tile per CTA, 6 warps: warp 0 = TMA producer (cp.async.bulk.tensor 3-D boxes
 // {32 B, 128 rows, 1 plane}, SWIZZLE_32B, 3 smem stages, mbarrier full/empty), warp 1 = MMA issuer
 // (one thread, tcgen05.mma.cta_group::1.kind::i8 M=128 N=128 K=32, accumulators in TMEM, one per level),
 // warps 2-5 = epilogue (tcgen05.ld -> int32 -> FP64 recombination -> global).  TMEM holds 4 level
@@ -210,221 +215,6 @@ ozaki_i8_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         for (int t = 0; t < 8; t += 2) {
           double2 o = make_double2(v[t] * srow * sT[r0 + c0 + t], v[t + 1] * srow * sT[r0 + c0 + t + 1]);
           double2* dst = reinterpret_cast<double2*>(crow + c0 + t);
-          if (pass > 0) {
-            double2 old = *dst;
-            o.x += old.x;
-            o.y += old.y;
-          }
-          *dst = o;
-        }
-      }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      oz_mbar_arrive(&acc_empty);
-    }
-  }
-  __syncthreads();
-  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(512) : "memory");
-}
-
-// ---------------------------------------------------------------------------------------------
-// v2: same contraction, fed in full 128-byte lines.
-//
-// v1 moves 32-byte-wide boxes (one L2 sector per row) and needs a whole k-chunk of all planes resident per
-// stage.  v2 streams single plane tiles [128 rows][128 B] (SWIZZLE_128B, 16 KB, four K=32 MMAs per pair)
-// through a ring of OZ2_NSLOT slots, each with its own full/empty mbarrier.  Within a k-chunk the pairs are
-// walked by A plane i = 1..smax; the T planes that A_i meets form a window [lo-i, hi-i] that slides down by
-// one per step, so only the window (<= 4 tiles) and A_i are live and every tile is released by a
-// tcgen05.commit right after its last MMA.  Producer and issuer enumerate the same acquisition order, so the
-// slot of the k-th acquired tile is k mod OZ2_NSLOT on both sides.
-// ---------------------------------------------------------------------------------------------
-#define OZ2_BK 128
-#define OZ2_SLOT_BYTES (128 * OZ2_BK)
-#define OZ2_NSLOT 13
-#define OZ2_SMEM_BYTES (OZ2_NSLOT * OZ2_SLOT_BYTES + 1024)
-
-// K-major, SWIZZLE_128B canonical tile [rows][128 B]: 8-row groups are 1024 B apart
-__device__ __forceinline__ uint64_t oz_desc_sw128(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-  d |= (uint64_t)1 << 16;                 // LBO: unused for swizzled K-major
-  d |= (uint64_t)(1024 >> 4) << 32;       // SBO
-  d |= (uint64_t)1 << 46;                 // descriptor version (sm_100)
-  d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
-  return d;
-}
-
-struct OzRing {
-  uint32_t seq = 0;
-  __device__ __forceinline__ void next(int& slot, uint32_t& phase) {
-    slot = (int)(seq % OZ2_NSLOT);
-    phase = (seq / OZ2_NSLOT) & 1u;
-    ++seq;
-  }
-};
-
-__global__ void __launch_bounds__(OZ_THREADS, 1)
-ozaki_i8_gemm_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmT,
-                        const double* __restrict__ sA, const double* __restrict__ sT, double* __restrict__ C, OzParams p) {
-  extern __shared__ uint8_t oz_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(oz_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ uint64_t full_bar[OZ2_NSLOT], empty_bar[OZ2_NSLOT], acc_full, acc_empty;
-  __shared__ uint32_t tmem_base_sh;
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int rb = (p.tri == 1) ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;
-  const int r0 = rb * OZ_BN, j0 = blockIdx.y * OZ_BM;
-  const int c_begin = (p.tri == 2) ? r0 : 0;
-  const int c_end = (p.tri == 1) ? min(p.K, r0 + OZ_BN) : p.K;
-  const int kchunks = (c_end - c_begin) / OZ2_BK;
-  const int npass = (p.lmax - 1 + 3) / 4;
-
-  if (warp == 0 && lane == 0) {
-    for (int s = 0; s < OZ2_NSLOT; ++s) {
-      oz_mbar_init(&full_bar[s], 1);
-      oz_mbar_init(&empty_bar[s], 1);
-    }
-    oz_mbar_init(&acc_full, 1);
-    oz_mbar_init(&acc_empty, 128);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmT)) : "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(oz_smem_u32(&tmem_base_sh)), "r"(512) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tbase = tmem_base_sh;
-
-  if (warp == 0) {
-    // ================= TMA producer =================
-    if (lane == 0) {
-      OzRing ring;
-      int slot;
-      uint32_t phase;
-      for (int pass = 0; pass < npass; ++pass) {
-        const int lo = 2 + 4 * pass, hi = min(p.lmax, lo + 3);
-        const int smax = min(p.ns, hi - 1);
-        for (int kc = 0; kc < kchunks; ++kc) {
-          const int c = c_begin + kc * OZ2_BK;
-          int have_lo = min(p.ns, hi - 1) + 1;                // lowest T plane already requested in this chunk
-          for (int i = 1; i <= smax; ++i) {
-            const int wlo = max(1, lo - i);
-            for (int ip = have_lo - 1; ip >= wlo; --ip) {
-              ring.next(slot, phase);
-              oz_mbar_wait(&empty_bar[slot], phase ^ 1);
-              if (p.dbg & 2) { oz_mbar_arrive(&full_bar[slot]); continue; }
-              oz_mbar_expect_tx(&full_bar[slot], OZ2_SLOT_BYTES);
-              oz_tma_load_3d(smem + slot * OZ2_SLOT_BYTES, &tmT, &full_bar[slot], c, r0, ip - 1);
-            }
-            have_lo = min(have_lo, wlo);
-            ring.next(slot, phase);
-            oz_mbar_wait(&empty_bar[slot], phase ^ 1);
-            if (p.dbg & 2) { oz_mbar_arrive(&full_bar[slot]); continue; }
-            oz_mbar_expect_tx(&full_bar[slot], OZ2_SLOT_BYTES);
-            oz_tma_load_3d(smem + slot * OZ2_SLOT_BYTES, &tmA, &full_bar[slot], c, j0, i - 1);
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
-      const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BN >> 3) << 17) | ((uint32_t)(OZ_BM >> 4) << 24);
-      const uint32_t sm0 = oz_smem_u32(smem);
-      OzRing ring;
-      int slot;
-      uint32_t phase;
-      int slotT[OZ_MAXS + 1];
-      for (int pass = 0; pass < npass; ++pass) {
-        const int lo = 2 + 4 * pass, hi = min(p.lmax, lo + 3);
-        const int smax = min(p.ns, hi - 1);
-        if (pass > 0) {
-          oz_mbar_wait(&acc_empty, (uint32_t)((pass - 1) & 1));
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        }
-        for (int kc = 0; kc < kchunks; ++kc) {
-          int have_lo = min(p.ns, hi - 1) + 1;
-          for (int i = 1; i <= smax; ++i) {
-            const int wlo = max(1, lo - i), whi = min(p.ns, hi - i);
-            for (int ip = have_lo - 1; ip >= wlo; --ip) {
-              ring.next(slot, phase);
-              oz_mbar_wait(&full_bar[slot], phase);
-              slotT[ip] = slot;
-            }
-            have_lo = min(have_lo, wlo);
-            ring.next(slot, phase);
-            oz_mbar_wait(&full_bar[slot], phase);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int slotA = slot;
-            const uint64_t da0 = oz_desc_sw128(sm0 + (uint32_t)(slotA * OZ2_SLOT_BYTES));
-            for (int ip = wlo; ip <= whi; ++ip) {
-              const int l = i + ip;
-              const uint32_t d_tmem = tbase + (uint32_t)((l - lo) * OZ_BN);
-              const uint64_t db0 = oz_desc_sw128(sm0 + (uint32_t)(slotT[ip] * OZ2_SLOT_BYTES));
-              const bool fresh = (kc == 0) && (i == max(1, l - p.ns));
-#pragma unroll
-              for (int k = 0; k < OZ2_BK / 32; ++k)
-                if (!(p.dbg & 1)) oz_mma_i8(d_tmem, da0 + (uint64_t)(k * 2), db0 + (uint64_t)(k * 2), idesc, (fresh && k == 0) ? 0u : 1u);
-            }
-            oz_commit(&empty_bar[slotA]);
-            if (i < smax) {
-              if (hi - i <= p.ns) oz_commit(&empty_bar[slotT[hi - i]]);
-            } else {
-              for (int ip = wlo; ip <= whi; ++ip) oz_commit(&empty_bar[slotT[ip]]);
-            }
-          }
-        }
-        oz_commit(&acc_full);
-      }
-    }
-  } else {
-    // ================= epilogue: TMEM -> FP64 -> global =================
-    const int quarter = warp & 3;
-    const int row = quarter * 32 + lane;
-    const size_t j = (size_t)(j0 + row);
-    const double srow = sA[j];
-    double* crow = C + j * p.ldc + r0;
-    const double* st = sT + r0;
-    const uint32_t lane_addr = tbase + ((uint32_t)(quarter * 32) << 16);
-    for (int pass = 0; pass < npass; ++pass) {
-      const int lo = 2 + 4 * pass, hi = min(p.lmax, lo + 3);
-      const int nl = hi - lo + 1;
-      double w[4];
-#pragma unroll
-      for (int t = 0; t < 4; ++t) w[t] = (t < nl) ? exp2((double)(2 - 8 * (lo + t))) * srow : 0.0;
-      oz_mbar_wait(&acc_full, (uint32_t)(pass & 1));
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      for (int c0 = 0; c0 < ((p.dbg & 4) ? 0 : OZ_BN); c0 += 8) {
-        uint32_t r[4][8];
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          if (t < nl) {
-            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                         : "=r"(r[t][0]), "=r"(r[t][1]), "=r"(r[t][2]), "=r"(r[t][3]), "=r"(r[t][4]), "=r"(r[t][5]),
-                           "=r"(r[t][6]), "=r"(r[t][7])
-                         : "r"(lane_addr + (uint32_t)(t * OZ_BN + c0)));
-          } else {
-#pragma unroll
-            for (int u = 0; u < 8; ++u) r[t][u] = 0u;
-          }
-        }
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        double v[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          double a = (double)(int)r[3][u] * w[3];             // smallest contributions first
-          a = fma((double)(int)r[2][u], w[2], a);
-          a = fma((double)(int)r[1][u], w[1], a);
-          a = fma((double)(int)r[0][u], w[0], a);
-          v[u] = a * st[c0 + u];
-        }
-#pragma unroll
-        for (int u = 0; u < 8; u += 2) {
-          double2 o = make_double2(v[u], v[u + 1]);
-          double2* dst = reinterpret_cast<double2*>(crow + c0 + u);
           if (pass > 0) {
             double2 old = *dst;
             o.x += old.x;
