@@ -1,0 +1,15 @@
+#!/bin/bash
+# HEAD verification: full GPU suite, smoke, bench (both arms), launch list.
+mkdir -p gpurun_out
+date
+timeout 1500 python -m pytest tests -m gpu -q -rA --no-header -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"
+tail -3 gpurun_out/pytest_gpu.log; grep -E "^(FAILED|ERROR)" gpurun_out/pytest_gpu.log | head; grep -E "^E  " gpurun_out/pytest_gpu.log | head
+date
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/smoke.log
+timeout 900 python bench.py > gpurun_out/bench.log 2>&1; echo "bench rc=$?"
+tail -1 gpurun_out/bench.log | cut -c1-1500
+date
+BENCH="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv $BENCH > gpurun_out/ncu_launches.log 2>&1
+echo "launch list rc=$?"
+date
