@@ -73,12 +73,13 @@ struct maf_ctx {
   int gemm_i8 = 1;                 // requested mode (default: INT8 digit slicing; DMMA when n > 8192)
   bool i8_ready = false;           // factor planes built for the current training set
   int oz_ns = 7, oz_lmax = 8;
+  int oz_ns_bwd = 6, oz_lmax_bwd = 7;   // reverse contraction Kbar10 = Vbar^T L0^-1: 6 planes / 21 products (MAF_OZ_NS_BWD)
   int oz_fuse = 3;                 // bit 0: cross-covariance, bit 1: Vbar written straight to digit planes (MAF_OZ_FUSE)
   int oz_sj = 4;                   // super-row height of the persistent tile order (MAF_OZ_SJ)
   int oz_hint_a = 0, oz_hint_t = 0; // L2 policy of the A / T plane loads: 0 normal, 1 evict-first, 2 evict-last (MAF_OZ_HINTS=at)
   int oz_pf = 0;                   // L2 prefetch of plane tiles two k-chunks ahead (MAF_OZ_PF)
   int oz_dbg = 0;                  // MAF_OZ_DBG diagnostics (results invalid)
-  int oz_variant = 4;              // 1: generic kernel; 3: static schedule, persistent; 4: 3 on CTA pairs (cta_group::2)
+  int oz_variant = 5;              // 1: generic kernel; 3: static schedule, persistent; 4: 3 on CTA pairs (cta_group::2); 5: 4 + register-stash epilogue
   Buf ozA, ozTL, ozTU;             // digit planes (int8, sized in doubles): candidates / Linv / LinvT
   Buf ozsA, ozsTL, ozsTU;          // row scales
   // fantasies (rank-4 observation sets)
@@ -342,6 +343,10 @@ static int launch_i8gemm(maf_ctx* ctx, int slot, int J, int N, int K, const Buf&
   CK(cudaFuncSetAttribute(ozaki_i8_gemm_v4_kernel<NS_, LM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, Oz4<NS_, LM_>::SMEM_BYTES))
     OZ4_ATTR(7, 8); OZ4_ATTR(6, 7); OZ4_ATTR(5, 6); OZ4_ATTR(4, 5); OZ4_ATTR(3, 4);
 #undef OZ4_ATTR
+#define OZ5_ATTR(NS_, LM_) \
+  CK(cudaFuncSetAttribute(ozaki_i8_gemm_v4_kernel<NS_, LM_, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Oz4<NS_, LM_>::SMEM_BYTES))
+    OZ5_ATTR(7, 8); OZ5_ATTR(6, 7); OZ5_ATTR(5, 6); OZ5_ATTR(4, 5); OZ5_ATTR(3, 4);
+#undef OZ5_ATTR
 #ifdef MAF_OZ_DIAG
 #define OZ3_DATTR(D_) CK(cudaFuncSetAttribute(ozaki_i8_gemm_v3_kernel<7, 8, D_>, cudaFuncAttributeMaxDynamicSharedMemorySize, Oz3<7, 8>::SMEM_BYTES))
     OZ3_DATTR(1); OZ3_DATTR(2); OZ3_DATTR(3); OZ3_DATTR(4); OZ3_DATTR(5); OZ3_DATTR(6); OZ3_DATTR(7);
@@ -351,6 +356,8 @@ static int launch_i8gemm(maf_ctx* ctx, int slot, int J, int N, int K, const Buf&
   }
   const bool v3ok = lmax == ns + 1 && ns >= 3 && ns <= 7;
   int variant = ctx->oz_variant;
+  const bool stash = variant == 5;                                // variant 5 = CTA pairs + register-stash epilogue
+  if (variant == 5) variant = 4;
   if (variant == 4 && (!v3ok || J % 256 != 0)) variant = 3;       // CTA pairs need 256-row blocks
   if (variant != 4 && variant != 3) variant = 1;
   if (variant == 3 && !v3ok) variant = 1;
@@ -391,13 +398,28 @@ static int launch_i8gemm(maf_ctx* ctx, int slot, int J, int N, int K, const Buf&
   case NS_:                                                                                                                  \
     ozaki_i8_gemm_v4_kernel<NS_, LM_><<<cgrid, OZ4_THREADS, Oz4<NS_, LM_>::SMEM_BYTES, ctx->stream>>>(tmA, tmT, sA.p, sT.p, C, prm, N / OZ_BN, J / 256); \
     break
-    switch (ns) {
-      OZ4_GO(7, 8);
-      OZ4_GO(6, 7);
-      OZ4_GO(5, 6);
-      OZ4_GO(4, 5);
-      OZ4_GO(3, 4);
+#define OZ5_GO(NS_, LM_)                                                                                                     \
+  case NS_:                                                                                                                  \
+    ozaki_i8_gemm_v4_kernel<NS_, LM_, 1><<<cgrid, OZ4_THREADS, Oz4<NS_, LM_>::SMEM_BYTES, ctx->stream>>>(tmA, tmT, sA.p, sT.p, C, prm, N / OZ_BN, J / 256); \
+    break
+    if (stash) {
+      switch (ns) {
+        OZ5_GO(7, 8);
+        OZ5_GO(6, 7);
+        OZ5_GO(5, 6);
+        OZ5_GO(4, 5);
+        OZ5_GO(3, 4);
+      }
+    } else {
+      switch (ns) {
+        OZ4_GO(7, 8);
+        OZ4_GO(6, 7);
+        OZ4_GO(5, 6);
+        OZ4_GO(4, 5);
+        OZ4_GO(3, 4);
+      }
     }
+#undef OZ5_GO
 #undef OZ4_GO
 #ifdef MAF_OZ_DIAG
     if (prm.stats) {
@@ -533,6 +555,8 @@ extern "C" int maf_create(int device, int dtype, maf_ctx** out) {
     // close to the bar); everything else, and the ABI, stays FP64.
     ctx->oz_ns = 5;
     ctx->oz_lmax = 6;
+    ctx->oz_ns_bwd = 5;
+    ctx->oz_lmax_bwd = 6;
   }
   CK(cudaSetDevice(device));
   cudaDeviceProp prop;
@@ -549,6 +573,10 @@ extern "C" int maf_create(int device, int dtype, maf_ctx** out) {
     if (h[0] && h[1]) ctx->oz_hint_t = h[1] - '0';
   }
   if (const char* pf = getenv("MAF_OZ_PF")) ctx->oz_pf = atoi(pf);
+  if (const char* nb = getenv("MAF_OZ_NS_BWD")) {
+    const int v = atoi(nb);
+    if (v >= 3 && v <= ctx->oz_ns) ctx->oz_ns_bwd = v, ctx->oz_lmax_bwd = v + 1;
+  }
   if (const char* sj = getenv("MAF_OZ_SJ")) ctx->oz_sj = atoi(sj) > 0 ? atoi(sj) : 1;
   CK(cudaMalloc((void**)&ctx->d_argmin_val, sizeof(double)));
   CK(cudaMalloc((void**)&ctx->d_argmin_idx, sizeof(long long)));
@@ -864,16 +892,18 @@ static int run_chunk(maf_ctx* ctx, const AcqDev& ap, bool posterior_only, bool c
   }
   if (!need_grad) return 0;
   if (fused_bwd) {
+    // the digit planes of L0^-T were written with oz_ns digits; their first oz_ns_bwd planes are the balanced
+    // expansion rounded to that many digits, so the same buffer serves the shorter reverse contraction
     const size_t bytes = (size_t)ctx->oz_ns * Jpad * npad;
     if (ensure(ctx, ctx->ozA, (bytes + 7) / 8) || ensure(ctx, ctx->ozsA, (size_t)Jpad)) return 1;
     {
       ProfScope ps(ctx, MAF_PROF_VBAR);
-      DISPATCH_Q(q, vbar_planes_kernel<Q><<<sc + (Jpad - J), 256, 0, ctx->stream>>>(Vt, npad, sc, Jpad, ctx->gamma, mubar, Sigbar, ctx->oz_ns,
+      DISPATCH_Q(q, vbar_planes_kernel<Q><<<sc + (Jpad - J), 256, 0, ctx->stream>>>(Vt, npad, sc, Jpad, ctx->gamma, mubar, Sigbar, ctx->oz_ns_bwd,
                                                                                    (int8_t*)ctx->ozA.p, ctx->ozsA.p));
       CKL();
     }
     if (launch_i8gemm(ctx, MAF_PROF_GEMM_BWD, Jpad, npad, npad, ctx->ozA, ctx->ozsA, ctx->ozTU, ctx->ozsTU, K10, npad, 2,
-                      ctx->oz_ns, ctx->oz_lmax))
+                      ctx->oz_ns_bwd, ctx->oz_lmax_bwd))
       return 1;
   } else {
     {
@@ -882,9 +912,9 @@ static int run_chunk(maf_ctx* ctx, const AcqDev& ap, bool posterior_only, bool c
       CKL();
     }
     if (ctx->i8_ready) {
-      if (oz_slice(ctx, MAF_PROF_VBAR, Vt, npad, J, Jpad, npad, ctx->oz_ns, 0.0, ctx->ozA, ctx->ozsA)) return 1;
+      if (oz_slice(ctx, MAF_PROF_VBAR, Vt, npad, J, Jpad, npad, ctx->oz_ns_bwd, 0.0, ctx->ozA, ctx->ozsA)) return 1;
       if (launch_i8gemm(ctx, MAF_PROF_GEMM_BWD, Jpad, npad, npad, ctx->ozA, ctx->ozsA, ctx->ozTU, ctx->ozsTU, K10, npad, 2,
-                        ctx->oz_ns, ctx->oz_lmax))
+                        ctx->oz_ns_bwd, ctx->oz_lmax_bwd))
         return 1;
     } else if (launch_gemm(ctx, MAF_PROF_GEMM_BWD, Jpad, npad, npad, Vt, npad, ctx->LinvT, npad, K10, npad, 2)) {
       return 1;
@@ -1210,9 +1240,9 @@ static int run_fantasies(maf_ctx* ctx, const maf_acq_params* prm, int S, const d
       CKL();
     }
     if (ctx->i8_ready) {
-      if (oz_slice(ctx, MAF_PROF_VBAR, ctx->Vt.p, npad, sc, Jpad, npad, ctx->oz_ns, 0.0, ctx->ozA, ctx->ozsA)) return 1;
+      if (oz_slice(ctx, MAF_PROF_VBAR, ctx->Vt.p, npad, sc, Jpad, npad, ctx->oz_ns_bwd, 0.0, ctx->ozA, ctx->ozsA)) return 1;
       if (launch_i8gemm(ctx, MAF_PROF_GEMM_BWD, Jpad, npad, npad, ctx->ozA, ctx->ozsA, ctx->ozTU, ctx->ozsTU, ctx->K10.p, npad, 2,
-                        ctx->oz_ns, ctx->oz_lmax))
+                        ctx->oz_ns_bwd, ctx->oz_lmax_bwd))
         return 1;
     } else if (launch_gemm(ctx, MAF_PROF_GEMM_BWD, Jpad, npad, npad, ctx->Vt.p, npad, ctx->LinvT, npad, ctx->K10.p, npad, 2)) {
       return 1;

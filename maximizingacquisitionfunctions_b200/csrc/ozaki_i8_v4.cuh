@@ -201,8 +201,123 @@ __device__ __forceinline__ void oz4_issue_pass(uint32_t desc0, uint32_t full0, u
   }
 }
 
-// nJ2 = row blocks of 256 (one per CTA pair); tile order as in v3 with 256-row blocks
+// ---- epilogue with the pass-0 partial result held in registers (EPI = 1, variant 5, default) ----------------------
+// Each epilogue lane owns the same 32 elements of the 128 x 128 tile in both passes (fragment layout of
+// tcgen05.ld.16x256b: lane t holds rows t/4 and t/4 + 8, columns 2 (t%4) + {0,1} of every 16 x 8 block).  A pass is
+// DRAINED into registers (tcgen05.ld + exact int64 Horner recombination of its <= 4 level accumulators) and tensor
+// memory goes back to the issuer at once; FP64 conversion (in place), scaling and the global stores run after the
+// hand-over, under the MMAs of the next pass / tile.  C is written exactly once and never read back:
+//   sum_l 2^(2-8l) S_l = 2^(2 - 8 hi1) (H0 2^(8 nl1) + H1),   H_p = sum_{l in pass p} S_l 2^(8 (hi_p - l)),
+// |H0| < 2^46 is exact in FP64, and the FMA rounds once (the EPI = 0 path rounds every pass: last-bit differences).
 template <int NS, int LMAX>
+__device__ __forceinline__ void oz4_epilogue_stash(const double* __restrict__ sA, const double* __restrict__ sT,
+                                                   double* __restrict__ C, const OzParams& p, int nN, int nJ2, int cluster_id,
+                                                   int nclusters, uint32_t rank, int warp, int lane, uint32_t tbase, uint32_t accf,
+                                                   uint32_t acce) {
+  using Z = Oz4<NS, LMAX>;
+  static_assert(Z::NPASS <= 2, "register-stash epilogue: at most two passes");
+  constexpr int EW = (OZ4_THREADS - 64) / 128;
+  constexpr int CW = OZ_BN / EW;
+  constexpr int NG = CW / 16;
+  constexpr int NE = NG * 2 * 8;                             // elements per lane
+  const int quarter = warp & 3;
+  const int part = (warp - 2) >> 2;
+  const int fr = lane >> 2, fc = (lane & 3) * 2;
+  const int ntiles = nN * nJ2;
+  uint32_t g = 0;
+  long long H[NE];                                           // [gq][h][n][e][c]; int64 after pass 0, FP64 bits afterwards
+  for (int t = cluster_id; t < ntiles; t += nclusters) {
+    const Oz3Tile x = oz3_tile(t, nN, nJ2, p);
+    const int j0 = 2 * x.j0 + 128 * (int)rank;
+#pragma unroll
+    for (int pass = 0; pass < Z::NPASS; ++pass) {
+      const int nl = Z::hi(pass) - Z::lo(pass) + 1;
+      oz3_wait(accf, g & 1u);
+      ++g;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#ifdef MAF_OZ_DIAG
+      const long long te0 = clock64();
+#endif
+#pragma unroll
+      for (int gq = 0; gq < NG; ++gq) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+          for (int n = 0; n < 2; ++n) {                      // one load = 16 rows x 8 columns: 4 registers per level
+            const uint32_t taddr = tbase + ((uint32_t)(quarter * 32 + h * 16) << 16) + (uint32_t)(part * CW + gq * 16 + n * 8);
+            uint32_t r[4][4];
+#pragma unroll
+            for (int tt = 0; tt < 4; ++tt) {
+              if (tt < nl) {
+                asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(r[tt][0]), "=r"(r[tt][1]), "=r"(r[tt][2]), "=r"(r[tt][3])
+                             : "r"(taddr + (uint32_t)(tt * OZ_BN)));
+              }
+            }
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {                    // u = 2 e + c
+              long long acc = (long long)(int)r[0][u];
+#pragma unroll
+              for (int tt = 1; tt < 4; ++tt)
+                if (tt < nl) acc = acc * 256 + (long long)(int)r[tt][u];
+              const int idx = ((gq * 2 + h) * 2 + n) * 4 + u;
+              if (pass == 0) {
+                H[idx] = acc;
+              } else {
+                const double tot = fma(__longlong_as_double(H[idx]), (double)(1ull << (8 * nl)), oz3_ll2double(acc));
+                H[idx] = __double_as_longlong(tot);
+              }
+            }
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) oz4_arrive_leader(acce);                // tensor memory is free again
+#ifdef MAF_OZ_DIAG
+      if (p.stats && rank == 0 && warp == 2 && lane == 0) p.stats[8 * cluster_id + 3] += clock64() - te0;   // drain (one warp)
+#endif
+      if (pass + 1 < Z::NPASS) {
+#pragma unroll
+        for (int idx = 0; idx < NE; ++idx) H[idx] = __double_as_longlong(oz3_ll2double(H[idx]));
+      } else {
+        const double w = exp2((double)(2 - 8 * Z::hi(pass)));
+#pragma unroll
+        for (int gq = 0; gq < NG; ++gq) {
+          double2 sc[2];
+#pragma unroll
+          for (int n = 0; n < 2; ++n) sc[n] = __ldg(reinterpret_cast<const double2*>(sT + x.r0 + part * CW + gq * 16 + fc + 8 * n));
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const size_t j = (size_t)(j0 + quarter * 32 + h * 16 + fr + 8 * e);
+              const double sa = __ldg(sA + j) * w;
+              double* crow = C + j * p.ldc + x.r0 + part * CW + gq * 16 + fc;
+#pragma unroll
+              for (int n = 0; n < 2; ++n) {
+                const int idx = ((gq * 2 + h) * 2 + n) * 4 + 2 * e;
+                double v0, v1;
+                if (Z::NPASS == 1) {
+                  v0 = oz3_ll2double(H[idx]);
+                  v1 = oz3_ll2double(H[idx + 1]);
+                } else {
+                  v0 = __longlong_as_double(H[idx]);
+                  v1 = __longlong_as_double(H[idx + 1]);
+                }
+                *reinterpret_cast<double2*>(crow + 8 * n) = make_double2(v0 * sc[n].x * sa, v1 * sc[n].y * sa);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// nJ2 = row blocks of 256 (one per CTA pair); tile order as in v3 with 256-row blocks
+template <int NS, int LMAX, int EPI = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(OZ4_THREADS, 1)
 ozaki_i8_gemm_v4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmT,
                         const double* __restrict__ sA, const double* __restrict__ sT, double* __restrict__ C, OzParams p,
@@ -299,6 +414,9 @@ ozaki_i8_gemm_v4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       }
 #endif
     }
+  } else if constexpr (EPI == 1) {
+    oz4_epilogue_stash<NS, LMAX>(sA, sT, C, p, nN, nJ2, cluster_id, nclusters, rank, warp, lane, tbase, oz_smem_u32(&acc_full),
+                                 oz_smem_u32(&acc_empty));
   } else {
     // ================= epilogue (both CTAs, own 128 rows): as v3 =================
     constexpr int EW = (OZ4_THREADS - 64) / 128;

@@ -45,10 +45,11 @@ def sliced_product(A, T, ns, lmax):
     return C * sa * st.T
 
 
-@pytest.mark.parametrize("variant", [4, 3, 1])
+@pytest.mark.parametrize("variant", [5, 4, 3, 1])
 @pytest.mark.parametrize("ns,lmax", [(1, 2), (2, 3), (2, 4), (3, 4), (4, 5), (5, 6), (6, 7), (5, 7), (7, 8), (7, 14)])
 def test_digit_planes_are_multiplied_exactly(ns, lmax, variant):
-    """variant 4 = statically scheduled persistent kernel on CTA pairs (tcgen05 cta_group::2; lmax == ns + 1,
+    """variant 5 = variant 4 with the register-stash epilogue (C written once, tensor memory handed back after the drain),
+    variant 4 = statically scheduled persistent kernel on CTA pairs (tcgen05 cta_group::2; lmax == ns + 1,
     3 <= ns <= 7, rows a multiple of 256), variant 3 = the same on single CTAs, variant 1 = generic kernel; a
     variant that does not cover a configuration hands over to the next one."""
     import os
