@@ -43,6 +43,8 @@ def build(force=False, verbose=False):
         return LIB
     # no CUDA math libraries: every kernel, including the training-set factorisation, is in csrc/
     cmd = [_nvcc()] + NVCC_FLAGS + ["-o", LIB, os.path.join(CSRC, "maf_api.cu")]
+    for extra in os.environ.get("MAF_NVCC_DEFS", "").split():   # tuning experiments: -DNAME=value overrides of kernel macros
+        cmd.insert(1, extra)
     if os.environ.get("MAF_OZ_DIAG"):
         cmd.insert(1, "-DMAF_OZ_DIAG")      # extra diagnostic instantiations of the INT8 kernel (MAF_OZ_DBG)
     if verbose:

@@ -56,6 +56,88 @@ __device__ __forceinline__ double kern_dr2(int kid, double r2) {
   return -1.5 * exp(-r);
 }
 
+// ---- lean FP64 sqrt / exp for the two FP64-pipe-bound covariance kernels (cross_fwd_planes, cross_bwd) -------------
+// Both kernels spend ~60 FP64 instructions per (candidate, training point) pair, a third of it inside the library's
+// sqrt (IEEE rounding, slow-path call) and exp (degree-11 polynomial).  The arguments here are confined
+// (u in [5 eps, ~1e3], r >= 0), so:
+//   sqrt: FP32 rsqrt seed (2^-22) + two coupled Heron steps  r <- r + (u - r^2) y/2 : error eps^2/2 + eps delta < 2^-60
+//         before rounding (6 FP64 instructions, <= 1 ulp);
+//   exp(-r) = 2^m T[j] e^f,  k = rint(-r 32/ln2) = 32 m + j,  |f| <= ln2/64: degree-6 Taylor (next term 3.5e-18),
+//         T[j] = 2^(j/32) from a 32-entry shared-memory table, 2^m folded into the exponent field (11 FP64 instructions,
+//         <= 2 ulp).  Results are a few ulp from the library's; the parity bar is 1e-9.
+#define MAF_ETAB 32
+// coefficients live in the constant bank so that every DFMA takes them as a c[][] operand (as literals the compiler
+// rebuilds each 64-bit immediate with two moves per use: 18 of the kernel's 126 instructions per element)
+__constant__ double MAF_FC[10] = {
+    -46.16624130844683,        // 0: -32/ln2
+    -0.021660849391992087,     // 1: -(ln2/32) high part 0x1.62e42fef8p-6 (34 bits: k * hi is exact)
+    -5.062034433330175e-13,    // 2: -(ln2/32) low part
+    1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0,        // 3..6: Taylor coefficients of e^f
+    1.0 / 3.0,                 // 7
+    6755399441055744.0,        // 8: 1.5 2^52
+    1.0e6};                    // 9: cap of the exponent argument
+__device__ __forceinline__ void maf_fill_etab(double* tab, int tid) {
+  if (tid < MAF_ETAB) tab[tid] = exp2((double)tid * (1.0 / MAF_ETAB));
+}
+// max(x, eps) for x >= 0: eps = 2^-52 has a zero low word, so the comparison is one integer compare on the high word
+__device__ __forceinline__ double maf_clamp_eps(double x) {
+  return (__double2hiint(x) < 0x3CB00000) ? MAF_EPS_F64 : x;
+}
+__device__ __forceinline__ double maf_sqrt_fast(double u) {   // 2^-126 < u < 2^127
+  float yf;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(yf) : "f"((float)u));
+  const double y = (double)yf;
+  const double hy = 0.5 * y;
+  double r = u * y;
+  r = fma(fma(-r, r, u), hy, r);
+  r = fma(fma(-r, r, u), hy, r);
+  return r;
+}
+__device__ __forceinline__ double maf_exp_neg_fast(double r, const double* __restrict__ tab) {   // r >= 0
+  if (__double2hiint(r) > 0x412E8480) r = MAF_FC[9];         // r > 1e6 (result 0 either way): keeps k inside int32
+  const double t = fma(r, MAF_FC[0], MAF_FC[8]);             // -r 32/ln2 rounded to an integer in the low word
+  const int k = __double2loint(t);
+  const double kd = t - MAF_FC[8];
+  double f = fma(kd, MAF_FC[1], -r);
+  f = fma(kd, MAF_FC[2], f);
+  double p = fma(f, MAF_FC[3], MAF_FC[4]);
+  p = fma(p, f, MAF_FC[5]);
+  p = fma(p, f, MAF_FC[6]);
+  p = fma(p, f, 0.5);
+  p = fma(p, f, 1.0);
+  p = fma(p, f, 1.0);
+  const double tj = tab[k & (MAF_ETAB - 1)];
+  const int m = max(k >> 5, -1021);                          // floor(k / 32) <= 0; below 2^-1021 the result is "tiny", not exact
+  const double s = __hiloint2double(__double2hiint(tj) + (m << 20), __double2loint(tj));
+  return s * p;
+}
+
+template <int KID>
+__device__ __forceinline__ double kern_val_fast(double r2, const double* __restrict__ tab) {
+  if (KID == MAF_KERNEL_SE) return maf_exp_neg_fast(0.5 * r2, tab);
+  if (KID == MAF_KERNEL_MATERN52) {
+    const double u = 5.0 * maf_clamp_eps(r2);
+    const double r = maf_sqrt_fast(u);
+    return fma(u, MAF_FC[7], 1.0 + r) * maf_exp_neg_fast(r, tab);
+  }
+  const double r = maf_sqrt_fast(3.0 * maf_clamp_eps(r2));
+  return (1.0 + r) * maf_exp_neg_fast(r, tab);
+}
+template <int KID>
+__device__ __forceinline__ double kern_dr2_fast(double r2, const double* __restrict__ tab) {
+  if (KID == MAF_KERNEL_SE) return -0.5 * maf_exp_neg_fast(0.5 * r2, tab);
+  const bool below = __double2hiint(r2) < 0x3CB00000;        // r2 < eps: the clamp blocks the gradient
+  const double rc = below ? MAF_EPS_F64 : r2;
+  if (KID == MAF_KERNEL_MATERN52) {
+    const double r = maf_sqrt_fast(5.0 * rc);
+    const double g = (1.0 + r) * maf_exp_neg_fast(r, tab);
+    return below ? 0.0 : -(5.0 / 6.0) * g;
+  }
+  const double r = maf_sqrt_fast(3.0 * rc);
+  const double g = maf_exp_neg_fast(r, tab);
+  return below ? 0.0 : -1.5 * g;
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -88,8 +88,14 @@ cross_fwd_kernel(const double* __restrict__ X, int J, const double* __restrict__
 // One warp per candidate row (block = one restart, q warps); lanes stride over k with
 // coalesced reads of Kbar10 and of the SoA training set; warp-shuffle reduction.
 // ---------------------------------------------------------------------------
-template <int D>
-__global__ void __launch_bounds__(512, (D > 0 && D <= 8) ? 2 : 1)      // <= 64 registers: 32 warps per SM
+#ifndef CROSS_BWD_MINB
+#define CROSS_BWD_MINB 2
+#endif
+#ifndef CROSS_BWD_UNROLL
+#define CROSS_BWD_UNROLL 1
+#endif
+template <int D, int KID>
+__global__ void __launch_bounds__(512, (D > 0 && D <= 8) ? CROSS_BWD_MINB : 1)      // MINB = 2: <= 64 registers, 32 warps per SM
 cross_bwd_kernel(const double* __restrict__ X, int S, int q, int p,
                                  const double* __restrict__ X0s, int n, int npad, ModelParams mp,
                                  const double* __restrict__ Kbar /*[S*q][npad]*/,
@@ -97,6 +103,9 @@ cross_bwd_kernel(const double* __restrict__ X, int S, int q, int p,
                                  double* __restrict__ grad /*[S][q-p][d]*/) {
   constexpr int DD = D > 0 ? D : MAF_MAX_D;
   const int d = D > 0 ? D : mp.d;
+  __shared__ double etab[MAF_ETAB];
+  maf_fill_etab(etab, threadIdx.x);
+  __syncthreads();
   const int s = blockIdx.x;
   const int i = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -109,6 +118,8 @@ cross_bwd_kernel(const double* __restrict__ X, int S, int q, int p,
     acc[c] = 0.0;
   }
   const double* kb = Kbar + j * npad;
+  constexpr int UNR = CROSS_BWD_UNROLL;
+#pragma unroll UNR
   for (int k = lane; k < n; k += 32) {
     double x0[DD];
     double r2 = 0.0;
@@ -120,7 +131,7 @@ cross_bwd_kernel(const double* __restrict__ X, int S, int q, int p,
         r2 += df * df;
       }
     }
-    double g = kb[k] * kern_dr2(mp.kernel_id, r2);
+    double g = kb[k] * kern_dr2_fast<KID>(r2, etab);
 #pragma unroll
     for (int c = 0; c < DD; ++c)
       if (c < d) acc[c] += g * (xi[c] - x0[c]);
@@ -139,7 +150,7 @@ cross_bwd_kernel(const double* __restrict__ X, int S, int q, int p,
       }
     }
     const double* sb = Sigbar + (size_t)s * q * q;
-    double g = (sb[i * q + lane] + sb[lane * q + i]) * kern_dr2(mp.kernel_id, r2);
+    double g = (sb[i * q + lane] + sb[lane * q + i]) * kern_dr2_fast<KID>(r2, etab);
 #pragma unroll
     for (int c = 0; c < DD; ++c)
       if (c < d) acc[c] += g * (xi[c] - xj[c]);

@@ -73,7 +73,10 @@ struct maf_ctx {
   int gemm_i8 = 1;                 // requested mode (default: INT8 digit slicing; DMMA when n > 8192)
   bool i8_ready = false;           // factor planes built for the current training set
   int oz_ns = 7, oz_lmax = 8;
-  int oz_ns_bwd = 6, oz_lmax_bwd = 7;   // reverse contraction Kbar10 = Vbar^T L0^-1: 6 planes / 21 products (MAF_OZ_NS_BWD)
+  // reverse contraction Kbar10 = Vbar^T L0^-1.  MAF_OZ_NS_BWD=6 (21 products instead of 28) makes it 25 % faster but the
+  // gradient error at n=4096 rises from the FP64 noise floor (4e-12 .. 2e-11) to 6e-10 .. 5e-9 for candidates next to
+  // training points (profiles/r01_accuracy_n4096.jsonl): above the 1e-9 bar, so the default keeps all 7 planes.
+  int oz_ns_bwd = 7, oz_lmax_bwd = 8;
   int oz_fuse = 3;                 // bit 0: cross-covariance, bit 1: Vbar written straight to digit planes (MAF_OZ_FUSE)
   int oz_sj = 4;                   // super-row height of the persistent tile order (MAF_OZ_SJ)
   int oz_hint_a = 0, oz_hint_t = 0; // L2 policy of the A / T plane loads: 0 normal, 1 evict-first, 2 evict-last (MAF_OZ_HINTS=at)
@@ -246,6 +249,19 @@ __global__ void diag_extract_kernel(const double* __restrict__ Sig, int S, int q
     case 8: { constexpr int D = 8; __VA_ARGS__; } break;                           \
     default: { constexpr int D = 0; __VA_ARGS__; } break;                          \
   }
+
+// compile-time input dimension D and kernel id KID (the two FP64-pipe-bound covariance kernels)
+#define DISPATCH_DK(d, kid, ...)                                                   \
+  switch (kid) {                                                                   \
+    case MAF_KERNEL_SE: { constexpr int KID = MAF_KERNEL_SE; DISPATCH_D(d, __VA_ARGS__) } break;             \
+    case MAF_KERNEL_MATERN52: { constexpr int KID = MAF_KERNEL_MATERN52; DISPATCH_D(d, __VA_ARGS__) } break; \
+    default: { constexpr int KID = MAF_KERNEL_MATERN32; DISPATCH_D(d, __VA_ARGS__) } break;                  \
+  }
+
+// ... and compile-time digit count NSC for the FP64-grade configuration (7 planes); other counts at run time
+#define DISPATCH_DKN(d, kid, ns, ...)                                              \
+  if ((ns) == 7) { constexpr int NSC = 7; DISPATCH_DK(d, kid, __VA_ARGS__) }       \
+  else { constexpr int NSC = 0; DISPATCH_DK(d, kid, __VA_ARGS__) }
 
 // GEMM variants (selected by MAF_GEMM_VARIANT at context creation; 0 is the default)
 template <int BM, int BN, int BK, int STAGES, int WJ, int WR, int MINB>
@@ -841,7 +857,7 @@ static int run_chunk(maf_ctx* ctx, const AcqDev& ap, bool posterior_only, bool c
     {
       ProfScope ps(ctx, MAF_PROF_CROSS_FWD);
       dim3 grid((npad + OZC_THREADS * 4 - 1) / (OZC_THREADS * 4), Jpad / OZC_TJ);
-      DISPATCH_D(d, cross_fwd_planes_kernel<D><<<grid, OZC_THREADS, 0, ctx->stream>>>(dX, J, Jpad, ctx->X0s, n, npad, ctx->mp, ctx->oz_ns,
+      DISPATCH_DKN(d, ctx->mp.kernel_id, ctx->oz_ns, cross_fwd_planes_kernel<D, KID, NSC><<<grid, OZC_THREADS, 0, ctx->stream>>>(dX, J, Jpad, ctx->X0s, n, npad, ctx->mp, ctx->oz_ns,
                                                                                   (int8_t*)ctx->ozA.p, ctx->ozsA.p));
       CKL();
     }
@@ -922,7 +938,7 @@ static int run_chunk(maf_ctx* ctx, const AcqDev& ap, bool posterior_only, bool c
   }
   {
     ProfScope ps(ctx, MAF_PROF_CROSS_BWD);
-    DISPATCH_D(d, cross_bwd_kernel<D><<<sc, 32 * q, 0, ctx->stream>>>(dX, sc, q, p, ctx->X0s, n, npad, ctx->mp, K10, Sigbar, dgrad));
+    DISPATCH_DK(d, ctx->mp.kernel_id, cross_bwd_kernel<D, KID><<<sc, 32 * q, 0, ctx->stream>>>(dX, sc, q, p, ctx->X0s, n, npad, ctx->mp, K10, Sigbar, dgrad));
     CKL();
   }
   return 0;
@@ -1190,7 +1206,7 @@ static int run_fantasies(maf_ctx* ctx, const maf_acq_params* prm, int S, const d
       {
         ProfScope ps(ctx, MAF_PROF_CROSS_FWD);
         dim3 grid((npad + OZC_THREADS * 4 - 1) / (OZC_THREADS * 4), Jpad / OZC_TJ);
-        DISPATCH_D(d, cross_fwd_planes_kernel<D><<<grid, OZC_THREADS, 0, ctx->stream>>>(dX, sc, Jpad, ctx->X0s, n, npad, ctx->mp, ctx->oz_ns,
+        DISPATCH_DKN(d, ctx->mp.kernel_id, ctx->oz_ns, cross_fwd_planes_kernel<D, KID, NSC><<<grid, OZC_THREADS, 0, ctx->stream>>>(dX, sc, Jpad, ctx->X0s, n, npad, ctx->mp, ctx->oz_ns,
                                                                                     (int8_t*)ctx->ozA.p, ctx->ozsA.p));
         CKL();
       }
@@ -1249,7 +1265,7 @@ static int run_fantasies(maf_ctx* ctx, const maf_acq_params* prm, int S, const d
     }
     {
       ProfScope ps(ctx, MAF_PROF_CROSS_BWD);
-      DISPATCH_D(d, cross_bwd_kernel<D><<<sc, 32, 0, ctx->stream>>>(dX, sc, 1, 0, ctx->X0s, n, npad, ctx->mp, ctx->K10.p,
+      DISPATCH_DK(d, ctx->mp.kernel_id, cross_bwd_kernel<D, KID><<<sc, 32, 0, ctx->stream>>>(dX, sc, 1, 0, ctx->X0s, n, npad, ctx->mp, ctx->K10.p,
                                                                      ctx->dSigbar.p + s0, ctx->dgrad.p + (size_t)s0 * d));
       CKL();
     }

@@ -262,6 +262,28 @@ __device__ __forceinline__ void oz_emit_digits4(const long long (&I)[4], int ns,
     }
   }
 }
+// compile-time digit count: plane addresses by pointer increments, no run-time shifts
+template <int NS>
+__device__ __forceinline__ void oz_emit_digits4_t(const long long (&I)[4], int8_t* __restrict__ dst, size_t plane_stride) {
+  constexpr unsigned long long bias = 0x0080808080808080ull >> (8 * (OZ_MAXS - NS));
+  constexpr int sh = 8 * (OZ_MAXS - NS);
+  unsigned lo[4], hi[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const unsigned long long u = (((unsigned long long)I[t] + bias) << sh) ^ 0x0080808080808080ull;
+    lo[t] = (unsigned)u;
+    hi[t] = (unsigned)(u >> 32);
+  }
+#pragma unroll
+  for (int i = 0; i < NS; ++i) {
+    const int b = 6 - i;
+    const unsigned sel = (unsigned)((b & 3) | (((b & 3) + 4) << 4));
+    const unsigned p01 = (b < 4) ? __byte_perm(lo[0], lo[1], sel) : __byte_perm(hi[0], hi[1], sel);
+    const unsigned p23 = (b < 4) ? __byte_perm(lo[2], lo[3], sel) : __byte_perm(hi[2], hi[3], sel);
+    *reinterpret_cast<unsigned*>(dst) = __byte_perm(p01, p23, 0x5410);
+    dst += plane_stride;
+  }
+}
 // two values -> one packed 16-bit store per plane (same digits as oz_emit_digits4)
 __device__ __forceinline__ void oz_emit_digits2(const long long (&I)[2], int ns, int8_t* __restrict__ dst, size_t plane_stride) {
   const unsigned long long bias = 0x0080808080808080ull >> (8 * (OZ_MAXS - ns));
@@ -346,13 +368,20 @@ ozaki_slice_rows_kernel(const double* __restrict__ X, int ldx, int R, int Rpad, 
 // packed int per plane, 128 contiguous bytes per warp.
 #define OZC_TJ 32
 #define OZC_THREADS 256
-template <int D>
-__global__ void __launch_bounds__(OZC_THREADS, (D > 0 && D <= 8) ? 3 : 1)
+#ifndef OZC_MINB
+#define OZC_MINB 3
+#endif
+// NS > 0: compile-time digit count (the FP64-grade configuration); NS == 0: run-time ns.
+template <int D, int KID, int NS>
+__global__ void __launch_bounds__(OZC_THREADS, (D > 0 && D <= 8) ? OZC_MINB : 1)
 cross_fwd_planes_kernel(const double* __restrict__ X, int J, int Jpad, const double* __restrict__ X0s, int n, int npad,
-                        ModelParams mp, int ns, int8_t* __restrict__ planes, double* __restrict__ scales) {
+                        ModelParams mp, int ns_rt, int8_t* __restrict__ planes, double* __restrict__ scales) {
   constexpr int DD = D > 0 ? D : MAF_MAX_D;
   const int d = D > 0 ? D : mp.d;
+  const int ns = NS > 0 ? NS : ns_rt;
   __shared__ double xs[OZC_TJ][DD];
+  __shared__ double etab[MAF_ETAB];
+  maf_fill_etab(etab, threadIdx.x);
   const int k = (blockIdx.x * OZC_THREADS + threadIdx.x) * 4;
   const int j0 = blockIdx.y * OZC_TJ;
   for (int t = threadIdx.x; t < OZC_TJ * d; t += OZC_THREADS) {
@@ -364,15 +393,19 @@ cross_fwd_planes_kernel(const double* __restrict__ X, int J, int Jpad, const dou
   if (blockIdx.x == 0 && threadIdx.x < OZC_TJ) scales[j0 + threadIdx.x] = (j0 + (int)threadIdx.x < J) ? ldexp(1.0, e) : 1.0;
   __syncthreads();
   if (k >= npad) return;
-  const double sc = ldexp(1.0, -e + 8 * ns - 1);
-  double x0[4][DD];
+  // a^2 2^(8 ns - 1 - e) per column, 0 on the pad columns k >= n (their digits must be zero): no per-element predicate
+  const double sc = mp.amp2 * ldexp(1.0, -e + 8 * ns - 1);
+  double x0[4][DD], cs[4];
 #pragma unroll
-  for (int t = 0; t < 4; ++t)
+  for (int t = 0; t < 4; ++t) {
+    cs[t] = (k + t) < n ? sc : 0.0;
 #pragma unroll
     for (int c = 0; c < DD; ++c) x0[t][c] = (c < d) ? X0s[(size_t)c * npad + k + t] : 0.0;
+  }
   const size_t plane_stride = (size_t)Jpad * npad;
+  const int jend = min(OZC_TJ, J - j0);                      // rows >= J of the last row block: zero digits
 #pragma unroll 2
-  for (int jj = 0; jj < OZC_TJ; ++jj) {
+  for (int jj = 0; jj < jend; ++jj) {
     long long I[4];
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
@@ -384,11 +417,14 @@ cross_fwd_planes_kernel(const double* __restrict__ X, int J, int Jpad, const dou
           r2 += df * df;
         }
       }
-      const double v = ((k + t) < n && (j0 + jj) < J) ? mp.amp2 * kern_val(mp.kernel_id, r2) : 0.0;
-      I[t] = __double2ll_rn(v * sc);
+      I[t] = __double2ll_rn(kern_val_fast<KID>(r2, etab) * cs[t]);
     }
-    oz_emit_digits4(I, ns, planes + (size_t)(j0 + jj) * npad + k, plane_stride);
+    int8_t* dst = planes + (size_t)(j0 + jj) * npad + k;
+    if constexpr (NS > 0) oz_emit_digits4_t<(NS > 0 ? NS : 1)>(I, dst, plane_stride);
+    else oz_emit_digits4(I, ns, dst, plane_stride);
   }
+  for (int jj = (jend > 0 ? jend : 0); jj < OZC_TJ; ++jj)
+    for (int i = 0; i < ns; ++i) *reinterpret_cast<unsigned*>(planes + i * plane_stride + (size_t)(j0 + jj) * npad + k) = 0u;
 }
 
 // Vbar^T[i][k] = mubar_i gamma_k - sum_j (Sbar_ij + Sbar_ji) V^T[j][k]  (vbar_kernel) straight to digit planes.
