@@ -56,10 +56,11 @@ __device__ __forceinline__ void oz4_commit2(uint32_t bar_addr) {
                : "memory");
 }
 // TMA load of this CTA's part of a plane tile; the bytes are accounted on the leader's barrier
-__device__ __forceinline__ void oz4_load(uint32_t dst, const CUtensorMap* tm, uint32_t leader_bar, int c0, int c1, int c2) {
+__device__ __forceinline__ void oz4_load(uint32_t dst, const CUtensorMap* tm, uint32_t leader_bar, int c0, int c1, int c2,
+                                         uint64_t hint) {
   asm volatile(
       "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], "
-      "[%2], %6;" ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "l"(OZ3_L2_NORMAL)
+      "[%2], %6;" ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "l"(hint)
       : "memory");
 }
 __device__ __forceinline__ void oz4_expect(uint32_t bar_addr, uint32_t bytes) {
@@ -84,7 +85,7 @@ __device__ __forceinline__ void oz4_arrive_leader(uint32_t local_bar_addr) {
 template <int NS, int LMAX, int PASS, int PAR>
 __device__ __forceinline__ void oz4_produce_chunk(const CUtensorMap* tmA, const CUtensorMap* tmT, uint32_t smem0, uint32_t full0,
                                                   uint32_t full0_leader, uint32_t empty0, uint32_t& ph_empty, int c, int jrow,
-                                                  int trow, bool leader, int dbg) {
+                                                  int trow, bool leader, int dbg, uint64_t hintA, uint64_t hintT) {
   using Z = Oz4<NS, LMAX>;
 #pragma unroll
   for (int i = 1; i <= Z::smax(PASS); ++i) {
@@ -102,7 +103,7 @@ __device__ __forceinline__ void oz4_produce_chunk(const CUtensorMap* tmA, const 
 #endif
           {
             if (leader) oz4_expect(full0 + 8u * s, 2u * OZ4_T_BYTES);
-            oz4_load(smem0 + (uint32_t)Z::offT(b), tmT, full0_leader + 8u * s, c, trow, ip - 1);
+            oz4_load(smem0 + (uint32_t)Z::offT(b), tmT, full0_leader + 8u * s, c, trow, ip - 1, hintT);
           }
         }
         __syncwarp();
@@ -120,7 +121,7 @@ __device__ __forceinline__ void oz4_produce_chunk(const CUtensorMap* tmA, const 
 #endif
         {
           if (leader) oz4_expect(full0 + 8u * s, 2u * OZ4_A_BYTES);
-          oz4_load(smem0 + (uint32_t)Z::offA(b), tmA, full0_leader + 8u * s, c, jrow, i - 1);
+          oz4_load(smem0 + (uint32_t)Z::offA(b), tmA, full0_leader + 8u * s, c, jrow, i - 1, hintA);
         }
       }
       __syncwarp();
@@ -185,11 +186,11 @@ __device__ __forceinline__ void oz4_issue_chunk(uint32_t desc0, uint32_t full0, 
 template <int NS, int LMAX, int PASS>
 __device__ __forceinline__ void oz4_produce_pass(const CUtensorMap* tmA, const CUtensorMap* tmT, uint32_t smem0, uint32_t full0,
                                                  uint32_t full0_leader, uint32_t empty0, uint32_t& ph_empty, int c_begin,
-                                                 int kchunks, int jrow, int trow, bool leader, int dbg) {
+                                                 int kchunks, int jrow, int trow, bool leader, int dbg, uint64_t hintA, uint64_t hintT) {
   for (int kc = 0; kc < kchunks; kc += 2) {
-    oz4_produce_chunk<NS, LMAX, PASS, 0>(tmA, tmT, smem0, full0, full0_leader, empty0, ph_empty, c_begin + kc * OZ3_BK, jrow, trow, leader, dbg);
+    oz4_produce_chunk<NS, LMAX, PASS, 0>(tmA, tmT, smem0, full0, full0_leader, empty0, ph_empty, c_begin + kc * OZ3_BK, jrow, trow, leader, dbg, hintA, hintT);
     if (kc + 1 < kchunks)
-      oz4_produce_chunk<NS, LMAX, PASS, 1>(tmA, tmT, smem0, full0, full0_leader, empty0, ph_empty, c_begin + (kc + 1) * OZ3_BK, jrow, trow, leader, dbg);
+      oz4_produce_chunk<NS, LMAX, PASS, 1>(tmA, tmT, smem0, full0, full0_leader, empty0, ph_empty, c_begin + (kc + 1) * OZ3_BK, jrow, trow, leader, dbg, hintA, hintT);
   }
 }
 template <int NS, int LMAX, int PASS>
@@ -306,7 +307,8 @@ __device__ __forceinline__ void oz4_epilogue_stash(const double* __restrict__ sA
                   v0 = __longlong_as_double(H[idx]);
                   v1 = __longlong_as_double(H[idx + 1]);
                 }
-                *reinterpret_cast<double2*>(crow + 8 * n) = make_double2(v0 * sc[n].x * sa, v1 * sc[n].y * sa);
+                // written once, read by the next kernel only after the whole 2 GB result: streaming store (evict-first)
+                __stcs(reinterpret_cast<double2*>(crow + 8 * n), make_double2(v0 * sc[n].x * sa, v1 * sc[n].y * sa));
               }
             }
           }
@@ -364,9 +366,9 @@ ozaki_i8_gemm_v4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     for (int t = cluster_id; t < ntiles; t += nclusters) {
       Oz3Tile x = oz3_tile(t, nN, nJ2, p);                     // j0 counts 128-row blocks: rescale to 256
       const int jrow = 2 * x.j0 + 128 * (int)rank, trow = x.r0 + 64 * (int)rank;
-      oz4_produce_pass<NS, LMAX, 0>(&tmA, &tmT, smem0, full0, full0_leader, empty0, ph_empty, x.c_begin, x.kchunks, jrow, trow, leader, p.dbg);
+      oz4_produce_pass<NS, LMAX, 0>(&tmA, &tmT, smem0, full0, full0_leader, empty0, ph_empty, x.c_begin, x.kchunks, jrow, trow, leader, p.dbg, p.hintA, p.hintT);
       if constexpr (Z::NPASS > 1)
-        oz4_produce_pass<NS, LMAX, 1>(&tmA, &tmT, smem0, full0, full0_leader, empty0, ph_empty, x.c_begin, x.kchunks, jrow, trow, leader, p.dbg);
+        oz4_produce_pass<NS, LMAX, 1>(&tmA, &tmT, smem0, full0, full0_leader, empty0, ph_empty, x.c_begin, x.kchunks, jrow, trow, leader, p.dbg, p.hintA, p.hintT);
     }
   } else if (warp == 1) {
     // ================= MMA issuer (leader CTA only) =================
