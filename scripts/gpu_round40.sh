@@ -1,0 +1,15 @@
+#!/bin/bash
+# round-1 v5 (final) evidence: bench both arms, launch list, ncu --set full of the INT8 contraction
+mkdir -p gpurun_out
+timeout 900 python bench.py > gpurun_out/bench.log 2>&1; echo "bench rc=$?"
+tail -1 gpurun_out/bench.log | cut -c1-300
+timeout 900 python bench.py --impl reference > gpurun_out/bench_reference.log 2>&1; echo "reference rc=$?"
+BENCH="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv $BENCH > gpurun_out/ncu_launches.log 2>&1
+echo "launch list rc=$?"
+SMALL="python bench.py --steps 1 --warmup 3 --restarts 16384 --no-cpu-baseline"
+$SMALL > gpurun_out/bench_small_plain.log 2>&1 &&
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:ozaki_i8_gemm_v4 -s 12 -c 2 -f -o gpurun_out/prof_gemm_v5 $SMALL > gpurun_out/ncu_full.log 2>&1
+echo "full capture rc=$?"; tail -2 gpurun_out/ncu_full.log
+timeout 300 python bench.py --gemm f64 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_f64.log 2>&1; echo "f64 rc=$?"; tail -1 gpurun_out/bench_f64.log | cut -c1-200
+timeout 300 python bench.py --dtype float32 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_f32.log 2>&1; echo "f32 rc=$?"; tail -1 gpurun_out/bench_f32.log | cut -c1-200
