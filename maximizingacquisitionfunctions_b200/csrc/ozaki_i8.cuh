@@ -493,7 +493,10 @@ vbar_planes_kernel(const double* __restrict__ Vt, int npad, int S, int Jpad, con
     sinv[tid] = ldexp(1.0, -e + 8 * ns - 1);
   }
   __syncthreads();
-  for (int k = tid * 2; k < npad; k += 256 * 2) {          // two columns per thread: q values of V^T each stay in registers
+  // two columns per thread (q values of V^T each stay in registers); sweep 2 walks the slab backwards, so the columns
+  // sweep 1 read last (the ones most likely still in L2) are re-read first
+  for (int k = ((npad - 1) / 512) * 512 + tid * 2; k >= 0; k -= 256 * 2) {
+    if (k >= npad) continue;
     double2 v[Q];
 #pragma unroll
     for (int i = 0; i < Q; ++i) v[i] = *reinterpret_cast<const double2*>(V + (size_t)i * npad + k);

@@ -1,0 +1,10 @@
+#!/bin/bash
+# quick check: GPU suite + a 3-step bench with the per-kernel split
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -m gpu -q -x --no-header -p no:cacheprovider 2>&1 | tail -3
+timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_quick.log 2>&1; echo "rc=$?"
+tail -1 gpurun_out/bench_quick.log | python -c "
+import json,sys
+d=json.loads(sys.stdin.read())
+print(d['value'], d['ms_per_step'], d['clocks']['sm_mhz'])
+print(d['roofline']['per_kernel_ms_per_step'])"
