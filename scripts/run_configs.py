@@ -41,8 +41,19 @@ def main():
         s_chk = min(S, 32)
         ts = orc.prepare_train(gp, X0, y0)
         lo, go = orc.value_and_grad(ts, orc.Acq(c["acq"], **c["kw"]), X[:s_chk], z)
+        # qEI is identically 0 on the synthetic C5 data (level = min of 4096 N(0,1) draws): the posterior and a qSR pass on
+        # the same restarts are the informative checks there
+        import torch
+        mu, cov, _ = eng.last_extras(S, q)
+        with torch.no_grad():
+            mo, co = orc.posterior(ts, torch.as_tensor(X[:s_chk]), full_cov=True)
+        ls, gs = eng.value_and_grad(acq_params("sr"), X[:s_chk], z)
+        lso, gso = orc.value_and_grad(ts, orc.Acq("sr"), X[:s_chk], z)
         rec = {"config": name, "ms_per_pass": ms, "evals_per_s": S * q * M / (ms * 1e-3), "setup_s": setup,
                "relerr_loss_vs_oracle": relerr(loss[:s_chk], lo), "relerr_grad_vs_oracle": relerr(grad[:s_chk], go),
+               "relerr_mu_vs_oracle": relerr(mu[:s_chk], mo.numpy().reshape(mu[:s_chk].shape)),
+               "relerr_cov_vs_oracle": relerr(cov[:s_chk], co.numpy()),
+               "relerr_qsr_loss_vs_oracle": relerr(ls, lso), "relerr_qsr_grad_vs_oracle": relerr(gs, gso),
                "argmin_matches_oracle_on_checked": int(np.argmin(loss[:s_chk])) == int(np.argmin(lo))}
         print(json.dumps(rec), flush=True)
         out.append(rec)
