@@ -22,6 +22,16 @@
  *     p..q-1 are trainable (reference: bayesian_optimization.prepare,
  *     src/agents/bayesian_optimization.py:1051-1125).
  *   - limits: 1 <= q <= MAF_MAX_Q, 1 <= d <= MAF_MAX_D.
+ *
+ * Environment (read once in maf_create; tuning / diagnostics, the defaults are the measured best):
+ *   MAF_GEMM_I8=0|1      contraction engine (1: exact INT8 digit planes on tcgen05, default; 0: FP64 DMMA)
+ *   MAF_OZ_VARIANT=1|3|4|5  INT8 kernel: generic / static schedule / CTA pairs / CTA pairs + register-stash epilogue (default)
+ *   MAF_OZ_NS_BWD=3..7   digit planes of the reverse contraction (default 7; 6 is 25 % faster but leaves the 1e-9 bar
+ *                        for candidates next to training points)
+ *   MAF_OZ_HINTS=<a><t>  L2 policy of the A / T plane loads, 0 normal, 1 evict-first, 2 evict-last (default 22)
+ *   MAF_OZ_SJ=<k>        row blocks per super-row of the persistent tile order (default 4)
+ *   MAF_OZ_FUSE=<bits>   bit 0: cross-covariance straight to digit planes, bit 1: Vbar straight to digit planes (default 3)
+ *   MAF_CHUNK_ROWS=<r>   candidate rows per chunk (default 65536: 4.3 GB of workspace)
  */
 #ifndef MAF_H_
 #define MAF_H_

@@ -85,6 +85,10 @@ struct maf_ctx {
   int oz_variant = 5;              // 1: generic kernel; 3: static schedule, persistent; 4: 3 on CTA pairs (cta_group::2); 5: 4 + register-stash epilogue
   Buf ozA, ozTL, ozTU;             // digit planes (int8, sized in doubles): candidates / Linv / LinvT
   Buf ozsA, ozsTL, ozsTU;          // row scales
+  struct OzSched { int nN, nJ2, tri, sj, pairs; int* d_list; int* d_begin; };
+  std::vector<OzSched> oz_scheds;  // balanced static tile schedules of the CTA-pair kernel, one per launch shape
+  int oz_sched = 1;                // MAF_OZ_SCHED=0: round-robin
+  double oz_sched_ovh = 1.5;       // per-tile overhead of the cost model, in k-chunks (MAF_OZ_SCHED_OVH)
   // fantasies (rank-4 observation sets)
   int F = 0, Fpad = 0;
   Buf fGamma, fGammaT, fmeans, flevels, fVG, fmubar;
@@ -342,6 +346,50 @@ static int oz_slice(maf_ctx* ctx, int slot, const double* X, int ldx, int R, int
   return 0;
 }
 
+// Balanced static schedule of the CTA-pair kernel (OzParams::tile_list): list scheduling of the supertiled tile order
+// onto `pairs` CTA pairs with cost kchunks + overhead.  Cached per launch shape.
+static int oz_schedule(maf_ctx* ctx, int nN, int nJ2, int K, int tri, int sj, int pairs, const int** d_list, const int** d_begin) {
+  for (const auto& sc : ctx->oz_scheds)
+    if (sc.nN == nN && sc.nJ2 == nJ2 && sc.tri == tri && sc.sj == sj && sc.pairs == pairs) {
+      *d_list = sc.d_list;
+      *d_begin = sc.d_begin;
+      return 0;
+    }
+  const int ntiles = nN * nJ2;
+  std::vector<std::vector<int>> per_pair(pairs);
+  std::vector<double> busy(pairs, 0.0);
+  for (int t = 0; t < ntiles; ++t) {                             // same arithmetic as oz3_tile
+    const int per = sj * nN, st = t / per, rem = t - st * per;
+    const int jcount = std::min(sj, nJ2 - st * sj);
+    const int rbi = rem / jcount;
+    const int rb = (tri == 1) ? (nN - 1 - rbi) : rbi;
+    const int r0 = rb * OZ_BN, c_begin = (tri == 2) ? r0 : 0, c_end = (tri == 1) ? std::min(K, r0 + OZ_BN) : K;
+    const double cost = (double)((c_end - c_begin) / OZ3_BK) + ctx->oz_sched_ovh;
+    int best = 0;
+    for (int c = 1; c < pairs; ++c)
+      if (busy[c] < busy[best]) best = c;
+    per_pair[best].push_back(t);
+    busy[best] += cost;
+  }
+  std::vector<int> list, begin(pairs + 1, 0);
+  list.reserve(ntiles);
+  for (int c = 0; c < pairs; ++c) {
+    begin[c] = (int)list.size();
+    list.insert(list.end(), per_pair[c].begin(), per_pair[c].end());
+  }
+  begin[pairs] = (int)list.size();
+  maf_ctx::OzSched sc{nN, nJ2, tri, sj, pairs, nullptr, nullptr};
+  CK(cudaMalloc((void**)&sc.d_list, sizeof(int) * list.size()));
+  CK(cudaMalloc((void**)&sc.d_begin, sizeof(int) * begin.size()));
+  CK(cudaMemcpyAsync(sc.d_list, list.data(), sizeof(int) * list.size(), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(sc.d_begin, begin.data(), sizeof(int) * begin.size(), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));                        // the host vectors go out of scope
+  ctx->oz_scheds.push_back(sc);
+  *d_list = sc.d_list;
+  *d_begin = sc.d_begin;
+  return 0;
+}
+
 static int launch_i8gemm(maf_ctx* ctx, int slot, int J, int N, int K, const Buf& Ap, const Buf& sA, const Buf& Tp,
                          const Buf& sT, double* C, int ldc, int tri, int ns, int lmax) {
   if (J % 128 || N % 128 || K % 128) return fail(ctx, "i8 gemm dims must be multiples of 128");
@@ -383,7 +431,8 @@ static int launch_i8gemm(maf_ctx* ctx, int slot, int J, int N, int K, const Buf&
       oz_make_tmap(ctx, &tmT, (const int8_t*)Tp.p, N, K, ns, bk, variant == 4 ? 64 : 128))
     return 1;
   static const unsigned long long pol[3] = {OZ3_L2_NORMAL, OZ3_L2_EVICT_FIRST, OZ3_L2_EVICT_LAST};
-  OzParams prm{K, ns, lmax, tri, ldc, ctx->oz_sj, pol[ctx->oz_hint_a % 3], pol[ctx->oz_hint_t % 3], ctx->oz_pf, nullptr, ctx->oz_dbg};
+  OzParams prm{K, ns, lmax, tri, ldc, ctx->oz_sj, pol[ctx->oz_hint_a % 3], pol[ctx->oz_hint_t % 3], ctx->oz_pf, nullptr, ctx->oz_dbg,
+               nullptr, nullptr};
   dim3 grid(N / OZ_BN, J / OZ_BM);
   static int num_sms = 0;
   if (!num_sms) CK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, ctx->device));
@@ -402,6 +451,9 @@ static int launch_i8gemm(maf_ctx* ctx, int slot, int J, int N, int K, const Buf&
     const long long ntiles2 = (long long)(N / OZ_BN) * (J / 256);
     const long long pairs = std::min<long long>(ntiles2, num_sms / 2);
     dim3 cgrid((unsigned)(2 * pairs));                           // persistent: one CTA pair per TPC
+    if (ctx->oz_sched && ntiles2 > pairs &&
+        oz_schedule(ctx, N / OZ_BN, J / 256, K, tri, ctx->oz_sj, (int)pairs, &prm.tile_list, &prm.tile_begin))
+      return 1;
 #ifdef MAF_OZ_DIAG
     static long long* dstats = nullptr;
     if (getenv("MAF_OZ_STATS")) {
@@ -589,6 +641,8 @@ extern "C" int maf_create(int device, int dtype, maf_ctx** out) {
     if (h[0] && h[1]) ctx->oz_hint_t = h[1] - '0';
   }
   if (const char* pf = getenv("MAF_OZ_PF")) ctx->oz_pf = atoi(pf);
+  if (const char* sc = getenv("MAF_OZ_SCHED")) ctx->oz_sched = atoi(sc);
+  if (const char* so = getenv("MAF_OZ_SCHED_OVH")) ctx->oz_sched_ovh = atof(so);
   if (const char* nb = getenv("MAF_OZ_NS_BWD")) {
     const int v = atoi(nb);
     if (v >= 3 && v <= ctx->oz_ns) ctx->oz_ns_bwd = v, ctx->oz_lmax_bwd = v + 1;
@@ -618,6 +672,10 @@ extern "C" int maf_destroy(maf_ctx* ctx) {
   for (Buf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (ctx->d_argmin_idx) cudaFree(ctx->d_argmin_idx);
+  for (auto& sc : ctx->oz_scheds) {
+    cudaFree(sc.d_list);
+    cudaFree(sc.d_begin);
+  }
   for (auto& ps : ctx->slots)
     for (auto e : ps.ev) cudaEventDestroy(e);
   for (auto e : ctx->timer_ev)

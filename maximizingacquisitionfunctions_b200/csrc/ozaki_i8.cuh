@@ -90,6 +90,12 @@ struct OzParams {
   int pf;           // persistent kernel: TMA-prefetch plane tiles into L2 two k-chunks ahead
   long long* stats; // MAF_OZ_DIAG builds: per-CTA cycle counters of the issuer / epilogue (or null)
   int dbg;          // diagnostics only (results invalid): 1 = issue no MMAs, 2 = issue no TMA loads, 4 = skip the epilogue body
+  // CTA-pair kernel: balanced static schedule.  Pair c walks tile_list[tile_begin[c] .. tile_begin[c + 1]) (positions in
+  // the supertiled order); null = round-robin t = c, c + pairs, ...  Built on the host by list scheduling (each tile of
+  // the global order goes to the pair that becomes free first under the cost model kchunks + overhead), so the pairs
+  // still work inside a moving window of the tile order, but none is left with 1.5 % more k-chunks than the mean.
+  const int* tile_list;
+  const int* tile_begin;
 };
 
 __global__ void __launch_bounds__(OZ_THREADS, 1)

@@ -81,6 +81,31 @@ __device__ __forceinline__ void oz4_arrive_leader(uint32_t local_bar_addr) {
       : "memory");
 }
 
+// tile walk of one CTA pair: balanced list (p.tile_list) or round-robin
+struct Oz4Walk {
+  int i, end, stride;
+  const int* list;
+  __device__ __forceinline__ Oz4Walk(const OzParams& p, int cluster_id, int nclusters, int ntiles) {
+    if (p.tile_list) {
+      list = p.tile_list;
+      i = __ldg(p.tile_begin + cluster_id);
+      end = __ldg(p.tile_begin + cluster_id + 1);
+      stride = 1;
+    } else {
+      list = nullptr;
+      i = cluster_id;
+      end = ntiles;
+      stride = nclusters;
+    }
+  }
+  __device__ __forceinline__ bool next(int& t) {
+    if (i >= end) return false;
+    t = list ? __ldg(list + i) : i;
+    i += stride;
+    return true;
+  }
+};
+
 // ---- one k-chunk of one pass: producer (both CTAs) ------------------------------------------------------
 template <int NS, int LMAX, int PASS, int PAR>
 __device__ __forceinline__ void oz4_produce_chunk(const CUtensorMap* tmA, const CUtensorMap* tmT, uint32_t smem0, uint32_t full0,
@@ -227,7 +252,8 @@ __device__ __forceinline__ void oz4_epilogue_stash(const double* __restrict__ sA
   const int ntiles = nN * nJ2;
   uint32_t g = 0;
   long long H[NE];                                           // [gq][h][n][e][c]; int64 after pass 0, FP64 bits afterwards
-  for (int t = cluster_id; t < ntiles; t += nclusters) {
+  Oz4Walk walk(p, cluster_id, nclusters, ntiles);
+  for (int t; walk.next(t);) {
     const Oz3Tile x = oz3_tile(t, nN, nJ2, p);
     const int j0 = 2 * x.j0 + 128 * (int)rank;
 #pragma unroll
@@ -363,7 +389,8 @@ ozaki_i8_gemm_v4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   if (warp == 0) {
     // ================= TMA producer (both CTAs) =================
     uint32_t ph_empty = 0xffffffffu;
-    for (int t = cluster_id; t < ntiles; t += nclusters) {
+    Oz4Walk walk(p, cluster_id, nclusters, ntiles);
+    for (int t; walk.next(t);) {
       Oz3Tile x = oz3_tile(t, nN, nJ2, p);                     // j0 counts 128-row blocks: rescale to 256
       const int jrow = 2 * x.j0 + 128 * (int)rank, trow = x.r0 + 64 * (int)rank;
       oz4_produce_pass<NS, LMAX, 0>(&tmA, &tmT, smem0, full0, full0_leader, empty0, ph_empty, x.c_begin, x.kchunks, jrow, trow, leader, p.dbg, p.hintA, p.hintT);
@@ -382,7 +409,8 @@ ozaki_i8_gemm_v4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 #ifdef MAF_OZ_DIAG
       const long long t_begin = clock64();
 #endif
-      for (int t = cluster_id; t < ntiles; t += nclusters) {
+      Oz4Walk walk(p, cluster_id, nclusters, ntiles);
+      for (int t; walk.next(t);) {
         const Oz3Tile x = oz3_tile(t, nN, nJ2, p);
         if (g > 0) {
           OZ4_T0();
@@ -429,7 +457,8 @@ ozaki_i8_gemm_v4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     const int fr = lane >> 2, fc = (lane & 3) * 2;
     const uint32_t accf = oz_smem_u32(&acc_full), acce = oz_smem_u32(&acc_empty);
     uint32_t g = 0;
-    for (int t = cluster_id; t < ntiles; t += nclusters) {
+    Oz4Walk walk(p, cluster_id, nclusters, ntiles);
+    for (int t; walk.next(t);) {
       const Oz3Tile x = oz3_tile(t, nN, nJ2, p);
       const int j0 = 2 * x.j0 + 128 * (int)rank;
       double sa[2][2];
