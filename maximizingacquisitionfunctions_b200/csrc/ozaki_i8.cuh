@@ -94,9 +94,12 @@ struct OzParams {
   // the supertiled order); null = round-robin t = c, c + pairs, ...  Built on the host by list scheduling (each tile of
   // the global order goes to the pair that becomes free first under the cost model kchunks + overhead), so the pairs
   // still work inside a moving window of the tile order, but none is left with 1.5 % more k-chunks than the mean.
+  // Entries with OZ_TILE_EXPLICIT set name the tile directly (row block * nN + column block): the host is then free to
+  // choose any order, e.g. column groups whose T planes stay in L2 while the A planes stream past (MAF_OZ_GROUPS).
   const int* tile_list;
   const int* tile_begin;
 };
+#define OZ_TILE_EXPLICIT 0x40000000
 
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 ozaki_i8_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmT,

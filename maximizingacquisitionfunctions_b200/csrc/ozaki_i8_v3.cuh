@@ -240,12 +240,20 @@ struct Oz3Tile {
   int r0, j0, c_begin, kchunks;
 };
 __device__ __forceinline__ Oz3Tile oz3_tile(int t, int nN, int nJ, const OzParams& p) {
-  const int OZ3_SJ = p.sj;
-  const int per = OZ3_SJ * nN;
-  const int st = t / per, rem = t - st * per;
-  const int jcount = min(OZ3_SJ, nJ - st * OZ3_SJ);
-  const int rbi = rem / jcount, jb = st * OZ3_SJ + (rem - rbi * jcount);
-  const int rb = (p.tri == 1) ? (nN - 1 - rbi) : rbi;
+  int rb, jb;
+  if (t & OZ_TILE_EXPLICIT) {                                  // host-built order: entry = row block * nN + column block
+    const int e = t & ~OZ_TILE_EXPLICIT;
+    jb = e / nN;
+    rb = e - jb * nN;
+  } else {                                                     // position in the supertiled order
+    const int OZ3_SJ = p.sj;
+    const int per = OZ3_SJ * nN;
+    const int st = t / per, rem = t - st * per;
+    const int jcount = min(OZ3_SJ, nJ - st * OZ3_SJ);
+    const int rbi = rem / jcount;
+    jb = st * OZ3_SJ + (rem - rbi * jcount);
+    rb = (p.tri == 1) ? (nN - 1 - rbi) : rbi;
+  }
   Oz3Tile x;
   x.r0 = rb * OZ_BN;
   x.j0 = jb * OZ_BM;
