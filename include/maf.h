@@ -29,7 +29,10 @@
  *   MAF_OZ_NS_BWD=3..7   digit planes of the reverse contraction (default 7; 6 is 25 % faster but leaves the 1e-9 bar
  *                        for candidates next to training points)
  *   MAF_OZ_HINTS=<a><t>  L2 policy of the A / T plane loads, 0 normal, 1 evict-first, 2 evict-last (default 22)
- *   MAF_OZ_SJ=<k>        row blocks per super-row of the persistent tile order (default 4)
+ *   MAF_OZ_SJ=<k>        row blocks per super-row of the persistent tile order (default 2)
+ *   MAF_OZ_SCHED=0|1     balanced static tile schedule of the CTA pairs (default 1; 0: round-robin walk)
+ *   MAF_OZ_GROUPS=<g>    column groups of the balanced schedule: the T planes of a group stay in L2 while all row
+ *                        blocks stream past (default 2)
  *   MAF_OZ_FUSE=<bits>   bit 0: cross-covariance straight to digit planes, bit 1: Vbar straight to digit planes (default 3)
  *   MAF_CHUNK_ROWS=<r>   candidate rows per chunk (default 65536: 4.3 GB of workspace)
  */

@@ -78,17 +78,18 @@ struct maf_ctx {
   // training points (profiles/r01_accuracy_n4096.jsonl): above the 1e-9 bar, so the default keeps all 7 planes.
   int oz_ns_bwd = 7, oz_lmax_bwd = 8;
   int oz_fuse = 3;                 // bit 0: cross-covariance, bit 1: Vbar written straight to digit planes (MAF_OZ_FUSE)
-  int oz_sj = 4;                   // super-row height of the persistent tile order (MAF_OZ_SJ)
+  int oz_sj = 2;                   // super-row height of the persistent tile order (MAF_OZ_SJ)
   int oz_hint_a = 2, oz_hint_t = 2; // L2 policy of the A / T plane loads: 0 normal, 1 evict-first, 2 evict-last (MAF_OZ_HINTS=at); evict-last on both: DRAM reads 19 -> 16.5 GB per launch, -3 % time (profiles/r01_i8gemm_v5_l2_policy_sweep.txt)
   int oz_pf = 0;                   // L2 prefetch of plane tiles two k-chunks ahead (MAF_OZ_PF)
   int oz_dbg = 0;                  // MAF_OZ_DBG diagnostics (results invalid)
   int oz_variant = 5;              // 1: generic kernel; 3: static schedule, persistent; 4: 3 on CTA pairs (cta_group::2); 5: 4 + register-stash epilogue
   Buf ozA, ozTL, ozTU;             // digit planes (int8, sized in doubles): candidates / Linv / LinvT
   Buf ozsA, ozsTL, ozsTU;          // row scales
-  struct OzSched { int nN, nJ2, tri, sj, pairs; int* d_list; int* d_begin; };
+  struct OzSched { int nN, nJ2, tri, sj, pairs, groups; int* d_list; int* d_begin; };
   std::vector<OzSched> oz_scheds;  // balanced static tile schedules of the CTA-pair kernel, one per launch shape
   int oz_sched = 1;                // MAF_OZ_SCHED=0: round-robin
   double oz_sched_ovh = 1.5;       // per-tile overhead of the cost model, in k-chunks (MAF_OZ_SCHED_OVH)
+  int oz_groups = 2;               // column groups of the balanced schedule (MAF_OZ_GROUPS)
   // fantasies (rank-4 observation sets)
   int F = 0, Fpad = 0;
   Buf fGamma, fGammaT, fmeans, flevels, fVG, fmubar;
@@ -349,36 +350,58 @@ static int oz_slice(maf_ctx* ctx, int slot, const double* X, int ldx, int R, int
 // Balanced static schedule of the CTA-pair kernel (OzParams::tile_list): list scheduling of the supertiled tile order
 // onto `pairs` CTA pairs with cost kchunks + overhead.  Cached per launch shape.
 static int oz_schedule(maf_ctx* ctx, int nN, int nJ2, int K, int tri, int sj, int pairs, const int** d_list, const int** d_begin) {
+  const int groups = std::max(1, std::min(ctx->oz_groups, nN));
   for (const auto& sc : ctx->oz_scheds)
-    if (sc.nN == nN && sc.nJ2 == nJ2 && sc.tri == tri && sc.sj == sj && sc.pairs == pairs) {
+    if (sc.nN == nN && sc.nJ2 == nJ2 && sc.tri == tri && sc.sj == sj && sc.pairs == pairs && sc.groups == groups) {
       *d_list = sc.d_list;
       *d_begin = sc.d_begin;
       return 0;
     }
-  const int ntiles = nN * nJ2;
+  // k-chunks of a column block (same arithmetic as oz3_tile), column blocks heaviest first
+  auto kchunks = [&](int rb) {
+    const int r0 = rb * OZ_BN, c_begin = (tri == 2) ? r0 : 0, c_end = (tri == 1) ? std::min(K, r0 + OZ_BN) : K;
+    return (c_end - c_begin) / OZ3_BK;
+  };
+  std::vector<int> cols(nN);
+  for (int i = 0; i < nN; ++i) cols[i] = (tri == 1) ? (nN - 1 - i) : i;
+  // column groups of equal T-plane bytes: a group's T planes stay in L2 while every row block streams past them
+  // (groups == 1: the supertiled order of oz3_tile).  A is then read `groups` times, T about once.
+  long long total = 0;
+  for (int rb : cols) total += kchunks(rb);
+  std::vector<int> gend;                                         // end index (in cols) of every group
+  {
+    long long acc = 0;
+    int g = 1;
+    for (int i = 0; i < nN; ++i) {
+      acc += kchunks(cols[i]);
+      if (g < groups && acc * groups >= total * g) gend.push_back(i + 1), ++g;
+    }
+    gend.push_back(nN);
+  }
+  std::vector<int> order;                                        // explicit tile entries: row block * nN + column block
+  order.reserve((size_t)nN * nJ2);
+  for (size_t g = 0, c0 = 0; g < gend.size(); c0 = gend[g], ++g)
+    for (int st = 0; st * sj < nJ2; ++st)                        // super-rows of sj row blocks; column outer, row inner
+      for (int ci = (int)c0; ci < gend[g]; ++ci)
+        for (int jb = st * sj; jb < std::min(nJ2, (st + 1) * sj); ++jb) order.push_back(jb * nN + cols[ci]);
   std::vector<std::vector<int>> per_pair(pairs);
   std::vector<double> busy(pairs, 0.0);
-  for (int t = 0; t < ntiles; ++t) {                             // same arithmetic as oz3_tile
-    const int per = sj * nN, st = t / per, rem = t - st * per;
-    const int jcount = std::min(sj, nJ2 - st * sj);
-    const int rbi = rem / jcount;
-    const int rb = (tri == 1) ? (nN - 1 - rbi) : rbi;
-    const int r0 = rb * OZ_BN, c_begin = (tri == 2) ? r0 : 0, c_end = (tri == 1) ? std::min(K, r0 + OZ_BN) : K;
-    const double cost = (double)((c_end - c_begin) / OZ3_BK) + ctx->oz_sched_ovh;
+  for (int e : order) {                                          // list scheduling: next tile to the pair that frees first
+    const double cost = (double)kchunks(e % nN) + ctx->oz_sched_ovh;
     int best = 0;
     for (int c = 1; c < pairs; ++c)
       if (busy[c] < busy[best]) best = c;
-    per_pair[best].push_back(t);
+    per_pair[best].push_back(e | OZ_TILE_EXPLICIT);
     busy[best] += cost;
   }
   std::vector<int> list, begin(pairs + 1, 0);
-  list.reserve(ntiles);
+  list.reserve(order.size());
   for (int c = 0; c < pairs; ++c) {
     begin[c] = (int)list.size();
     list.insert(list.end(), per_pair[c].begin(), per_pair[c].end());
   }
   begin[pairs] = (int)list.size();
-  maf_ctx::OzSched sc{nN, nJ2, tri, sj, pairs, nullptr, nullptr};
+  maf_ctx::OzSched sc{nN, nJ2, tri, sj, pairs, groups, nullptr, nullptr};
   CK(cudaMalloc((void**)&sc.d_list, sizeof(int) * list.size()));
   CK(cudaMalloc((void**)&sc.d_begin, sizeof(int) * begin.size()));
   CK(cudaMemcpyAsync(sc.d_list, list.data(), sizeof(int) * list.size(), cudaMemcpyHostToDevice, ctx->stream));
@@ -643,6 +666,7 @@ extern "C" int maf_create(int device, int dtype, maf_ctx** out) {
   if (const char* pf = getenv("MAF_OZ_PF")) ctx->oz_pf = atoi(pf);
   if (const char* sc = getenv("MAF_OZ_SCHED")) ctx->oz_sched = atoi(sc);
   if (const char* so = getenv("MAF_OZ_SCHED_OVH")) ctx->oz_sched_ovh = atof(so);
+  if (const char* sg = getenv("MAF_OZ_GROUPS")) ctx->oz_groups = atoi(sg);
   if (const char* nb = getenv("MAF_OZ_NS_BWD")) {
     const int v = atoi(nb);
     if (v >= 3 && v <= ctx->oz_ns) ctx->oz_ns_bwd = v, ctx->oz_lmax_bwd = v + 1;
