@@ -131,7 +131,11 @@ cross_bwd_kernel(const double* __restrict__ X, int S, int q, int p,
         r2 += df * df;
       }
     }
+#ifdef CROSS_BWD_PLAIN_LOAD
     double g = kb[k] * kern_dr2_fast<KID>(r2, etab);
+#else
+    double g = __ldcs(kb + k) * kern_dr2_fast<KID>(r2, etab);   // streamed once: keep the training set in L1 instead
+#endif
 #pragma unroll
     for (int c = 0; c < DD; ++c)
       if (c < d) acc[c] += g * (xi[c] - x0[c]);

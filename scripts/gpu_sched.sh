@@ -1,5 +1,5 @@
 #!/bin/bash
-# A/B of schedule knobs of the CTA-pair contraction on the bench workload: env assignments per run
+# A/B of environment knobs on the bench workload: one line of env assignments per run
 mkdir -p gpurun_out
 run() {
   env "$@" timeout 600 python bench.py --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/bench_sched.log 2>&1; echo "$* rc=$?"
@@ -7,14 +7,13 @@ run() {
 import json,sys
 d=json.loads(sys.stdin.read())
 k=d['roofline']['per_kernel_ms_per_step']
-print(d['value'], d['ms_per_step'], d['clocks']['sm_mhz'], 'gemm_fwd %.2f gemm_bwd %.2f' % (k['gemm_fwd'], k['gemm_bwd']))"
+print(d['value'], d['ms_per_step'], d['clocks']['sm_mhz'], ' '.join('%s %.2f' % (a, k[a]) for a in k))"
 }
 while read -r line; do [ -n "$line" ] && run $line; done <<CFG
-MAF_OZ_GROUPS=1 MAF_OZ_SJ=4
-MAF_OZ_GROUPS=2 MAF_OZ_SJ=2
-MAF_OZ_GROUPS=2 MAF_OZ_SJ=1
-MAF_OZ_GROUPS=1 MAF_OZ_SJ=4
-MAF_OZ_GROUPS=2 MAF_OZ_SJ=2
-MAF_OZ_GROUPS=3 MAF_OZ_SJ=2
+MAF_CHUNK_ROWS=65536
+MAF_CHUNK_ROWS=32768
+MAF_CHUNK_ROWS=16384
+MAF_CHUNK_ROWS=49152
+MAF_CHUNK_ROWS=65536
+MAF_CHUNK_ROWS=32768
 CFG
-MAF_OZ_GROUPS=2 MAF_OZ_SJ=2 timeout 600 python -m pytest tests/test_gpu_ozaki.py -m gpu -q --no-header -p no:cacheprovider 2>&1 | tail -3
