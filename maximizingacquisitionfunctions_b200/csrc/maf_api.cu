@@ -89,6 +89,15 @@ struct maf_ctx {
   std::vector<OzSched> oz_scheds;  // balanced static tile schedules of the CTA-pair kernel, one per launch shape
   int oz_sched = 1;                // MAF_OZ_SCHED=0: round-robin
   double oz_sched_ovh = 1.5;       // per-tile overhead of the cost model, in k-chunks (MAF_OZ_SCHED_OVH)
+  // replayed optimizer steps: one CUDA graph per session (MAF_GRAPH=0: every step launched from the host)
+  int graph_on = 1;
+  long long generation = 0;        // bumped whenever a device buffer moves or the model / training set / engine changes
+  cudaGraphExec_t adam_graph = nullptr;
+  long long adam_graph_gen = -1;
+  int adam_graph_M = 0, adam_graph_trace = 0;
+  int64_t adam_graph_kernels = 0;  // kernels per replay
+  Buf adam_zcur, adam_coef, adam_trace;
+  long long* adam_ctr = nullptr;   // device: {step being executed, next step} within the current maf_adam_steps call
   int oz_groups = 2;               // column groups of the balanced schedule (MAF_OZ_GROUPS)
   // fantasies (rank-4 observation sets)
   int F = 0, Fpad = 0;
@@ -128,6 +137,7 @@ static int ensure(maf_ctx* ctx, Buf& b, size_t need) {
   if (b.p) CK(cudaFree(b.p));
   b.p = nullptr;
   b.cap = 0;
+  ctx->generation++;                                       // a captured graph holds the old address
   size_t bytes = std::max<size_t>(need, 1) * sizeof(double);
   cudaError_t e = cudaMalloc((void**)&b.p, bytes);
   if (e != cudaSuccess) return fail(ctx, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
@@ -667,6 +677,7 @@ extern "C" int maf_create(int device, int dtype, maf_ctx** out) {
   if (const char* sc = getenv("MAF_OZ_SCHED")) ctx->oz_sched = atoi(sc);
   if (const char* so = getenv("MAF_OZ_SCHED_OVH")) ctx->oz_sched_ovh = atof(so);
   if (const char* sg = getenv("MAF_OZ_GROUPS")) ctx->oz_groups = atoi(sg);
+  if (const char* gr = getenv("MAF_GRAPH")) ctx->graph_on = atoi(gr);
   if (const char* nb = getenv("MAF_OZ_NS_BWD")) {
     const int v = atoi(nb);
     if (v >= 3 && v <= ctx->oz_ns) ctx->oz_ns_bwd = v, ctx->oz_lmax_bwd = v + 1;
@@ -692,10 +703,13 @@ extern "C" int maf_destroy(maf_ctx* ctx) {
   Buf* bufs[] = {&ctx->K10, &ctx->Vt, &ctx->dX, &ctx->dz, &ctx->dw, &ctx->dinc, &ctx->dmu, &ctx->dSig, &ctx->dchol,
                  &ctx->dmubar, &ctx->dSigbar, &ctx->dloss, &ctx->dgrad, &ctx->adam_X, &ctx->adam_m, &ctx->adam_v,
                  &ctx->adam_g, &ctx->adam_z, &ctx->fGamma, &ctx->fGammaT, &ctx->fmeans, &ctx->flevels, &ctx->fVG,
-                 &ctx->fmubar, &ctx->ozA, &ctx->ozTL, &ctx->ozTU, &ctx->ozsA, &ctx->ozsTL, &ctx->ozsTU};
+                 &ctx->fmubar, &ctx->ozA, &ctx->ozTL, &ctx->ozTU, &ctx->ozsA, &ctx->ozsTL, &ctx->ozsTU, &ctx->adam_zcur,
+                 &ctx->adam_coef, &ctx->adam_trace};
   for (Buf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (ctx->d_argmin_idx) cudaFree(ctx->d_argmin_idx);
+  if (ctx->adam_graph) cudaGraphExecDestroy(ctx->adam_graph);
+  if (ctx->adam_ctr) cudaFree(ctx->adam_ctr);
   for (auto& sc : ctx->oz_scheds) {
     cudaFree(sc.d_list);
     cudaFree(sc.d_begin);
@@ -749,6 +763,7 @@ extern "C" int maf_d2h(maf_ctx* ctx, void* dst, const void* src, size_t bytes) {
 extern "C" int maf_set_model(maf_ctx* ctx, int kernel_id, int d, const double* lenscales, double amplitude,
                              double noise, double mean, double jitter) {
   if (!ctx) return 1;
+  ctx->generation++;
   if (d < 1 || d > MAF_MAX_D) return fail(ctx, "d=%d outside 1..%d", d, MAF_MAX_D);
   if (kernel_id < 0 || kernel_id > 2) return fail(ctx, "unknown kernel id %d", kernel_id);
   ModelParams mp{};
@@ -770,6 +785,7 @@ extern "C" int maf_set_model(maf_ctx* ctx, int kernel_id, int d, const double* l
 
 extern "C" int maf_set_train(maf_ctx* ctx, int n, const double* X0, const double* y0) {
   if (!ctx) return 1;
+  ctx->generation++;
   if (!ctx->model_set) return fail(ctx, "maf_set_model must be called first");
   if (n < 1) return fail(ctx, "n must be >= 1");
   CK(cudaSetDevice(ctx->device));
@@ -1209,6 +1225,7 @@ extern "C" int maf_mc_from_moments(maf_ctx* ctx, const maf_acq_params* prm, int 
 // ---- fantasies ------------------------------------------------------------------------------------
 extern "C" int maf_set_fantasies(maf_ctx* ctx, int F, const double* Y) {
   if (!ctx) return 1;
+  ctx->generation++;
   if (!ctx->train_set) return fail(ctx, "maf_set_train must be called first");
   if (F < 1 || !Y) return fail(ctx, "bad arguments");
   CK(cudaSetDevice(ctx->device));
@@ -1422,6 +1439,7 @@ extern "C" int maf_adam_begin(maf_ctx* ctx, const maf_acq_params* prm, int S, in
   CK(cudaMemsetAsync(ctx->adam_m.p, 0, sizeof(double) * nt, ctx->stream));
   CK(cudaMemsetAsync(ctx->adam_v.p, 0, sizeof(double) * nt, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  ctx->generation++;                                       // new session: the replayed step is captured again
   ctx->adam_prm = *prm;
   ctx->adam_S = S;
   ctx->adam_q = q;
@@ -1441,11 +1459,116 @@ extern "C" int maf_adam_begin(maf_ctx* ctx, const maf_acq_params* prm, int S, in
 
 extern "C" int maf_adam_set_method(maf_ctx* ctx, int method, double momentum) {
   if (!ctx) return 1;
+  ctx->generation++;
   if (!ctx->adam_on) return fail(ctx, "maf_adam_begin must be called first");
   if (method != MAF_OPT_ADAM && method != MAF_OPT_GD && method != MAF_OPT_MOMENTUM) return fail(ctx, "unknown optimizer %d", method);
   if (ctx->opt_t != 0) return fail(ctx, "the optimizer cannot change after the first step");
   ctx->opt_method = method;
   ctx->opt_momentum = method == MAF_OPT_MOMENTUM ? momentum : 0.0;
+  return 0;
+}
+
+// One optimizer step in the replayable form: nothing in the launch arguments depends on the step index (base samples,
+// learning-rate coefficient and trace row are picked on the device from ctx->adam_ctr), so the kernel sequence can be
+// captured once per session and replayed.  The arithmetic is the host-driven loop's, bit for bit.
+static int adam_step_body(maf_ctx* ctx, bool closed, int M, size_t zsz, bool trace) {
+  const int S = ctx->adam_S, q = ctx->adam_q, p = ctx->adam_p, d = ctx->mp.d;
+  const size_t nt = (size_t)S * (q - p) * d;
+  {
+    ProfScope ps(ctx, MAF_PROF_ADAM);
+    adam_step_in_kernel<<<1, 256, 0, ctx->stream>>>(ctx->adam_ctr, ctx->adam_z.p, zsz, ctx->adam_zcur.p);
+    CKL();
+  }
+  if (run_all(ctx, &ctx->adam_prm, false, S, q, p, ctx->adam_X.p, M, closed ? nullptr : ctx->adam_zcur.p, nullptr, nullptr,
+              ctx->dloss.p, ctx->adam_g.p))
+    return 1;
+  {
+    ProfScope ps(ctx, MAF_PROF_ADAM);
+    if (ctx->opt_method == MAF_OPT_ADAM)
+      adam_clip_kernel<<<(unsigned)((nt + 255) / 256), 256, 0, ctx->stream>>>(
+          ctx->adam_X.p, ctx->adam_g.p, ctx->adam_m.p, ctx->adam_v.p, nt, q, p, d, 0.0, ctx->adam_b1, ctx->adam_b2,
+          ctx->adam_eps, ctx->adam_coef.p, ctx->adam_ctr);
+    else
+      sgd_clip_kernel<<<(unsigned)((nt + 255) / 256), 256, 0, ctx->stream>>>(ctx->adam_X.p, ctx->adam_g.p, ctx->adam_m.p, nt, q, p,
+                                                                              d, 0.0, ctx->opt_momentum, ctx->adam_coef.p,
+                                                                              ctx->adam_ctr);
+    CKL();
+  }
+  if (trace) {
+    ProfScope ps(ctx, MAF_PROF_ADAM);
+    adam_step_out_kernel<<<(S + 255) / 256, 256, 0, ctx->stream>>>(ctx->adam_ctr, ctx->dloss.p, S, ctx->adam_trace.p);
+    CKL();
+  }
+  return 0;
+}
+
+// Learning-rate coefficient of the next step, then advance the host copy of the optimizer state
+// (TF-1 Adam: lr sqrt(1 - b2^t) / (1 - b1^t); GradientDescent / Momentum: lr (global_step + 1)^-0.7, :405-412).
+static double adam_next_coef(maf_ctx* ctx) {
+  const double c = ctx->opt_method == MAF_OPT_ADAM ? ctx->adam_lr * std::sqrt(1.0 - ctx->adam_b2p) / (1.0 - ctx->adam_b1p)
+                                                   : ctx->adam_lr * std::pow((double)(ctx->opt_t + 1), -0.7);
+  ctx->adam_b1p *= ctx->adam_b1;
+  ctx->adam_b2p *= ctx->adam_b2;
+  ctx->opt_t += 1;
+  return c;
+}
+
+// Replayed loop: step 0 of the first call of a session is launched directly (it sizes every work buffer), one step is
+// captured into a CUDA graph, and the graph is launched for the remaining steps of this and the following calls.
+// Returns 0 on success, 1 on an error, -1 if the session cannot be replayed (nothing has been executed then).
+static int adam_steps_replayed(maf_ctx* ctx, int steps, int M, bool closed, size_t zsz, const double* z_steps,
+                               double* out_loss_trace) {
+  const int S = ctx->adam_S;
+  const bool trace = out_loss_trace != nullptr;
+  if (!ctx->adam_ctr) CK(cudaMalloc((void**)&ctx->adam_ctr, 2 * sizeof(long long)));
+  if (ensure(ctx, ctx->adam_z, std::max<size_t>(zsz * steps, 1)) || ensure(ctx, ctx->adam_zcur, std::max<size_t>(zsz, 1)) ||
+      ensure(ctx, ctx->adam_coef, (size_t)steps) || ensure(ctx, ctx->dloss, (size_t)S) ||
+      (trace && ensure(ctx, ctx->adam_trace, (size_t)steps * S)))
+    return 1;
+  std::vector<double> coef(steps);
+  for (int t = 0; t < steps; ++t) coef[t] = adam_next_coef(ctx);
+  CK(cudaMemsetAsync(ctx->adam_ctr, 0, 2 * sizeof(long long), ctx->stream));
+  CK(cudaMemcpyAsync(ctx->adam_coef.p, coef.data(), sizeof(double) * steps, cudaMemcpyHostToDevice, ctx->stream));
+  if (!closed) CK(cudaMemcpyAsync(ctx->adam_z.p, z_steps, sizeof(double) * zsz * steps, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));                        // coef goes out of scope; z_steps belongs to the caller
+  int t = 0;
+  const bool valid = ctx->adam_graph && ctx->adam_graph_gen == ctx->generation && ctx->adam_graph_M == M &&
+                     ctx->adam_graph_trace == (int)trace;
+  if (!valid) {
+    if (ctx->adam_graph) cudaGraphExecDestroy(ctx->adam_graph), ctx->adam_graph = nullptr;
+    if (adam_step_body(ctx, closed, M, zsz, trace)) return 1;    // direct launch: allocates, builds tile schedules
+    t = 1;
+    const long long gen = ctx->generation;                       // buffers have their final addresses now
+    const int64_t before = ctx->launch_count;
+    cudaGraph_t graph = nullptr;
+    bool ok = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+    if (ok) {
+      const int rc = adam_step_body(ctx, closed, M, zsz, trace);
+      ok = cudaStreamEndCapture(ctx->stream, &graph) == cudaSuccess && rc == 0 && graph != nullptr && gen == ctx->generation;
+    }
+    ctx->adam_graph_kernels = ctx->launch_count - before;
+    ctx->launch_count = before;                                  // captured, not launched
+    if (ok) ok = cudaGraphInstantiate(&ctx->adam_graph, graph, 0) == cudaSuccess;
+    if (graph) cudaGraphDestroy(graph);
+    if (!ok) {                                                   // keep going from the host, one launch at a time
+      cudaGetLastError();
+      ctx->adam_graph = nullptr;
+      ctx->graph_on = 0;
+      for (; t < steps; ++t)
+        if (adam_step_body(ctx, closed, M, zsz, trace)) return 1;
+    } else {
+      ctx->adam_graph_gen = gen;
+      ctx->adam_graph_M = M;
+      ctx->adam_graph_trace = (int)trace;
+    }
+  }
+  for (; t < steps; ++t) {
+    if (cudaGraphLaunch(ctx->adam_graph, ctx->stream) != cudaSuccess) return fail(ctx, "graph launch failed in the optimizer loop");
+    ctx->launch_count += ctx->adam_graph_kernels;
+  }
+  if (trace)
+    CK(cudaMemcpyAsync(out_loss_trace, ctx->adam_trace.p, sizeof(double) * (size_t)steps * S, cudaMemcpyDeviceToHost, ctx->stream));
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return fail(ctx, "stream sync failed in adam loop");
   return 0;
 }
 
@@ -1458,6 +1581,8 @@ extern "C" int maf_adam_steps(maf_ctx* ctx, int steps, int M, const double* z_st
   const int S = ctx->adam_S, q = ctx->adam_q, p = ctx->adam_p, d = ctx->mp.d;
   const size_t nt = (size_t)S * (q - p) * d;
   const size_t zsz = closed ? 0 : (size_t)M * q;
+  // four or more steps per call and no per-kernel timing: replay one captured step (MAF_GRAPH=0 keeps the host loop)
+  if (ctx->graph_on && !ctx->prof && steps >= 4) return adam_steps_replayed(ctx, steps, closed ? 0 : M, closed, zsz, z_steps, out_loss_trace);
   if (ensure(ctx, ctx->adam_z, std::max<size_t>(zsz * std::max(steps, 1), 1)) || ensure(ctx, ctx->dloss, (size_t)S)) return 1;
   if (!closed)
     CK(cudaMemcpyAsync(ctx->adam_z.p, z_steps, sizeof(double) * zsz * steps, cudaMemcpyHostToDevice, ctx->stream));
@@ -1469,22 +1594,15 @@ extern "C" int maf_adam_steps(maf_ctx* ctx, int steps, int M, const double* z_st
     rc = run_all(ctx, &ctx->adam_prm, false, S, q, p, ctx->adam_X.p, M, closed ? nullptr : ctx->adam_z.p + zsz * t,
                  nullptr, nullptr, lossp, ctx->adam_g.p);
     if (rc) break;
-    if (ctx->opt_method == MAF_OPT_ADAM) {
-      const double alpha = ctx->adam_lr * std::sqrt(1.0 - ctx->adam_b2p) / (1.0 - ctx->adam_b1p);
-      ProfScope ps(ctx, MAF_PROF_ADAM);
+    const double coef = adam_next_coef(ctx);
+    ProfScope ps(ctx, MAF_PROF_ADAM);
+    if (ctx->opt_method == MAF_OPT_ADAM)
       adam_clip_kernel<<<(unsigned)((nt + 255) / 256), 256, 0, ctx->stream>>>(
-          ctx->adam_X.p, ctx->adam_g.p, ctx->adam_m.p, ctx->adam_v.p, nt, q, p, d, alpha, ctx->adam_b1,
-          ctx->adam_b2, ctx->adam_eps);
-    } else {
-      const double lr_t = ctx->adam_lr * std::pow((double)(ctx->opt_t + 1), -0.7);   // decay of :405-412
-      ProfScope ps(ctx, MAF_PROF_ADAM);
+          ctx->adam_X.p, ctx->adam_g.p, ctx->adam_m.p, ctx->adam_v.p, nt, q, p, d, coef, ctx->adam_b1, ctx->adam_b2, ctx->adam_eps);
+    else
       sgd_clip_kernel<<<(unsigned)((nt + 255) / 256), 256, 0, ctx->stream>>>(ctx->adam_X.p, ctx->adam_g.p, ctx->adam_m.p, nt, q, p,
-                                                                              d, lr_t, ctx->opt_momentum);
-    }
+                                                                              d, coef, ctx->opt_momentum);
     if (cudaGetLastError() != cudaSuccess) rc = fail(ctx, "optimizer update kernel launch failed");
-    ctx->adam_b1p *= ctx->adam_b1;
-    ctx->adam_b2p *= ctx->adam_b2;
-    ctx->opt_t += 1;
   }
   if (rc == 0 && dtrace) {
     if (cudaMemcpyAsync(out_loss_trace, dtrace, sizeof(double) * (size_t)steps * S, cudaMemcpyDeviceToHost,
@@ -1493,9 +1611,6 @@ extern "C" int maf_adam_steps(maf_ctx* ctx, int steps, int M, const double* z_st
   }
   if (cudaStreamSynchronize(ctx->stream) != cudaSuccess && rc == 0) rc = fail(ctx, "stream sync failed in adam loop");
   if (dtrace) cudaFree(dtrace);
-  if (rc == 0 && steps > 0 && dtrace == nullptr) {
-    // dloss holds the last step's losses
-  }
   return rc;
 }
 
@@ -1585,6 +1700,7 @@ extern "C" int maf_host_free(maf_ctx* ctx, void* p) {
 
 extern "C" int maf_set_gemm_mode(maf_ctx* ctx, int mode) {
   if (!ctx) return 1;
+  ctx->generation++;
   if (mode != 0 && mode != 1) return fail(ctx, "unknown gemm mode %d", mode);
   ctx->gemm_i8 = mode;
   ctx->i8_ready = false;

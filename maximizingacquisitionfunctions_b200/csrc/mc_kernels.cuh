@@ -355,9 +355,11 @@ __global__ void fant_vbar_kernel(double* __restrict__ Vt, const double* __restri
 // X is the full pool tensor [S][q][d]; only rows >= p are trainable; g is [S][q-p][d].
 __global__ void adam_clip_kernel(double* __restrict__ X, const double* __restrict__ g,
                                  double* __restrict__ m, double* __restrict__ v, size_t ntrain,
-                                 int q, int p, int d, double alpha, double beta1, double beta2, double eps) {
+                                 int q, int p, int d, double alpha, double beta1, double beta2, double eps,
+                                 const double* __restrict__ coef = nullptr, const long long* __restrict__ kcur = nullptr) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= ntrain) return;
+  if (coef) alpha = coef[*kcur];                            // replayed step (CUDA graph): this step's lr_t from the table
   const int qn = q - p;
   size_t s = t / ((size_t)qn * d);
   size_t rem = t - s * (size_t)qn * d;
@@ -372,12 +374,35 @@ __global__ void adam_clip_kernel(double* __restrict__ X, const double* __restric
   X[xi] = fmin(fmax(x, 0.0), 1.0);
 }
 
+// ---- replayed optimizer steps (one CUDA graph per session, maf_adam_steps) ------------------------------------
+// The step index lives on the device: ctr[0] = index of the step being executed, ctr[1] = index of the next one.
+// step_in (one block, first kernel of a step) advances it and stages the step's base samples at a fixed address;
+// step_out files the step's losses in the trace.
+__global__ void adam_step_in_kernel(long long* __restrict__ ctr, const double* __restrict__ zbase, size_t zsz,
+                                    double* __restrict__ zcur) {
+  const long long k = ctr[1];
+  __syncthreads();                                          // every thread has read the index before it moves on
+  for (size_t i = threadIdx.x; i < zsz; i += blockDim.x) zcur[i] = zbase[(size_t)k * zsz + i];
+  if (threadIdx.x == 0) {
+    ctr[0] = k;
+    ctr[1] = k + 1;
+  }
+}
+
+__global__ void adam_step_out_kernel(const long long* __restrict__ ctr, const double* __restrict__ loss, int S,
+                                     double* __restrict__ trace) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < S) trace[(size_t)ctr[0] * S + i] = loss[i];
+}
+
 // ---- GradientDescent / Momentum + clip (bayesian_optimization.py:405-412; TF ApplyMomentum without Nesterov:
 // accum = momentum * accum + g, x -= lr_t * accum; momentum == 0 is plain gradient descent) ----
 __global__ void sgd_clip_kernel(double* __restrict__ X, const double* __restrict__ g, double* __restrict__ accum,
-                                size_t ntrain, int q, int p, int d, double lr_t, double momentum) {
+                                size_t ntrain, int q, int p, int d, double lr_t, double momentum,
+                                const double* __restrict__ coef = nullptr, const long long* __restrict__ kcur = nullptr) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= ntrain) return;
+  if (coef) lr_t = coef[*kcur];
   const int qn = q - p;
   size_t s = t / ((size_t)qn * d);
   size_t rem = t - s * (size_t)qn * d;

@@ -10,6 +10,7 @@ import pytest
 import scipy.linalg as spla
 import torch
 
+from maximizingacquisitionfunctions_b200.engine import Engine
 from oracle import maf_oracle as orc
 
 pytestmark = pytest.mark.gpu
@@ -238,6 +239,40 @@ def test_gd_and_momentum_loops_vs_oracle(eng, method, momentum):
     assert relerr(trg, tro) < 1e-7
     assert np.abs(xg - xo).max() < 1e-7
     assert xg.min() >= 0.0 and xg.max() <= 1.0
+
+
+@pytest.mark.parametrize("method", ["adam", "momentum"])
+def test_replayed_steps_equal_host_loop_bitwise(eng, method):
+    """maf_adam_steps replays one captured step (CUDA graph) when a call has >= 4 steps: same bits as the loop that
+    launches every step from the host (MAF_GRAPH=0), across calls of different length, with and without a trace."""
+    n, d, q, S, M = 80, 4, 3, 24, 32
+    ts, X0, y0, X, z = setup_problem(eng, n, d, q, S, M, seed=21)
+    zs = np.random.RandomState(5).randn(17, M, q)
+    outs = []
+    for graph in ("1", "0"):
+        os.environ["MAF_GRAPH"] = graph
+        try:
+            e = Engine(0)
+        finally:
+            del os.environ["MAF_GRAPH"]
+        e.set_gemm_mode(eng.test_gemm_mode)
+        e.set_model("matern52", np.full(d, math.sqrt(d) / 4), 1.0, 1e-3, 0.0, 1e-6)
+        e.set_train(X0, y0)
+        kw = dict(lr=0.05, method=method, momentum=0.9) if method != "adam" else {}
+        e.adam_begin(prm("ei"), X, **kw)
+        n0 = e.launch_count
+        tr = [e.adam_steps(zs[:6], want_trace=True)]
+        per_step = (e.launch_count - n0) / 6.0
+        tr.append(e.adam_steps(zs[6:8], want_trace=True))           # short call: host loop in both engines
+        e.adam_steps(zs[8:12])                                        # no trace: a different captured step
+        tr.append(e.adam_steps(zs[12:17], want_trace=True))
+        l_last, _ = e.value_and_grad(prm("ei"), e.adam_peek(), z)    # another entry point between the calls
+        outs.append((np.concatenate(tr), e.adam_end(), l_last, per_step))
+        e.close()
+    assert np.array_equal(outs[0][0], outs[1][0])
+    assert np.array_equal(outs[0][1], outs[1][1])
+    assert np.array_equal(outs[0][2], outs[1][2])
+    assert outs[0][3] == outs[1][3] + 2                              # step_in and step_out kernels of the replayed form
 
 
 def test_errors_are_loud(eng):
