@@ -92,7 +92,7 @@ cross_fwd_kernel(const double* __restrict__ X, int J, const double* __restrict__
 #define CROSS_BWD_MINB 2
 #endif
 #ifndef CROSS_BWD_UNROLL
-#define CROSS_BWD_UNROLL 1
+#define CROSS_BWD_UNROLL 2
 #endif
 template <int D, int KID>
 __global__ void __launch_bounds__(512, (D > 0 && D <= 8) ? CROSS_BWD_MINB : 1)      // MINB = 2: <= 64 registers, 32 warps per SM
