@@ -34,6 +34,7 @@
  *   MAF_OZ_GROUPS=<g>    column groups of the balanced schedule: the T planes of a group stay in L2 while all row
  *                        blocks stream past (default 2)
  *   MAF_OZ_FUSE=<bits>   bit 0: cross-covariance straight to digit planes, bit 1: Vbar straight to digit planes (default 3)
+ *   MAF_OZ_ROWMAX=0|1    row maxima of V^T from the forward contraction's epilogue (default 1) or from a sweep of the Vbar producer
  *   MAF_GRAPH=0|1        maf_adam_steps with >= 4 steps replays one captured step (CUDA graph; default 1), bit-identical to
  *                        the host-driven loop
  *   MAF_CHUNK_ROWS=<r>   candidate rows per chunk (default 65536: 4.3 GB of workspace)

@@ -85,6 +85,8 @@ struct maf_ctx {
   int oz_variant = 5;              // 1: generic kernel; 3: static schedule, persistent; 4: 3 on CTA pairs (cta_group::2); 5: 4 + register-stash epilogue
   Buf ozA, ozTL, ozTU;             // digit planes (int8, sized in doubles): candidates / Linv / LinvT
   Buf ozsA, ozsTL, ozsTU;          // row scales
+  Buf ozVmax;                      // row maxima of V^T left by the forward contraction's epilogue
+  int oz_rowmax = 1;               // MAF_OZ_ROWMAX=0: the Vbar producer sweeps V^T for them
   struct OzSched { int nN, nJ2, tri, sj, pairs, groups; int* d_list; int* d_begin; };
   std::vector<OzSched> oz_scheds;  // balanced static tile schedules of the CTA-pair kernel, one per launch shape
   int oz_sched = 1;                // MAF_OZ_SCHED=0: round-robin
@@ -424,7 +426,9 @@ static int oz_schedule(maf_ctx* ctx, int nN, int nJ2, int K, int tri, int sj, in
 }
 
 static int launch_i8gemm(maf_ctx* ctx, int slot, int J, int N, int K, const Buf& Ap, const Buf& sA, const Buf& Tp,
-                         const Buf& sT, double* C, int ldc, int tri, int ns, int lmax) {
+                         const Buf& sT, double* C, int ldc, int tri, int ns, int lmax, double* rowmax = nullptr,
+                         bool* rowmax_done = nullptr) {
+  if (rowmax_done) *rowmax_done = false;
   if (J % 128 || N % 128 || K % 128) return fail(ctx, "i8 gemm dims must be multiples of 128");
   if (tri != 0 && K != N) return fail(ctx, "triangular gemm needs K == N");
   if (ns < 1 || ns > OZ_MAXS || lmax < 2 || lmax > 2 * ns) return fail(ctx, "bad digit configuration ns=%d lmax=%d", ns, lmax);
@@ -465,7 +469,12 @@ static int launch_i8gemm(maf_ctx* ctx, int slot, int J, int N, int K, const Buf&
     return 1;
   static const unsigned long long pol[3] = {OZ3_L2_NORMAL, OZ3_L2_EVICT_FIRST, OZ3_L2_EVICT_LAST};
   OzParams prm{K, ns, lmax, tri, ldc, ctx->oz_sj, pol[ctx->oz_hint_a % 3], pol[ctx->oz_hint_t % 3], ctx->oz_pf, nullptr, ctx->oz_dbg,
-               nullptr, nullptr};
+               nullptr, nullptr, nullptr};
+  if (rowmax && stash && variant == 4) {                           // only the register-stash epilogue emits row maxima
+    CK(cudaMemsetAsync(rowmax, 0, sizeof(double) * J, ctx->stream));
+    prm.rowmax = rowmax;
+    if (rowmax_done) *rowmax_done = true;
+  }
   dim3 grid(N / OZ_BN, J / OZ_BM);
   static int num_sms = 0;
   if (!num_sms) CK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, ctx->device));
@@ -678,6 +687,7 @@ extern "C" int maf_create(int device, int dtype, maf_ctx** out) {
   if (const char* so = getenv("MAF_OZ_SCHED_OVH")) ctx->oz_sched_ovh = atof(so);
   if (const char* sg = getenv("MAF_OZ_GROUPS")) ctx->oz_groups = atoi(sg);
   if (const char* gr = getenv("MAF_GRAPH")) ctx->graph_on = atoi(gr);
+  if (const char* rm = getenv("MAF_OZ_ROWMAX")) ctx->oz_rowmax = atoi(rm);
   if (const char* nb = getenv("MAF_OZ_NS_BWD")) {
     const int v = atoi(nb);
     if (v >= 3 && v <= ctx->oz_ns) ctx->oz_ns_bwd = v, ctx->oz_lmax_bwd = v + 1;
@@ -704,7 +714,7 @@ extern "C" int maf_destroy(maf_ctx* ctx) {
                  &ctx->dmubar, &ctx->dSigbar, &ctx->dloss, &ctx->dgrad, &ctx->adam_X, &ctx->adam_m, &ctx->adam_v,
                  &ctx->adam_g, &ctx->adam_z, &ctx->fGamma, &ctx->fGammaT, &ctx->fmeans, &ctx->flevels, &ctx->fVG,
                  &ctx->fmubar, &ctx->ozA, &ctx->ozTL, &ctx->ozTU, &ctx->ozsA, &ctx->ozsTL, &ctx->ozsTU, &ctx->adam_zcur,
-                 &ctx->adam_coef, &ctx->adam_trace};
+                 &ctx->adam_coef, &ctx->adam_trace, &ctx->ozVmax};
   for (Buf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (ctx->d_argmin_idx) cudaFree(ctx->d_argmin_idx);
@@ -948,6 +958,11 @@ static int run_chunk(maf_ctx* ctx, const AcqDev& ap, bool posterior_only, bool c
   double* K10 = ctx->K10.p;
   double* Vt = ctx->Vt.p;
   const bool fused = ctx->i8_ready && (ctx->oz_fuse & 1), fused_bwd = ctx->i8_ready && (ctx->oz_fuse & 2);
+  // the Vbar producer needs the row maxima of V^T: the forward contraction's epilogue leaves them behind
+  const bool want_rowmax = fused_bwd && ctx->oz_rowmax && !posterior_only && dgrad != nullptr;
+  bool have_rowmax = false;
+  if (want_rowmax && ensure(ctx, ctx->ozVmax, (size_t)Jpad)) return 1;
+  double* const rowmax = want_rowmax ? ctx->ozVmax.p : nullptr;
   if (fused) {
     // K10 goes straight to digit planes (bounded by a^2: fixed row scale), FP64 K10 is never materialised
     const size_t bytes = (size_t)ctx->oz_ns * Jpad * npad;
@@ -960,7 +975,7 @@ static int run_chunk(maf_ctx* ctx, const AcqDev& ap, bool posterior_only, bool c
       CKL();
     }
     if (launch_i8gemm(ctx, MAF_PROF_GEMM_FWD, Jpad, npad, npad, ctx->ozA, ctx->ozsA, ctx->ozTL, ctx->ozsTL, Vt, npad, 1,
-                      ctx->oz_ns, ctx->oz_lmax))
+                      ctx->oz_ns, ctx->oz_lmax, rowmax, &have_rowmax))
       return 1;
   } else {
     {
@@ -973,7 +988,7 @@ static int run_chunk(maf_ctx* ctx, const AcqDev& ap, bool posterior_only, bool c
       // cross-covariances are bounded by a^2: fixed row scale, no reduction pass
       if (oz_slice(ctx, MAF_PROF_CROSS_FWD, K10, npad, J, Jpad, npad, ctx->oz_ns, ctx->mp.amp2, ctx->ozA, ctx->ozsA)) return 1;
       if (launch_i8gemm(ctx, MAF_PROF_GEMM_FWD, Jpad, npad, npad, ctx->ozA, ctx->ozsA, ctx->ozTL, ctx->ozsTL, Vt, npad, 1,
-                        ctx->oz_ns, ctx->oz_lmax))
+                        ctx->oz_ns, ctx->oz_lmax, rowmax, &have_rowmax))
         return 1;
     } else if (launch_gemm(ctx, MAF_PROF_GEMM_FWD, Jpad, npad, npad, K10, npad, ctx->Linv, npad, Vt, npad, 1)) {
       return 1;
@@ -1013,7 +1028,7 @@ static int run_chunk(maf_ctx* ctx, const AcqDev& ap, bool posterior_only, bool c
     {
       ProfScope ps(ctx, MAF_PROF_VBAR);
       DISPATCH_Q(q, vbar_planes_kernel<Q><<<sc + (Jpad - J), 256, 0, ctx->stream>>>(Vt, npad, sc, Jpad, ctx->gamma, mubar, Sigbar, ctx->oz_ns_bwd,
-                                                                                   (int8_t*)ctx->ozA.p, ctx->ozsA.p));
+                                                                                   (int8_t*)ctx->ozA.p, ctx->ozsA.p, have_rowmax ? rowmax : nullptr));
       CKL();
     }
     if (launch_i8gemm(ctx, MAF_PROF_GEMM_BWD, Jpad, npad, npad, ctx->ozA, ctx->ozsA, ctx->ozTU, ctx->ozsTU, K10, npad, 2,

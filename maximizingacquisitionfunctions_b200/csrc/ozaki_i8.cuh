@@ -98,6 +98,9 @@ struct OzParams {
   // choose any order, e.g. column groups whose T planes stay in L2 while the A planes stream past (MAF_OZ_GROUPS).
   const int* tile_list;
   const int* tile_begin;
+  // register-stash epilogue only: row maxima of |C| (atomicMax on the bit patterns; the caller zeroes the array).  The
+  // Vbar producer takes its row scales from them instead of sweeping V^T once more (17 GB per step at the headline size).
+  double* rowmax;
 };
 #define OZ_TILE_EXPLICIT 0x40000000
 
@@ -444,7 +447,7 @@ template <int Q>
 __global__ void __launch_bounds__(256, Q <= 8 ? 3 : 1)
 vbar_planes_kernel(const double* __restrict__ Vt, int npad, int S, int Jpad, const double* __restrict__ gamma,
                    const double* __restrict__ mubar, const double* __restrict__ Sigbar, int ns,
-                   int8_t* __restrict__ planes, double* __restrict__ scales) {
+                   int8_t* __restrict__ planes, double* __restrict__ scales, const double* __restrict__ vmax = nullptr) {
   __shared__ double W[Q][Q];
   __shared__ double mb[Q];
   __shared__ double red[8][Q];
@@ -471,13 +474,18 @@ vbar_planes_kernel(const double* __restrict__ Vt, int npad, int S, int Jpad, con
   // Sweep 1: row maxima of V^T and of gamma only (no q x q work, q + 1 registers); the row scale of Vbar^T comes from
   // the bound |Vbar_ik| <= |mubar_i| max|gamma| + sum_j |W_ij| max_k |V_jk|, at most a factor q + 1 (3.2 bits of the
   // 55) above the true maximum.
+  // (vmax != nullptr: the forward contraction's epilogue has already left the row maxima of V^T there.)
   double mx[Q], gx = 0.0;
 #pragma unroll
   for (int i = 0; i < Q; ++i) mx[i] = 0.0;
-  for (int k = tid; k < npad; k += 256) {
+  if (vmax) {
+    for (int k = tid; k < npad; k += 256) gx = fmax(gx, fabs(gamma[k]));
+  } else {
+    for (int k = tid; k < npad; k += 256) {
 #pragma unroll
-    for (int i = 0; i < Q; ++i) mx[i] = fmax(mx[i], fabs(V[(size_t)i * npad + k]));
-    gx = fmax(gx, fabs(gamma[k]));
+      for (int i = 0; i < Q; ++i) mx[i] = fmax(mx[i], fabs(V[(size_t)i * npad + k]));
+      gx = fmax(gx, fabs(gamma[k]));
+    }
   }
 #pragma unroll
   for (int i = 0; i < Q; ++i) {
@@ -495,6 +503,7 @@ vbar_planes_kernel(const double* __restrict__ Vt, int npad, int S, int Jpad, con
     for (int j = 0; j < Q; ++j) {
       double vm = red[0][j];
       for (int w = 1; w < 8; ++w) vm = fmax(vm, red[w][j]);
+      if (vmax) vm = vmax[(size_t)s * Q + j];
       bound += fabs(W[tid][j]) * vm;
     }
     const int e = oz_exponent_for(bound);

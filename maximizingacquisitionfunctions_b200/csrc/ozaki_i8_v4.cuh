@@ -310,6 +310,7 @@ __device__ __forceinline__ void oz4_epilogue_stash(const double* __restrict__ sA
         for (int idx = 0; idx < NE; ++idx) H[idx] = __double_as_longlong(oz3_ll2double(H[idx]));
       } else {
         const double w = exp2((double)(2 - 8 * Z::hi(pass)));
+        double rm[2][2] = {{0.0, 0.0}, {0.0, 0.0}};          // |C| maxima of this lane's four rows (p.rowmax)
 #pragma unroll
         for (int gq = 0; gq < NG; ++gq) {
           double2 sc[2];
@@ -334,8 +335,24 @@ __device__ __forceinline__ void oz4_epilogue_stash(const double* __restrict__ sA
                   v1 = __longlong_as_double(H[idx + 1]);
                 }
                 // written once, read by the next kernel only after the whole 2 GB result: streaming store (evict-first)
-                __stcs(reinterpret_cast<double2*>(crow + 8 * n), make_double2(v0 * sc[n].x * sa, v1 * sc[n].y * sa));
+                const double o0 = v0 * sc[n].x * sa, o1 = v1 * sc[n].y * sa;
+                __stcs(reinterpret_cast<double2*>(crow + 8 * n), make_double2(o0, o1));
+                if (p.rowmax) rm[h][e] = fmax(rm[h][e], fmax(fabs(o0), fabs(o1)));
               }
+            }
+          }
+        }
+        if (p.rowmax) {                                      // four lanes share a row: two shuffles, one atomic per row
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              double m = rm[h][e];
+              m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 1));
+              m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 2));
+              if ((lane & 3) == 0)
+                atomicMax(reinterpret_cast<unsigned long long*>(p.rowmax + (size_t)(j0 + quarter * 32 + h * 16 + fr + 8 * e)),
+                          (unsigned long long)__double_as_longlong(m));
             }
           }
         }
