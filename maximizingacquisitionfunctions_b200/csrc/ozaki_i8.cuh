@@ -381,7 +381,13 @@ ozaki_slice_rows_kernel(const double* __restrict__ X, int ldx, int R, int Rpad, 
 #define OZC_TJ 32
 #define OZC_THREADS 256
 #ifndef OZC_MINB
-#define OZC_MINB 3
+#define OZC_MINB 2
+#endif
+#ifndef OZC_UNROLL
+#define OZC_UNROLL 2
+#endif
+#ifndef OZC_UNROLL
+#define OZC_UNROLL 2
 #endif
 // NS > 0: compile-time digit count (the FP64-grade configuration); NS == 0: run-time ns.
 template <int D, int KID, int NS>
@@ -416,7 +422,8 @@ cross_fwd_planes_kernel(const double* __restrict__ X, int J, int Jpad, const dou
   }
   const size_t plane_stride = (size_t)Jpad * npad;
   const int jend = min(OZC_TJ, J - j0);                      // rows >= J of the last row block: zero digits
-#pragma unroll 2
+  constexpr int UNRJ = OZC_UNROLL;
+#pragma unroll UNRJ
   for (int jj = 0; jj < jend; ++jj) {
     long long I[4];
 #pragma unroll
