@@ -20,10 +20,21 @@ Pinning status
     :229-256, tolerance 100*eps) and scipy ``cdist`` (tests/test_utils.py:43-67)
     -- see tests/golden/make_golden.py and tests/test_oracle.py.
   * q=1 MC UCB -> closed form identity pinned against tests/test_qUCB.py:47-53.
-  * acquisition value / gradient / Adam trajectory / selected index: the
-    reference has no asserting test for them => "parity unpinned" at that
-    level; they are anchored on the reference call sites cited per function,
-    on the MC->closed-form limits and on finite differences.
+  * acquisition value, posterior moments, Cholesky factor and gradient of
+    sum(losses) w.r.t. the pools: PINNED against the reference's OWN code --
+    src/losses/{myopic_loss,negative_ei,negative_pi,simple_regret,
+    confidence_bound}.py, src/models/{gaussian_process,kernels}.py, src/utils/*,
+    src/misc/sharded_fn.py imported unmodified and executed on an eager
+    torch-backed stand-in for the ``tensorflow`` module
+    (tests/golden/tf_eager_shim, tests/golden/make_golden_acq.py ->
+    tests/golden/ref_acq.npz; 13 cases: qEI/qPI soft+hard/qSR/qLCB/qUCB, three
+    kernels, weights, incumbents, explicit level, sharding, q=1 closed forms;
+    the oracle agrees to 1e-11, tests/test_oracle.py).  What that cannot pin is
+    TensorFlow's own kernels (cholesky, cholesky_solve, reduce_min gradient):
+    their published TF-1 semantics are what the stand-in implements.
+  * Adam trajectory / selected index: no reference test and no reference code
+    outside the TF optimizer => "parity unpinned" at that level; anchored on
+    the TF-1 ApplyAdam formula cited at adam_step and on np.argmin semantics.
 
 All ``file:line`` citations are relative to the reference root.
 """

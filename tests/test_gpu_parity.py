@@ -390,3 +390,34 @@ def test_adam_closed_form_q1_vs_oracle(eng):
     trg = eng.adam_steps(None, want_trace=True, steps=4)
     xg = eng.adam_end()
     assert relerr(trg, tro) < 1e-8 and np.abs(xg - xo).max() < 1e-8
+
+
+def _reference_acq_case_names():
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_acq.npz"))
+    return [str(c) for c in g["cases"]]
+
+
+@pytest.mark.parametrize("name", _reference_acq_case_names())
+def test_reference_code_golden(eng, name):
+    """The CUDA path against golden vectors written by the reference's OWN src.losses / src.models code (run on the
+    eager TF shim, tests/golden/make_golden_acq.py): value, posterior moments, Cholesky factor and gradient, 1e-9."""
+    from tests.test_oracle import load_reference_acq_case
+    rec, gp, acq = load_reference_acq_case(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"), name)
+    pools = rec["pools"]
+    S, q, d = pools.shape
+    eng.set_model(gp.kernel_id, rec["lenscales"], float(rec["amplitude"]), float(rec["noise"]), float(rec["mean"]),
+                  float(rec["jitter"]))
+    eng.set_train(rec["X0"], rec["Y0"])
+    p = prm(acq.kind, level=acq.level, temperature=acq.temperature, beta=acq.beta, lower=acq.lower)
+    lg, gg = eng.value_and_grad(p, pools, rec.get("z"), weights=rec.get("weights"), incumbents=rec.get("incumbents"))
+    assert relerr(lg, rec["losses"].reshape(-1)) < TOL
+    if np.abs(rec["grad"]).max() > 0:
+        assert relerr(gg, rec["grad"]) < TOL
+    else:
+        assert np.abs(gg).max() == 0.0
+    if q > 1:
+        mu, cov, chol = eng.last_extras(S, q)
+        assert relerr(mu, rec["means"]) < TOL and relerr(cov, rec["cov"]) < TOL and relerr(chol, rec["chol"]) < TOL
+    else:
+        mu, var = eng.posterior(pools, full_cov=False)
+        assert relerr(mu, rec["means"]) < TOL and relerr(var, rec["cov"]) < TOL
