@@ -114,6 +114,31 @@ def main():
         out["%s/meta" % name] = np.array([cls, kernel_id, repr(sorted(ctor.items()))])
         print("%-12s %-18s losses %s  |grad| max %.3e" % (name, cls, np.array2string(rec["losses"].ravel()[:3], precision=6),
                                                             np.abs(rec["grad"]).max()))
+    # ---- negative log posterior of gaussian_process.fit (log_likelihood :78-106 + default priors :55-62) and its
+    # gradient with respect to every state variable (what ScipyOptimizerInterface differentiates, :283-325)
+    nll_names = []
+    for k, kernel_id in enumerate(("matern52", "squared_exponential", "matern32")):
+        rs = np.random.RandomState(2000 + k)
+        n, d = 36, 3
+        X0, Y0 = rs.rand(n, d), rs.randn(n, 1)
+        hyp = dict(log_lenscales=np.log(0.3 + 0.5 * rs.rand(d)), log_amplitude=0.2 * rs.randn(), log_noise=-4.0 - rs.rand(),
+                   mean=0.1 * rs.randn())
+        model = models.gaussian_process(kernel_id=kernel_id, dtype="float64", seed=1, name="gpnll_%s" % kernel_id, **hyp)
+        for v in model.state.values():
+            v.t.requires_grad_(True)
+        nll = model.log_likelihood(tf.Tensor(torch.as_tensor(X0)), tf.Tensor(torch.as_tensor(Y0)), as_negative=True)
+        nll.t.backward()
+        name = "nll_%s" % kernel_id
+        nll_names.append(name)
+        out["%s/X0" % name], out["%s/Y0" % name] = X0, Y0
+        out["%s/kernel_id" % name] = np.array(kernel_id)
+        out["%s/jitter" % name] = np.asarray(model.jitter)
+        out["%s/value" % name] = nll.numpy()
+        for key, v in hyp.items():
+            out["%s/%s" % (name, key)] = np.asarray(v)
+            out["%s/grad_%s" % (name, key)] = model.state[key].t.grad.numpy()
+        print("%-24s nll %.12f  d/dlog_noise %.6e" % (name, float(nll.numpy()), float(model.state["log_noise"].t.grad)))
+    out["nll_cases"] = np.array(nll_names)
     path = os.path.join(HERE, "ref_acq.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")

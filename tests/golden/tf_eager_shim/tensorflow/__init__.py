@@ -111,6 +111,8 @@ def _raw(x):
         return x.t
     if isinstance(x, np.ndarray):
         return torch.as_tensor(x)
+    if isinstance(x, Int):
+        return int(x)
     if isinstance(x, (list, tuple)) and any(isinstance(e, Tensor) for e in x):
         return torch.stack([torch.as_tensor(_raw(e)) for e in x])
     return x
@@ -294,6 +296,11 @@ def zeros(shp, dtype=float64, name=None):
 
 def ones(shp, dtype=float64, name=None):
     return Tensor(torch.ones([int(s) for s in shp], dtype=as_dtype(dtype).torch))
+
+
+def fill(dims, value, name=None):
+    v = torch.as_tensor(_raw(value))
+    return Tensor(torch.full([int(s) for s in dims], v.item(), dtype=v.dtype))
 
 
 def zeros_like(x, name=None):
