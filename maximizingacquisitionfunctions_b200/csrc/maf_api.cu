@@ -104,6 +104,7 @@ struct maf_ctx {
   // fantasies (rank-4 observation sets)
   int F = 0, Fpad = 0;
   Buf fGamma, fGammaT, fmeans, flevels, fVG, fmubar;
+  double flevel_min = 0.0;         // minimum over ALL fantasised outputs (the level of negative_pi, see run_fantasies)
   double adam_lr = 0, adam_b1 = 0, adam_b2 = 0, adam_eps = 0, adam_b1p = 0, adam_b2p = 0;
   // profiling
   cudaEvent_t timer_ev[2] = {nullptr, nullptr};
@@ -1263,6 +1264,7 @@ extern "C" int maf_set_fantasies(maf_ctx* ctx, int F, const double* Y) {
     means[f] = m;
     levels[f] = lo;
   }
+  ctx->flevel_min = *std::min_element(levels.begin(), levels.begin() + F);
   const size_t fn = (size_t)Fpad * npad;
   if (ensure(ctx, ctx->fGamma, fn) || ensure(ctx, ctx->fGammaT, fn) || ensure(ctx, ctx->fmeans, Fpad) ||
       ensure(ctx, ctx->flevels, Fpad) || ensure(ctx, ctx->Vt, fn))
@@ -1296,6 +1298,13 @@ static int run_fantasies(maf_ctx* ctx, const maf_acq_params* prm, int S, const d
   if (prm) {
     if (resolve_acq(ctx, prm, &ap)) return 1;
     use_flevels = !(prm->level == prm->level);
+    // negative_pi's default level is tf.reduce_min(outputs_old) over the WHOLE rank-4 tensor, one scalar for all
+    // fantasies (negative_pi.py:32-34); negative_ei reduces along axis -2 only, one level per fantasy
+    // (negative_ei.py:31-34).  Checked against the reference's code: tests/golden/ref_acq.npz, fan_negative_pi.
+    if (use_flevels && prm->acq == MAF_ACQ_PI) {
+      ap.level = ctx->flevel_min;
+      use_flevels = 0;
+    }
   } else {
     ap.acq = MAF_ACQ_SR;
   }

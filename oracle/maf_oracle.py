@@ -436,6 +436,22 @@ def closed_form_losses(ts: TrainState, acq: Acq, pools: torch.Tensor,
     return torch.cat(outs)
 
 
+def fantasy_closed_form_losses(gp: GP, X0, Y, acq: Acq, pools: torch.Tensor) -> torch.Tensor:
+    """losses[S] for pools[S,1,d] under fantasy-padded observations (inputs_old [F,1,n,d], outputs_old [F,1,n,1],
+    scripts/run_bayesopt_incremental.py:150-179): the q == 1 closed form per fantasy through the rank-4 branch of
+    _predict_nd (gaussian_process.py:195-206), then the mean over the fantasy axis (appraise_inputs,
+    bayesian_optimization.py:227-229).  Default levels: negative_ei reduces outputs_old along axis -2 (one level per
+    fantasy, negative_ei.py:31-34); negative_pi takes tf.reduce_min(outputs_old) over the WHOLE tensor (one level for
+    all fantasies, negative_pi.py:32-34).  Pinned by tests/golden/ref_acq.npz (fan_* cases)."""
+    Y = np.asarray(Y, dtype=np.float64)
+    if acq.kind == "pi" and acq.level is None:
+        acq = Acq("pi", temperature=acq.temperature, beta=acq.beta, lower=acq.lower, level=float(Y.min()))
+    tot = 0
+    for y in Y:
+        tot = tot + closed_form_losses(prepare_train(gp, X0, y), acq, pools).reshape(-1)
+    return tot / Y.shape[0]
+
+
 def value_and_grad(ts: TrainState, acq: Acq, X_new, z, X_pend=None,
                    weights=None, incumbents=None, shard_limit: int = 2 ** 12):
     """Loss vector and d(sum of losses)/d(inputs_new).

@@ -139,6 +139,42 @@ def main():
             out["%s/grad_%s" % (name, key)] = model.state[key].t.grad.numpy()
         print("%-24s nll %.12f  d/dlog_noise %.6e" % (name, float(nll.numpy()), float(model.state["log_noise"].t.grad)))
     out["nll_cases"] = np.array(nll_names)
+
+    # ---- fantasy-padded observations of the incremental greedy script (scripts/run_bayesopt_incremental.py:150-179):
+    # inputs_old [F,1,n,d], outputs_old [F,1,n,1], q = 1 closed forms through the rank-4 branch of _predict_nd
+    # (gaussian_process.py:195-206) with the precomputed rank-4 Cholesky factor (appraise_inputs :188-198), then the
+    # mean over the fantasy axis (appraise_inputs :227-229)
+    fan_names = []
+    for k, (cls, ctor) in enumerate((("negative_ei", {}), ("negative_pi", {}), ("simple_regret", {}),
+                                     ("confidence_bound", {"beta": 2.0, "lower": True}))):
+        rs = np.random.RandomState(3000 + k)
+        n, d, S, F = 18, 2, 7, 5
+        X0 = rs.rand(n, d)
+        Y = rs.randn(1, n) + 0.3 * rs.randn(F, n)              # F fantasised output vectors over the same inputs
+        pools = rs.rand(S, 1, d)
+        pools[:3, 0] = np.clip(X0[np.argmin(Y.mean(0))] + 0.03 * rs.randn(3, d), 0, 1)   # near the incumbent: EI / PI of order 1
+        ls = 0.3 + 0.5 * rs.rand(d)
+        amp, noise, mean = 0.8 + 0.4 * rs.rand(), 0.05, 0.1 * rs.randn()
+        name = "fan_%s" % cls
+        model = models.gaussian_process(kernel_id="matern52", dtype="float64", seed=1, name="gp_%s" % name,
+                                        log_lenscales=np.log(ls), log_amplitude=np.log(amp), log_noise=np.log(noise), mean=mean)
+        loss_fn = getattr(losses, cls)(model=model, seed=2, name="loss_%s" % name, **ctor)
+        X0_4 = np.tile(X0[None, None], [F, 1, 1, 1])
+        Y0_4 = Y[:, None, :, None]
+        tX0, tY0 = tf.Tensor(torch.as_tensor(X0_4)), tf.Tensor(torch.as_tensor(Y0_4))
+        chol4 = model.compute_cholesky(tX0, noisy=True)
+        tp = torch.as_tensor(pools).clone().requires_grad_(True)
+        vals, _extras = loss_fn.closed_form(tf.Tensor(tp), tX0, tY0, predict_kwargs={"chol": chol4})
+        assert vals.shape.ndims == 4 and tuple(vals.shape) == (F, S, 1, 1)
+        vals = tf.reduce_mean(vals, 0)
+        vals.t.sum().backward()
+        fan_names.append(name)
+        for key, v in dict(X0=X0, Y=Y, pools=pools, lenscales=ls, amplitude=amp, noise=noise, mean=mean, jitter=model.jitter,
+                           losses=vals.numpy(), grad=tp.grad.numpy()).items():
+            out["%s/%s" % (name, key)] = np.asarray(v)
+        out["%s/meta" % name] = np.array([cls, "matern52", repr(sorted(ctor.items()))])
+        print("%-24s losses %s |grad| max %.3e" % (name, np.array2string(vals.numpy().ravel()[:3], precision=6), np.abs(tp.grad.numpy()).max()))
+    out["fantasy_cases"] = np.array(fan_names)
     path = os.path.join(HERE, "ref_acq.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")

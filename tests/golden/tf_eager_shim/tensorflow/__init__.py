@@ -115,6 +115,8 @@ def _raw(x):
         return int(x)
     if isinstance(x, (list, tuple)) and any(isinstance(e, Tensor) for e in x):
         return torch.stack([torch.as_tensor(_raw(e)) for e in x])
+    if isinstance(x, (list, tuple)) and x and all(isinstance(e, (int, np.integer)) for e in x):
+        return [int(e) for e in x]                         # static shape vector
     return x
 
 
@@ -163,6 +165,11 @@ class Tensor:
     def __gt__(self, o): return Tensor(self.t > _raw(o))
     def __ge__(self, o): return Tensor(self.t >= _raw(o))
     def __bool__(self): return builtins_bool(self.t)
+    def __int__(self): return int(self.t)
+    def __index__(self): return int(self.t)
+    def __float__(self): return float(self.t)
+    def __len__(self): return self.t.shape[0]
+    def __iter__(self): return (Tensor(t) for t in self.t)
     def __repr__(self): return "shim.Tensor(%r)" % (self.t,)
 
     def numpy(self):
@@ -304,11 +311,11 @@ def fill(dims, value, name=None):
 
 
 def zeros_like(x, name=None):
-    return Tensor(torch.zeros_like(_raw(x)))
+    return Tensor(torch.zeros_like(torch.as_tensor(_raw(x))))
 
 
 def ones_like(x, name=None):
-    return Tensor(torch.ones_like(_raw(x)))
+    return Tensor(torch.ones_like(torch.as_tensor(_raw(x))))
 
 
 def eye(n, dtype=float64, name=None):

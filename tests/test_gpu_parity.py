@@ -369,11 +369,7 @@ def test_fantasy_conditioned_closed_form(eng, acq, kw):
     eng.set_fantasies(Y)
     lg, gg = eng.fantasies_value_and_grad(prm(acq, **kw), X[:, 0, :])
     Xt = torch.as_tensor(X).clone().requires_grad_(True)
-    tot = 0
-    for f in range(F):
-        tsf = orc.prepare_train(ts.gp, X0, Y[f])
-        tot = tot + orc.closed_form_losses(tsf, orc.Acq(acq, **kw), Xt).reshape(-1)
-    lo = tot / F
+    lo = orc.fantasy_closed_form_losses(ts.gp, X0, Y, orc.Acq(acq, **kw), Xt)
     lo.sum().backward()
     assert relerr(lg, lo.detach().numpy()) < TOL
     assert relerr(gg, Xt.grad.numpy()[:, 0, :]) < TOL
@@ -421,3 +417,22 @@ def test_reference_code_golden(eng, name):
     else:
         mu, var = eng.posterior(pools, full_cov=False)
         assert relerr(mu, rec["means"]) < TOL and relerr(var, rec["cov"]) < TOL
+
+
+def _fantasy_case_names():
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_acq.npz"))
+    return [str(c) for c in g["fantasy_cases"]]
+
+
+@pytest.mark.parametrize("name", _fantasy_case_names())
+def test_fantasy_padded_reference_code_golden(eng, name):
+    """maf_fantasies_value_grad against the reference's own rank-4 path (golden vectors, fan_* cases)."""
+    from tests.test_oracle import fantasy_case
+    rec, gp, acq = fantasy_case(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"), name)
+    eng.set_model(gp.kernel_id, rec["lenscales"], float(rec["amplitude"]), float(rec["noise"]), float(rec["mean"]),
+                  float(rec["jitter"]))
+    eng.set_train(rec["X0"], rec["Y"][0])
+    eng.set_fantasies(rec["Y"])
+    lg, gg = eng.fantasies_value_and_grad(prm(acq.kind, beta=acq.beta, lower=acq.lower), rec["pools"][:, 0, :])
+    assert relerr(lg, rec["losses"].reshape(-1)) < TOL
+    assert relerr(gg, rec["grad"][:, 0, :]) < TOL
