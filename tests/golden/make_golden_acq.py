@@ -175,6 +175,29 @@ def main():
         out["%s/meta" % name] = np.array([cls, "matern52", repr(sorted(ctor.items()))])
         print("%-24s losses %s |grad| max %.3e" % (name, np.array2string(vals.numpy().ravel()[:3], precision=6), np.abs(tp.grad.numpy()).max()))
     out["fantasy_cases"] = np.array(fan_names)
+
+    # ---- gaussian_process.draw_samples (:328-349) with explicit base samples: at a point set (rank 2, first greedy
+    # step of the incremental script) and under fantasy-padded observations (rank 4, later steps)
+    rs = np.random.RandomState(4000)
+    n, d, m, ns, F = 20, 3, 4, 6, 5
+    X0, Y0 = rs.rand(n, d), rs.randn(n, 1)
+    ls = 0.3 + 0.5 * rs.rand(d)
+    amp, noise, mean = 1.1, 1e-3, 0.05
+    model = models.gaussian_process(kernel_id="matern52", dtype="float64", seed=1, name="gp_draw", log_lenscales=np.log(ls),
+                                    log_amplitude=np.log(amp), log_noise=np.log(noise), mean=mean)
+    X1, eps = rs.rand(m, d), rs.randn(ns, m)
+    smp = model.draw_samples(ns, tf.Tensor(torch.as_tensor(X1)), tf.Tensor(torch.as_tensor(X0)), tf.Tensor(torch.as_tensor(Y0)),
+                             base_rvs=tf.Tensor(torch.as_tensor(eps)))
+    assert tuple(smp.shape) == (ns, m)
+    Yf = Y0.reshape(1, n) + 0.3 * rs.randn(F, n)
+    x1, eps1 = rs.rand(1, d), rs.randn(1, 1)
+    smp4 = model.draw_samples(1, tf.Tensor(torch.as_tensor(x1)), tf.Tensor(torch.as_tensor(np.tile(X0[None, None], [F, 1, 1, 1]))),
+                              tf.Tensor(torch.as_tensor(Yf[:, None, :, None])), base_rvs=tf.Tensor(torch.as_tensor(eps1)))
+    assert tuple(smp4.shape) == (F, 1, 1, 1)
+    for key, v in dict(X0=X0, Y0=Y0, lenscales=ls, amplitude=amp, noise=noise, mean=mean, X1=X1, eps=eps, samples=smp.numpy(),
+                       Yf=Yf, x1=x1, eps1=eps1, samples4=smp4.numpy()).items():
+        out["draw/%s" % key] = np.asarray(v)
+    print("draw_samples rank 2 %s rank 4 %s" % (smp.numpy()[0, :2], smp4.numpy().ravel()[:2]))
     path = os.path.join(HERE, "ref_acq.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")

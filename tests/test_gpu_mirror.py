@@ -132,3 +132,26 @@ def test_successive_halving_and_gd_variants():
     (xhg, lhg, xmg, lmg), (xhr, lhr, xmr, lmr) = run_both(flow)
     assert np.abs(xhg - xhr).max() < 1e-9 and abs(lhg - lhr) < 1e-8 * max(1.0, abs(lhr))
     assert np.abs(xmg - xmr).max() < 1e-6 and abs(lmg - lmr) < 1e-8 * max(1.0, abs(lmr))
+
+
+def test_draw_samples_reference_code_golden():
+    """models.gaussian_process.draw_samples of the mirror (on the CUDA engine) against golden vectors written by the
+    reference's own draw_samples (:328-349; tests/golden/make_golden_acq.py) with the same base samples: at a point
+    set, and at one point under fantasy-padded (rank-4) observations as the incremental greedy script calls it."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_acq.npz"))
+    r = {k.split("/", 1)[1]: g[k] for k in g.files if k.startswith("draw/")}
+    runtime.set_engine_factory(None)
+    runtime.release_engines()
+    try:
+        model = models.gaussian_process(kernel_id="matern52", seed=1, log_lenscales=np.log(r["lenscales"]),
+                                        log_amplitude=float(np.log(r["amplitude"])), log_noise=float(np.log(r["noise"])),
+                                        mean=float(r["mean"]))
+        s2 = model.draw_samples(r["eps"].shape[0], r["X1"], r["X0"], r["Y0"], base_rvs=r["eps"])
+        F, n = r["Yf"].shape
+        s4 = model.draw_samples(1, r["x1"], np.tile(r["X0"][None, None], [F, 1, 1, 1]), r["Yf"][:, None, :, None],
+                                base_rvs=r["eps1"])
+    finally:
+        runtime.release_engines()
+    assert s2.shape == r["samples"].shape and np.abs(s2 - r["samples"]).max() < 1e-9 * np.abs(r["samples"]).max()
+    assert np.shape(s4) == r["samples4"].shape and np.abs(s4 - r["samples4"]).max() < 1e-9 * np.abs(r["samples4"]).max()

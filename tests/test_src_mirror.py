@@ -274,3 +274,21 @@ def test_adam_closed_form_q1():
                                        config={"step_limit": 10})
     l1 = np.ravel(agent.loss_fn(nodes["inputs_new"].value, X0, Y0, model=agent.model)[0])
     assert seq.shape == (60,) and l1.mean() < l0.mean()
+
+
+def test_draw_samples_matches_reference_code_golden(golden_dir):
+    """Host logic of models.gaussian_process.draw_samples (rank 2 and fantasy-padded rank 4) against golden vectors
+    from the reference's own draw_samples (:328-349) with the same base samples (oracle-backed engine here; the CUDA
+    engine is checked by tests/test_gpu_mirror.py::test_draw_samples_reference_code_golden)."""
+    import os
+    g = np.load(os.path.join(golden_dir, "ref_acq.npz"))
+    r = {k.split("/", 1)[1]: g[k] for k in g.files if k.startswith("draw/")}
+    model = models.gaussian_process(kernel_id="matern52", seed=1, log_lenscales=np.log(r["lenscales"]),
+                                    log_amplitude=float(np.log(r["amplitude"])), log_noise=float(np.log(r["noise"])),
+                                    mean=float(r["mean"]))
+    s2 = model.draw_samples(r["eps"].shape[0], r["X1"], r["X0"], r["Y0"], base_rvs=r["eps"])
+    F, n = r["Yf"].shape
+    s4 = model.draw_samples(1, r["x1"], np.tile(r["X0"][None, None], [F, 1, 1, 1]), r["Yf"][:, None, :, None],
+                            base_rvs=r["eps1"])
+    assert s2.shape == r["samples"].shape and np.abs(s2 - r["samples"]).max() < 1e-11
+    assert np.shape(s4) == r["samples4"].shape and np.abs(s4 - r["samples4"]).max() < 1e-11
