@@ -946,7 +946,7 @@ static int resolve_acq(maf_ctx* ctx, const maf_acq_params* prm, AcqDev* out) {
 template <int Q>
 static void launch_posterior(maf_ctx* ctx, int sc, const double* Vt, int npad, const double* dX, double* mu, double* Sig) {
   if constexpr (Q <= 8)
-    posterior_reg_kernel<Q><<<sc, POST_THREADS, 0, ctx->stream>>>(Vt, npad, ctx->gamma, dX, ctx->mp, ctx->mean_val, mu, Sig);
+    posterior_reg_kernel<Q><<<sc, POST_REG_THREADS, 0, ctx->stream>>>(Vt, npad, ctx->gamma, dX, ctx->mp, ctx->mean_val, mu, Sig);
   else
     posterior_kernel<Q><<<sc, POST_THREADS, 0, ctx->stream>>>(Vt, npad, ctx->gamma, dX, ctx->mp, ctx->mean_val, mu, Sig);
 }

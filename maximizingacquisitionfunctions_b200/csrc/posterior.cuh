@@ -9,6 +9,11 @@
 
 #define POST_TK 256
 #define POST_THREADS 256
+// register-accumulating kernel (Q <= 8): 64 threads per restart measured best at n = 4096 (256: 4.5, 128: 3.8, 96: 3.9,
+// 64: 3.5 ms per step): more CTAs per SM keep more loads in flight and the block reduction of the 44 sums gets shorter
+#ifndef POST_REG_THREADS
+#define POST_REG_THREADS 64
+#endif
 
 // One CTA per restart.  The q x POST_TK slab of V^T is staged in shared memory once and
 // every warp accumulates the Gram rows it owns (warp w -> rows w and w+8).
@@ -92,12 +97,12 @@ posterior_kernel(const double* __restrict__ Vt, int npad, const double* __restri
 // pipe): one thread owns a strided set of training columns, keeps its Q values of V^T in registers and accumulates the
 // Q (Q+1)/2 Gram entries and the Q mean terms there; one block reduction at the end.  Streams V^T once (HBM-bound).
 template <int Q>
-__global__ void __launch_bounds__(POST_THREADS)
+__global__ void __launch_bounds__(POST_REG_THREADS)
 posterior_reg_kernel(const double* __restrict__ Vt, int npad, const double* __restrict__ gamma,
                      const double* __restrict__ X, ModelParams mp, double mean,
                      double* __restrict__ mu, double* __restrict__ Sig) {
   constexpr int NG = Q * (Q + 1) / 2;
-  __shared__ double red[POST_THREADS / 32][NG + Q];
+  __shared__ double red[POST_REG_THREADS / 32][NG + Q];
   __shared__ double G[Q][Q];
   __shared__ double mus[Q];
   const int s = blockIdx.x;
@@ -108,7 +113,7 @@ posterior_reg_kernel(const double* __restrict__ Vt, int npad, const double* __re
   for (int t = 0; t < NG; ++t) acc[t] = 0.0;
 #pragma unroll
   for (int i = 0; i < Q; ++i) m[i] = 0.0;
-  for (int k = tid; k < npad; k += POST_THREADS) {
+  for (int k = tid; k < npad; k += POST_REG_THREADS) {
     double v[Q];
 #pragma unroll
     for (int i = 0; i < Q; ++i) v[i] = V[(size_t)i * npad + k];
@@ -131,9 +136,9 @@ posterior_reg_kernel(const double* __restrict__ Vt, int npad, const double* __re
     if (lane == 0) red[warp][NG + i] = v;
   }
   __syncthreads();
-  for (int t = tid; t < NG + Q; t += POST_THREADS) {
+  for (int t = tid; t < NG + Q; t += POST_REG_THREADS) {
     double v = 0.0;
-    for (int w = 0; w < POST_THREADS / 32; ++w) v += red[w][t];
+    for (int w = 0; w < POST_REG_THREADS / 32; ++w) v += red[w][t];
     if (t < NG) {
       int i = 0;
       while ((i + 1) * (i + 2) / 2 <= t) ++i;
@@ -144,7 +149,7 @@ posterior_reg_kernel(const double* __restrict__ Vt, int npad, const double* __re
   }
   __syncthreads();
   const double* xs = X + (size_t)s * Q * mp.d;
-  for (int t = tid; t < Q * Q; t += POST_THREADS) {
+  for (int t = tid; t < Q * Q; t += POST_REG_THREADS) {
     int i = t / Q, j = t - i * Q;
     double r2 = 0.0;
     if (i != j) {
