@@ -1028,7 +1028,7 @@ static int run_chunk(maf_ctx* ctx, const AcqDev& ap, bool posterior_only, bool c
     if (ensure(ctx, ctx->ozA, (bytes + 7) / 8) || ensure(ctx, ctx->ozsA, (size_t)Jpad)) return 1;
     {
       ProfScope ps(ctx, MAF_PROF_VBAR);
-      DISPATCH_Q(q, vbar_planes_kernel<Q><<<sc + (Jpad - J), 256, 0, ctx->stream>>>(Vt, npad, sc, Jpad, ctx->gamma, mubar, Sigbar, ctx->oz_ns_bwd,
+      DISPATCH_Q(q, vbar_planes_kernel<Q><<<sc + (Jpad - J), VBP_THREADS, 0, ctx->stream>>>(Vt, npad, sc, Jpad, ctx->gamma, mubar, Sigbar, ctx->oz_ns_bwd,
                                                                                    (int8_t*)ctx->ozA.p, ctx->ozsA.p, have_rowmax ? rowmax : nullptr));
       CKL();
     }

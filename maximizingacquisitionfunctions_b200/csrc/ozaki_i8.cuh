@@ -450,15 +450,21 @@ cross_fwd_planes_kernel(const double* __restrict__ X, int J, int Jpad, const dou
 // One CTA per restart.  Sweep 1 bounds the row maxima of Vbar^T from the row maxima of V^T, sweep 2 (the q x n slab
 // of V^T re-read from L2) computes Vbar^T two columns per thread and emits its digits.  Rows >= J of the last
 // row block are zeroed by the CTAs with s >= S.
+#ifndef VBP_THREADS
+#define VBP_THREADS 128
+#endif
+#ifndef VBP_MINB
+#define VBP_MINB 4
+#endif
 template <int Q>
-__global__ void __launch_bounds__(256, Q <= 8 ? 3 : 1)
+__global__ void __launch_bounds__(VBP_THREADS, Q <= 8 ? VBP_MINB : 1)
 vbar_planes_kernel(const double* __restrict__ Vt, int npad, int S, int Jpad, const double* __restrict__ gamma,
                    const double* __restrict__ mubar, const double* __restrict__ Sigbar, int ns,
                    int8_t* __restrict__ planes, double* __restrict__ scales, const double* __restrict__ vmax = nullptr) {
   __shared__ double W[Q][Q];
   __shared__ double mb[Q];
-  __shared__ double red[8][Q];
-  __shared__ double redg[8];
+  __shared__ double red[VBP_THREADS / 32][Q];
+  __shared__ double redg[VBP_THREADS / 32];
   __shared__ double sinv[Q];
   const int s = blockIdx.x, tid = threadIdx.x;
   const size_t plane_stride = (size_t)Jpad * npad;
@@ -466,12 +472,12 @@ vbar_planes_kernel(const double* __restrict__ Vt, int npad, int S, int Jpad, con
     const int r = S * Q + (s - S);
     if (r >= Jpad) return;
     for (int i = 0; i < ns; ++i)
-      for (int k = tid * 4; k < npad; k += 256 * 4) *reinterpret_cast<int*>(planes + i * plane_stride + (size_t)r * npad + k) = 0;
+      for (int k = tid * 4; k < npad; k += VBP_THREADS * 4) *reinterpret_cast<int*>(planes + i * plane_stride + (size_t)r * npad + k) = 0;
     if (tid == 0) scales[r] = 1.0;
     return;
   }
   const double* sb = Sigbar + (size_t)s * Q * Q;
-  for (int t = tid; t < Q * Q; t += 256) {
+  for (int t = tid; t < Q * Q; t += VBP_THREADS) {
     int i = t / Q, j = t - i * Q;
     W[i][j] = sb[i * Q + j] + sb[j * Q + i];
   }
@@ -486,9 +492,9 @@ vbar_planes_kernel(const double* __restrict__ Vt, int npad, int S, int Jpad, con
 #pragma unroll
   for (int i = 0; i < Q; ++i) mx[i] = 0.0;
   if (vmax) {
-    for (int k = tid; k < npad; k += 256) gx = fmax(gx, fabs(gamma[k]));
+    for (int k = tid; k < npad; k += VBP_THREADS) gx = fmax(gx, fabs(gamma[k]));
   } else {
-    for (int k = tid; k < npad; k += 256) {
+    for (int k = tid; k < npad; k += VBP_THREADS) {
 #pragma unroll
       for (int i = 0; i < Q; ++i) mx[i] = fmax(mx[i], fabs(V[(size_t)i * npad + k]));
       gx = fmax(gx, fabs(gamma[k]));
@@ -505,11 +511,11 @@ vbar_planes_kernel(const double* __restrict__ Vt, int npad, int S, int Jpad, con
   __syncthreads();
   if (tid < Q) {
     double gm = redg[0];
-    for (int w = 1; w < 8; ++w) gm = fmax(gm, redg[w]);
+    for (int w = 1; w < VBP_THREADS / 32; ++w) gm = fmax(gm, redg[w]);
     double bound = fabs(mb[tid]) * gm;
     for (int j = 0; j < Q; ++j) {
       double vm = red[0][j];
-      for (int w = 1; w < 8; ++w) vm = fmax(vm, red[w][j]);
+      for (int w = 1; w < VBP_THREADS / 32; ++w) vm = fmax(vm, red[w][j]);
       if (vmax) vm = vmax[(size_t)s * Q + j];
       bound += fabs(W[tid][j]) * vm;
     }
@@ -520,7 +526,7 @@ vbar_planes_kernel(const double* __restrict__ Vt, int npad, int S, int Jpad, con
   __syncthreads();
   // two columns per thread (q values of V^T each stay in registers); sweep 2 walks the slab backwards, so the columns
   // sweep 1 read last (the ones most likely still in L2) are re-read first
-  for (int k = ((npad - 1) / 512) * 512 + tid * 2; k >= 0; k -= 256 * 2) {
+  for (int k = ((npad - 1) / (2 * VBP_THREADS)) * (2 * VBP_THREADS) + tid * 2; k >= 0; k -= VBP_THREADS * 2) {
     if (k >= npad) continue;
     double2 v[Q];
 #pragma unroll
