@@ -1,5 +1,5 @@
 #!/bin/bash
-# round-1 v8 evidence: GPU parity suite, smoke, bench both arms, launch list,
+# round-1 v9 evidence: GPU parity suite, smoke, bench both arms, launch list,
 # ncu --set full of the INT8 contraction.  Every ncu run follows a plain run of the same command that exited 0.
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -q -rA --no-header -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"
@@ -13,5 +13,5 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
 echo "launch list rc=$?"
 SMALL="python bench.py --steps 1 --warmup 3 --restarts 16384 --no-cpu-baseline"
 $SMALL > gpurun_out/bench_small_plain.log 2>&1 &&
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:ozaki_i8_gemm_v4 -s 12 -c 2 -f -o gpurun_out/prof_gemm_v8 $SMALL > gpurun_out/ncu_full.log 2>&1
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:ozaki_i8_gemm_v4 -s 12 -c 2 -f -o gpurun_out/prof_gemm_v9 $SMALL > gpurun_out/ncu_full.log 2>&1
 echo "full capture rc=$?"; tail -2 gpurun_out/ncu_full.log
