@@ -176,6 +176,39 @@ def main():
         print("%-24s losses %s |grad| max %.3e" % (name, np.array2string(vals.numpy().ravel()[:3], precision=6), np.abs(tp.grad.numpy()).max()))
     out["fantasy_cases"] = np.array(fan_names)
 
+    # ---- pending points: pools = concat(tile(expand_to(inputs_pend, 3), [S,1,1]), inputs_new, axis=-2) as
+    # bayesian_optimization.prepare builds them (:1106-1123; same tf / utils calls), gradient w.r.t. inputs_new only
+    from src import utils as ref_utils
+    rs = np.random.RandomState(5000)
+    n, d, S, M, p_pend, q_new = 26, 3, 5, 24, 2, 3
+    X0, Y0 = rs.rand(n, d), rs.randn(n, 1)
+    ls = 0.3 + 0.5 * rs.rand(d)
+    amp, noise, mean = 0.9, 1e-3, -0.05
+    Xpend, Xnew, z = rs.rand(p_pend, d), rs.rand(S, q_new, d), rs.randn(M, p_pend + q_new)
+    Xpend = np.clip(X0[np.argsort(Y0[:, 0])[-p_pend:]] + 0.05 * rs.randn(p_pend, d), 0, 1)   # pending jobs at poor locations
+    model = models.gaussian_process(kernel_id="matern52", dtype="float64", seed=1, name="gp_pend", log_lenscales=np.log(ls),
+                                    log_amplitude=np.log(amp), log_noise=np.log(noise), mean=mean)
+    pend_names = []
+    for cls, ctor in (("negative_ei", {}), ("confidence_bound", {"beta": 2.0, "lower": True})):
+        loss_fn = getattr(losses, cls)(model=model, seed=2, name="loss_pend_%s" % cls, **ctor)
+        tn = torch.as_tensor(Xnew).clone().requires_grad_(True)
+        inputs_new = tf.Tensor(tn)
+        shape_n = tf.shape(inputs_new)
+        tiled = tf.tile(ref_utils.expand_to(tf.Tensor(torch.as_tensor(Xpend)), 3), (shape_n.__getitem__(0), 1, 1))
+        pools = tf.concat((tiled, inputs_new), axis=-2)
+        kw = {"levels": tf.Tensor(torch.full((1, 1), float(np.median(Y0)), dtype=torch.float64))} if cls == "negative_ei" else {}
+        vals, _extras = loss_fn.monte_carlo(pools, tf.Tensor(torch.as_tensor(X0)), tf.Tensor(torch.as_tensor(Y0)),
+                                            fantasy_rvs=tf.Tensor(torch.as_tensor(z)), parallelism=p_pend + q_new, **kw)
+        vals.t.sum().backward()
+        name = "pend_%s" % cls
+        pend_names.append(name)
+        for key, v in dict(X0=X0, Y0=Y0, lenscales=ls, amplitude=amp, noise=noise, mean=mean, jitter=model.jitter, Xpend=Xpend,
+                           Xnew=Xnew, z=z, level=float(np.median(Y0)), losses=vals.numpy(), grad=tn.grad.numpy()).items():
+            out["%s/%s" % (name, key)] = np.asarray(v)
+        out["%s/meta" % name] = np.array([cls, "matern52", repr(sorted(ctor.items()))])
+        print("%-24s losses %s |grad| max %.3e" % (name, np.array2string(vals.numpy()[:3], precision=6), np.abs(tn.grad.numpy()).max()))
+    out["pending_cases"] = np.array(pend_names)
+
     # ---- gaussian_process.draw_samples (:328-349) with explicit base samples: at a point set (rank 2, first greedy
     # step of the incremental script) and under fantasy-padded observations (rank 4, later steps)
     rs = np.random.RandomState(4000)

@@ -436,3 +436,18 @@ def test_fantasy_padded_reference_code_golden(eng, name):
     lg, gg = eng.fantasies_value_and_grad(prm(acq.kind, beta=acq.beta, lower=acq.lower), rec["pools"][:, 0, :])
     assert relerr(lg, rec["losses"].reshape(-1)) < TOL
     assert relerr(gg, rec["grad"][:, 0, :]) < TOL
+
+
+@pytest.mark.parametrize("name", ["pend_negative_ei", "pend_confidence_bound"])
+def test_pending_points_reference_code_golden(eng, name):
+    """p_pending > 0 through the C ABI against the reference's own pools construction and loss code (golden vectors)."""
+    from tests.test_oracle import pending_case
+    rec, gp, acq = pending_case(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"), name)
+    eng.set_model(gp.kernel_id, rec["lenscales"], float(rec["amplitude"]), float(rec["noise"]), float(rec["mean"]),
+                  float(rec["jitter"]))
+    eng.set_train(rec["X0"], rec["Y0"])
+    S, p = rec["Xnew"].shape[0], rec["Xpend"].shape[0]
+    pools = np.concatenate([np.tile(rec["Xpend"][None], [S, 1, 1]), rec["Xnew"]], axis=1)
+    lg, gg = eng.value_and_grad(prm(acq.kind, level=acq.level, beta=acq.beta, lower=acq.lower), pools, rec["z"], p_pending=p)
+    assert relerr(lg, rec["losses"]) < TOL
+    assert gg.shape == rec["grad"].shape and relerr(gg, rec["grad"]) < TOL
