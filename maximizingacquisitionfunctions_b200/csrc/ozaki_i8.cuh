@@ -378,7 +378,9 @@ ozaki_slice_rows_kernel(const double* __restrict__ X, int ldx, int R, int Rpad, 
 // ozaki_slice_rows_kernel with the fixed bound a^2).  One thread owns 4 consecutive training points (their
 // scaled coordinates stay in registers), OZC_TJ candidate rows per CTA from shared memory; each store is one
 // packed int per plane, 128 contiguous bytes per warp.
+#ifndef OZC_TJ
 #define OZC_TJ 32
+#endif
 #define OZC_THREADS 256
 #ifndef OZC_MINB
 #define OZC_MINB 2
