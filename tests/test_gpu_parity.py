@@ -275,6 +275,27 @@ def test_replayed_steps_equal_host_loop_bitwise(eng, method):
     assert outs[0][3] == outs[1][3] + 2                              # step_in and step_out kernels of the replayed form
 
 
+# degenerate and boundary shapes: one training point, one restart, one MC sample, d = 1 and d = MAF_MAX_D, q = MAF_MAX_Q,
+# n one below / on / one above the 128-row tile of the contraction
+EDGE_SHAPES = [(1, 1, 2, 1, 1), (2, 1, 8, 3, 2), (127, 16, 16, 2, 5), (128, 16, 2, 1, 3), (129, 1, 3, 2, 1), (1, 3, 16, 4, 1)]
+
+
+@pytest.mark.parametrize("acq", ["sr", "ei", "cb"])
+@pytest.mark.parametrize("n,d,q,S,M", EDGE_SHAPES)
+def test_edge_shapes_vs_oracle(eng, acq, n, d, q, S, M):
+    ts, X0, y0, X, z = setup_problem(eng, n, d, q, S, M, seed=3)
+    lo, go = orc.value_and_grad(ts, orc.Acq(acq), X, z)
+    lg, gg = eng.value_and_grad(prm(acq), X, z)
+    assert lg.shape == (S,) and gg.shape == (S, q, d)
+    assert relerr(lg, lo) < TOL, ("loss", relerr(lg, lo))
+    if np.abs(go).max() > 0:
+        assert relerr(gg, go) < TOL, ("grad", relerr(gg, go))
+    else:
+        assert np.abs(gg).max() == 0
+    idx, val = eng.argmin_last()
+    assert idx == int(np.argmin(lo)) and val == lg[idx]
+
+
 def test_errors_are_loud(eng):
     from maximizingacquisitionfunctions_b200.engine import MafError
     setup_problem(eng, 32, 2, 2, 4, 8)
