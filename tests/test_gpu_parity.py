@@ -296,6 +296,40 @@ def test_edge_shapes_vs_oracle(eng, acq, n, d, q, S, M):
     assert idx == int(np.argmin(lo)) and val == lg[idx]
 
 
+@pytest.mark.parametrize("n,d,S", [(1, 1, 1), (1, 16, 7), (127, 2, 3), (129, 16, 1)])
+@pytest.mark.parametrize("acq", ["ei", "pi", "sr", "cb"])
+def test_closed_form_edge_shapes(eng, acq, n, d, S):
+    ts, X0, y0, X, z = setup_problem(eng, n, d, 1, S, 1, seed=5)
+    lo, go = orc.value_and_grad(ts, orc.Acq(acq), X, np.zeros((1, 1)))
+    lg, gg = eng.value_and_grad(prm(acq), X, None)
+    assert lg.shape == (S,) and gg.shape == (S, 1, d)
+    assert relerr(lg, lo) < TOL and relerr(gg, go) < TOL
+
+
+def test_all_but_one_pending_at_max_pool(eng):
+    """q = MAF_MAX_Q with 15 pending points: one free row per restart, gradient [S, 1, d]."""
+    n, d, q, S, M = 130, 3, 16, 5, 17
+    ts, X0, y0, X, z = setup_problem(eng, n, d, q, S, M, seed=8)
+    pend, Xn = X[0, :15], X[:, 15:]
+    pools = np.ascontiguousarray(np.concatenate([np.broadcast_to(pend, (S, 15, d)), Xn], axis=1))
+    for acq in ("cb", "sr"):
+        lo, go = orc.value_and_grad(ts, orc.Acq(acq), Xn, z, X_pend=pend)
+        lg, gg = eng.value_and_grad(prm(acq), pools, z, p_pending=15)
+        assert gg.shape == (S, 1, d)
+        assert relerr(lg, lo) < TOL and relerr(gg, go) < TOL
+
+
+def test_adam_loop_single_restart_single_sample(eng):
+    n, d, q, S, M, steps = 5, 1, 2, 1, 1, 6
+    ts, X0, y0, X, z = setup_problem(eng, n, d, q, S, M, seed=21)
+    zs = np.random.RandomState(97).randn(steps, M, q)
+    xo, tro = orc.adam_run(ts, orc.Acq("sr"), X, zs)
+    eng.adam_begin(prm("sr"), X)
+    trg = eng.adam_steps(zs, want_trace=True)
+    xg = eng.adam_end()
+    assert relerr(trg, tro) < 1e-7 and np.abs(xg - xo).max() < 1e-7
+
+
 def test_errors_are_loud(eng):
     from maximizingacquisitionfunctions_b200.engine import MafError
     setup_problem(eng, 32, 2, 2, 4, 8)
