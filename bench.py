@@ -213,6 +213,8 @@ def main():
                     help="contraction engine: f64 = DMMA, i8 = exact INT8 digit slicing on tcgen05 (FP64-grade)")
     ap.add_argument("--dtype", type=str, default="float64", choices=["float64", "float32"],
                     help="float32 = the reference's dtype='float32' mode (jitter 1e-4, 1e-4 bar): 15 digit-plane products")
+    ap.add_argument("--digits", type=str, default=None,
+                    help="F,B: digit planes of the forward / reverse INT8 contraction (default 7,7; float32 mode 5,5)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -236,7 +238,12 @@ def main():
     eng = Engine(local, args.dtype)
     eng.set_gemm_mode(1 if args.gemm == "i8" else 0)
     f32 = args.dtype == "float32"
-    pairs = 15 if f32 else OZ_PAIRS
+    ns_f, ns_b = (5, 5) if f32 else (7, 7)
+    if args.digits:
+        ns_f, ns_b = (int(v) for v in args.digits.split(","))
+        eng.set_digits(ns_f, ns_b)
+    pairs_f, pairs_b = ns_f * (ns_f + 1) // 2, ns_b * (ns_b + 1) // 2     # products with level i + i' <= ns + 1
+    pairs = 0.5 * (pairs_f + pairs_b)
     eng.set_model(w["kernel"], np.full(d, math.sqrt(d) / 4), 1.0, 1e-3, 0.0, 1e-4 if f32 else 1e-6)
     t0 = time.perf_counter()
     eng.set_train(X0, y0)
@@ -292,14 +299,20 @@ def main():
         peak8, peak8_src, peak8_issue = load_i8_peak()
         achieved = fp64_equiv * pairs
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peak8, "unit": "TOP/s", "frac": achieved / peak8,
-                    "traffic": load_traffic("i8"), "kernel": "ozaki_i8_gemm_v4_kernel<%s,1> (tcgen05.mma.cta_group::2 kind::i8, TMA, TMEM; persistent CTA pairs, register-stash epilogue)" % ("5,6" if f32 else "7,8"),
+                    "traffic": load_traffic("i8"), "kernel": "ozaki_i8_gemm_v4_kernel<%d,%d,1> forward / <%d,%d,1> reverse (tcgen05.mma.cta_group::2 kind::i8, TMA, TMEM; persistent CTA pairs, register-stash epilogue)" % (ns_f, ns_f + 1, ns_b, ns_b + 1),
                     "peak_source": peak8_src,
                     "peak_note": "the driver's sustained cuBLAS bf16 figure is itself power-capped (1335 MHz median), so "
                                  "frac can exceed 1 when this kernel holds higher clocks under the same 1 kW cap; "
                                  "frac_of_own_tcgen05_i8_issue_peak is against the raw kind::i8 issue rate measured "
                                  "with an MMA-only loop (profiles/i8_peaks.json)",
                     "frac_of_own_tcgen05_i8_issue_peak": achieved / peak8_issue if peak8_issue else None,
-                    "algorithmic": "n^2 q flops per restart per launch x %d digit-plane products (%s)" % (pairs, "ns=5, levels<=6" if f32 else "ns=7, levels<=8"),
+                    "algorithmic": "n^2 q flops per restart per launch x %d (forward, ns=%d) / %d (reverse, ns=%d) exact int8 digit-plane products" % (pairs_f, ns_f, pairs_b, ns_b),
+                    "products": {"forward": pairs_f, "reverse": pairs_b},
+                    # what the int8 pipe allows with every other kernel free: issue rate / (products per FP64 flop)
+                    "pipe_ceiling": None if not peak8_issue else {
+                        "fp64_equivalent_tflops": peak8_issue / pairs,
+                        "evals_per_s_per_gpu": M * peak8_issue * 1e12 / (npad * npad * (pairs_f + pairs_b)),
+                        "note": "raw tcgen05 kind::i8 issue rate (profiles/i8_peaks.json) / products; target of BASELINE.json is 1e9"},
                     "fp64_equivalent_tflops": fp64_equiv, "fp64_dgemm_peak_tflops": peak64,
                     "fp64_equivalent_over_dgemm_peak": fp64_equiv / peak64}
     else:
@@ -314,7 +327,7 @@ def main():
     hgrad = eng.pinned_empty((S, q, d))
     hX[...] = X
     hz[...] = z
-    e2e_steps = max(2, min(args.steps, 3))
+    e2e_steps = max(2, args.steps)
     eng.value_and_grad(prm, hX, hz, out_loss=hloss, out_grad=hgrad)
     mdist.barrier()
     torch.cuda.synchronize()

@@ -28,6 +28,10 @@
  *   MAF_OZ_VARIANT=1|3|4|5  INT8 kernel: generic / static schedule / CTA pairs / CTA pairs + register-stash epilogue (default)
  *   MAF_OZ_NS_BWD=3..7   digit planes of the reverse contraction (default 7; 6 is 25 % faster but leaves the 1e-9 bar
  *                        for candidates next to training points)
+ *   MAF_OZ_NS_FWD=3..7   digit planes of K10 in the forward contraction (default 7)
+ *   MAF_MU_ALPHA=0|1     posterior mean as m + K10 . alpha in FP64 inside the cross-covariance kernel and its gradient
+ *                        inside the reverse covariance kernel (default 1) instead of m + V^T gamma through the contractions
+ *   MAF_VBAR_TIGHT=0|1   row scales of the Vbar digit planes from the true row maxima (one more sweep; default 0)
  *   MAF_OZ_HINTS=<a><t>  L2 policy of the A / T plane loads, 0 normal, 1 evict-first, 2 evict-last (default 22)
  *   MAF_OZ_SJ=<k>        row blocks per super-row of the persistent tile order (default 2)
  *   MAF_OZ_SCHED=0|1     balanced static tile schedule of the CTA pairs (default 1; 0: round-robin walk)
@@ -209,6 +213,10 @@ int maf_gemm_nt_i8_dev(maf_ctx* ctx, int J, int N, int K, const double* dA, int 
 /* 1 (default): FP64-grade contractions by exact INT8 digit slicing on tcgen05 (n <= 8192; larger n uses DMMA);
  * 0: FP64 DMMA contractions.  Takes effect at the next maf_set_train.  Environment override: MAF_GEMM_I8. */
 int maf_set_gemm_mode(maf_ctx* ctx, int mode);
+/* Digit planes of the two INT8 contractions (levels <= planes + 1 are kept): forward V^T = K10 L0^-T and reverse
+ * Kbar10 = Vbar^T L0^-1.  7 / 7 (28 + 28 exact products) is the FP64-grade default, 3 <= ns <= 7 (5 / 5 in MAF_F32 mode).
+ * Accuracy studies and the level switch of the host layer use it; takes effect at the next evaluation. */
+int maf_set_digits(maf_ctx* ctx, int ns_fwd, int ns_bwd);
 void* maf_dev_alloc(maf_ctx* ctx, size_t bytes);
 int maf_dev_free(maf_ctx* ctx, void* p);
 int maf_h2d(maf_ctx* ctx, void* dst, const void* src, size_t bytes);

@@ -66,6 +66,7 @@ SIGNATURES = {
     "maf_gemm_nt_i8_dev": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int, C.c_int,
                                      C.c_int, C.c_int]),
     "maf_set_gemm_mode": (C.c_int, [_vp, C.c_int]),
+    "maf_set_digits": (C.c_int, [_vp, C.c_int, C.c_int]),
     "maf_adam_set_method": (C.c_int, [_vp, C.c_int, C.c_double]),
     "maf_dev_alloc": (_vp, [_vp, C.c_size_t]),
     "maf_dev_free": (C.c_int, [_vp, _vp]),

@@ -66,6 +66,11 @@ __device__ __forceinline__ double kern_dr2(int kid, double r2) {
 //         T[j] = 2^(j/32) from a 32-entry shared-memory table, 2^m folded into the exponent field (11 FP64 instructions,
 //         <= 2 ulp).  Results are a few ulp from the library's; the parity bar is 1e-9.
 #define MAF_ETAB 32
+// The table index is data dependent, so a plain 32-entry table costs shared-memory bank conflicts (ncu round 1: 39 % /
+// 49 % of the shared wavefronts of cross_fwd_planes / cross_bwd): entries j and j + 16 share a bank pair.  The table
+// is therefore replicated per lane, tab[j][lane] (8 KB): lane l always reads bank pair l, two wavefronts per warp-wide
+// 64-bit load, the minimum.  Kernels pass `etab + lane`.
+#define MAF_ETAB_WORDS (MAF_ETAB * 32)
 // coefficients live in the constant bank so that every DFMA takes them as a c[][] operand (as literals the compiler
 // rebuilds each 64-bit immediate with two moves per use: 18 of the kernel's 126 instructions per element)
 __constant__ double MAF_FC[10] = {
@@ -76,8 +81,8 @@ __constant__ double MAF_FC[10] = {
     1.0 / 3.0,                 // 7
     6755399441055744.0,        // 8: 1.5 2^52
     1.0e6};                    // 9: cap of the exponent argument
-__device__ __forceinline__ void maf_fill_etab(double* tab, int tid) {
-  if (tid < MAF_ETAB) tab[tid] = exp2((double)tid * (1.0 / MAF_ETAB));
+__device__ __forceinline__ void maf_fill_etab(double* tab, int tid, int nthreads) {
+  for (int t = tid; t < MAF_ETAB_WORDS; t += nthreads) tab[t] = exp2((double)(t >> 5) * (1.0 / MAF_ETAB));
 }
 // max(x, eps) for x >= 0: eps = 2^-52 has a zero low word, so the comparison is one integer compare on the high word
 __device__ __forceinline__ double maf_clamp_eps(double x) {
@@ -106,7 +111,7 @@ __device__ __forceinline__ double maf_exp_neg_fast(double r, const double* __res
   p = fma(p, f, 0.5);
   p = fma(p, f, 1.0);
   p = fma(p, f, 1.0);
-  const double tj = tab[k & (MAF_ETAB - 1)];
+  const double tj = tab[(k & (MAF_ETAB - 1)) << 5];          // tab = table + lane (replicated per lane)
   const int m = max(k >> 5, -1021);                          // floor(k / 32) <= 0; below 2^-1021 the result is "tiny", not exact
   const double s = __hiloint2double(__double2hiint(tj) + (m << 20), __double2loint(tj));
   return s * p;

@@ -100,11 +100,16 @@ cross_bwd_kernel(const double* __restrict__ X, int S, int q, int p,
                                  const double* __restrict__ X0s, int n, int npad, ModelParams mp,
                                  const double* __restrict__ Kbar /*[S*q][npad]*/,
                                  const double* __restrict__ Sigbar /*[S][q][q]*/,
-                                 double* __restrict__ grad /*[S][q-p][d]*/) {
+                                 double* __restrict__ grad /*[S][q-p][d]*/,
+                                 const double* __restrict__ alpha = nullptr /*[npad]: K00^-1 (y0 - m)*/,
+                                 const double* __restrict__ mubar = nullptr /*[S][q]*/) {
+  // alpha != nullptr: Kbar holds only the covariance part -(Sbar + Sbar^T) B^T of d loss / d K10; the mean part
+  // mubar_j alpha_k (mu_j = m + K10[j][:] alpha, exact in FP64) is added here and never passes through a contraction.
   constexpr int DD = D > 0 ? D : MAF_MAX_D;
   const int d = D > 0 ? D : mp.d;
-  __shared__ double etab[MAF_ETAB];
-  maf_fill_etab(etab, threadIdx.x);
+  __shared__ double etab_sh[MAF_ETAB_WORDS];
+  maf_fill_etab(etab_sh, threadIdx.x, blockDim.x);
+  const double* etab = etab_sh + (threadIdx.x & 31);
   __syncthreads();
   const int s = blockIdx.x;
   const int i = threadIdx.x >> 5;
@@ -118,6 +123,7 @@ cross_bwd_kernel(const double* __restrict__ X, int S, int q, int p,
     acc[c] = 0.0;
   }
   const double* kb = Kbar + j * npad;
+  const double mbj = alpha != nullptr ? mubar[j] : 0.0;
   constexpr int UNR = CROSS_BWD_UNROLL;
 #pragma unroll UNR
   for (int k = lane; k < n; k += 32) {
@@ -131,11 +137,9 @@ cross_bwd_kernel(const double* __restrict__ X, int S, int q, int p,
         r2 += df * df;
       }
     }
-#ifdef CROSS_BWD_PLAIN_LOAD
-    double g = kb[k] * kern_dr2_fast<KID>(r2, etab);
-#else
-    double g = __ldcs(kb + k) * kern_dr2_fast<KID>(r2, etab);   // streamed once: keep the training set in L1 instead
-#endif
+    double kbv = __ldcs(kb + k);                                // streamed once: keep the training set in L1 instead
+    if (alpha != nullptr) kbv = fma(mbj, alpha[k], kbv);
+    double g = kbv * kern_dr2_fast<KID>(r2, etab);
 #pragma unroll
     for (int c = 0; c < DD; ++c)
       if (c < d) acc[c] += g * (xi[c] - x0[c]);

@@ -42,6 +42,63 @@ __global__ void trmv_upper_kernel(const double* __restrict__ LinvT, const double
   if (lane == 0) alpha[row] = a;
 }
 
+// Residual of the training system in twice the working precision (compensated dot product, Ogita-Rump-Oishi Dot2):
+//   res_i = rho_i - sum_k K00[i][k] alpha_k,   K00 recomputed entry by entry exactly as k00_kernel wrote it.
+// One warp per row.  Drives the iterative refinement of alpha = K00^-1 rho in maf_set_train: alpha feeds the posterior
+// mean (K10 . alpha) and its gradient directly, so it is made accurate to the last bits once per training set instead
+// of carrying cond(K00) eps = 4e-10 of relative error.
+__device__ __forceinline__ void maf_two_sum(double a, double b, double& s, double& e) {
+  s = a + b;
+  const double bb = s - a;
+  e = (a - (s - bb)) + (b - bb);
+}
+__global__ void alpha_residual_kernel(const double* __restrict__ X0s, int n, int npad, ModelParams mp,
+                                      const double* __restrict__ rho, const double* __restrict__ alpha,
+                                      double* __restrict__ res) {
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (i >= npad) return;
+  if (i >= n) {
+    if (lane == 0) res[i] = 0.0;
+    return;
+  }
+  double xi[MAF_MAX_D];
+  for (int c = 0; c < mp.d; ++c) xi[c] = X0s[(size_t)c * npad + i];
+  double sh = 0.0, sl = 0.0;
+  for (int k = lane; k < n; k += 32) {
+    double r2 = 0.0;
+    for (int c = 0; c < mp.d; ++c) {
+      const double df = xi[c] - X0s[(size_t)c * npad + k];
+      r2 += df * df;
+    }
+    double v = mp.amp2 * kern_val(mp.kernel_id, r2);
+    if (i == k) v = (v + mp.noise) + mp.jitter;
+    const double a = alpha[k];
+    const double p = v * a, pe = fma(v, a, -p);
+    double t, te;
+    maf_two_sum(sh, p, t, te);
+    sh = t;
+    sl += te + pe;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const double oh = __shfl_xor_sync(0xffffffffu, sh, o), ol = __shfl_xor_sync(0xffffffffu, sl, o);
+    double t, te;
+    maf_two_sum(sh, oh, t, te);
+    sh = t;
+    sl += te + ol;
+  }
+  if (lane == 0) {
+    double t, te;
+    maf_two_sum(rho[i], -sh, t, te);
+    res[i] = t + (te - sl);
+  }
+}
+
+__global__ void axpy_kernel(double* __restrict__ y, const double* __restrict__ x, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] += x[i];
+}
+
 // out[c] (c < d): d/dlog l_c ; out[d]: d/dlog a ; out[d+1]: d/dlog noise ; out[d+2]: d/dmean.
 // grid (ceil(npad/256), n): thread = one (i, j) entry.
 __global__ void nll_grad_kernel(const double* __restrict__ X0s, int n, int npad, ModelParams mp,

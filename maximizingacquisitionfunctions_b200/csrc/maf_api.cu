@@ -39,6 +39,11 @@ struct maf_ctx {
   cudaStream_t stream = nullptr;
   std::string err;
   int64_t launch_count = 0;
+  // cudaFuncSetAttribute is per device: the opt-ins are tracked per context, never per process
+  unsigned attr_gemm_mask = 0;     // launch_gemm_cfg variants
+  bool attr_oz = false, attr_chol = false;
+  unsigned attr_mc_mask = 0;       // mc_acq_kernel<Q>, bit Q
+  int num_sms = 0;
 
   // model
   bool model_set = false;
@@ -49,6 +54,13 @@ struct maf_ctx {
   int n = 0, npad = 0;
   double mean_val = 0.0, y_min = 0.0;
   double *X0s = nullptr, *L0 = nullptr, *Linv = nullptr, *LinvT = nullptr, *gamma = nullptr;
+  double* alpha = nullptr;         // K00^-1 (y0 - m), refined (maf_set_train); [npad], zero on the pad
+  // Posterior mean by the exact FP64 route mu = m + K10 . alpha inside the cross-covariance kernel, its gradient
+  // mubar_j alpha_k added inside cross_bwd_kernel: the mean no longer passes through the digit-sliced contractions
+  // (INT8 engine with both fused producers only; MAF_MU_ALPHA=0 restores mu = m + V^T gamma).
+  int mu_alpha = 1;
+  int vbar_tight = 0;              // MAF_VBAR_TIGHT=1: exact row maxima for the Vbar digit planes (one more sweep)
+  Buf mu_part;                     // [column blocks of 1024][Jpad] partial sums of K10 . alpha
   size_t cap_train = 0;        // npad the factor buffers were sized for
   int cap_train_d = 0;
   // GEMM workspace (chunk of candidate rows)
@@ -77,6 +89,7 @@ struct maf_ctx {
   // gradient error at n=4096 rises from the FP64 noise floor (4e-12 .. 2e-11) to 6e-10 .. 5e-9 for candidates next to
   // training points (profiles/r01_accuracy_n4096.jsonl): above the 1e-9 bar, so the default keeps all 7 planes.
   int oz_ns_bwd = 7, oz_lmax_bwd = 8;
+  int oz_ns_fwd = 7;               // digit planes of K10 in the forward contraction (levels <= oz_ns_fwd + 1)
   int oz_fuse = 3;                 // bit 0: cross-covariance, bit 1: Vbar written straight to digit planes (MAF_OZ_FUSE)
   int oz_sj = 2;                   // super-row height of the persistent tile order (MAF_OZ_SJ)
   int oz_hint_a = 2, oz_hint_t = 2; // L2 policy of the A / T plane loads: 0 normal, 1 evict-first, 2 evict-last (MAF_OZ_HINTS=at); evict-last on both: DRAM reads 19 -> 16.5 GB per launch, -3 % time (profiles/r01_i8gemm_v5_l2_policy_sweep.txt)
@@ -283,16 +296,15 @@ __global__ void diag_extract_kernel(const double* __restrict__ Sig, int S, int q
 
 // GEMM variants (selected by MAF_GEMM_VARIANT at context creation; 0 is the default)
 template <int BM, int BN, int BK, int STAGES, int WJ, int WR, int MINB>
-static int launch_gemm_cfg(maf_ctx* ctx, int J, int N, const double* A, int lda, const double* T, int ldt, double* C,
+static int launch_gemm_cfg(maf_ctx* ctx, int vbit, int J, int N, const double* A, int lda, const double* T, int ldt, double* C,
                            int ldc, int K, int tri, int epi) {
   using Cfg = GemmCfg<BM, BN, BK, STAGES, WJ, WR, MINB>;
-  static bool attr = false;
-  if (!attr) {
+  if (!(ctx->attr_gemm_mask & (1u << vbit))) {
     CK(cudaFuncSetAttribute(gemm_nt_f64_kernel<BM, BN, BK, STAGES, WJ, WR, MINB>,
                             cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     CK(cudaFuncSetAttribute(gemm_nt_f64_kernel<BM, BN, BK, STAGES, WJ, WR, MINB>,
                             cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    attr = true;
+    ctx->attr_gemm_mask |= 1u << vbit;
   }
   dim3 grid(N / BN, J / BM);
   gemm_nt_f64_kernel<BM, BN, BK, STAGES, WJ, WR, MINB><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, ctx->stream>>>(
@@ -308,14 +320,14 @@ static int launch_gemm(maf_ctx* ctx, int slot, int J, int N, int K, const double
   int rc;
   switch (ctx->gemm_variant) {
     // <BM, BN, BK, STAGES, WJ, WR, CTAs/SM>; measured on B200 (profiles/gemm_variants_r01.jsonl)
-    case 1: rc = launch_gemm_cfg<128, 128, 16, 4, 2, 4, 1>(ctx, J, N, A, lda, T, ldt, C, ldc, K, tri, epi); break;  // v0: 32.0 TF
-    case 2: rc = launch_gemm_cfg<128, 64, 16, 3, 2, 2, 2>(ctx, J, N, A, lda, T, ldt, C, ldc, K, tri, epi); break;   // 35.0 TF
-    case 3: rc = launch_gemm_cfg<64, 128, 16, 3, 1, 4, 2>(ctx, J, N, A, lda, T, ldt, C, ldc, K, tri, epi); break;   // 33.2 TF
-    case 4: rc = launch_gemm_cfg<128, 64, 32, 2, 2, 2, 2>(ctx, J, N, A, lda, T, ldt, C, ldc, K, tri, epi); break;   // 35.0 TF
-    case 5: rc = launch_gemm_cfg<64, 64, 16, 3, 2, 2, 3>(ctx, J, N, A, lda, T, ldt, C, ldc, K, tri, epi); break;    // 35.2 TF
-    case 6: rc = launch_gemm_cfg<64, 64, 32, 2, 2, 2, 3>(ctx, J, N, A, lda, T, ldt, C, ldc, K, tri, epi); break;    // BK 32
-    case 7: rc = launch_gemm_cfg<64, 128, 16, 3, 2, 4, 2>(ctx, J, N, A, lda, T, ldt, C, ldc, K, tri, epi); break;   // 8 warps of 32x32, 2/SM
-    default: rc = launch_gemm_cfg<64, 64, 16, 2, 2, 2, 4>(ctx, J, N, A, lda, T, ldt, C, ldc, K, tri, epi); break;   // 4 CTAs/SM: 35.7 TF
+    case 1: rc = launch_gemm_cfg<128, 128, 16, 4, 2, 4, 1>(ctx, 1, J, N, A, lda, T, ldt, C, ldc, K, tri, epi); break;  // v0: 32.0 TF
+    case 2: rc = launch_gemm_cfg<128, 64, 16, 3, 2, 2, 2>(ctx, 2, J, N, A, lda, T, ldt, C, ldc, K, tri, epi); break;   // 35.0 TF
+    case 3: rc = launch_gemm_cfg<64, 128, 16, 3, 1, 4, 2>(ctx, 3, J, N, A, lda, T, ldt, C, ldc, K, tri, epi); break;   // 33.2 TF
+    case 4: rc = launch_gemm_cfg<128, 64, 32, 2, 2, 2, 2>(ctx, 4, J, N, A, lda, T, ldt, C, ldc, K, tri, epi); break;   // 35.0 TF
+    case 5: rc = launch_gemm_cfg<64, 64, 16, 3, 2, 2, 3>(ctx, 5, J, N, A, lda, T, ldt, C, ldc, K, tri, epi); break;    // 35.2 TF
+    case 6: rc = launch_gemm_cfg<64, 64, 32, 2, 2, 2, 3>(ctx, 6, J, N, A, lda, T, ldt, C, ldc, K, tri, epi); break;    // BK 32
+    case 7: rc = launch_gemm_cfg<64, 128, 16, 3, 2, 4, 2>(ctx, 7, J, N, A, lda, T, ldt, C, ldc, K, tri, epi); break;   // 8 warps of 32x32, 2/SM
+    default: rc = launch_gemm_cfg<64, 64, 16, 2, 2, 2, 4>(ctx, 0, J, N, A, lda, T, ldt, C, ldc, K, tri, epi); break;   // 4 CTAs/SM: 35.7 TF
   }
   if (rc) return rc;
   CKL();
@@ -434,8 +446,7 @@ static int launch_i8gemm(maf_ctx* ctx, int slot, int J, int N, int K, const Buf&
   if (tri != 0 && K != N) return fail(ctx, "triangular gemm needs K == N");
   if (ns < 1 || ns > OZ_MAXS || lmax < 2 || lmax > 2 * ns) return fail(ctx, "bad digit configuration ns=%d lmax=%d", ns, lmax);
   if (K > 8192) return fail(ctx, "i8 gemm: K=%d would overflow the int32 level accumulators (max 8192)", K);
-  static bool attr = false;
-  if (!attr) {
+  if (!ctx->attr_oz) {
     CK(cudaFuncSetAttribute(ozaki_i8_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES));
 #define OZ3_ATTR(NS_, LM_) \
   CK(cudaFuncSetAttribute(ozaki_i8_gemm_v3_kernel<NS_, LM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, Oz3<NS_, LM_>::SMEM_BYTES))
@@ -454,7 +465,7 @@ static int launch_i8gemm(maf_ctx* ctx, int slot, int J, int N, int K, const Buf&
     OZ3_DATTR(1); OZ3_DATTR(2); OZ3_DATTR(3); OZ3_DATTR(4); OZ3_DATTR(5); OZ3_DATTR(6); OZ3_DATTR(7);
 #undef OZ3_DATTR
 #endif
-    attr = true;
+    ctx->attr_oz = true;
   }
   const bool v3ok = lmax == ns + 1 && ns >= 3 && ns <= 7;
   int variant = ctx->oz_variant;
@@ -477,8 +488,8 @@ static int launch_i8gemm(maf_ctx* ctx, int slot, int J, int N, int K, const Buf&
     if (rowmax_done) *rowmax_done = true;
   }
   dim3 grid(N / OZ_BN, J / OZ_BM);
-  static int num_sms = 0;
-  if (!num_sms) CK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, ctx->device));
+  if (!ctx->num_sms) CK(cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, ctx->device));
+  const int num_sms = ctx->num_sms;
   const long long ntiles = (long long)(N / OZ_BN) * (J / OZ_BM);
   dim3 pgrid((unsigned)(ntiles < num_sms ? ntiles : num_sms));   // persistent: one CTA per SM
   ProfScope ps(ctx, slot);
@@ -568,10 +579,9 @@ static int launch_i8gemm(maf_ctx* ctx, int slot, int J, int N, int K, const Buf&
 // ---- training-set factorisation (factor.cuh): blocked Cholesky + triangular inverse by block doubling ------------
 static int factorize(maf_ctx* ctx) {
   const int npad = ctx->npad, nb = npad / FAC_NB;
-  static bool attr = false;
-  if (!attr) {
+  if (!ctx->attr_chol) {
     CK(cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FAC_SMEM_BYTES));
-    attr = true;
+    ctx->attr_chol = true;
   }
   double *dinv = nullptr, *panel = nullptr, *scratch = nullptr;
   int* dinfo = nullptr;
@@ -668,6 +678,7 @@ extern "C" int maf_create(int device, int dtype, maf_ctx** out) {
     ctx->oz_lmax = 6;
     ctx->oz_ns_bwd = 5;
     ctx->oz_lmax_bwd = 6;
+    ctx->oz_ns_fwd = 5;
   }
   CK(cudaSetDevice(device));
   cudaDeviceProp prop;
@@ -689,6 +700,12 @@ extern "C" int maf_create(int device, int dtype, maf_ctx** out) {
   if (const char* sg = getenv("MAF_OZ_GROUPS")) ctx->oz_groups = atoi(sg);
   if (const char* gr = getenv("MAF_GRAPH")) ctx->graph_on = atoi(gr);
   if (const char* rm = getenv("MAF_OZ_ROWMAX")) ctx->oz_rowmax = atoi(rm);
+  if (const char* ma = getenv("MAF_MU_ALPHA")) ctx->mu_alpha = atoi(ma);
+  if (const char* vt = getenv("MAF_VBAR_TIGHT")) ctx->vbar_tight = atoi(vt);
+  if (const char* nf = getenv("MAF_OZ_NS_FWD")) {
+    const int v = atoi(nf);
+    if (v >= 3 && v <= ctx->oz_ns) ctx->oz_ns_fwd = v;
+  }
   if (const char* nb = getenv("MAF_OZ_NS_BWD")) {
     const int v = atoi(nb);
     if (v >= 3 && v <= ctx->oz_ns) ctx->oz_ns_bwd = v, ctx->oz_lmax_bwd = v + 1;
@@ -708,14 +725,14 @@ extern "C" int maf_destroy(maf_ctx* ctx) {
   if (!ctx) return 0;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  double* raw[] = {ctx->X0s, ctx->L0, ctx->Linv, ctx->LinvT, ctx->gamma, ctx->d_argmin_val};
+  double* raw[] = {ctx->X0s, ctx->L0, ctx->Linv, ctx->LinvT, ctx->gamma, ctx->alpha, ctx->d_argmin_val};
   for (double* b : raw)
     if (b) cudaFree(b);
   Buf* bufs[] = {&ctx->K10, &ctx->Vt, &ctx->dX, &ctx->dz, &ctx->dw, &ctx->dinc, &ctx->dmu, &ctx->dSig, &ctx->dchol,
                  &ctx->dmubar, &ctx->dSigbar, &ctx->dloss, &ctx->dgrad, &ctx->adam_X, &ctx->adam_m, &ctx->adam_v,
                  &ctx->adam_g, &ctx->adam_z, &ctx->fGamma, &ctx->fGammaT, &ctx->fmeans, &ctx->flevels, &ctx->fVG,
                  &ctx->fmubar, &ctx->ozA, &ctx->ozTL, &ctx->ozTU, &ctx->ozsA, &ctx->ozsTL, &ctx->ozsTU, &ctx->adam_zcur,
-                 &ctx->adam_coef, &ctx->adam_trace, &ctx->ozVmax};
+                 &ctx->adam_coef, &ctx->adam_trace, &ctx->ozVmax, &ctx->mu_part};
   for (Buf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (ctx->d_argmin_idx) cudaFree(ctx->d_argmin_idx);
@@ -804,7 +821,7 @@ extern "C" int maf_set_train(maf_ctx* ctx, int n, const double* X0, const double
   const int npad = round_up(n, 128);
   ctx->train_set = false;
   if ((size_t)npad != ctx->cap_train || d != ctx->cap_train_d) {
-    double** bufs[] = {&ctx->X0s, &ctx->L0, &ctx->Linv, &ctx->LinvT, &ctx->gamma};
+    double** bufs[] = {&ctx->X0s, &ctx->L0, &ctx->Linv, &ctx->LinvT, &ctx->gamma, &ctx->alpha};
     for (double** b : bufs) {
       if (*b) CK(cudaFree(*b));
       *b = nullptr;
@@ -816,6 +833,7 @@ extern "C" int maf_set_train(maf_ctx* ctx, int n, const double* X0, const double
     CK(cudaMalloc((void**)&ctx->Linv, sizeof(double) * nn));
     CK(cudaMalloc((void**)&ctx->LinvT, sizeof(double) * nn));
     CK(cudaMalloc((void**)&ctx->gamma, sizeof(double) * npad));
+    CK(cudaMalloc((void**)&ctx->alpha, sizeof(double) * npad));
     ctx->cap_train = npad;
     ctx->cap_train_d = d;
   }
@@ -860,6 +878,28 @@ extern "C" int maf_set_train(maf_ctx* ctx, int n, const double* X0, const double
     ProfScope ps(ctx, MAF_PROF_CROSS_FWD);
     trmv_lower_kernel<<<(npad + 7) / 8, 256, 0, ctx->stream>>>(ctx->Linv, drho, npad, ctx->gamma);
     CKL();
+  }
+  // alpha = L0^-T gamma, then two steps of iterative refinement with the residual in twice the working precision
+  {
+    ProfScope ps(ctx, MAF_PROF_CROSS_FWD);
+    trmv_upper_kernel<<<(npad + 7) / 8, 256, 0, ctx->stream>>>(ctx->LinvT, ctx->gamma, npad, ctx->alpha);
+    CKL();
+  }
+  {
+    double *res = nullptr, *tmp = nullptr;
+    CK(cudaMalloc((void**)&res, sizeof(double) * npad));
+    CK(cudaMalloc((void**)&tmp, sizeof(double) * npad));
+    for (int it = 0; it < 2; ++it) {
+      ProfScope ps(ctx, MAF_PROF_CROSS_FWD);
+      alpha_residual_kernel<<<(npad + 7) / 8, 256, 0, ctx->stream>>>(ctx->X0s, n, npad, ctx->mp, drho, ctx->alpha, res);
+      trmv_lower_kernel<<<(npad + 7) / 8, 256, 0, ctx->stream>>>(ctx->Linv, res, npad, tmp);
+      trmv_upper_kernel<<<(npad + 7) / 8, 256, 0, ctx->stream>>>(ctx->LinvT, tmp, npad, res);
+      axpy_kernel<<<(npad + 255) / 256, 256, 0, ctx->stream>>>(ctx->alpha, res, npad);
+      CKL();
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaFree(res));
+    CK(cudaFree(tmp));
   }
   ctx->i8_ready = false;
   if (ctx->gemm_i8 && npad <= 8192) {   // int32 level accumulators hold K <= 8192; larger n keeps the DMMA contraction
@@ -944,11 +984,13 @@ static int resolve_acq(maf_ctx* ctx, const maf_acq_params* prm, AcqDev* out) {
 // forward (+ optional backward) over one chunk of restarts
 // posterior mean / covariance of one chunk: register-accumulating kernel for Q <= 8, shared-memory slab beyond
 template <int Q>
-static void launch_posterior(maf_ctx* ctx, int sc, const double* Vt, int npad, const double* dX, double* mu, double* Sig) {
+static void launch_posterior(maf_ctx* ctx, int sc, const double* Vt, int npad, const double* dX, double* mu, double* Sig,
+                             const double* mu_part, int nparts, int Jpad) {
+  const double* gam = mu_part ? nullptr : ctx->gamma;         // mean from K10 . alpha: no gamma sweep
   if constexpr (Q <= 8)
-    posterior_reg_kernel<Q><<<sc, POST_REG_THREADS, 0, ctx->stream>>>(Vt, npad, ctx->gamma, dX, ctx->mp, ctx->mean_val, mu, Sig);
+    posterior_reg_kernel<Q><<<sc, POST_REG_THREADS, 0, ctx->stream>>>(Vt, npad, gam, dX, ctx->mp, ctx->mean_val, mu, Sig, mu_part, nparts, Jpad);
   else
-    posterior_kernel<Q><<<sc, POST_THREADS, 0, ctx->stream>>>(Vt, npad, ctx->gamma, dX, ctx->mp, ctx->mean_val, mu, Sig);
+    posterior_kernel<Q><<<sc, POST_THREADS, 0, ctx->stream>>>(Vt, npad, gam, dX, ctx->mp, ctx->mean_val, mu, Sig, mu_part, nparts, Jpad);
 }
 
 static int run_chunk(maf_ctx* ctx, const AcqDev& ap, bool posterior_only, bool closed_form, int sc, int q, int p,
@@ -959,6 +1001,11 @@ static int run_chunk(maf_ctx* ctx, const AcqDev& ap, bool posterior_only, bool c
   double* K10 = ctx->K10.p;
   double* Vt = ctx->Vt.p;
   const bool fused = ctx->i8_ready && (ctx->oz_fuse & 1), fused_bwd = ctx->i8_ready && (ctx->oz_fuse & 2);
+  const bool mu_alpha = fused && fused_bwd && ctx->mu_alpha;    // mean and its gradient outside the contractions
+  const int ns_fwd = std::min(ctx->oz_ns_fwd, ctx->oz_ns);
+  const int nparts = (npad + OZC_THREADS * 4 - 1) / (OZC_THREADS * 4);
+  if (mu_alpha && ensure(ctx, ctx->mu_part, (size_t)nparts * Jpad)) return 1;
+  const double* mu_part = mu_alpha ? ctx->mu_part.p : nullptr;
   // the Vbar producer needs the row maxima of V^T: the forward contraction's epilogue leaves them behind
   const bool want_rowmax = fused_bwd && ctx->oz_rowmax && !posterior_only && dgrad != nullptr;
   bool have_rowmax = false;
@@ -970,13 +1017,13 @@ static int run_chunk(maf_ctx* ctx, const AcqDev& ap, bool posterior_only, bool c
     if (ensure(ctx, ctx->ozA, (bytes + 7) / 8) || ensure(ctx, ctx->ozsA, (size_t)Jpad)) return 1;
     {
       ProfScope ps(ctx, MAF_PROF_CROSS_FWD);
-      dim3 grid((npad + OZC_THREADS * 4 - 1) / (OZC_THREADS * 4), Jpad / OZC_TJ);
-      DISPATCH_DKN(d, ctx->mp.kernel_id, ctx->oz_ns, cross_fwd_planes_kernel<D, KID, NSC><<<grid, OZC_THREADS, 0, ctx->stream>>>(dX, J, Jpad, ctx->X0s, n, npad, ctx->mp, ctx->oz_ns,
-                                                                                  (int8_t*)ctx->ozA.p, ctx->ozsA.p));
+      dim3 grid(nparts, Jpad / OZC_TJ);
+      DISPATCH_DKN(d, ctx->mp.kernel_id, ns_fwd, cross_fwd_planes_kernel<D, KID, NSC><<<grid, OZC_THREADS, 0, ctx->stream>>>(dX, J, Jpad, ctx->X0s, n, npad, ctx->mp, ns_fwd,
+                                                                                  (int8_t*)ctx->ozA.p, ctx->ozsA.p, mu_alpha ? ctx->alpha : nullptr, ctx->mu_part.p));
       CKL();
     }
     if (launch_i8gemm(ctx, MAF_PROF_GEMM_FWD, Jpad, npad, npad, ctx->ozA, ctx->ozsA, ctx->ozTL, ctx->ozsTL, Vt, npad, 1,
-                      ctx->oz_ns, ctx->oz_lmax, rowmax, &have_rowmax))
+                      ns_fwd, ns_fwd + 1, rowmax, &have_rowmax))
       return 1;
   } else {
     {
@@ -997,7 +1044,7 @@ static int run_chunk(maf_ctx* ctx, const AcqDev& ap, bool posterior_only, bool c
   }
   {
     ProfScope ps(ctx, MAF_PROF_POSTERIOR);
-    DISPATCH_Q(q, launch_posterior<Q>(ctx, sc, Vt, npad, dX, mu, Sig));
+    DISPATCH_Q(q, launch_posterior<Q>(ctx, sc, Vt, npad, dX, mu, Sig, mu_part, nparts, Jpad));
     CKL();
   }
   if (posterior_only) return 0;
@@ -1009,10 +1056,9 @@ static int run_chunk(maf_ctx* ctx, const AcqDev& ap, bool posterior_only, bool c
     } else {
       DISPATCH_Q(q, {
         const size_t smem = sizeof(McSmem<Q>);
-        static bool attr_set = false;
-        if (!attr_set && smem > 48 * 1024) {
+        if (smem > 48 * 1024 && !(ctx->attr_mc_mask & (1u << Q))) {
           CK(cudaFuncSetAttribute(mc_acq_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          attr_set = true;
+          ctx->attr_mc_mask |= 1u << Q;
         }
         mc_acq_kernel<Q><<<(sc + MC_WARPS - 1) / MC_WARPS, MC_WARPS * 32, smem, ctx->stream>>>(
             sc, M, mu, Sig, dz, dw, dinc, ap, ctx->mp.jitter, need_grad, dloss, mubar, Sigbar, chol);
@@ -1028,8 +1074,8 @@ static int run_chunk(maf_ctx* ctx, const AcqDev& ap, bool posterior_only, bool c
     if (ensure(ctx, ctx->ozA, (bytes + 7) / 8) || ensure(ctx, ctx->ozsA, (size_t)Jpad)) return 1;
     {
       ProfScope ps(ctx, MAF_PROF_VBAR);
-      DISPATCH_Q(q, vbar_planes_kernel<Q><<<sc + (Jpad - J), VBP_THREADS, 0, ctx->stream>>>(Vt, npad, sc, Jpad, ctx->gamma, mubar, Sigbar, ctx->oz_ns_bwd,
-                                                                                   (int8_t*)ctx->ozA.p, ctx->ozsA.p, have_rowmax ? rowmax : nullptr));
+      DISPATCH_Q(q, vbar_planes_kernel<Q><<<sc + (Jpad - J), VBP_THREADS, 0, ctx->stream>>>(Vt, npad, sc, Jpad, ctx->gamma, mu_alpha ? nullptr : mubar, Sigbar, ctx->oz_ns_bwd,
+                                                                                   (int8_t*)ctx->ozA.p, ctx->ozsA.p, have_rowmax ? rowmax : nullptr, ctx->vbar_tight));
       CKL();
     }
     if (launch_i8gemm(ctx, MAF_PROF_GEMM_BWD, Jpad, npad, npad, ctx->ozA, ctx->ozsA, ctx->ozTU, ctx->ozsTU, K10, npad, 2,
@@ -1052,7 +1098,8 @@ static int run_chunk(maf_ctx* ctx, const AcqDev& ap, bool posterior_only, bool c
   }
   {
     ProfScope ps(ctx, MAF_PROF_CROSS_BWD);
-    DISPATCH_DK(d, ctx->mp.kernel_id, cross_bwd_kernel<D, KID><<<sc, 32 * q, 0, ctx->stream>>>(dX, sc, q, p, ctx->X0s, n, npad, ctx->mp, K10, Sigbar, dgrad));
+    DISPATCH_DK(d, ctx->mp.kernel_id, cross_bwd_kernel<D, KID><<<sc, 32 * q, 0, ctx->stream>>>(dX, sc, q, p, ctx->X0s, n, npad, ctx->mp, K10, Sigbar, dgrad,
+                                                                                         mu_alpha ? ctx->alpha : nullptr, mubar));
     CKL();
   }
   return 0;
@@ -1219,8 +1266,10 @@ extern "C" int maf_mc_from_moments(maf_ctx* ctx, const maf_acq_params* prm, int 
     ProfScope ps(ctx, MAF_PROF_MC);
     DISPATCH_Q(q, {
       const size_t smem = sizeof(McSmem<Q>);
-      if (smem > 48 * 1024)
+      if (smem > 48 * 1024 && !(ctx->attr_mc_mask & (1u << Q))) {
         CK(cudaFuncSetAttribute(mc_acq_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ctx->attr_mc_mask |= 1u << Q;
+      }
       mc_acq_kernel<Q><<<(S + MC_WARPS - 1) / MC_WARPS, MC_WARPS * 32, smem, ctx->stream>>>(
           S, M, ctx->dmu.p, ctx->dSig.p, ctx->dz.p, dw, dinc, ap, ctx->mp.jitter, need_grad, ctx->dloss.p,
           ctx->dmubar.p, ctx->dSigbar.p, ctx->dchol.p);
@@ -1729,6 +1778,17 @@ extern "C" int maf_set_gemm_mode(maf_ctx* ctx, int mode) {
   ctx->gemm_i8 = mode;
   ctx->i8_ready = false;
   ctx->train_set = false;       // the factor planes are built by maf_set_train
+  return 0;
+}
+
+extern "C" int maf_set_digits(maf_ctx* ctx, int ns_fwd, int ns_bwd) {
+  if (!ctx) return 1;
+  if (ns_fwd < 3 || ns_fwd > ctx->oz_ns || ns_bwd < 3 || ns_bwd > ctx->oz_ns)
+    return fail(ctx, "digit planes must lie in 3..%d (got %d forward, %d reverse)", ctx->oz_ns, ns_fwd, ns_bwd);
+  ctx->generation++;                                            // a captured optimizer step holds the old launch shapes
+  ctx->oz_ns_fwd = ns_fwd;
+  ctx->oz_ns_bwd = ns_bwd;
+  ctx->oz_lmax_bwd = ns_bwd + 1;
   return 0;
 }
 

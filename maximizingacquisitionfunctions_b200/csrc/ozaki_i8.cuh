@@ -395,13 +395,20 @@ ozaki_slice_rows_kernel(const double* __restrict__ X, int ldx, int R, int Rpad, 
 template <int D, int KID, int NS>
 __global__ void __launch_bounds__(OZC_THREADS, (D > 0 && D <= 8) ? OZC_MINB : 1)
 cross_fwd_planes_kernel(const double* __restrict__ X, int J, int Jpad, const double* __restrict__ X0s, int n, int npad,
-                        ModelParams mp, int ns_rt, int8_t* __restrict__ planes, double* __restrict__ scales) {
+                        ModelParams mp, int ns_rt, int8_t* __restrict__ planes, double* __restrict__ scales,
+                        const double* __restrict__ alpha = nullptr, double* __restrict__ mu_part = nullptr) {
+  // alpha != nullptr: the posterior mean goes the exact FP64 way, mu_j = m + sum_k K10[j][k] alpha_k with
+  // alpha = K00^-1 (y0 - m) (Means = mean_fn + Beta . resid, gaussian_process.py:204-208): every kernel value is in a
+  // register here anyway.  The partial sum of this CTA's 1024 columns goes to mu_part[blockIdx.x][j] (fixed summation
+  // order: lanes by shuffle tree, warps and column blocks in index order, so results do not depend on scheduling).
   constexpr int DD = D > 0 ? D : MAF_MAX_D;
   const int d = D > 0 ? D : mp.d;
   const int ns = NS > 0 ? NS : ns_rt;
   __shared__ double xs[OZC_TJ][DD];
-  __shared__ double etab[MAF_ETAB];
-  maf_fill_etab(etab, threadIdx.x);
+  __shared__ double etab_sh[MAF_ETAB_WORDS];
+  __shared__ double msum[OZC_THREADS / 32][OZC_TJ];
+  maf_fill_etab(etab_sh, threadIdx.x, blockDim.x);
+  const double* etab = etab_sh + (threadIdx.x & 31);
   const int k = (blockIdx.x * OZC_THREADS + threadIdx.x) * 4;
   const int j0 = blockIdx.y * OZC_TJ;
   for (int t = threadIdx.x; t < OZC_TJ * d; t += OZC_THREADS) {
@@ -412,40 +419,66 @@ cross_fwd_planes_kernel(const double* __restrict__ X, int J, int Jpad, const dou
   const int e = oz_exponent_for(mp.amp2);
   if (blockIdx.x == 0 && threadIdx.x < OZC_TJ) scales[j0 + threadIdx.x] = (j0 + (int)threadIdx.x < J) ? ldexp(1.0, e) : 1.0;
   __syncthreads();
-  if (k >= npad) return;
+  const bool active = k < npad;                              // npad is a multiple of 128, the column block is 1024 wide
   // a^2 2^(8 ns - 1 - e) per column, 0 on the pad columns k >= n (their digits must be zero): no per-element predicate
   const double sc = mp.amp2 * ldexp(1.0, -e + 8 * ns - 1);
-  double x0[4][DD], cs[4];
+  double x0[4][DD], cs[4], al[4];
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
-    cs[t] = (k + t) < n ? sc : 0.0;
+    cs[t] = (active && (k + t) < n) ? sc : 0.0;
+    al[t] = (alpha != nullptr && active) ? alpha[k + t] : 0.0;
 #pragma unroll
-    for (int c = 0; c < DD; ++c) x0[t][c] = (c < d) ? X0s[(size_t)c * npad + k + t] : 0.0;
+    for (int c = 0; c < DD; ++c) x0[t][c] = (c < d && active) ? X0s[(size_t)c * npad + k + t] : 0.0;
   }
   const size_t plane_stride = (size_t)Jpad * npad;
   const int jend = min(OZC_TJ, J - j0);                      // rows >= J of the last row block: zero digits
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int UNRJ = OZC_UNROLL;
+  if (!active) {                                             // whole warps (npad is a multiple of 128): nothing to add
+    if (alpha != nullptr && lane == 0)
+      for (int jj = 0; jj < OZC_TJ; ++jj) msum[warp][jj] = 0.0;
+  } else {
 #pragma unroll UNRJ
-  for (int jj = 0; jj < jend; ++jj) {
-    long long I[4];
+    for (int jj = 0; jj < jend; ++jj) {
+      long long I[4];
+      double pm = 0.0;
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      double r2 = 0.0;
+      for (int t = 0; t < 4; ++t) {
+        double r2 = 0.0;
 #pragma unroll
-      for (int c = 0; c < DD; ++c) {
-        if (c < d) {
-          double df = xs[jj][c] - x0[t][c];
-          r2 += df * df;
+        for (int c = 0; c < DD; ++c) {
+          if (c < d) {
+            double df = xs[jj][c] - x0[t][c];
+            r2 += df * df;
+          }
         }
+        const double v = kern_val_fast<KID>(r2, etab) * cs[t];
+        pm = fma(v, al[t], pm);
+        I[t] = __double2ll_rn(v);
       }
-      I[t] = __double2ll_rn(kern_val_fast<KID>(r2, etab) * cs[t]);
+      int8_t* dst = planes + (size_t)(j0 + jj) * npad + k;
+      if constexpr (NS > 0) oz_emit_digits4_t<(NS > 0 ? NS : 1)>(I, dst, plane_stride);
+      else oz_emit_digits4(I, ns, dst, plane_stride);
+      if (alpha != nullptr) {
+        pm = warp_sum(pm);
+        if (lane == 0) msum[warp][jj] = pm;
+      }
     }
-    int8_t* dst = planes + (size_t)(j0 + jj) * npad + k;
-    if constexpr (NS > 0) oz_emit_digits4_t<(NS > 0 ? NS : 1)>(I, dst, plane_stride);
-    else oz_emit_digits4(I, ns, dst, plane_stride);
   }
-  for (int jj = (jend > 0 ? jend : 0); jj < OZC_TJ; ++jj)
-    for (int i = 0; i < ns; ++i) *reinterpret_cast<unsigned*>(planes + i * plane_stride + (size_t)(j0 + jj) * npad + k) = 0u;
+  if (active)
+    for (int jj = (jend > 0 ? jend : 0); jj < OZC_TJ; ++jj)
+      for (int i = 0; i < ns; ++i) *reinterpret_cast<unsigned*>(planes + i * plane_stride + (size_t)(j0 + jj) * npad + k) = 0u;
+  if (alpha != nullptr) {
+    __syncthreads();
+    if (threadIdx.x < OZC_TJ) {
+      double a = 0.0;
+      if ((int)threadIdx.x < jend) {
+#pragma unroll
+        for (int w = 0; w < OZC_THREADS / 32; ++w) a += msum[w][threadIdx.x];
+      }
+      mu_part[(size_t)blockIdx.x * Jpad + j0 + threadIdx.x] = a * ldexp(1.0, e - 8 * ns + 1);   // undo the fixed-point factor (exact)
+    }
+  }
 }
 
 // Vbar^T[i][k] = mubar_i gamma_k - sum_j (Sbar_ij + Sbar_ji) V^T[j][k]  (vbar_kernel) straight to digit planes.
@@ -462,7 +495,12 @@ template <int Q>
 __global__ void __launch_bounds__(VBP_THREADS, Q <= 8 ? VBP_MINB : 1)
 vbar_planes_kernel(const double* __restrict__ Vt, int npad, int S, int Jpad, const double* __restrict__ gamma,
                    const double* __restrict__ mubar, const double* __restrict__ Sigbar, int ns,
-                   int8_t* __restrict__ planes, double* __restrict__ scales, const double* __restrict__ vmax = nullptr) {
+                   int8_t* __restrict__ planes, double* __restrict__ scales, const double* __restrict__ vmax = nullptr,
+                   int tight = 0) {
+  // mubar == nullptr: the mean part of the gradient does not pass through the reverse contraction (cross_bwd_kernel
+  // adds mubar_j alpha_k); Vbar^T = -(Sbar + Sbar^T) V^T only.
+  // tight != 0: the row scales come from the TRUE row maxima of Vbar^T (one more sweep over the slab, which the L2
+  // mostly still holds) instead of the bound below: up to log2(q + 1) bits more of the fixed-point range are used.
   __shared__ double W[Q][Q];
   __shared__ double mb[Q];
   __shared__ double red[VBP_THREADS / 32][Q];
@@ -483,23 +521,45 @@ vbar_planes_kernel(const double* __restrict__ Vt, int npad, int S, int Jpad, con
     int i = t / Q, j = t - i * Q;
     W[i][j] = sb[i * Q + j] + sb[j * Q + i];
   }
-  if (tid < Q) mb[tid] = mubar[(size_t)s * Q + tid];
+  if (tid < Q) mb[tid] = mubar != nullptr ? mubar[(size_t)s * Q + tid] : 0.0;
   __syncthreads();
   const double* V = Vt + (size_t)s * Q * npad;
-  // Sweep 1: row maxima of V^T and of gamma only (no q x q work, q + 1 registers); the row scale of Vbar^T comes from
-  // the bound |Vbar_ik| <= |mubar_i| max|gamma| + sum_j |W_ij| max_k |V_jk|, at most a factor q + 1 (3.2 bits of the
-  // 55) above the true maximum.
-  // (vmax != nullptr: the forward contraction's epilogue has already left the row maxima of V^T there.)
   double mx[Q], gx = 0.0;
 #pragma unroll
   for (int i = 0; i < Q; ++i) mx[i] = 0.0;
-  if (vmax) {
-    for (int k = tid; k < npad; k += VBP_THREADS) gx = fmax(gx, fabs(gamma[k]));
+  if (tight) {
+    // Sweep 1 (tight): the values themselves, |.| maxima per row.  The row loop is rolled like sweep 2 (register
+    // budget), so the running maxima are selected with a compile-time unrolled compare instead of a dynamic index.
+    for (int k = tid * 2; k < npad; k += VBP_THREADS * 2) {
+      double2 v[Q];
+#pragma unroll
+      for (int i = 0; i < Q; ++i) v[i] = *reinterpret_cast<const double2*>(V + (size_t)i * npad + k);
+      double2 g = make_double2(0.0, 0.0);
+      if (mubar != nullptr) g = *reinterpret_cast<const double2*>(gamma + k);
+#pragma unroll 1
+      for (int i = 0; i < Q; ++i) {
+        double o0 = mb[i] * g.x, o1 = mb[i] * g.y;
+#pragma unroll
+        for (int j = 0; j < Q; ++j) {
+          o0 -= W[i][j] * v[j].x;
+          o1 -= W[i][j] * v[j].y;
+        }
+        const double a = fmax(fabs(o0), fabs(o1));
+#pragma unroll
+        for (int u = 0; u < Q; ++u) mx[u] = (u == i) ? fmax(mx[u], a) : mx[u];
+      }
+    }
+  } else if (vmax) {
+    // Sweep 1 bounds the row maxima of Vbar^T from the row maxima of V^T and of gamma only (no q x q work):
+    // |Vbar_ik| <= |mubar_i| max|gamma| + sum_j |W_ij| max_k |V_jk|, at most a factor q + 1 above the true maximum.
+    // (vmax: the forward contraction's epilogue has already left the row maxima of V^T there.)
+    if (mubar != nullptr)
+      for (int k = tid; k < npad; k += VBP_THREADS) gx = fmax(gx, fabs(gamma[k]));
   } else {
     for (int k = tid; k < npad; k += VBP_THREADS) {
 #pragma unroll
       for (int i = 0; i < Q; ++i) mx[i] = fmax(mx[i], fabs(V[(size_t)i * npad + k]));
-      gx = fmax(gx, fabs(gamma[k]));
+      if (mubar != nullptr) gx = fmax(gx, fabs(gamma[k]));
     }
   }
 #pragma unroll
@@ -512,14 +572,21 @@ vbar_planes_kernel(const double* __restrict__ Vt, int npad, int S, int Jpad, con
   if ((tid & 31) == 0) redg[tid >> 5] = gx;
   __syncthreads();
   if (tid < Q) {
-    double gm = redg[0];
-    for (int w = 1; w < VBP_THREADS / 32; ++w) gm = fmax(gm, redg[w]);
-    double bound = fabs(mb[tid]) * gm;
-    for (int j = 0; j < Q; ++j) {
-      double vm = red[0][j];
-      for (int w = 1; w < VBP_THREADS / 32; ++w) vm = fmax(vm, red[w][j]);
-      if (vmax) vm = vmax[(size_t)s * Q + j];
-      bound += fabs(W[tid][j]) * vm;
+    double bound;
+    if (tight) {
+      bound = red[0][tid];
+      for (int w = 1; w < VBP_THREADS / 32; ++w) bound = fmax(bound, red[w][tid]);
+      bound *= 1.0 + 1e-12;                                 // sweep 2 recomputes the values: a last-bit difference stays inside
+    } else {
+      double gm = redg[0];
+      for (int w = 1; w < VBP_THREADS / 32; ++w) gm = fmax(gm, redg[w]);
+      bound = fabs(mb[tid]) * gm;
+      for (int j = 0; j < Q; ++j) {
+        double vm = red[0][j];
+        for (int w = 1; w < VBP_THREADS / 32; ++w) vm = fmax(vm, red[w][j]);
+        if (vmax) vm = vmax[(size_t)s * Q + j];
+        bound += fabs(W[tid][j]) * vm;
+      }
     }
     const int e = oz_exponent_for(bound);
     scales[(size_t)s * Q + tid] = ldexp(1.0, e);
@@ -533,7 +600,8 @@ vbar_planes_kernel(const double* __restrict__ Vt, int npad, int S, int Jpad, con
     double2 v[Q];
 #pragma unroll
     for (int i = 0; i < Q; ++i) v[i] = *reinterpret_cast<const double2*>(V + (size_t)i * npad + k);
-    const double2 g = *reinterpret_cast<const double2*>(gamma + k);
+    double2 g = make_double2(0.0, 0.0);
+    if (mubar != nullptr) g = *reinterpret_cast<const double2*>(gamma + k);
 #pragma unroll 1
     for (int i = 0; i < Q; ++i) {
       double o0 = mb[i] * g.x, o1 = mb[i] * g.y;

@@ -21,7 +21,8 @@ template <int Q>
 __global__ void __launch_bounds__(POST_THREADS)
 posterior_kernel(const double* __restrict__ Vt, int npad, const double* __restrict__ gamma,
                  const double* __restrict__ X, ModelParams mp, double mean,
-                 double* __restrict__ mu, double* __restrict__ Sig) {
+                 double* __restrict__ mu, double* __restrict__ Sig,
+                 const double* __restrict__ mu_part = nullptr, int nparts = 0, int Jpad = 0) {
   __shared__ double tile[Q][POST_TK];
   __shared__ double gs[POST_TK];
   __shared__ double G[Q][Q];
@@ -39,7 +40,7 @@ posterior_kernel(const double* __restrict__ Vt, int npad, const double* __restri
     const int k = k0 + tid;
 #pragma unroll
     for (int i = 0; i < Q; ++i) tile[i][tid] = (k < npad) ? V[(size_t)i * npad + k] : 0.0;
-    gs[tid] = (k < npad) ? gamma[k] : 0.0;
+    gs[tid] = (k < npad && gamma != nullptr) ? gamma[k] : 0.0;
     __syncthreads();
     for (int kk = lane; kk < POST_TK; kk += 32) {
       if (i0 < Q) {
@@ -90,7 +91,14 @@ posterior_kernel(const double* __restrict__ Vt, int npad, const double* __restri
     double g = (i >= j) ? G[i][j] : G[j][i];
     Sig[(size_t)s * Q * Q + t] = mp.amp2 * kern_val(mp.kernel_id, r2) - g;
   }
-  if (tid < Q) mu[(size_t)s * Q + tid] = mean + mus[tid];
+  if (tid < Q) {
+    double m = mus[tid];
+    if (mu_part != nullptr) {                         // mean from K10 . alpha (cross_fwd_planes_kernel), column blocks in order
+      m = 0.0;
+      for (int b = 0; b < nparts; ++b) m += mu_part[(size_t)b * Jpad + (size_t)s * Q + tid];
+    }
+    mu[(size_t)s * Q + tid] = mean + m;
+  }
 }
 
 // Same result for Q <= 8 without the shared-memory slab (ncu: posterior_kernel runs at 94 % of the L1/shared
@@ -100,7 +108,8 @@ template <int Q>
 __global__ void __launch_bounds__(POST_REG_THREADS)
 posterior_reg_kernel(const double* __restrict__ Vt, int npad, const double* __restrict__ gamma,
                      const double* __restrict__ X, ModelParams mp, double mean,
-                     double* __restrict__ mu, double* __restrict__ Sig) {
+                     double* __restrict__ mu, double* __restrict__ Sig,
+                     const double* __restrict__ mu_part = nullptr, int nparts = 0, int Jpad = 0) {
   constexpr int NG = Q * (Q + 1) / 2;
   __shared__ double red[POST_REG_THREADS / 32][NG + Q];
   __shared__ double G[Q][Q];
@@ -117,7 +126,7 @@ posterior_reg_kernel(const double* __restrict__ Vt, int npad, const double* __re
     double v[Q];
 #pragma unroll
     for (int i = 0; i < Q; ++i) v[i] = V[(size_t)i * npad + k];
-    const double g = gamma[k];
+    const double g = gamma != nullptr ? gamma[k] : 0.0;      // nullptr: the mean comes from mu_part
 #pragma unroll
     for (int i = 0; i < Q; ++i) {
       m[i] += v[i] * g;
@@ -161,7 +170,14 @@ posterior_reg_kernel(const double* __restrict__ Vt, int npad, const double* __re
     double g = (i >= j) ? G[i][j] : G[j][i];
     Sig[(size_t)s * Q * Q + t] = mp.amp2 * kern_val(mp.kernel_id, r2) - g;
   }
-  if (tid < Q) mu[(size_t)s * Q + tid] = mean + mus[tid];
+  if (tid < Q) {
+    double m = mus[tid];
+    if (mu_part != nullptr) {
+      m = 0.0;
+      for (int b = 0; b < nparts; ++b) m += mu_part[(size_t)b * Jpad + (size_t)s * Q + tid];
+    }
+    mu[(size_t)s * Q + tid] = mean + m;
+  }
 }
 
 // Vbar^T[i][k] = mubar_i gamma_k - sum_j (Sbar_ij + Sbar_ji) V^T[j][k], in place.

@@ -72,6 +72,8 @@ class Engine:
         self._pinned = []
         self.d = None
         self.n = None
+        self._fingerprint = None
+        self._fantasy_key = None
 
     # -- plumbing ---------------------------------------------------------------------------
     def _err(self) -> str:
@@ -132,6 +134,7 @@ class Engine:
                   noise: Optional[float], mean: Optional[float], jitter: float):
         ls = nat.as_f64(np.atleast_1d(lenscales))
         self.d = int(ls.shape[0])
+        self._fingerprint = self._fantasy_key = None      # the factors (and fantasies) belong to the old model
         self._ck(self._lib.maf_set_model(
             self._ctx, nat.KERNEL_IDS[kernel_id], self.d, nat.ptr(ls), float(amplitude),
             float("nan") if noise is None else float(noise),
@@ -142,6 +145,7 @@ class Engine:
         y0 = nat.as_f64(np.reshape(y0, -1))
         assert X0.ndim == 2 and X0.shape[1] == self.d and y0.shape[0] == X0.shape[0]
         self.n = int(X0.shape[0])
+        self._fantasy_key = None                          # maf_set_train resets F to 0 on the device
         self._ck(self._lib.maf_set_train(self._ctx, self.n, nat.ptr(X0), nat.ptr(y0)))
 
     def factors(self):
@@ -309,6 +313,10 @@ class Engine:
         """0 = FP64 DMMA contractions, 1 = INT8 digit-sliced contractions (effective at the next set_train)."""
         self._ck(self._lib.maf_set_gemm_mode(self._ctx, int(mode)))
         self._fingerprint = None
+
+    def set_digits(self, ns_fwd: int, ns_bwd: int):
+        """Digit planes of the forward / reverse INT8 contraction (7 / 7: FP64-grade, 28 + 28 products)."""
+        self._ck(self._lib.maf_set_digits(self._ctx, int(ns_fwd), int(ns_bwd)))
 
     def gemm_nt_i8(self, A: np.ndarray, T: np.ndarray, tri: int = 0, ns: int = 7, lmax: int = 8) -> np.ndarray:
         A, T = nat.as_f64(A), nat.as_f64(T)

@@ -63,4 +63,5 @@ def bind(engine, hyper: dict, X0: np.ndarray, y0: np.ndarray):
         engine.set_model(**hyper)
         engine.set_train(np.asarray(X0, dtype=np.float64), np.asarray(y0, dtype=np.float64).reshape(-1))
         engine._fingerprint = fp
+        engine._fantasy_key = None      # maf_set_train drops the device-side fantasies (F = 0)
     return engine

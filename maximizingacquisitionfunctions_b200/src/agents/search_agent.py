@@ -66,18 +66,29 @@ class search_agent(module):
         return np.asarray(points, dtype=dtype)
 
     def _sobol(self, shape):
-        """Low-discrepancy sets with a random skip (:96-112).  The reference calls its vendored Burkardt generator;
-        SciPy's unscrambled Sobol sequence fast-forwarded by the same random skip stands in for it."""
+        """Low-discrepancy sets with a random skip (:96-112).  The reference calls its vendored Burkardt generator
+        ``i4_sobol_generate(width, count, skip).T``; when that module is loaded (compat.launcher registers the
+        reference's own file as ``src.third_party.sobol_lib``) it is used, so seeded runs pick the reference's
+        candidates.  Without a reference checkout SciPy's unscrambled Sobol sequence fast-forwarded by the same
+        random skip stands in (different direction numbers: same discrepancy, different points)."""
         count, width = _split_shape(shape)
         if width > SOBOL_MAX_DIM:
             logger.warning("Sobol sequence not available for >40d spaces; using uniform random values instead")
             return self.rng.rand(*shape)
-        from scipy.stats import qmc
         skip = int(self.rng.randint(2 ** 13 - 1))
+        import sys
+        ref = sys.modules.get("src.third_party.sobol_lib")
+        if ref is not None and hasattr(ref, "i4_sobol_generate"):
+            return np.reshape(ref.i4_sobol_generate(width, count, skip).T, shape)
+        import warnings
+        from scipy.stats import qmc
         sequence = qmc.Sobol(d=width, scramble=False)
         if skip:
             sequence.fast_forward(skip)
-        return np.reshape(sequence.random(count), shape)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", UserWarning)        # count is not a power of two in general
+            points = sequence.random(count)
+        return np.reshape(points, shape)
 
     def _distinct_subsets(self, options, shape):
         """`count` different size-`k` subsets of the option rows (:114-132): rejection sampling while there are more

@@ -1,7 +1,7 @@
 """Base class of the four myopic acquisition losses (reference: src/losses/myopic_loss.py).
 
 Everything is a loss to minimise.  ``evaluate`` dispatches like the reference (:84-90): a pool of
-size one without base samples takes the closed form, anything else the reparameterised
+size one takes the closed form (with or without base samples), anything else the reparameterised
 Monte-Carlo estimator with base samples ``fantasy_rvs[M, q]``.  Evaluation is eager: NumPy in,
 NumPy out, computed by the CUDA library; ``value_and_grad`` is the counterpart of the
 ``tf.gradients`` pass the reference's optimisers add.
@@ -67,7 +67,9 @@ class myopic_loss(abstract_loss):
             out = (losses.reshape(S, 1, 1), None)
             return out + (None if grad is None else grad.reshape(S, 1, d),) if return_grad else out
         prm = self.acq_params(outputs_old=outputs_old, **kwargs)
-        closed = (q == 1 and fantasy_rvs is None) if subroutine is None else (subroutine == self.closed_form)
+        # reference dispatch (:84-90): a pool of one takes the closed form whether or not base samples were
+        # passed; the Monte-Carlo estimator at q == 1 has to be asked for (subroutine=self.monte_carlo)
+        closed = (q == 1) if subroutine is None else (subroutine == self.closed_form)
         if closed:
             assert q == 1, "closed forms exist for q == 1 only"
             losses, grad = eng.value_and_grad(prm, pools, None, need_grad=return_grad)

@@ -26,7 +26,12 @@ class gaussian_process(abstract_model):
         self.jitter = jitter
         self.kernel_id = kernel_id
         self.device = device
-        self.priors = dict(priors or {})
+        if priors:
+            # the MAP objective below hard-codes the reference's defaults (log-normal amplitude, horseshoe(0.1) noise,
+            # :55-62); silently ignoring user priors would change what `fit` optimises
+            raise NotImplementedError("custom hyper-priors are outside the accelerated path; the defaults of "
+                                      "gaussian_process.py:55-62 are built in")
+        self.priors = dict()
         self.spo_config = self.update_dict({
             "method": "L-BFGS-B",
             "var_to_bounds": {

@@ -29,6 +29,7 @@ class FakeEngine:
     def set_train(self, X0, y0):
         self.ts = orc.prepare_train(self.gp, X0, y0)
         self.n = len(X0)
+        self.F, self._fY, self._fts = 0, None, None      # like maf_set_train: the fantasies are dropped
 
     def factors(self):
         L = self.ts.chol.numpy()
@@ -99,6 +100,8 @@ class FakeEngine:
         self._fts = [orc.prepare_train(self.gp, self.ts.X0.numpy(), y) for y in np.asarray(Y)]
 
     def fantasies_value_and_grad(self, prm, X, need_grad=True):
+        if not getattr(self, "F", 0):
+            raise RuntimeError("maf_set_fantasies must be called first")
         X = np.asarray(X, dtype=np.float64).reshape(-1, self.d)
         acq = self._acq(prm)
         Xt = torch.as_tensor(X[:, None, :]).clone().requires_grad_(True)
@@ -109,6 +112,8 @@ class FakeEngine:
         return losses.detach().numpy(), None
 
     def fantasies_posterior(self, X):
+        if not getattr(self, "F", 0):
+            raise RuntimeError("maf_set_fantasies must be called first")
         X = np.asarray(X, dtype=np.float64).reshape(-1, 1, self.d)
         mus, var = [], None
         with torch.no_grad():

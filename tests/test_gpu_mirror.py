@@ -155,3 +155,20 @@ def test_draw_samples_reference_code_golden():
         runtime.release_engines()
     assert s2.shape == r["samples"].shape and np.abs(s2 - r["samples"]).max() < 1e-9 * np.abs(r["samples"]).max()
     assert np.shape(s4) == r["samples4"].shape and np.abs(s4 - r["samples4"]).max() < 1e-9 * np.abs(r["samples4"]).max()
+
+
+def test_random_subroutine_on_the_cuda_engine():
+    """_optimize_inputs_random (:337-374): forward-only evaluation of uniform shards, the best shard_size sets kept;
+    CUDA engine vs the oracle-backed engine on identical host-RNG streams, q > 1 (Monte-Carlo) and q == 1 (closed form)."""
+    def flow():
+        agent, X0, Y0 = build(3, 48, "hartmann3", 11, "negative_ei")
+        agent.loss_fn.num_fantasies = 128
+        xq, lq = agent.suggest_inputs(2, X0, Y0, None, num_options=32, subroutine=agent._optimize_inputs_random,
+                                      config={"eval_limit": 256})
+        x1, l1 = agent.suggest_inputs(1, X0, Y0, None, num_options=64, subroutine=agent._optimize_inputs_random,
+                                      config={"eval_limit": 512})
+        return xq, lq, x1, l1
+    (xqg, lqg, x1g, l1g), (xqr, lqr, x1r, l1r) = run_both(flow)
+    assert xqg.shape == (2, 3) and x1g.shape == (1, 3)
+    assert np.array_equal(xqg, xqr) and abs(lqg - lqr) < 1e-9 * max(1.0, abs(lqr))
+    assert np.array_equal(x1g, x1r) and abs(l1g - l1r) < 1e-9 * max(1.0, abs(l1r))

@@ -506,3 +506,108 @@ def test_pending_points_reference_code_golden(eng, name):
     lg, gg = eng.value_and_grad(prm(acq.kind, level=acq.level, beta=acq.beta, lower=acq.lower), pools, rec["z"], p_pending=p)
     assert relerr(lg, rec["losses"]) < TOL
     assert gg.shape == rec["grad"].shape and relerr(gg, rec["grad"]) < TOL
+
+
+# ---------------------------------------------------------------- the configurations bench.py / run_configs.py time
+def per_restart_err(a, b):
+    a, b = np.asarray(a), np.asarray(b).reshape(np.shape(a))
+    return max(float(np.abs(a[s] - b[s]).max() / max(np.abs(b[s]).max(), 1e-300)) for s in range(a.shape[0]))
+
+
+def test_bench_workload_qei_median_level(eng):
+    """EXACTLY what bench.py times: qEI, n=4096, d=6, q=8, M=128, white-noise outputs, level = median(y0) (every restart
+    has a non-zero loss and gradient), uniform random candidates.  64 restarts against the oracle: 1e-9 per tensor AND
+    per restart (negative_ei.py:31-74 with an explicit level), identical selected restart."""
+    n, d, q, S, M = 4096, 6, 8, 64, 128
+    ts, X0, y0, X, z = setup_problem(eng, n, d, q, S, M, seed=0)
+    level = float(np.median(y0))
+    lo, go = orc.value_and_grad(ts, orc.Acq("ei", level=level), X, z)
+    lg, gg = eng.value_and_grad(prm("ei", level=level), X, z)
+    assert np.abs(lo).min() > 0 and min(np.abs(go[s]).max() for s in range(S)) > 0, "the workload must not be degenerate"
+    assert relerr(lg, lo) < TOL and relerr(gg, go) < TOL
+    assert per_restart_err(lg.reshape(S, 1), lo.reshape(S, 1)) < TOL
+    assert per_restart_err(gg, go) < TOL
+    mu, cov, chol = eng.last_extras(S, q)
+    with torch.no_grad():
+        mo, co = orc.posterior(ts, torch.as_tensor(X), full_cov=True)
+    assert relerr(mu, mo.numpy()) < TOL and relerr(cov, co.numpy()) < TOL
+    assert per_restart_err(mu, mo.numpy()) < TOL and per_restart_err(cov, co.numpy()) < TOL
+    assert int(np.argmin(lg)) == int(np.argmin(lo))
+    idx, _ = eng.argmin_last()
+    assert idx == int(np.argmin(lo))
+
+
+@pytest.mark.parametrize("p", [0, 15])
+def test_c4_shape_levy_q16_pending(eng, p):
+    """BASELINE config 4: Levy d=6, n=2048, q=16, qLCB (beta=2), M=128; joint (p=0) and the last step of the pending-point
+    greedy construction (15 pending points shared by every restart, one trainable row;
+    bayesian_optimization.py:1106-1123, scripts/run_bayesopt.py:137-176)."""
+    from maximizingacquisitionfunctions_b200 import tasks
+    n, d, q, S, M = 2048, 6, 16, 32, 128
+    gp, X0, y0, X, z = orc.synthetic_problem(n, d, q, S, M, seed=2, task=tasks.levy)
+    ts = orc.prepare_train(gp, X0, y0)
+    eng.set_model("matern52", np.full(d, math.sqrt(d) / 4), 1.0, 1e-3, 0.0, 1e-6)
+    eng.set_train(X0, y0)
+    if p:
+        pend, Xn = X[0, :p], X[:, p:]
+        pools = np.ascontiguousarray(np.concatenate([np.broadcast_to(pend, (S, p, d)), Xn], axis=1))
+        lo, go = orc.value_and_grad(ts, orc.Acq("cb", beta=2.0, lower=True), Xn, z, X_pend=pend)
+    else:
+        pools = X
+        lo, go = orc.value_and_grad(ts, orc.Acq("cb", beta=2.0, lower=True), X, z)
+    lg, gg = eng.value_and_grad(prm("cb", beta=2.0, lower=True), pools, z, p_pending=p)
+    assert gg.shape == (S, q - p, d)
+    assert relerr(lg, lo) < TOL and relerr(gg, go) < TOL
+    assert per_restart_err(lg.reshape(S, 1), lo.reshape(S, 1)) < TOL and per_restart_err(gg, go) < TOL
+    assert int(np.argmin(lg)) == int(np.argmin(lo))
+
+
+def test_c5_shape_m1024_nondegenerate_level(eng):
+    """BASELINE config 5: n=4096, d=6, q=8, M=1024 base samples; level = median(y0) so that no restart is identically 0."""
+    n, d, q, S, M = 4096, 6, 8, 32, 1024
+    ts, X0, y0, X, z = setup_problem(eng, n, d, q, S, M, seed=1)
+    level = float(np.median(y0))
+    lo, go = orc.value_and_grad(ts, orc.Acq("ei", level=level), X, z)
+    lg, gg = eng.value_and_grad(prm("ei", level=level), X, z)
+    assert np.abs(lo).min() > 0
+    assert relerr(lg, lo) < TOL and relerr(gg, go) < TOL
+    assert per_restart_err(lg.reshape(S, 1), lo.reshape(S, 1)) < TOL and per_restart_err(gg, go) < TOL
+    assert int(np.argmin(lg)) == int(np.argmin(lo))
+
+
+@pytest.mark.parametrize("task_name,n,d,q,acq,kw", [
+    ("hartmann3", 32, 3, 2, "ei", {}),
+    ("braninhoo", 256, 2, 4, "pi", {"temperature": 0.01}),
+    ("braninhoo", 256, 2, 4, "sr", {}),
+    ("hartmann6", 1024, 6, 8, "ei", {}),
+])
+def test_baseline_configs_on_their_task_outputs(eng, task_name, n, d, q, acq, kw):
+    """C1-C3 with the outputs of the task each is named after (tasks.py restates tasks/*._numpy) + sqrt(1e-3) noise, the
+    reference's default level min(y0)."""
+    from maximizingacquisitionfunctions_b200 import tasks
+    S, M = 48, 128
+    gp, X0, y0, X, z = orc.synthetic_problem(n, d, q, S, M, seed=3, task=getattr(tasks, task_name))
+    ts = orc.prepare_train(gp, X0, y0)
+    eng.set_model("matern52", np.full(d, math.sqrt(d) / 4), 1.0, 1e-3, 0.0, 1e-6)
+    eng.set_train(X0, y0)
+    lo, go = orc.value_and_grad(ts, orc.Acq(acq, **kw), X, z)
+    lg, gg = eng.value_and_grad(prm(acq, **kw), X, z)
+    assert relerr(lg, lo) < TOL and relerr(gg, go) < TOL
+    assert int(np.argmin(lg)) == int(np.argmin(lo))
+
+
+def test_digit_switch_api(eng):
+    """maf_set_digits: 7/7 is the default grade; fewer planes change the result only inside their documented error."""
+    if not eng.test_gemm_mode:
+        pytest.skip("INT8 engine only")
+    ts, X0, y0, X, z = setup_problem(eng, 512, 4, 4, 16, 64, seed=5)
+    l7, g7 = eng.value_and_grad(prm("sr"), X, z)
+    eng.set_digits(5, 5)
+    l5, g5 = eng.value_and_grad(prm("sr"), X, z)
+    eng.set_digits(7, 7)
+    l7b, g7b = eng.value_and_grad(prm("sr"), X, z)
+    assert np.array_equal(l7, l7b) and np.array_equal(g7, g7b)
+    assert 0 < relerr(l5, l7) < 1e-5
+    from maximizingacquisitionfunctions_b200.engine import MafError
+    with pytest.raises(MafError):
+        eng.set_digits(8, 7)

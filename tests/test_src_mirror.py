@@ -292,3 +292,21 @@ def test_draw_samples_matches_reference_code_golden(golden_dir):
                             base_rvs=r["eps1"])
     assert s2.shape == r["samples"].shape and np.abs(s2 - r["samples"]).max() < 1e-11
     assert np.shape(s4) == r["samples4"].shape and np.abs(s4 - r["samples4"]).max() < 1e-11
+
+
+def test_fantasies_are_rebound_after_the_training_set_was_reloaded():
+    """appraise rank-4 -> predict on 2-D data (reloads the training set, the device drops its fantasies) ->
+    appraise the same rank-4 set again: the fantasy cache key must not outlive the device state."""
+    agent, X0, Y0 = make(d=2, n=12)
+    F = 4
+    rng = np.random.RandomState(5)
+    Xf = np.tile(X0[None, None], (F, 1, 1, 1))
+    Yf = Y0[None, None] + 0.1 * rng.randn(F, 1, len(Y0), 1)
+    cand = rng.rand(3, 1, 2)
+    l_a = np.ravel(agent.loss_fn(cand, Xf, Yf, model=agent.model)[0])
+    agent.model.predict(cand[:, 0], X0[:8], Y0[:8])                   # another (X0, y0): set_train, F = 0
+    l_b = np.ravel(agent.loss_fn(cand, Xf, Yf, model=agent.model)[0])
+    assert np.array_equal(l_a, l_b)
+    agent.model.predict(cand[:, 0], X0, Y0)                           # SAME inputs as the fantasy set, 2-D outputs
+    l_c = np.ravel(agent.loss_fn(cand, Xf, Yf, model=agent.model)[0])
+    assert np.array_equal(l_a, l_c)
