@@ -213,6 +213,10 @@ def main():
                     help="contraction engine: f64 = DMMA, i8 = exact INT8 digit slicing on tcgen05 (FP64-grade)")
     ap.add_argument("--dtype", type=str, default="float64", choices=["float64", "float32"],
                     help="float32 = the reference's dtype='float32' mode (jitter 1e-4, 1e-4 bar): 15 digit-plane products")
+    ap.add_argument("--scaling", type=str, default="weak", choices=["weak", "strong"],
+                    help="weak: --restarts per GPU (default, the driver's scaling run); strong: BASELINE config 5, --restarts "
+                         "in TOTAL (65536) sharded over the ranks, 1024 base samples")
+    ap.add_argument("--mc-samples", type=int, default=None, help="base samples M (default 128; 1024 with --scaling strong)")
     ap.add_argument("--digits", type=str, default=None,
                     help="F,B: digit planes of the forward / reverse INT8 contraction (default 7,7; float32 mode 5,5)")
     args = ap.parse_args()
@@ -230,9 +234,18 @@ def main():
 
     w = dict(WORKLOAD)
     w["level"] = args.level
-    S = int(args.restarts)
+    strong = args.scaling == "strong"
+    w["M"] = int(args.mc_samples) if args.mc_samples else (1024 if strong else w["M"])
     n, d, q, M = w["n"], w["d"], w["q"], w["M"]
-    # every rank owns S restarts (weak scaling); its shard of the global restart index space
+    if strong:
+        # BASELINE config 5: a fixed set of restarts partitioned contiguously over the ranks (dist.shard_range)
+        S_total = int(args.restarts)
+        lo, hi = mdist.shard_range(S_total, rank, ws)
+        S, offset = hi - lo, lo
+    else:
+        # every rank owns S restarts (weak scaling); its shard of the global restart index space
+        S = int(args.restarts)
+        S_total, offset = ws * S, rank * S
     X0, y0, _, z = make_inputs(1, w)
     X = np.random.RandomState(w["seed"] + 2 + 1000 * rank).rand(S, q, d)
     eng = Engine(local, args.dtype)
@@ -256,15 +269,20 @@ def main():
     dloss = eng.alloc(S * 8)
     dgrad = eng.alloc(X.nbytes)
 
+    Xshape = np.broadcast_to(0.0, (S, q, d))
+
     def step_dev():
         eng.value_and_grad_dev(prm, S, q, 0, dX, M, dz, dloss, dgrad)
-        idx, val = eng.argmin_last()              # rank-local selection (device kernel + 16-byte D2H)
         if ws > 1:
-            mdist.select_global_best(val, rank * S + idx, X[idx])
+            # selection record assembled on the device, ONE NCCL all-gather, one read-back of the W x (2 + q d) table
+            val, idx, _ = mdist.global_best(eng, None, Xshape, offset)
+        else:
+            idx, val = eng.argmin_last()          # device kernel + 16-byte D2H
         return idx, val
 
     for _ in range(args.warmup):
         step_dev()
+    eng.level_switch_stats(reset=True)
     eng.profile_enable(True)
     eng.profile_reset()
     mdist.barrier()
@@ -279,17 +297,24 @@ def main():
     torch.cuda.synchronize()
     mdist.barrier()
     launches = eng.launch_count - launches0
+    lsw = eng.level_switch_stats()
+    if lsw["restarts"]:
+        # level switch on: one plane less first (ns - 1), the recomputed share again on all planes
+        cheap_f, cheap_b = (ns_f - 1) * ns_f // 2, (ns_b - 1) * ns_b // 2
+        pairs_f = cheap_f + pairs_f * lsw["recomputed_forward"] / lsw["restarts"]
+        pairs_b = cheap_b + pairs_b * lsw["recomputed_reverse"] / lsw["restarts"]
+        pairs = 0.5 * (pairs_f + pairs_b)
     clocks = sampler.stop()
     prof = eng.profile_read()
     eng.profile_enable(False)
     ms = mdist.max_over_ranks(ms)
-    value = ws * S * q * M * args.steps / (ms * 1e-3)
+    value = S_total * q * M * args.steps / (ms * 1e-3)
 
     # ---- roofline of the dominant kernel (FP64 DMMA contraction) --------------------------------
     gemm_ms = prof["gemm_fwd"][0] + prof["gemm_bwd"][0]
     gemm_launches = prof["gemm_fwd"][1] + prof["gemm_bwd"][1]
     npad = (n + 127) // 128 * 128
-    flops_per_step = 2.0 * npad * npad * q * S            # n^2 q per triangular GEMM, two GEMMs
+    flops_per_step = 2.0 * npad * npad * q * S            # n^2 q per triangular GEMM, two GEMMs (this rank's restarts)
     peak64, peak64_src = load_fp64_peak()
     fp64_equiv = flops_per_step * args.steps / (gemm_ms * 1e-3) * 1e-12 if gemm_ms > 0 else 0.0
     common = {"kernel_ms_per_launch": gemm_ms / max(gemm_launches, 1), "kernel_share_of_step": gemm_ms / ms,
@@ -306,7 +331,7 @@ def main():
                                  "frac_of_own_tcgen05_i8_issue_peak is against the raw kind::i8 issue rate measured "
                                  "with an MMA-only loop (profiles/i8_peaks.json)",
                     "frac_of_own_tcgen05_i8_issue_peak": achieved / peak8_issue if peak8_issue else None,
-                    "algorithmic": "n^2 q flops per restart per launch x %d (forward, ns=%d) / %d (reverse, ns=%d) exact int8 digit-plane products" % (pairs_f, ns_f, pairs_b, ns_b),
+                    "algorithmic": "n^2 q flops per restart per launch x %.2f (forward) / %.2f (reverse) exact int8 digit-plane products per FP64 product (ns=%d/%d planes; level switch: %s)" % (pairs_f, pairs_b, ns_f, ns_b, "on" if lsw["restarts"] else "off"),
                     "products": {"forward": pairs_f, "reverse": pairs_b},
                     # what the int8 pipe allows with every other kernel free: issue rate / (products per FP64 flop)
                     "pipe_ceiling": None if not peak8_issue else {
@@ -336,10 +361,10 @@ def main():
         eng.value_and_grad(prm, hX, hz, out_loss=hloss, out_grad=hgrad)
         i = int(np.argmin(hloss))
         if ws > 1:
-            mdist.select_global_best(float(hloss[i]), rank * S + i, hX[i])
+            mdist.select_global_best(float(hloss[i]), offset + i, hX[i])
     torch.cuda.synchronize()
     e2e_s = mdist.max_over_ranks(time.perf_counter() - t0)
-    e2e = {"value": ws * S * q * M * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(hX.nbytes + hz.nbytes),
+    e2e = {"value": S_total * q * M * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(hX.nbytes + hz.nbytes),
            "d2h_bytes_per_step": int(hloss.nbytes + hgrad.nbytes), "steps": e2e_steps}
 
     # ---- Adam loop on the device (steps x S x q x M / time), fresh z per step, same S --------------
@@ -354,7 +379,7 @@ def main():
     torch.cuda.synchronize()
     adam_s = mdist.max_over_ranks(time.perf_counter() - t0)
     eng.adam_end()
-    adam_loop = {"value": ws * S * q * M * adam_steps / adam_s, "unit": UNIT, "steps": adam_steps,
+    adam_loop = {"value": S_total * q * M * adam_steps / adam_s, "unit": UNIT, "steps": adam_steps,
                  "note": "maf_adam_steps: value+gradient, Adam update and clip per step on the device (one captured step replayed as a CUDA graph); z uploaded once per call"}
 
     # ---- CPU baseline (rank 0, N=1) ------------------------------------------------------------------
@@ -368,15 +393,21 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": ("f32-grade (contractions: 5 int8 digit planes per operand = 39-bit fixed point; everything else f64)" if f32 else
                       "f64" if args.gemm == "f64" else "f64 (contractions: exact int8 digit planes, int32 accumulate, FP64 recombination)"),
             "data": "synthetic",
-            "config": {"workload": "qEI value+grad, n=%d d=%d q=%d M=%d matern52, level=%s of y0, S=%d restarts per GPU" % (n, d, q, M, w["level"], S),
+            "config": {"workload": ("qEI value+grad, n=%d d=%d q=%d M=%d matern52, level=%s of y0, " % (n, d, q, M, w["level"])) +
+                                   ("S=%d restarts in total sharded over the ranks (BASELINE config 5)" % S_total if strong else "S=%d restarts per GPU" % S),
                        "contraction": args.gemm,
-                       "parallelism": "restarts sharded x%d, replicated training factor, one all-gather per step" % ws,
+                       "parallelism": "restarts sharded x%d, replicated training factor, one device-side all-gather of the selection records per step" % ws,
                        "l2_policy": "working set per chunk (K10 + V^T = %.1f GB) >> 126 MB L2; no flush needed" % (2 * min(S * q, 65536) * npad * 8 / 1e9),
                        "setup_s_not_timed": setup_s},
+            "level_switch": None if not lsw["restarts"] else {
+                "restarts": lsw["restarts"], "recomputed_forward": lsw["recomputed_forward"], "recomputed_reverse": lsw["recomputed_reverse"],
+                "tol": lsw["tol"], "calibrated_err_cov_abs": lsw["err_cov_abs"], "calibrated_err_grad_per_scale": lsw["err_grad_per_scale"],
+                "products_forward_avg": pairs_f, "products_reverse_avg": pairs_b,
+                "note": "both contractions first keep 6 of 7 digit planes (21 exact products); restarts whose own result does not tolerate the calibrated error of that level within tol are recomputed on all planes (28) inside the same call"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "adam_loop": adam_loop, "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

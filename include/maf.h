@@ -31,6 +31,9 @@
  *   MAF_OZ_NS_FWD=3..7   digit planes of K10 in the forward contraction (default 7)
  *   MAF_MU_ALPHA=0|1     posterior mean as m + K10 . alpha in FP64 inside the cross-covariance kernel and its gradient
  *                        inside the reverse covariance kernel (default 1) instead of m + V^T gamma through the contractions
+ *   MAF_LEVEL_SWITCH=0|1 error-bounded level switch of the two contractions (default 1, see maf_set_level_switch);
+ *                        MAF_LEVEL_SWITCH_TOL=<rel> its tolerance (default 2.5e-10), MAF_LEVEL_SWITCH_MIN_N=<n> smallest padded
+ *                        training-set size it applies to (default 1024)
  *   MAF_VBAR_TIGHT=0|1   row scales of the Vbar digit planes from the true row maxima (one more sweep; default 0)
  *   MAF_OZ_HINTS=<a><t>  L2 policy of the A / T plane loads, 0 normal, 1 evict-first, 2 evict-last (default 22)
  *   MAF_OZ_SJ=<k>        row blocks per super-row of the persistent tile order (default 2)
@@ -183,6 +186,12 @@ int maf_adam_end(maf_ctx* ctx, double* X_out);
  * a host loss vector is the caller's; this is the device-side variant over the losses
  * of the last evaluation: index and value of the first minimum (NaNs never win). */
 int maf_argmin_last(maf_ctx* ctx, int64_t* idx, double* value);
+/* Multi-GPU selection (restarts sharded over ranks, src/misc/sharded_fn.py:106-132 maps over independent restarts):
+ * writes this rank's record [loss*, index_offset + local index, X*[q][d]] of the last evaluation to DEVICE memory
+ * d_rec[2 + q*d], asynchronously on maf_stream(ctx) (index -1 / loss +inf when no loss is finite).  One all-gather
+ * of these records over NCCL and an arg-min with the lowest index winning ties reproduces np.argmin over all
+ * restarts (src/agents/bayesian_optimization.py:152). */
+int maf_best_record_dev(maf_ctx* ctx, int64_t index_offset, double* d_rec);
 
 /* ---- profiling (CUDA events on the context's stream) -------------------- */
 enum maf_prof_slot {
@@ -217,6 +226,15 @@ int maf_set_gemm_mode(maf_ctx* ctx, int mode);
  * Kbar10 = Vbar^T L0^-1.  7 / 7 (28 + 28 exact products) is the FP64-grade default, 3 <= ns <= 7 (5 / 5 in MAF_F32 mode).
  * Accuracy studies and the level switch of the host layer use it; takes effect at the next evaluation. */
 int maf_set_digits(maf_ctx* ctx, int ns_fwd, int ns_bwd);
+/* Level switch (default on in MAF_F64 mode for n >= 1024; MAF_LEVEL_SWITCH=0 turns it off): both contractions first keep
+ * one digit plane less (21 instead of 28 exact products).  maf_set_train measures the error that level leaves on the
+ * posterior covariance and on the gradient against the full level on 512 probe candidates; every restart whose own result
+ * (max |Sigma_s|, max |gradient_s|) does not tolerate that error within `tol` (relative; default 2.5e-10, a quarter of
+ * the 1e-9 parity bar; NaN keeps the current value) is recomputed with all planes, on the device, inside the same call.
+ * maf_level_switch_stats: counts[3] = restarts evaluated / recomputed forward / recomputed reverse since the last
+ * reset, errs[3] = calibrated covariance error, calibrated gradient error per unit row scale, tolerance. */
+int maf_set_level_switch(maf_ctx* ctx, int on, double tol);
+int maf_level_switch_stats(maf_ctx* ctx, int64_t* counts, double* errs, int reset);
 void* maf_dev_alloc(maf_ctx* ctx, size_t bytes);
 int maf_dev_free(maf_ctx* ctx, void* p);
 int maf_h2d(maf_ctx* ctx, void* dst, const void* src, size_t bytes);

@@ -54,6 +54,7 @@ SIGNATURES = {
     "maf_adam_peek": (C.c_int, [_vp, _vp]),
     "maf_adam_end": (C.c_int, [_vp, _vp]),
     "maf_argmin_last": (C.c_int, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
+    "maf_best_record_dev": (C.c_int, [_vp, C.c_int64, _vp]),
     "maf_profile_enable": (C.c_int, [_vp, C.c_int]),
     "maf_profile_read": (C.c_int, [_vp, _vp, _vp]),
     "maf_profile_reset": (C.c_int, [_vp]),
@@ -67,6 +68,8 @@ SIGNATURES = {
                                      C.c_int, C.c_int]),
     "maf_set_gemm_mode": (C.c_int, [_vp, C.c_int]),
     "maf_set_digits": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "maf_set_level_switch": (C.c_int, [_vp, C.c_int, C.c_double]),
+    "maf_level_switch_stats": (C.c_int, [_vp, _vp, _vp, C.c_int]),
     "maf_adam_set_method": (C.c_int, [_vp, C.c_int, C.c_double]),
     "maf_dev_alloc": (_vp, [_vp, C.c_size_t]),
     "maf_dev_free": (C.c_int, [_vp, _vp]),

@@ -31,6 +31,23 @@ struct AcqDev {
 
 __host__ __device__ __forceinline__ int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
+// Level switch (error-bounded choice of the digit planes of a contraction, per restart).  A contraction first runs with
+// one plane less (21 instead of 28 exact products); the kernel that consumes its result compares the calibrated absolute
+// error of that cheaper level (err, measured against the full level on probe candidates when the training set was
+// loaded) with what the restart tolerates (tol x the scale of its own result) and appends the restarts that fail to
+// a list.  A second pass recomputes exactly those restarts with all planes on COMPACT rows (position pos of the list
+// <-> rows pos q .. pos q + q - 1); later kernels pick the rows of a restart by its slot.  Everything stays on the
+// device (no host decision, replayable in a CUDA graph); a restart's result depends only on that restart.
+struct LevelSwitch {
+  const int* sel;         // second pass: compact position -> restart (null: first pass / switch off)
+  const int* sel_count;   // second pass: number of selected restarts
+  int* flag_count;        // first pass: counter of the restarts that fail the test (null: no test)
+  int* flag_sel;          // first pass: their list
+  int* flag_slot;         // first pass: restart -> position in the list, or -1
+  double err;             // calibrated error of the cheaper level (absolute, or per unit row scale)
+  double tol;             // relative tolerance the result must keep
+};
+
 // kappa(r2): src/models/kernels.py:32-49 (eps clamp inside the Matern kernels only).
 __device__ __forceinline__ double kern_val(int kid, double r2) {
   if (kid == MAF_KERNEL_SE) return exp(-0.5 * r2);
@@ -81,8 +98,19 @@ __constant__ double MAF_FC[10] = {
     1.0 / 3.0,                 // 7
     6755399441055744.0,        // 8: 1.5 2^52
     1.0e6};                    // 9: cap of the exponent argument
+// 2^(j/32), j = 0..31, correctly rounded (hex literals): the fill below is four constant-bank reads per thread, not 1024
+// calls of exp2 per CTA (cross_bwd runs one small CTA per restart)
+__constant__ double MAF_ETAB_C[MAF_ETAB] = {
+    0x1.0000000000000p+0, 0x1.059b0d3158574p+0, 0x1.0b5586cf9890fp+0, 0x1.11301d0125b51p+0,
+    0x1.172b83c7d517bp+0, 0x1.1d4873168b9aap+0, 0x1.2387a6e756238p+0, 0x1.29e9df51fdee1p+0,
+    0x1.306fe0a31b715p+0, 0x1.371a7373aa9cbp+0, 0x1.3dea64c123422p+0, 0x1.44e086061892dp+0,
+    0x1.4bfdad5362a27p+0, 0x1.5342b569d4f82p+0, 0x1.5ab07dd485429p+0, 0x1.6247eb03a5585p+0,
+    0x1.6a09e667f3bcdp+0, 0x1.71f75e8ec5f74p+0, 0x1.7a11473eb0187p+0, 0x1.82589994cce13p+0,
+    0x1.8ace5422aa0dbp+0, 0x1.93737b0cdc5e5p+0, 0x1.9c49182a3f090p+0, 0x1.a5503b23e255dp+0,
+    0x1.ae89f995ad3adp+0, 0x1.b7f76f2fb5e47p+0, 0x1.c199bdd85529cp+0, 0x1.cb720dcef9069p+0,
+    0x1.d5818dcfba487p+0, 0x1.dfc97337b9b5fp+0, 0x1.ea4afa2a490dap+0, 0x1.f50765b6e4540p+0};
 __device__ __forceinline__ void maf_fill_etab(double* tab, int tid, int nthreads) {
-  for (int t = tid; t < MAF_ETAB_WORDS; t += nthreads) tab[t] = exp2((double)(t >> 5) * (1.0 / MAF_ETAB));
+  for (int t = tid; t < MAF_ETAB_WORDS; t += nthreads) tab[t] = MAF_ETAB_C[t >> 5];
 }
 // max(x, eps) for x >= 0: eps = 2^-52 has a zero low word, so the comparison is one integer compare on the high word
 __device__ __forceinline__ double maf_clamp_eps(double x) {

@@ -102,7 +102,12 @@ cross_bwd_kernel(const double* __restrict__ X, int S, int q, int p,
                                  const double* __restrict__ Sigbar /*[S][q][q]*/,
                                  double* __restrict__ grad /*[S][q-p][d]*/,
                                  const double* __restrict__ alpha = nullptr /*[npad]: K00^-1 (y0 - m)*/,
-                                 const double* __restrict__ mubar = nullptr /*[S][q]*/) {
+                                 const double* __restrict__ mubar = nullptr /*[S][q]*/,
+                                 const double* __restrict__ kscale = nullptr /*row scales of the Vbar digit planes*/,
+                                 LevelSwitch ls = LevelSwitch{}) {
+  // Level switch of the reverse contraction.  First pass (ls.flag_count): the truncation error of the cheaper level on
+  // row j is ls.err x kscale[j] (calibrated per unit row scale); restarts where it exceeds ls.tol x max|gradient| are
+  // listed for the second pass.  Second pass (ls.sel): CTA r serves restart ls.sel[r] from compact Kbar rows r q + i.
   // alpha != nullptr: Kbar holds only the covariance part -(Sbar + Sbar^T) B^T of d loss / d K10; the mean part
   // mubar_j alpha_k (mu_j = m + K10[j][:] alpha, exact in FP64) is added here and never passes through a contraction.
   constexpr int DD = D > 0 ? D : MAF_MAX_D;
@@ -110,11 +115,18 @@ cross_bwd_kernel(const double* __restrict__ X, int S, int q, int p,
   __shared__ double etab_sh[MAF_ETAB_WORDS];
   maf_fill_etab(etab_sh, threadIdx.x, blockDim.x);
   const double* etab = etab_sh + (threadIdx.x & 31);
+  __shared__ double wmax[MAF_MAX_Q], werr[MAF_MAX_Q];
   __syncthreads();
-  const int s = blockIdx.x;
+  const int rc = blockIdx.x;
+  int s = rc;
+  if (ls.sel != nullptr) {
+    if (rc >= __ldg(ls.sel_count)) return;
+    s = __ldg(ls.sel + rc);
+  }
   const int i = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  if (i >= q || i < p) return;
+  const bool row_active = i < q && i >= p;
+  if (!row_active && ls.flag_count == nullptr) return;
   const size_t j = (size_t)s * q + i;
   double xi[DD], acc[DD];
 #pragma unroll
@@ -122,11 +134,12 @@ cross_bwd_kernel(const double* __restrict__ X, int S, int q, int p,
     xi[c] = (c < d) ? X[j * d + c] * mp.inv_ls[c] : 0.0;
     acc[c] = 0.0;
   }
-  const double* kb = Kbar + j * npad;
-  const double mbj = alpha != nullptr ? mubar[j] : 0.0;
+  const double* kb = Kbar + ((size_t)rc * q + i) * npad;
+  const double mbj = (alpha != nullptr && row_active) ? mubar[j] : 0.0;
   constexpr int UNR = CROSS_BWD_UNROLL;
+  const int nk = row_active ? n : 0;
 #pragma unroll UNR
-  for (int k = lane; k < n; k += 32) {
+  for (int k = lane; k < nk; k += 32) {
     double x0[DD];
     double r2 = 0.0;
 #pragma unroll
@@ -145,7 +158,7 @@ cross_bwd_kernel(const double* __restrict__ X, int S, int q, int p,
       if (c < d) acc[c] += g * (xi[c] - x0[c]);
   }
   // self-covariance term (K11 = a^2 kappa(r2(X_s, X_s)); diagonal has zero gradient)
-  if (lane < q && lane != i) {
+  if (row_active && lane < q && lane != i) {
     const double* xo = X + ((size_t)s * q + lane) * d;
     double xj[DD];
     double r2 = 0.0;
@@ -163,12 +176,32 @@ cross_bwd_kernel(const double* __restrict__ X, int S, int q, int p,
     for (int c = 0; c < DD; ++c)
       if (c < d) acc[c] += g * (xi[c] - xj[c]);
   }
+  double gmx = 0.0;
 #pragma unroll
   for (int c = 0; c < DD; ++c) {
     if (c < d) {
       double v = warp_sum(acc[c]);
-      if (lane == 0)
-        grad[((size_t)s * (q - p) + (i - p)) * d + c] = 2.0 * mp.amp2 * mp.inv_ls[c] * v;
+      const double gv = 2.0 * mp.amp2 * mp.inv_ls[c] * v;
+      gmx = fmax(gmx, fabs(gv));
+      if (lane == 0 && row_active) grad[((size_t)s * (q - p) + (i - p)) * d + c] = gv;
+    }
+  }
+  if (ls.flag_count != nullptr) {
+    if (lane == 0 && i < q) {
+      wmax[i] = row_active ? gmx : 0.0;
+      werr[i] = row_active ? ls.err * kscale[(size_t)rc * q + i] : 0.0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double mx = 0.0, er = 0.0;
+      for (int u = 0; u < q; ++u) {
+        mx = fmax(mx, wmax[u]);
+        er = fmax(er, werr[u]);
+      }
+      if (!(er <= ls.tol * mx)) {
+        const int slot = atomicAdd(ls.flag_count, 1);
+        ls.flag_sel[slot] = s;
+      }
     }
   }
 }

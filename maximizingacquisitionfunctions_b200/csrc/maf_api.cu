@@ -61,6 +61,22 @@ struct maf_ctx {
   int mu_alpha = 1;
   int vbar_tight = 0;              // MAF_VBAR_TIGHT=1: exact row maxima for the Vbar digit planes (one more sweep)
   Buf mu_part;                     // [column blocks of 1024][Jpad] partial sums of K10 . alpha
+  // Level switch (common.cuh, struct LevelSwitch): both contractions first run with one digit plane less (21 products
+  // instead of 28); restarts whose result does not tolerate the calibrated error of that level are recomputed with all
+  // planes on compact rows.  MAF_LEVEL_SWITCH=0 / maf_set_level_switch turn it off (every restart on all planes).
+  int lsw_on = 1;
+  double lsw_tol = 2.5e-10;        // relative error the cheaper level may leave (a quarter of the 1e-9 parity bar)
+  int lsw_min_npad = 1024;         // below this the contractions do not dominate and the extra launches cost more than they save
+  bool lsw_ready = false;          // calibrated for the current training set
+  bool lsw_busy = false;           // calibration in progress (plain passes)
+  double lsw_err_fwd = 0.0;        // max |Sigma(cheaper level) - Sigma(all planes)| over the probe candidates
+  double lsw_err_bwd = 0.0;        // max |grad(cheaper) - grad(all)| / row scale of Vbar over the probe candidates
+  Buf Vt2, rowmax2;                // forward second pass: V^T rows / row maxima of the recomputed restarts (compact)
+  int *lsw_cnt = nullptr;          // device: [0] forward count, [1] reverse count, [2..3] unused
+  long long* lsw_stats = nullptr;  // device: restarts recomputed forward / reverse since the last reset
+  long long lsw_evaluated = 0;     // host: restarts that went through the switch since the last reset
+  int *lsw_selF = nullptr, *lsw_slotF = nullptr, *lsw_selB = nullptr;
+  size_t lsw_cap = 0;              // restarts the three lists were sized for
   size_t cap_train = 0;        // npad the factor buffers were sized for
   int cap_train_d = 0;
   // GEMM workspace (chunk of candidate rows)
@@ -71,6 +87,7 @@ struct maf_ctx {
   Buf dX, dz, dw, dinc, dmu, dSig, dchol, dmubar, dSigbar, dloss, dgrad;
   int last_S = 0, last_q = 0;
   bool last_has_chol = false;
+  const double* last_dX = nullptr;   // device pools of the last evaluation (maf_best_record_dev)
   double* d_argmin_val = nullptr;
   long long* d_argmin_idx = nullptr;
   // Adam state
@@ -292,6 +309,7 @@ __global__ void diag_extract_kernel(const double* __restrict__ Sig, int S, int q
 // ... and compile-time digit count NSC for the FP64-grade configuration (7 planes); other counts at run time
 #define DISPATCH_DKN(d, kid, ns, ...)                                              \
   if ((ns) == 7) { constexpr int NSC = 7; DISPATCH_DK(d, kid, __VA_ARGS__) }       \
+  else if ((ns) == 6) { constexpr int NSC = 6; DISPATCH_DK(d, kid, __VA_ARGS__) }  \
   else { constexpr int NSC = 0; DISPATCH_DK(d, kid, __VA_ARGS__) }
 
 // GEMM variants (selected by MAF_GEMM_VARIANT at context creation; 0 is the default)
@@ -440,7 +458,7 @@ static int oz_schedule(maf_ctx* ctx, int nN, int nJ2, int K, int tri, int sj, in
 
 static int launch_i8gemm(maf_ctx* ctx, int slot, int J, int N, int K, const Buf& Ap, const Buf& sA, const Buf& Tp,
                          const Buf& sT, double* C, int ldc, int tri, int ns, int lmax, double* rowmax = nullptr,
-                         bool* rowmax_done = nullptr) {
+                         bool* rowmax_done = nullptr, const int* nrows_dev = nullptr, int nrows_mul = 1) {
   if (rowmax_done) *rowmax_done = false;
   if (J % 128 || N % 128 || K % 128) return fail(ctx, "i8 gemm dims must be multiples of 128");
   if (tri != 0 && K != N) return fail(ctx, "triangular gemm needs K == N");
@@ -481,7 +499,12 @@ static int launch_i8gemm(maf_ctx* ctx, int slot, int J, int N, int K, const Buf&
     return 1;
   static const unsigned long long pol[3] = {OZ3_L2_NORMAL, OZ3_L2_EVICT_FIRST, OZ3_L2_EVICT_LAST};
   OzParams prm{K, ns, lmax, tri, ldc, ctx->oz_sj, pol[ctx->oz_hint_a % 3], pol[ctx->oz_hint_t % 3], ctx->oz_pf, nullptr, ctx->oz_dbg,
-               nullptr, nullptr, nullptr};
+               nullptr, nullptr, nullptr, nullptr, 1};
+  if (nrows_dev) {
+    if (variant != 4) return fail(ctx, "a device-side row count needs the CTA-pair contraction kernel");
+    prm.nrows_dev = nrows_dev;
+    prm.nrows_mul = nrows_mul;
+  }
   if (rowmax && stash && variant == 4) {                           // only the register-stash epilogue emits row maxima
     CK(cudaMemsetAsync(rowmax, 0, sizeof(double) * J, ctx->stream));
     prm.rowmax = rowmax;
@@ -702,6 +725,9 @@ extern "C" int maf_create(int device, int dtype, maf_ctx** out) {
   if (const char* rm = getenv("MAF_OZ_ROWMAX")) ctx->oz_rowmax = atoi(rm);
   if (const char* ma = getenv("MAF_MU_ALPHA")) ctx->mu_alpha = atoi(ma);
   if (const char* vt = getenv("MAF_VBAR_TIGHT")) ctx->vbar_tight = atoi(vt);
+  if (const char* lw = getenv("MAF_LEVEL_SWITCH")) ctx->lsw_on = atoi(lw);
+  if (const char* lt = getenv("MAF_LEVEL_SWITCH_TOL")) ctx->lsw_tol = atof(lt);
+  if (const char* ln = getenv("MAF_LEVEL_SWITCH_MIN_N")) ctx->lsw_min_npad = atoi(ln);
   if (const char* nf = getenv("MAF_OZ_NS_FWD")) {
     const int v = atoi(nf);
     if (v >= 3 && v <= ctx->oz_ns) ctx->oz_ns_fwd = v;
@@ -732,12 +758,14 @@ extern "C" int maf_destroy(maf_ctx* ctx) {
                  &ctx->dmubar, &ctx->dSigbar, &ctx->dloss, &ctx->dgrad, &ctx->adam_X, &ctx->adam_m, &ctx->adam_v,
                  &ctx->adam_g, &ctx->adam_z, &ctx->fGamma, &ctx->fGammaT, &ctx->fmeans, &ctx->flevels, &ctx->fVG,
                  &ctx->fmubar, &ctx->ozA, &ctx->ozTL, &ctx->ozTU, &ctx->ozsA, &ctx->ozsTL, &ctx->ozsTU, &ctx->adam_zcur,
-                 &ctx->adam_coef, &ctx->adam_trace, &ctx->ozVmax, &ctx->mu_part};
+                 &ctx->adam_coef, &ctx->adam_trace, &ctx->ozVmax, &ctx->mu_part, &ctx->Vt2, &ctx->rowmax2};
   for (Buf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (ctx->d_argmin_idx) cudaFree(ctx->d_argmin_idx);
   if (ctx->adam_graph) cudaGraphExecDestroy(ctx->adam_graph);
   if (ctx->adam_ctr) cudaFree(ctx->adam_ctr);
+  for (void* b : {(void*)ctx->lsw_cnt, (void*)ctx->lsw_stats, (void*)ctx->lsw_selF, (void*)ctx->lsw_slotF, (void*)ctx->lsw_selB})
+    if (b) cudaFree(b);
   for (auto& sc : ctx->oz_scheds) {
     cudaFree(sc.d_list);
     cudaFree(sc.d_begin);
@@ -810,6 +838,8 @@ extern "C" int maf_set_model(maf_ctx* ctx, int kernel_id, int d, const double* l
   ctx->train_set = false;   // factors depend on the hyper-parameters
   return 0;
 }
+
+static int lsw_calibrate(maf_ctx* ctx, int n, const double* X0);
 
 extern "C" int maf_set_train(maf_ctx* ctx, int n, const double* X0, const double* y0) {
   if (!ctx) return 1;
@@ -913,7 +943,7 @@ extern "C" int maf_set_train(maf_ctx* ctx, int n, const double* X0, const double
   ctx->train_set = true;
   ctx->adam_on = false;
   ctx->F = 0;
-  return 0;
+  return lsw_calibrate(ctx, n, X0);
 }
 
 extern "C" int maf_get_factors(maf_ctx* ctx, double* L0, double* Linv, double* gamma) {
@@ -981,18 +1011,44 @@ static int resolve_acq(maf_ctx* ctx, const maf_acq_params* prm, AcqDev* out) {
   return 0;
 }
 
-// forward (+ optional backward) over one chunk of restarts
 // posterior mean / covariance of one chunk: register-accumulating kernel for Q <= 8, shared-memory slab beyond
 template <int Q>
 static void launch_posterior(maf_ctx* ctx, int sc, const double* Vt, int npad, const double* dX, double* mu, double* Sig,
-                             const double* mu_part, int nparts, int Jpad) {
+                             const double* mu_part, int nparts, int Jpad, LevelSwitch ls = LevelSwitch{}) {
   const double* gam = mu_part ? nullptr : ctx->gamma;         // mean from K10 . alpha: no gamma sweep
   if constexpr (Q <= 8)
-    posterior_reg_kernel<Q><<<sc, POST_REG_THREADS, 0, ctx->stream>>>(Vt, npad, gam, dX, ctx->mp, ctx->mean_val, mu, Sig, mu_part, nparts, Jpad);
+    posterior_reg_kernel<Q><<<sc, POST_REG_THREADS, 0, ctx->stream>>>(Vt, npad, gam, dX, ctx->mp, ctx->mean_val, mu, Sig, mu_part, nparts, Jpad, ls);
   else
-    posterior_kernel<Q><<<sc, POST_THREADS, 0, ctx->stream>>>(Vt, npad, gam, dX, ctx->mp, ctx->mean_val, mu, Sig, mu_part, nparts, Jpad);
+    posterior_kernel<Q><<<sc, POST_THREADS, 0, ctx->stream>>>(Vt, npad, gam, dX, ctx->mp, ctx->mean_val, mu, Sig, mu_part, nparts, Jpad, ls);
 }
 
+// lists and compact buffers of the level switch for chunks of up to `sc` restarts / `Jpad` candidate rows
+static int lsw_ensure(maf_ctx* ctx, int sc, int Jpad, int npad) {
+  if (!ctx->lsw_cnt) {
+    CK(cudaMalloc((void**)&ctx->lsw_cnt, 4 * sizeof(int)));
+    CK(cudaMalloc((void**)&ctx->lsw_stats, 2 * sizeof(long long)));
+    CK(cudaMemsetAsync(ctx->lsw_stats, 0, 2 * sizeof(long long), ctx->stream));
+  }
+  if ((size_t)sc > ctx->lsw_cap) {
+    for (int** b : {&ctx->lsw_selF, &ctx->lsw_slotF, &ctx->lsw_selB}) {
+      if (*b) CK(cudaFree(*b));
+      *b = nullptr;
+    }
+    ctx->generation++;
+    CK(cudaMalloc((void**)&ctx->lsw_selF, sizeof(int) * sc));
+    CK(cudaMalloc((void**)&ctx->lsw_slotF, sizeof(int) * sc));
+    CK(cudaMalloc((void**)&ctx->lsw_selB, sizeof(int) * sc));
+    ctx->lsw_cap = (size_t)sc;
+  }
+  return ensure(ctx, ctx->Vt2, (size_t)Jpad * npad) || ensure(ctx, ctx->rowmax2, (size_t)Jpad);
+}
+
+__global__ void lsw_accumulate_kernel(const int* __restrict__ cnt, long long* __restrict__ stats) {
+  stats[0] += cnt[0];
+  stats[1] += cnt[1];
+}
+
+// forward (+ optional backward) over one chunk of restarts
 static int run_chunk(maf_ctx* ctx, const AcqDev& ap, bool posterior_only, bool closed_form, int sc, int q, int p,
                      const double* dX, int M, const double* dz, const double* dw, const double* dinc, double* mu,
                      double* Sig, double* chol, double* mubar, double* Sigbar, double* dloss, double* dgrad) {
@@ -1002,15 +1058,22 @@ static int run_chunk(maf_ctx* ctx, const AcqDev& ap, bool posterior_only, bool c
   double* Vt = ctx->Vt.p;
   const bool fused = ctx->i8_ready && (ctx->oz_fuse & 1), fused_bwd = ctx->i8_ready && (ctx->oz_fuse & 2);
   const bool mu_alpha = fused && fused_bwd && ctx->mu_alpha;    // mean and its gradient outside the contractions
-  const int ns_fwd = std::min(ctx->oz_ns_fwd, ctx->oz_ns);
+  const int need_grad = (!posterior_only && dgrad != nullptr) ? 1 : 0;
+  // level switch: cheaper level first, failing restarts again with all planes (see LevelSwitch in common.cuh)
+  const bool lsw = mu_alpha && ctx->lsw_on && ctx->lsw_ready && !ctx->lsw_busy && ctx->dtype == MAF_F64 && ctx->oz_variant == 5 &&
+                   npad >= ctx->lsw_min_npad && ctx->oz_ns_fwd == ctx->oz_ns && ctx->oz_ns_bwd == ctx->oz_ns && ctx->oz_ns >= 4;
+  if (lsw && lsw_ensure(ctx, sc, Jpad, npad)) return 1;
+  const int ns_fwd = lsw ? ctx->oz_ns - 1 : std::min(ctx->oz_ns_fwd, ctx->oz_ns);
+  const int ns_bwd = lsw ? ctx->oz_ns - 1 : ctx->oz_ns_bwd;
   const int nparts = (npad + OZC_THREADS * 4 - 1) / (OZC_THREADS * 4);
   if (mu_alpha && ensure(ctx, ctx->mu_part, (size_t)nparts * Jpad)) return 1;
   const double* mu_part = mu_alpha ? ctx->mu_part.p : nullptr;
   // the Vbar producer needs the row maxima of V^T: the forward contraction's epilogue leaves them behind
-  const bool want_rowmax = fused_bwd && ctx->oz_rowmax && !posterior_only && dgrad != nullptr;
+  const bool want_rowmax = fused_bwd && ctx->oz_rowmax && need_grad;
   bool have_rowmax = false;
   if (want_rowmax && ensure(ctx, ctx->ozVmax, (size_t)Jpad)) return 1;
   double* const rowmax = want_rowmax ? ctx->ozVmax.p : nullptr;
+  if (lsw) CK(cudaMemsetAsync(ctx->lsw_cnt, 0, 4 * sizeof(int), ctx->stream));
   if (fused) {
     // K10 goes straight to digit planes (bounded by a^2: fixed row scale), FP64 K10 is never materialised
     const size_t bytes = (size_t)ctx->oz_ns * Jpad * npad;
@@ -1044,11 +1107,38 @@ static int run_chunk(maf_ctx* ctx, const AcqDev& ap, bool posterior_only, bool c
   }
   {
     ProfScope ps(ctx, MAF_PROF_POSTERIOR);
-    DISPATCH_Q(q, launch_posterior<Q>(ctx, sc, Vt, npad, dX, mu, Sig, mu_part, nparts, Jpad));
+    LevelSwitch ls{};
+    if (lsw) ls = LevelSwitch{nullptr, nullptr, ctx->lsw_cnt, ctx->lsw_selF, ctx->lsw_slotF, ctx->lsw_err_fwd, ctx->lsw_tol};
+    DISPATCH_Q(q, launch_posterior<Q>(ctx, sc, Vt, npad, dX, mu, Sig, mu_part, nparts, Jpad, ls));
     CKL();
   }
-  if (posterior_only) return 0;
-  const int need_grad = dgrad != nullptr;
+  bool have_rowmax2 = false;
+  if (lsw) {
+    // second pass of the forward switch: the listed restarts again with all planes, on compact rows
+    const int nsf = ctx->oz_ns;
+    {
+      ProfScope ps(ctx, MAF_PROF_CROSS_FWD);
+      dim3 grid(nparts, Jpad / OZC_TJ);
+      DISPATCH_DKN(d, ctx->mp.kernel_id, nsf, cross_fwd_planes_kernel<D, KID, NSC><<<grid, OZC_THREADS, 0, ctx->stream>>>(dX, J, Jpad, ctx->X0s, n, npad, ctx->mp, nsf,
+                                                                                  (int8_t*)ctx->ozA.p, ctx->ozsA.p, ctx->alpha, ctx->mu_part.p, ctx->lsw_selF, ctx->lsw_cnt, q));
+      CKL();
+    }
+    if (launch_i8gemm(ctx, MAF_PROF_GEMM_FWD, Jpad, npad, npad, ctx->ozA, ctx->ozsA, ctx->ozTL, ctx->ozsTL, ctx->Vt2.p, npad, 1,
+                      nsf, nsf + 1, want_rowmax ? ctx->rowmax2.p : nullptr, &have_rowmax2, ctx->lsw_cnt, q))
+      return 1;
+    ProfScope ps(ctx, MAF_PROF_POSTERIOR);
+    const LevelSwitch ls{ctx->lsw_selF, ctx->lsw_cnt, nullptr, nullptr, nullptr, 0.0, 0.0};
+    DISPATCH_Q(q, launch_posterior<Q>(ctx, sc, ctx->Vt2.p, npad, dX, mu, Sig, mu_part, nparts, Jpad, ls));
+    CKL();
+  }
+  if (posterior_only) {
+    if (lsw) {
+      ProfScope ps(ctx, MAF_PROF_ADAM);
+      lsw_accumulate_kernel<<<1, 1, 0, ctx->stream>>>(ctx->lsw_cnt, ctx->lsw_stats);
+      ctx->lsw_evaluated += sc;
+    }
+    return 0;
+  }
   {
     ProfScope ps(ctx, MAF_PROF_MC);
     if (closed_form) {
@@ -1066,20 +1156,30 @@ static int run_chunk(maf_ctx* ctx, const AcqDev& ap, bool posterior_only, bool c
     }
     CKL();
   }
-  if (!need_grad) return 0;
+  if (!need_grad) {
+    if (lsw) {
+      ProfScope ps(ctx, MAF_PROF_ADAM);
+      lsw_accumulate_kernel<<<1, 1, 0, ctx->stream>>>(ctx->lsw_cnt, ctx->lsw_stats);
+      ctx->lsw_evaluated += sc;
+    }
+    return 0;
+  }
   if (fused_bwd) {
-    // the digit planes of L0^-T were written with oz_ns digits; their first oz_ns_bwd planes are the balanced
+    // the digit planes of L0^-T were written with oz_ns digits; their first ns_bwd planes are the balanced
     // expansion rounded to that many digits, so the same buffer serves the shorter reverse contraction
     const size_t bytes = (size_t)ctx->oz_ns * Jpad * npad;
     if (ensure(ctx, ctx->ozA, (bytes + 7) / 8) || ensure(ctx, ctx->ozsA, (size_t)Jpad)) return 1;
+    const int* vslot = lsw ? ctx->lsw_slotF : nullptr;       // restarts whose V^T rows live in Vt2 (compact)
+    const double* vmax2 = (lsw && have_rowmax2) ? ctx->rowmax2.p : nullptr;
+    const double* vmax1 = (have_rowmax && (!lsw || have_rowmax2)) ? rowmax : nullptr;
     {
       ProfScope ps(ctx, MAF_PROF_VBAR);
-      DISPATCH_Q(q, vbar_planes_kernel<Q><<<sc + (Jpad - J), VBP_THREADS, 0, ctx->stream>>>(Vt, npad, sc, Jpad, ctx->gamma, mu_alpha ? nullptr : mubar, Sigbar, ctx->oz_ns_bwd,
-                                                                                   (int8_t*)ctx->ozA.p, ctx->ozsA.p, have_rowmax ? rowmax : nullptr, ctx->vbar_tight));
+      DISPATCH_Q(q, vbar_planes_kernel<Q><<<sc + (Jpad - J), VBP_THREADS, 0, ctx->stream>>>(Vt, npad, sc, Jpad, ctx->gamma, mu_alpha ? nullptr : mubar, Sigbar, ns_bwd,
+                                                                                   (int8_t*)ctx->ozA.p, ctx->ozsA.p, vmax1, ctx->vbar_tight, vslot, ctx->Vt2.p, vmax2));
       CKL();
     }
     if (launch_i8gemm(ctx, MAF_PROF_GEMM_BWD, Jpad, npad, npad, ctx->ozA, ctx->ozsA, ctx->ozTU, ctx->ozsTU, K10, npad, 2,
-                      ctx->oz_ns_bwd, ctx->oz_lmax_bwd))
+                      ns_bwd, ns_bwd + 1))
       return 1;
   } else {
     {
@@ -1098,9 +1198,37 @@ static int run_chunk(maf_ctx* ctx, const AcqDev& ap, bool posterior_only, bool c
   }
   {
     ProfScope ps(ctx, MAF_PROF_CROSS_BWD);
+    LevelSwitch ls{};
+    if (lsw) ls = LevelSwitch{nullptr, nullptr, ctx->lsw_cnt + 1, ctx->lsw_selB, nullptr, ctx->lsw_err_bwd, ctx->lsw_tol};
     DISPATCH_DK(d, ctx->mp.kernel_id, cross_bwd_kernel<D, KID><<<sc, 32 * q, 0, ctx->stream>>>(dX, sc, q, p, ctx->X0s, n, npad, ctx->mp, K10, Sigbar, dgrad,
-                                                                                         mu_alpha ? ctx->alpha : nullptr, mubar));
+                                                                                         mu_alpha ? ctx->alpha : nullptr, mubar, ctx->ozsA.p, ls));
     CKL();
+  }
+  if (lsw) {
+    // second pass of the reverse switch: Vbar planes of the listed restarts with all planes on compact rows, contraction
+    // into the (now free) V^T buffer, gradient of those restarts again
+    const int nsb = ctx->oz_ns;
+    const LevelSwitch ls{ctx->lsw_selB, ctx->lsw_cnt + 1, nullptr, nullptr, nullptr, 0.0, 0.0};
+    const double* vmax2 = have_rowmax2 ? ctx->rowmax2.p : nullptr;
+    const double* vmax1 = (have_rowmax && have_rowmax2) ? rowmax : nullptr;
+    {
+      ProfScope ps(ctx, MAF_PROF_VBAR);
+      DISPATCH_Q(q, vbar_planes_kernel<Q><<<sc, VBP_THREADS, 0, ctx->stream>>>(Vt, npad, sc, Jpad, ctx->gamma, nullptr, Sigbar, nsb, (int8_t*)ctx->ozA.p,
+                                                                       ctx->ozsA.p, vmax1, ctx->vbar_tight, ctx->lsw_slotF, ctx->Vt2.p, vmax2, ls));
+      CKL();
+    }
+    if (launch_i8gemm(ctx, MAF_PROF_GEMM_BWD, Jpad, npad, npad, ctx->ozA, ctx->ozsA, ctx->ozTU, ctx->ozsTU, Vt, npad, 2, nsb, nsb + 1,
+                      nullptr, nullptr, ctx->lsw_cnt + 1, q))
+      return 1;
+    {
+      ProfScope ps(ctx, MAF_PROF_CROSS_BWD);
+      DISPATCH_DK(d, ctx->mp.kernel_id, cross_bwd_kernel<D, KID><<<sc, 32 * q, 0, ctx->stream>>>(dX, sc, q, p, ctx->X0s, n, npad, ctx->mp, Vt, Sigbar, dgrad,
+                                                                                           ctx->alpha, mubar, nullptr, ls));
+      CKL();
+    }
+    ProfScope ps(ctx, MAF_PROF_ADAM);
+    lsw_accumulate_kernel<<<1, 1, 0, ctx->stream>>>(ctx->lsw_cnt, ctx->lsw_stats);
+    ctx->lsw_evaluated += sc;
   }
   return 0;
 }
@@ -1148,6 +1276,112 @@ static int run_all(maf_ctx* ctx, const maf_acq_params* prm, bool posterior_only,
   ctx->last_S = S;
   ctx->last_q = q;
   ctx->last_has_chol = !posterior_only && !closed_form;
+  ctx->last_dX = dX;
+  return 0;
+}
+
+// Calibration of the level switch for the loaded training set: the error the cheaper level (one digit plane less)
+// leaves on the posterior covariance (absolute) and on the gradient (per unit row scale of Vbar^T), measured against the
+// full level on 512 probe candidates -- half of them 1e-3 away from training points, where V has full norm and the
+// posterior variance sits at the noise level (the worst case for Sigma = K11 - V^T V), half uniform.  The truncation error
+// is a sum over ~n digit products with the fixed row scales of L0^-1, so its size does not depend on which candidates
+// are evaluated later; the per-restart test in the kernels compares it with what each restart's own result tolerates.
+static int lsw_calibrate(maf_ctx* ctx, int n, const double* X0) {
+  ctx->lsw_ready = false;
+  const bool eligible = ctx->lsw_on && ctx->i8_ready && (ctx->oz_fuse & 3) == 3 && ctx->mu_alpha && ctx->dtype == MAF_F64 &&
+                        ctx->oz_variant == 5 && ctx->npad >= ctx->lsw_min_npad && ctx->oz_ns >= 4 &&
+                        ctx->oz_ns_fwd == ctx->oz_ns && ctx->oz_ns_bwd == ctx->oz_ns;
+  if (!eligible) return 0;
+  const int d = ctx->mp.d, S = 512, ns = ctx->oz_ns;
+  std::vector<double> X((size_t)S * d);
+  unsigned long long st = 0x9E3779B97F4A7C15ull;
+  auto u01 = [&st]() {                                       // splitmix64: fixed probe set, independent of any host RNG
+    st += 0x9E3779B97F4A7C15ull;
+    unsigned long long z = st;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (double)(z >> 11) * (1.0 / 9007199254740992.0);
+  };
+  for (int s = 0; s < S; ++s)
+    for (int c = 0; c < d; ++c) {
+      double v = u01();
+      if (s < S / 2) {
+        const int i = (int)((long long)s * n / (S / 2));
+        v = std::min(1.0, std::max(0.0, X0[(size_t)i * d + c] + 2e-3 * (v - 0.5)));
+      }
+      X[(size_t)s * d + c] = v;
+    }
+  if (ensure(ctx, ctx->dX, (size_t)S * d) || ensure(ctx, ctx->dloss, (size_t)S) || ensure(ctx, ctx->dgrad, (size_t)S * d)) return 1;
+  CK(cudaMemcpyAsync(ctx->dX.p, X.data(), sizeof(double) * S * d, cudaMemcpyHostToDevice, ctx->stream));
+  std::vector<double> v6(S), v7(S), g6((size_t)S * d), g7((size_t)S * d), sc6(S);
+  maf_acq_params prm{MAF_ACQ_CB, 1, NAN, NAN, 2.0};
+  ctx->lsw_busy = true;
+  int rc = 0;
+  for (int pass = 0; pass < 2 && rc == 0; ++pass) {
+    const int nsp = pass == 0 ? ns - 1 : ns;
+    ctx->oz_ns_fwd = nsp;
+    ctx->oz_ns_bwd = ns;
+    rc = run_all(ctx, nullptr, true, S, 1, 0, ctx->dX.p, 0, nullptr, nullptr, nullptr, nullptr, nullptr);
+    if (rc == 0 && cudaMemcpyAsync((pass == 0 ? v6 : v7).data(), ctx->dSig.p, sizeof(double) * S, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+      rc = fail(ctx, "level-switch calibration: copy failed");
+    ctx->oz_ns_fwd = ns;
+    ctx->oz_ns_bwd = nsp;
+    ctx->oz_lmax_bwd = nsp + 1;
+    if (rc == 0) rc = run_all(ctx, &prm, false, S, 1, 0, ctx->dX.p, 0, nullptr, nullptr, nullptr, ctx->dloss.p, ctx->dgrad.p);
+    if (rc == 0 && cudaMemcpyAsync((pass == 0 ? g6 : g7).data(), ctx->dgrad.p, sizeof(double) * S * d, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+      rc = fail(ctx, "level-switch calibration: copy failed");
+    if (rc == 0 && pass == 0 && cudaMemcpyAsync(sc6.data(), ctx->ozsA.p, sizeof(double) * S, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+      rc = fail(ctx, "level-switch calibration: copy failed");
+    if (rc == 0 && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(ctx, "level-switch calibration failed on the device");
+  }
+  ctx->oz_ns_fwd = ctx->oz_ns_bwd = ns;
+  ctx->oz_lmax_bwd = ns + 1;
+  ctx->lsw_busy = false;
+  ctx->last_S = 0;
+  if (rc) return rc;
+  double ef = 0.0, eb = 0.0;
+  for (int s = 0; s < S; ++s) {
+    ef = std::max(ef, std::fabs(v6[s] - v7[s]));
+    if (sc6[s] > 0.0)
+      for (int c = 0; c < d; ++c) eb = std::max(eb, std::fabs(g6[(size_t)s * d + c] - g7[(size_t)s * d + c]) / sc6[s]);
+  }
+  ctx->lsw_err_fwd = ef;
+  ctx->lsw_err_bwd = eb;
+  ctx->lsw_ready = true;
+  return 0;
+}
+
+extern "C" int maf_set_level_switch(maf_ctx* ctx, int on, double tol) {
+  if (!ctx) return 1;
+  if (tol == tol && !(tol > 0.0)) return fail(ctx, "the tolerance of the level switch must be positive");
+  ctx->generation++;
+  ctx->lsw_on = on ? 1 : 0;
+  if (tol == tol) ctx->lsw_tol = tol;
+  if (on && !ctx->lsw_ready) ctx->train_set = false;           // calibrated by the next maf_set_train
+  return 0;
+}
+
+extern "C" int maf_level_switch_stats(maf_ctx* ctx, int64_t* counts, double* errs, int reset) {
+  if (!ctx) return 1;
+  CK(cudaSetDevice(ctx->device));
+  long long h[2] = {0, 0};
+  if (ctx->lsw_stats) {
+    CK(cudaMemcpyAsync(h, ctx->lsw_stats, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (reset) CK(cudaMemsetAsync(ctx->lsw_stats, 0, sizeof(h), ctx->stream));
+  }
+  if (counts) {
+    counts[0] = (int64_t)ctx->lsw_evaluated;
+    counts[1] = (int64_t)h[0];
+    counts[2] = (int64_t)h[1];
+  }
+  if (errs) {
+    errs[0] = ctx->lsw_ready ? ctx->lsw_err_fwd : NAN;
+    errs[1] = ctx->lsw_ready ? ctx->lsw_err_bwd : NAN;
+    errs[2] = ctx->lsw_tol;
+  }
+  if (reset) ctx->lsw_evaluated = 0;
   return 0;
 }
 
@@ -1284,6 +1518,7 @@ extern "C" int maf_mc_from_moments(maf_ctx* ctx, const maf_acq_params* prm, int 
   ctx->last_S = S;
   ctx->last_q = q;
   ctx->last_has_chol = true;
+  ctx->last_dX = nullptr;                                       // moments came from the caller: no candidate sets on the device
   return 0;
 }
 
@@ -1493,6 +1728,19 @@ extern "C" int maf_argmin_last(maf_ctx* ctx, int64_t* idx, double* value) {
   CK(cudaStreamSynchronize(ctx->stream));
   if (idx) *idx = (int64_t)hi;
   if (value) *value = hv;
+  return 0;
+}
+
+extern "C" int maf_best_record_dev(maf_ctx* ctx, int64_t index_offset, double* d_rec) {
+  if (!ctx) return 1;
+  if (!d_rec) return fail(ctx, "null device pointer");
+  if (ctx->last_S == 0 || !ctx->dloss.p || !ctx->last_dX) return fail(ctx, "no evaluation to report");
+  CK(cudaSetDevice(ctx->device));
+  ProfScope ps(ctx, MAF_PROF_ADAM);
+  argmin_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->dloss.p, ctx->last_S, ctx->d_argmin_val, ctx->d_argmin_idx);
+  best_record_kernel<<<1, 128, 0, ctx->stream>>>(ctx->d_argmin_val, ctx->d_argmin_idx, ctx->last_dX, ctx->last_q * ctx->mp.d,
+                                                 (long long)index_offset, d_rec);
+  CKL();
   return 0;
 }
 

@@ -447,3 +447,17 @@ __global__ void argmin_kernel(const double* __restrict__ loss, int S, double* ou
     if (lane == 0) { *out_val = bv; *out_idx = bi; }
   }
 }
+
+// ---- selection record of one rank: rec = [loss*, global index, X*[q][d]] (index -1, loss +inf if nothing finite) ------
+// Follows argmin_kernel on the same stream; what the single all-gather of the multi-GPU selection carries
+// (np.argmin over all restarts, src/agents/bayesian_optimization.py:152, lowest index wins ties).
+__global__ void best_record_kernel(const double* __restrict__ val, const long long* __restrict__ idx,
+                                   const double* __restrict__ X, int qd, long long offset, double* __restrict__ rec) {
+  const long long i = *idx;
+  if (threadIdx.x == 0) {
+    rec[0] = i >= 0 ? *val : INFINITY;
+    rec[1] = i >= 0 ? (double)(offset + i) : -1.0;
+  }
+  for (int t = threadIdx.x; t < qd; t += blockDim.x) rec[2 + t] = i >= 0 ? X[(size_t)i * qd + t] : 0.0;
+}
+

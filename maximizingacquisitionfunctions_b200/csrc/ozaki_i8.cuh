@@ -101,6 +101,10 @@ struct OzParams {
   // register-stash epilogue only: row maxima of |C| (atomicMax on the bit patterns; the caller zeroes the array).  The
   // Vbar producer takes its row scales from them instead of sweeping V^T once more (17 GB per step at the headline size).
   double* rowmax;
+  // CTA-pair kernel, second pass of the level switch: only the first *nrows_dev rows of A (a device-side count, rounded up
+  // to whole 256-row blocks) are contracted; tiles of later row blocks are skipped by all three roles.  null = all rows.
+  const int* nrows_dev;
+  int nrows_mul;    // rows = *nrows_dev x nrows_mul (restarts x pool size)
 };
 #define OZ_TILE_EXPLICIT 0x40000000
 
@@ -396,7 +400,10 @@ template <int D, int KID, int NS>
 __global__ void __launch_bounds__(OZC_THREADS, (D > 0 && D <= 8) ? OZC_MINB : 1)
 cross_fwd_planes_kernel(const double* __restrict__ X, int J, int Jpad, const double* __restrict__ X0s, int n, int npad,
                         ModelParams mp, int ns_rt, int8_t* __restrict__ planes, double* __restrict__ scales,
-                        const double* __restrict__ alpha = nullptr, double* __restrict__ mu_part = nullptr) {
+                        const double* __restrict__ alpha = nullptr, double* __restrict__ mu_part = nullptr,
+                        const int* __restrict__ sel = nullptr, const int* __restrict__ sel_count = nullptr, int q = 1) {
+  // sel != nullptr (second pass of the level switch): compact row r = pos q + i holds candidate row sel[pos] q + i of
+  // X for pos < *sel_count; J is ignored.
   // alpha != nullptr: the posterior mean goes the exact FP64 way, mu_j = m + sum_k K10[j][k] alpha_k with
   // alpha = K00^-1 (y0 - m) (Means = mean_fn + Beta . resid, gaussian_process.py:204-208): every kernel value is in a
   // register here anyway.  The partial sum of this CTA's 1024 columns goes to mu_part[blockIdx.x][j] (fixed summation
@@ -411,10 +418,18 @@ cross_fwd_planes_kernel(const double* __restrict__ X, int J, int Jpad, const dou
   const double* etab = etab_sh + (threadIdx.x & 31);
   const int k = (blockIdx.x * OZC_THREADS + threadIdx.x) * 4;
   const int j0 = blockIdx.y * OZC_TJ;
+  if (sel != nullptr) {
+    J = __ldg(sel_count) * q;
+    if (j0 >= J) return;                                     // nothing selected in this row block (rows stay stale, unread)
+  }
   for (int t = threadIdx.x; t < OZC_TJ * d; t += OZC_THREADS) {
     int jj = t / d, c = t - jj * d;
     int j = j0 + jj;
-    xs[jj][c] = (j < J) ? X[(size_t)j * d + c] * mp.inv_ls[c] : 0.0;
+    if (sel != nullptr && j < J) {
+      const int pos = j / q;
+      j = __ldg(sel + pos) * q + (j - pos * q);
+    }
+    xs[jj][c] = (j0 + jj < J) ? X[(size_t)j * d + c] * mp.inv_ls[c] : 0.0;
   }
   const int e = oz_exponent_for(mp.amp2);
   if (blockIdx.x == 0 && threadIdx.x < OZC_TJ) scales[j0 + threadIdx.x] = (j0 + (int)threadIdx.x < J) ? ldexp(1.0, e) : 1.0;
@@ -496,7 +511,11 @@ __global__ void __launch_bounds__(VBP_THREADS, Q <= 8 ? VBP_MINB : 1)
 vbar_planes_kernel(const double* __restrict__ Vt, int npad, int S, int Jpad, const double* __restrict__ gamma,
                    const double* __restrict__ mubar, const double* __restrict__ Sigbar, int ns,
                    int8_t* __restrict__ planes, double* __restrict__ scales, const double* __restrict__ vmax = nullptr,
-                   int tight = 0) {
+                   int tight = 0, const int* __restrict__ vslot = nullptr, const double* __restrict__ Vt2 = nullptr,
+                   const double* __restrict__ vmax2 = nullptr, LevelSwitch ls = LevelSwitch{}) {
+  // vslot != nullptr: restarts whose forward contraction was redone with all planes (level switch) keep their V^T rows
+  // at compact position vslot[s] of Vt2 (row maxima in vmax2).  ls.sel != nullptr: this is the second pass of the REVERSE
+  // switch; CTA r serves restart ls.sel[r] and writes compact rows r q .. r q + q - 1.
   // mubar == nullptr: the mean part of the gradient does not pass through the reverse contraction (cross_bwd_kernel
   // adds mubar_j alpha_k); Vbar^T = -(Sbar + Sbar^T) V^T only.
   // tight != 0: the row scales come from the TRUE row maxima of Vbar^T (one more sweep over the slab, which the L2
@@ -506,9 +525,14 @@ vbar_planes_kernel(const double* __restrict__ Vt, int npad, int S, int Jpad, con
   __shared__ double red[VBP_THREADS / 32][Q];
   __shared__ double redg[VBP_THREADS / 32];
   __shared__ double sinv[Q];
-  const int s = blockIdx.x, tid = threadIdx.x;
+  const int tid = threadIdx.x;
+  const int rc = blockIdx.x;                                // row group written (compact position in the second pass)
+  int s = rc;                                               // restart served
   const size_t plane_stride = (size_t)Jpad * npad;
-  if (s >= S) {                                             // pad rows [S Q, Jpad): zero digits, unit scale
+  if (ls.sel != nullptr) {
+    if (rc >= __ldg(ls.sel_count)) return;                  // (pad rows of the compact block stay stale: never read back)
+    s = __ldg(ls.sel + rc);
+  } else if (s >= S) {                                      // pad rows [S Q, Jpad): zero digits, unit scale
     const int r = S * Q + (s - S);
     if (r >= Jpad) return;
     for (int i = 0; i < ns; ++i)
@@ -523,7 +547,9 @@ vbar_planes_kernel(const double* __restrict__ Vt, int npad, int S, int Jpad, con
   }
   if (tid < Q) mb[tid] = mubar != nullptr ? mubar[(size_t)s * Q + tid] : 0.0;
   __syncthreads();
-  const double* V = Vt + (size_t)s * Q * npad;
+  const int vs = vslot != nullptr ? __ldg(vslot + s) : -1;
+  const double* V = vs >= 0 ? Vt2 + (size_t)vs * Q * npad : Vt + (size_t)s * Q * npad;
+  if (vs >= 0 && vmax != nullptr) vmax = vmax2 + (size_t)vs * Q - (size_t)s * Q;   // indexed by s Q + j below
   double mx[Q], gx = 0.0;
 #pragma unroll
   for (int i = 0; i < Q; ++i) mx[i] = 0.0;
@@ -589,7 +615,8 @@ vbar_planes_kernel(const double* __restrict__ Vt, int npad, int S, int Jpad, con
       }
     }
     const int e = oz_exponent_for(bound);
-    scales[(size_t)s * Q + tid] = ldexp(1.0, e);
+    // an all-zero row (no gradient reaches it) gets scale 0: its product is exactly 0 and carries no truncation error
+    scales[(size_t)rc * Q + tid] = bound > 0.0 ? ldexp(1.0, e) : 0.0;
     sinv[tid] = ldexp(1.0, -e + 8 * ns - 1);
   }
   __syncthreads();
@@ -611,7 +638,7 @@ vbar_planes_kernel(const double* __restrict__ Vt, int npad, int S, int Jpad, con
         o1 -= W[i][j] * v[j].y;
       }
       const long long I[2] = {__double2ll_rn(o0 * sinv[i]), __double2ll_rn(o1 * sinv[i])};
-      oz_emit_digits2(I, ns, planes + ((size_t)s * Q + i) * npad + k, plane_stride);
+      oz_emit_digits2(I, ns, planes + ((size_t)rc * Q + i) * npad + k, plane_stride);
     }
   }
 }

@@ -252,9 +252,11 @@ __device__ __forceinline__ void oz4_epilogue_stash(const double* __restrict__ sA
   const int ntiles = nN * nJ2;
   uint32_t g = 0;
   long long H[NE];                                           // [gq][h][n][e][c]; int64 after pass 0, FP64 bits afterwards
+  const int nrows = p.nrows_dev ? __ldg(p.nrows_dev) * p.nrows_mul : 0x7fffffff;
   Oz4Walk walk(p, cluster_id, nclusters, ntiles);
   for (int t; walk.next(t);) {
     const Oz3Tile x = oz3_tile(t, nN, nJ2, p);
+    if (2 * x.j0 >= nrows) continue;
     const int j0 = 2 * x.j0 + 128 * (int)rank;
 #pragma unroll
     for (int pass = 0; pass < Z::NPASS; ++pass) {
@@ -406,9 +408,11 @@ ozaki_i8_gemm_v4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   if (warp == 0) {
     // ================= TMA producer (both CTAs) =================
     uint32_t ph_empty = 0xffffffffu;
+    const int nrows = p.nrows_dev ? __ldg(p.nrows_dev) * p.nrows_mul : 0x7fffffff;
     Oz4Walk walk(p, cluster_id, nclusters, ntiles);
     for (int t; walk.next(t);) {
       Oz3Tile x = oz3_tile(t, nN, nJ2, p);                     // j0 counts 128-row blocks: rescale to 256
+      if (2 * x.j0 >= nrows) continue;
       const int jrow = 2 * x.j0 + 128 * (int)rank, trow = x.r0 + 64 * (int)rank;
       oz4_produce_pass<NS, LMAX, 0>(&tmA, &tmT, smem0, full0, full0_leader, empty0, ph_empty, x.c_begin, x.kchunks, jrow, trow, leader, p.dbg, p.hintA, p.hintT);
       if constexpr (Z::NPASS > 1)
@@ -426,9 +430,11 @@ ozaki_i8_gemm_v4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 #ifdef MAF_OZ_DIAG
       const long long t_begin = clock64();
 #endif
+      const int nrows = p.nrows_dev ? __ldg(p.nrows_dev) * p.nrows_mul : 0x7fffffff;
       Oz4Walk walk(p, cluster_id, nclusters, ntiles);
       for (int t; walk.next(t);) {
         const Oz3Tile x = oz3_tile(t, nN, nJ2, p);
+        if (2 * x.j0 >= nrows) continue;
         if (g > 0) {
           OZ4_T0();
           oz4_wait_cluster(acce, (g - 1) & 1u);
@@ -474,9 +480,11 @@ ozaki_i8_gemm_v4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     const int fr = lane >> 2, fc = (lane & 3) * 2;
     const uint32_t accf = oz_smem_u32(&acc_full), acce = oz_smem_u32(&acc_empty);
     uint32_t g = 0;
+    const int nrows = p.nrows_dev ? __ldg(p.nrows_dev) * p.nrows_mul : 0x7fffffff;
     Oz4Walk walk(p, cluster_id, nclusters, ntiles);
     for (int t; walk.next(t);) {
       const Oz3Tile x = oz3_tile(t, nN, nJ2, p);
+      if (2 * x.j0 >= nrows) continue;
       const int j0 = 2 * x.j0 + 128 * (int)rank;
       double sa[2][2];
       double2 sc[NG][2];

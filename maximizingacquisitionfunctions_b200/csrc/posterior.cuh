@@ -22,14 +22,20 @@ __global__ void __launch_bounds__(POST_THREADS)
 posterior_kernel(const double* __restrict__ Vt, int npad, const double* __restrict__ gamma,
                  const double* __restrict__ X, ModelParams mp, double mean,
                  double* __restrict__ mu, double* __restrict__ Sig,
-                 const double* __restrict__ mu_part = nullptr, int nparts = 0, int Jpad = 0) {
+                 const double* __restrict__ mu_part = nullptr, int nparts = 0, int Jpad = 0, LevelSwitch ls = LevelSwitch{}) {
   __shared__ double tile[Q][POST_TK];
   __shared__ double gs[POST_TK];
   __shared__ double G[Q][Q];
   __shared__ double mus[Q];
-  const int s = blockIdx.x;
+  __shared__ double sabs[Q * Q];
+  const int r = blockIdx.x;                      // row group of V^T (compact position in the second pass)
+  int s = r;                                     // restart the result belongs to
+  if (ls.sel != nullptr) {
+    if (r >= __ldg(ls.sel_count)) return;
+    s = __ldg(ls.sel + r);
+  }
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const double* V = Vt + (size_t)s * Q * npad;
+  const double* V = Vt + (size_t)r * Q * npad;
   const int i0 = warp, i1 = warp + 8;
   double acc0[Q], acc1[Q], m0 = 0.0, m1 = 0.0;
 #pragma unroll
@@ -89,15 +95,30 @@ posterior_kernel(const double* __restrict__ Vt, int npad, const double* __restri
       }
     }
     double g = (i >= j) ? G[i][j] : G[j][i];
-    Sig[(size_t)s * Q * Q + t] = mp.amp2 * kern_val(mp.kernel_id, r2) - g;
+    const double sv = mp.amp2 * kern_val(mp.kernel_id, r2) - g;
+    Sig[(size_t)s * Q * Q + t] = sv;
+    sabs[t] = fabs(sv);
   }
   if (tid < Q) {
     double m = mus[tid];
     if (mu_part != nullptr) {                         // mean from K10 . alpha (cross_fwd_planes_kernel), column blocks in order
       m = 0.0;
-      for (int b = 0; b < nparts; ++b) m += mu_part[(size_t)b * Jpad + (size_t)s * Q + tid];
+      for (int b = 0; b < nparts; ++b) m += mu_part[(size_t)b * Jpad + (size_t)r * Q + tid];
     }
     mu[(size_t)s * Q + tid] = mean + m;
+  }
+  if (ls.flag_count != nullptr) {                     // level switch: does this restart tolerate the cheaper level?
+    __syncthreads();
+    if (tid == 0) {
+      double mx = 0.0;
+      for (int t = 0; t < Q * Q; ++t) mx = fmax(mx, sabs[t]);
+      int slot = -1;
+      if (!(ls.err <= ls.tol * mx)) {
+        slot = atomicAdd(ls.flag_count, 1);
+        ls.flag_sel[slot] = s;
+      }
+      ls.flag_slot[s] = slot;
+    }
   }
 }
 
@@ -109,14 +130,20 @@ __global__ void __launch_bounds__(POST_REG_THREADS)
 posterior_reg_kernel(const double* __restrict__ Vt, int npad, const double* __restrict__ gamma,
                      const double* __restrict__ X, ModelParams mp, double mean,
                      double* __restrict__ mu, double* __restrict__ Sig,
-                     const double* __restrict__ mu_part = nullptr, int nparts = 0, int Jpad = 0) {
+                     const double* __restrict__ mu_part = nullptr, int nparts = 0, int Jpad = 0, LevelSwitch ls = LevelSwitch{}) {
   constexpr int NG = Q * (Q + 1) / 2;
   __shared__ double red[POST_REG_THREADS / 32][NG + Q];
   __shared__ double G[Q][Q];
   __shared__ double mus[Q];
-  const int s = blockIdx.x;
+  __shared__ double sabs[Q * Q];
+  const int r = blockIdx.x;                      // row group of V^T (compact position in the second pass)
+  int s = r;                                     // restart the result belongs to
+  if (ls.sel != nullptr) {
+    if (r >= __ldg(ls.sel_count)) return;
+    s = __ldg(ls.sel + r);
+  }
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const double* V = Vt + (size_t)s * Q * npad;
+  const double* V = Vt + (size_t)r * Q * npad;
   double acc[NG], m[Q];
 #pragma unroll
   for (int t = 0; t < NG; ++t) acc[t] = 0.0;
@@ -168,15 +195,30 @@ posterior_reg_kernel(const double* __restrict__ Vt, int npad, const double* __re
       }
     }
     double g = (i >= j) ? G[i][j] : G[j][i];
-    Sig[(size_t)s * Q * Q + t] = mp.amp2 * kern_val(mp.kernel_id, r2) - g;
+    const double sv = mp.amp2 * kern_val(mp.kernel_id, r2) - g;
+    Sig[(size_t)s * Q * Q + t] = sv;
+    sabs[t] = fabs(sv);
   }
   if (tid < Q) {
     double m = mus[tid];
     if (mu_part != nullptr) {
       m = 0.0;
-      for (int b = 0; b < nparts; ++b) m += mu_part[(size_t)b * Jpad + (size_t)s * Q + tid];
+      for (int b = 0; b < nparts; ++b) m += mu_part[(size_t)b * Jpad + (size_t)r * Q + tid];
     }
     mu[(size_t)s * Q + tid] = mean + m;
+  }
+  if (ls.flag_count != nullptr) {                     // level switch: does this restart tolerate the cheaper level?
+    __syncthreads();
+    if (tid == 0) {
+      double mx = 0.0;
+      for (int t = 0; t < Q * Q; ++t) mx = fmax(mx, sabs[t]);
+      int slot = -1;
+      if (!(ls.err <= ls.tol * mx)) {
+        slot = atomicAdd(ls.flag_count, 1);
+        ls.flag_sel[slot] = s;
+      }
+      ls.flag_slot[s] = slot;
+    }
   }
 }
 

@@ -74,6 +74,7 @@ class Engine:
         self.n = None
         self._fingerprint = None
         self._fantasy_key = None
+        self.last_eval_shape = None        # (S, q, d) of the last value_and_grad: what best_record_dev reports on
 
     # -- plumbing ---------------------------------------------------------------------------
     def _err(self) -> str:
@@ -196,6 +197,7 @@ class Engine:
         self._ck(self._lib.maf_acq_value_grad(self._ctx, C.byref(prm), S, q, int(p_pending), nat.ptr(X), M,
                                               nat.ptr(z), nat.ptr(weights), nat.ptr(incumbents),
                                               nat.ptr(loss), nat.ptr(grad)))
+        self.last_eval_shape = (S, q, d)
         return loss, grad
 
     def value_and_grad_dev(self, prm: nat.AcqParams, S: int, q: int, p_pending: int, dX: DeviceBuffer, M: int,
@@ -204,6 +206,7 @@ class Engine:
         self._ck(self._lib.maf_acq_value_grad_dev(self._ctx, C.byref(prm), S, q, int(p_pending), dX.ptr, M,
                                                   dz.ptr if dz else None, None, None, dloss.ptr,
                                                   dgrad.ptr if dgrad else None))
+        self.last_eval_shape = (S, q, self.d)
 
     def mc_from_moments(self, prm: nat.AcqParams, mu: np.ndarray, cov: np.ndarray, z: np.ndarray,
                         weights=None, incumbents=None, need_grad: bool = False):
@@ -257,6 +260,10 @@ class Engine:
         idx, val = C.c_int64(-1), C.c_double(0.0)
         self._ck(self._lib.maf_argmin_last(self._ctx, C.byref(idx), C.byref(val)))
         return int(idx.value), float(val.value)
+
+    def best_record_dev(self, index_offset: int, d_rec_ptr: int):
+        """[loss*, index_offset + argmin, X*[q][d]] of the last evaluation into device memory (asynchronous)."""
+        self._ck(self._lib.maf_best_record_dev(self._ctx, int(index_offset), C.c_void_p(int(d_rec_ptr))))
 
     # -- Adam loop -----------------------------------------------------------------------------------
     OPTIMIZERS = {"adam": 0, "gd": 1, "momentum": 2}
@@ -317,6 +324,18 @@ class Engine:
     def set_digits(self, ns_fwd: int, ns_bwd: int):
         """Digit planes of the forward / reverse INT8 contraction (7 / 7: FP64-grade, 28 + 28 products)."""
         self._ck(self._lib.maf_set_digits(self._ctx, int(ns_fwd), int(ns_bwd)))
+
+    def set_level_switch(self, on: bool, tol: Optional[float] = None):
+        """Error-bounded level switch of the contractions (see include/maf.h); effective at the next set_train."""
+        self._ck(self._lib.maf_set_level_switch(self._ctx, 1 if on else 0, float("nan") if tol is None else float(tol)))
+        self._fingerprint = None
+
+    def level_switch_stats(self, reset: bool = False):
+        counts = np.zeros(3, dtype=np.int64)
+        errs = np.zeros(3)
+        self._ck(self._lib.maf_level_switch_stats(self._ctx, counts.ctypes.data_as(C.c_void_p), nat.ptr(errs), 1 if reset else 0))
+        return {"restarts": int(counts[0]), "recomputed_forward": int(counts[1]), "recomputed_reverse": int(counts[2]),
+                "err_cov_abs": float(errs[0]), "err_grad_per_scale": float(errs[1]), "tol": float(errs[2])}
 
     def gemm_nt_i8(self, A: np.ndarray, T: np.ndarray, tri: int = 0, ns: int = 7, lmax: int = 8) -> np.ndarray:
         A, T = nat.as_f64(A), nat.as_f64(T)

@@ -16,6 +16,7 @@ import logging
 import numpy as np
 from scipy.optimize import minimize as _scipy_minimize
 
+from ... import dist as mdist
 from ..utils import atleast_pools, join_pools
 from .search_agent import search_agent
 
@@ -91,20 +92,46 @@ class bayesian_optimization(search_agent):
             inputs_new = self.sample_inputs([num_options, num_suggest, input_dim], options=options,
                                             use_sobol=use_sobol, dtype=dtype)
 
-        nodes, loss_seq = self.optimize_inputs(
-            sess=sess, inputs_new=inputs_new, inputs_old=inputs_old, outputs_old=outputs_old,
-            inputs_pend=inputs_pend, time_limit=time_limit - (self.timer() - start_time),
-            subroutine=subroutine, **kwargs)
+        # Restarts are independent (the loss is a per-restart vector, sharded_fn maps over them, src/misc/sharded_fn.py:
+        # 106-132): under torchrun every rank draws the same starts from the same host-RNG stream, optimises and
+        # re-evaluates its contiguous slice with the same base samples, and one all-gather of the per-rank
+        # (loss, index, set) records picks the global arg-min with np.argmin's tie-break (:152).  The joint L-BFGS-B
+        # subroutine couples the restarts of one rank only (its line search is shared), the others not at all.
+        rank, world_size = mdist.active()
+        lo, hi = mdist.shard_range(len(inputs_new), rank, world_size)
+        if world_size > 1:
+            inputs_new = inputs_new[lo:hi]
 
+        if len(inputs_new):
+            nodes, loss_seq = self.optimize_inputs(
+                sess=sess, inputs_new=inputs_new, inputs_old=inputs_old, outputs_old=outputs_old,
+                inputs_pend=inputs_pend, time_limit=time_limit - (self.timer() - start_time),
+                subroutine=subroutine, **kwargs)
+            inputs_new = np.array(nodes["inputs_new"].value)
         # re-evaluate the optimised sets with fresh base samples of size loss_fn.num_fantasies
-        inputs_new = np.array(nodes["inputs_new"].value)
-        losses_op, feed_dict, nodes = self.appraise_inputs(
-            sess=sess, inputs_new=inputs_new, inputs_old=inputs_old, outputs_old=outputs_old,
-            inputs_pend=inputs_pend, nodes=nodes, **{**kwargs, "inputs_as_var": False})[:3]
-        losses = np.atleast_1d(np.squeeze(losses_op))
+        if world_size > 1:
+            mdist.sync_seed(self.loss_fn)                   # same fresh base samples on every rank
+            mdist.sync_seed(self)
+        losses = np.empty([0])
+        if len(inputs_new):
+            losses_op, feed_dict, nodes = self.appraise_inputs(
+                sess=sess, inputs_new=inputs_new, inputs_old=inputs_old, outputs_old=outputs_old,
+                inputs_pend=inputs_pend, nodes=nodes, **{**kwargs, "inputs_as_var": False})[:3]
+            losses = np.atleast_1d(np.squeeze(losses_op))
 
-        argmin = int(np.argmin(losses))
-        suggestions = inputs_new[argmin]
+        if world_size > 1:
+            eng = self.model.bind(inputs_old, outputs_old) if (np.ndim(inputs_old) == 2 and len(inputs_new)) else None
+            num_pending = 0 if inputs_pend is None else len(inputs_pend)
+            best_loss, self.last_argmin, suggestions = mdist.global_best(
+                eng, losses, inputs_new, lo, pool_shape=(num_pending + num_suggest, input_dim))
+            suggestions = np.array(suggestions)
+            losses, argmin = np.array([best_loss]), 0
+            mdist.sync_seed(self.loss_fn)                   # ranks with an empty slice drew nothing: realign the streams
+            mdist.sync_seed(self)
+        else:
+            argmin = int(np.argmin(losses))
+            self.last_argmin = argmin
+            suggestions = inputs_new[argmin]
         if not allow_duplicates:
             exclude = np.vstack([a for a in (inputs_old, inputs_pend) if a is not None])
             replaced = 0
@@ -270,8 +297,12 @@ class bayesian_optimization(search_agent):
         if use_averaging:
             block = 1
         loss_seq, mean_x, done = [], None, 0
+        world_size = mdist.active()[1]
         while done < step_limit:
-            if self.timer() - start_time >= time_limit:
+            timed_out = self.timer() - start_time >= time_limit
+            if world_size > 1 and np.isfinite(time_limit):
+                timed_out = mdist.any_rank(timed_out)        # ranks stop after the same step: same host-RNG state
+            if timed_out:
                 break
             k = int(min(block, step_limit - done))
             if q == 1:                                      # deterministic closed-form loss, no base samples
@@ -528,13 +559,23 @@ class bayesian_optimization(search_agent):
         options, losses = [], []
         start_time = self.timer()
         total_shards, k = eval_limit // shard_size, 0
+        rank, world_size = mdist.active()
         while k < total_shards:
-            if self.timer() - start_time > time_limit:
+            timed_out = self.timer() - start_time > time_limit
+            if world_size > 1 and np.isfinite(time_limit):
+                timed_out = mdist.any_rank(timed_out)        # every rank leaves the sweep after the same shard
+            if timed_out:
                 break
             g = int(min(shards_per_call, total_shards - k))
             batch = [self.rng.rand(shard_size, input_dim) for _ in range(g)]
             options.extend(batch)
-            l = losses_op.evaluate(None, inputs_new=np.vstack(batch)[:, None, :])[0]
+            cand = np.vstack(batch)[:, None, :]
+            if world_size > 1:                               # independent candidates: each rank scores its slice
+                lo, hi = mdist.shard_range(len(cand), rank, world_size)
+                l = losses_op.evaluate(None, inputs_new=cand[lo:hi])[0] if hi > lo else np.empty([0])
+                l = mdist.all_gather_concat(np.ravel(l), len(cand))
+            else:
+                l = losses_op.evaluate(None, inputs_new=cand)[0]
             losses.append(np.atleast_1d(np.squeeze(l)))
             k += g
         losses = np.hstack(losses)

@@ -89,3 +89,61 @@ def test_global_argmin_world_size_2_gloo(tmp_path):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env={**os.environ, "OMP_NUM_THREADS": "1"})
     assert res.returncode == 0, res.stdout + res.stderr
     assert res.stdout.count("ok") == 2
+
+
+_SHARD_WORKER = r"""
+import json, math, os, sys
+import numpy as np
+sys.path.insert(0, {root!r})
+from maximizingacquisitionfunctions_b200 import dist as mdist, runtime
+from maximizingacquisitionfunctions_b200.src import agents, losses, models
+from tests.fake_engine import FakeEngine
+runtime.set_engine_factory(lambda device, dtype: FakeEngine(device, dtype))
+rank, ws, _ = mdist.world()
+d, n = 2, 24
+rng = np.random.RandomState(0)
+X0 = rng.rand(n, d)
+Y0 = np.sin(3 * X0.sum(-1, keepdims=True)) + 0.03 * rng.randn(n, 1)
+model = models.gaussian_process(kernel_id="matern52", seed=1, log_lenscales=np.log(math.sqrt(d) / 4) * np.ones(d),
+                                log_amplitude=0.0, log_noise=np.log(1e-3), mean=0.0)
+loss_fn = losses.negative_ei(seed=2, num_fantasies=64)
+agent = agents.bayesian_optimization(loss_fn=loss_fn, model=model, seed=3)
+out = []
+pend = None
+for it in range(2):                                   # second call: one pending point, streams must still agree
+    x, l = agent.suggest_inputs(2, X0, Y0, None, inputs_pend=pend, num_to_optimize=7,
+                                subroutine=agent._optimize_inputs_sgd, config={{"step_limit": 6, "batch_size": 16}})
+    out.append([x.tolist(), float(l), int(agent.last_argmin)])
+    pend = x[:1]
+x1, l1 = agent.suggest_inputs(1, X0, Y0, None, num_to_optimize=5, subroutine=agent._optimize_inputs_sgd,
+                              config={{"step_limit": 4}})   # q == 1: closed form
+out.append([x1.tolist(), float(l1), int(agent.last_argmin)])
+if rank == 0:
+    open({out!r} + ".%d" % ws, "w").write(json.dumps(out))
+mdist.barrier()
+"""
+
+
+def test_suggest_inputs_shards_restarts_over_ranks(tmp_path):
+    """agent.suggest_inputs under torchrun (world_size 2, gloo, oracle-backed engine): restarts are partitioned over
+    the ranks inside the product API and the result -- suggestion, loss AND selected restart index -- is the one a
+    single process finds (same host-RNG streams, same base samples, lowest-index tie-break)."""
+    import json
+    script = tmp_path / "shard_worker.py"
+    out = str(tmp_path / "result.json")
+    script.write_text(_SHARD_WORKER.format(root=ROOT, out=out))
+    env = {**os.environ, "OMP_NUM_THREADS": "1"}
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)
+    res = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=600, env=env)
+    assert res.returncode == 0, res.stdout + res.stderr
+    port = 29500 + ((os.getpid() + 7) % 2000)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    assert res.returncode == 0, res.stdout + res.stderr
+    one, two = json.load(open(out + ".1")), json.load(open(out + ".2"))
+    assert len(one) == len(two) == 3
+    for (x1, l1, i1), (x2, l2, i2) in zip(one, two):
+        assert i1 == i2
+        assert np.array_equal(np.asarray(x1), np.asarray(x2)) and l1 == l2
