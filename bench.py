@@ -299,10 +299,12 @@ def main():
     launches = eng.launch_count - launches0
     lsw = eng.level_switch_stats()
     if lsw["restarts"]:
-        # level switch on: one plane less first (ns - 1), the recomputed share again on all planes
+        # level switch on: restarts tested run one plane less first (ns - 1), the recomputed ones again on all planes;
+        # a direction the switch has parked (more than 40 % recomputed) runs on all planes directly
+        N_eval = float(S * args.steps)
         cheap_f, cheap_b = (ns_f - 1) * ns_f // 2, (ns_b - 1) * ns_b // 2
-        pairs_f = cheap_f + pairs_f * lsw["recomputed_forward"] / lsw["restarts"]
-        pairs_b = cheap_b + pairs_b * lsw["recomputed_reverse"] / lsw["restarts"]
+        pairs_f = (lsw["tested_forward"] * cheap_f + (lsw["recomputed_forward"] + N_eval - lsw["tested_forward"]) * pairs_f) / N_eval
+        pairs_b = (lsw["tested_reverse"] * cheap_b + (lsw["recomputed_reverse"] + N_eval - lsw["tested_reverse"]) * pairs_b) / N_eval
         pairs = 0.5 * (pairs_f + pairs_b)
     clocks = sampler.stop()
     prof = eng.profile_read()
@@ -404,7 +406,8 @@ def main():
                        "l2_policy": "working set per chunk (K10 + V^T = %.1f GB) >> 126 MB L2; no flush needed" % (2 * min(S * q, 65536) * npad * 8 / 1e9),
                        "setup_s_not_timed": setup_s},
             "level_switch": None if not lsw["restarts"] else {
-                "restarts": lsw["restarts"], "recomputed_forward": lsw["recomputed_forward"], "recomputed_reverse": lsw["recomputed_reverse"],
+                "restarts": int(S * args.steps), "tested_forward": lsw["tested_forward"], "recomputed_forward": lsw["recomputed_forward"],
+                "tested_reverse": lsw["tested_reverse"], "recomputed_reverse": lsw["recomputed_reverse"],
                 "tol": lsw["tol"], "calibrated_err_cov_abs": lsw["err_cov_abs"], "calibrated_err_grad_per_scale": lsw["err_grad_per_scale"],
                 "products_forward_avg": pairs_f, "products_reverse_avg": pairs_b,
                 "note": "both contractions first keep 6 of 7 digit planes (21 exact products); restarts whose own result does not tolerate the calibrated error of that level within tol are recomputed on all planes (28) inside the same call"},

@@ -231,7 +231,9 @@ int maf_set_digits(maf_ctx* ctx, int ns_fwd, int ns_bwd);
  * posterior covariance and on the gradient against the full level on 512 probe candidates; every restart whose own result
  * (max |Sigma_s|, max |gradient_s|) does not tolerate that error within `tol` (relative; default 2.5e-10, a quarter of
  * the 1e-9 parity bar; NaN keeps the current value) is recomputed with all planes, on the device, inside the same call.
- * maf_level_switch_stats: counts[3] = restarts evaluated / recomputed forward / recomputed reverse since the last
+ * A direction whose cheaper level fails for more than 40 % of the restarts runs on all planes directly for the next 64
+ * evaluations (a host decision between evaluations; results never depend on it).
+ * maf_level_switch_stats: counts[4] = restarts tested / recomputed forward, tested / recomputed reverse since the last
  * reset, errs[3] = calibrated covariance error, calibrated gradient error per unit row scale, tolerance. */
 int maf_set_level_switch(maf_ctx* ctx, int on, double tol);
 int maf_level_switch_stats(maf_ctx* ctx, int64_t* counts, double* errs, int reset);

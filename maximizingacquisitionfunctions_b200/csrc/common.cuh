@@ -83,11 +83,23 @@ __device__ __forceinline__ double kern_dr2(int kid, double r2) {
 //         T[j] = 2^(j/32) from a 32-entry shared-memory table, 2^m folded into the exponent field (11 FP64 instructions,
 //         <= 2 ulp).  Results are a few ulp from the library's; the parity bar is 1e-9.
 #define MAF_ETAB 32
-// The table index is data dependent, so a plain 32-entry table costs shared-memory bank conflicts (ncu round 1: 39 % /
-// 49 % of the shared wavefronts of cross_fwd_planes / cross_bwd): entries j and j + 16 share a bank pair.  The table
-// is therefore replicated per lane, tab[j][lane] (8 KB): lane l always reads bank pair l, two wavefronts per warp-wide
-// 64-bit load, the minimum.  Kernels pass `etab + lane`.
+// The table index is data dependent, so the plain 32-entry table costs shared-memory bank conflicts (ncu round 1: 39 % /
+// 49 % of the shared wavefronts of cross_fwd_planes / cross_bwd: entries j and j + 16 share a bank pair).
+// MAF_ETAB_REPL=1 replicates the table per lane, tab[j][lane] (8 KB, conflict-free).  Measured on one box
+// (profiles/r02_etab_layout_ab.txt): no difference in either direction -- the conflicts are not what limits these kernels
+// (FP64 pipe and load latency are) -- so the plain 256-byte table stays the default.
+#ifndef MAF_ETAB_REPL
+#define MAF_ETAB_REPL 0
+#endif
+#if MAF_ETAB_REPL
 #define MAF_ETAB_WORDS (MAF_ETAB * 32)
+#define MAF_ETAB_IDX(j) ((j) << 5)
+#define MAF_ETAB_LANE(tid) ((tid) & 31)
+#else
+#define MAF_ETAB_WORDS MAF_ETAB
+#define MAF_ETAB_IDX(j) (j)
+#define MAF_ETAB_LANE(tid) 0
+#endif
 // coefficients live in the constant bank so that every DFMA takes them as a c[][] operand (as literals the compiler
 // rebuilds each 64-bit immediate with two moves per use: 18 of the kernel's 126 instructions per element)
 __constant__ double MAF_FC[10] = {
@@ -110,7 +122,7 @@ __constant__ double MAF_ETAB_C[MAF_ETAB] = {
     0x1.ae89f995ad3adp+0, 0x1.b7f76f2fb5e47p+0, 0x1.c199bdd85529cp+0, 0x1.cb720dcef9069p+0,
     0x1.d5818dcfba487p+0, 0x1.dfc97337b9b5fp+0, 0x1.ea4afa2a490dap+0, 0x1.f50765b6e4540p+0};
 __device__ __forceinline__ void maf_fill_etab(double* tab, int tid, int nthreads) {
-  for (int t = tid; t < MAF_ETAB_WORDS; t += nthreads) tab[t] = MAF_ETAB_C[t >> 5];
+  for (int t = tid; t < MAF_ETAB_WORDS; t += nthreads) tab[t] = MAF_ETAB_C[MAF_ETAB_REPL ? (t >> 5) : t];
 }
 // max(x, eps) for x >= 0: eps = 2^-52 has a zero low word, so the comparison is one integer compare on the high word
 __device__ __forceinline__ double maf_clamp_eps(double x) {
@@ -139,7 +151,7 @@ __device__ __forceinline__ double maf_exp_neg_fast(double r, const double* __res
   p = fma(p, f, 0.5);
   p = fma(p, f, 1.0);
   p = fma(p, f, 1.0);
-  const double tj = tab[(k & (MAF_ETAB - 1)) << 5];          // tab = table + lane (replicated per lane)
+  const double tj = tab[MAF_ETAB_IDX(k & (MAF_ETAB - 1))];
   const int m = max(k >> 5, -1021);                          // floor(k / 32) <= 0; below 2^-1021 the result is "tiny", not exact
   const double s = __hiloint2double(__double2hiint(tj) + (m << 20), __double2loint(tj));
   return s * p;

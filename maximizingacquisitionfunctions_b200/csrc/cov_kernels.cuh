@@ -94,39 +94,32 @@ cross_fwd_kernel(const double* __restrict__ X, int J, const double* __restrict__
 #ifndef CROSS_BWD_UNROLL
 #define CROSS_BWD_UNROLL 2
 #endif
-template <int D, int KID>
+template <int D, int KID, bool SEL = false>
 __global__ void __launch_bounds__(512, (D > 0 && D <= 8) ? CROSS_BWD_MINB : 1)      // MINB = 2: <= 64 registers, 32 warps per SM
 cross_bwd_kernel(const double* __restrict__ X, int S, int q, int p,
                                  const double* __restrict__ X0s, int n, int npad, ModelParams mp,
                                  const double* __restrict__ Kbar /*[S*q][npad]*/,
                                  const double* __restrict__ Sigbar /*[S][q][q]*/,
                                  double* __restrict__ grad /*[S][q-p][d]*/,
-                                 const double* __restrict__ alpha = nullptr /*[npad]: K00^-1 (y0 - m)*/,
-                                 const double* __restrict__ mubar = nullptr /*[S][q]*/,
-                                 const double* __restrict__ kscale = nullptr /*row scales of the Vbar digit planes*/,
-                                 LevelSwitch ls = LevelSwitch{}) {
-  // Level switch of the reverse contraction.  First pass (ls.flag_count): the truncation error of the cheaper level on
-  // row j is ls.err x kscale[j] (calibrated per unit row scale); restarts where it exceeds ls.tol x max|gradient| are
-  // listed for the second pass.  Second pass (ls.sel): CTA r serves restart ls.sel[r] from compact Kbar rows r q + i.
-  // alpha != nullptr: Kbar holds only the covariance part -(Sbar + Sbar^T) B^T of d loss / d K10; the mean part
-  // mubar_j alpha_k (mu_j = m + K10[j][:] alpha, exact in FP64) is added here and never passes through a contraction.
+                                 const int* __restrict__ sel = nullptr, const int* __restrict__ sel_count = nullptr) {
+  // SEL (second pass of the reverse level switch): CTA r serves restart sel[r] from compact Kbar rows r q + i.
+  // (With the mean computed as m + K10 . alpha the mean part of d loss / d K10, mubar_j alpha_k, is added to Kbar by the
+  // reverse contraction's epilogue in FP64: this kernel always sees the complete Kbar.)
   constexpr int DD = D > 0 ? D : MAF_MAX_D;
   const int d = D > 0 ? D : mp.d;
   __shared__ double etab_sh[MAF_ETAB_WORDS];
   maf_fill_etab(etab_sh, threadIdx.x, blockDim.x);
-  const double* etab = etab_sh + (threadIdx.x & 31);
-  __shared__ double wmax[MAF_MAX_Q], werr[MAF_MAX_Q];
+  const double* etab = etab_sh + MAF_ETAB_LANE(threadIdx.x);
   __syncthreads();
-  const int rc = blockIdx.x;
-  int s = rc;
-  if (ls.sel != nullptr) {
-    if (rc >= __ldg(ls.sel_count)) return;
-    s = __ldg(ls.sel + rc);
+  int s = blockIdx.x;
+  size_t krow0 = (size_t)s * q;
+  if (SEL) {
+    if ((int)blockIdx.x >= __ldg(sel_count)) return;
+    s = __ldg(sel + blockIdx.x);
   }
   const int i = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const bool row_active = i < q && i >= p;
-  if (!row_active && ls.flag_count == nullptr) return;
+  if (i >= q || i < p) return;
   const size_t j = (size_t)s * q + i;
   double xi[DD], acc[DD];
 #pragma unroll
@@ -134,12 +127,10 @@ cross_bwd_kernel(const double* __restrict__ X, int S, int q, int p,
     xi[c] = (c < d) ? X[j * d + c] * mp.inv_ls[c] : 0.0;
     acc[c] = 0.0;
   }
-  const double* kb = Kbar + ((size_t)rc * q + i) * npad;
-  const double mbj = (alpha != nullptr && row_active) ? mubar[j] : 0.0;
+  const double* kb = Kbar + (krow0 + i) * npad;
   constexpr int UNR = CROSS_BWD_UNROLL;
-  const int nk = row_active ? n : 0;
 #pragma unroll UNR
-  for (int k = lane; k < nk; k += 32) {
+  for (int k = lane; k < n; k += 32) {
     double x0[DD];
     double r2 = 0.0;
 #pragma unroll
@@ -150,15 +141,13 @@ cross_bwd_kernel(const double* __restrict__ X, int S, int q, int p,
         r2 += df * df;
       }
     }
-    double kbv = __ldcs(kb + k);                                // streamed once: keep the training set in L1 instead
-    if (alpha != nullptr) kbv = fma(mbj, alpha[k], kbv);
-    double g = kbv * kern_dr2_fast<KID>(r2, etab);
+    double g = __ldcs(kb + k) * kern_dr2_fast<KID>(r2, etab);   // streamed once: keep the training set in L1 instead
 #pragma unroll
     for (int c = 0; c < DD; ++c)
       if (c < d) acc[c] += g * (xi[c] - x0[c]);
   }
   // self-covariance term (K11 = a^2 kappa(r2(X_s, X_s)); diagonal has zero gradient)
-  if (row_active && lane < q && lane != i) {
+  if (lane < q && lane != i) {
     const double* xo = X + ((size_t)s * q + lane) * d;
     double xj[DD];
     double r2 = 0.0;
@@ -176,32 +165,29 @@ cross_bwd_kernel(const double* __restrict__ X, int S, int q, int p,
     for (int c = 0; c < DD; ++c)
       if (c < d) acc[c] += g * (xi[c] - xj[c]);
   }
-  double gmx = 0.0;
 #pragma unroll
   for (int c = 0; c < DD; ++c) {
     if (c < d) {
       double v = warp_sum(acc[c]);
-      const double gv = 2.0 * mp.amp2 * mp.inv_ls[c] * v;
-      gmx = fmax(gmx, fabs(gv));
-      if (lane == 0 && row_active) grad[((size_t)s * (q - p) + (i - p)) * d + c] = gv;
+      if (lane == 0)
+        grad[((size_t)s * (q - p) + (i - p)) * d + c] = 2.0 * mp.amp2 * mp.inv_ls[c] * v;
     }
   }
-  if (ls.flag_count != nullptr) {
-    if (lane == 0 && i < q) {
-      wmax[i] = row_active ? gmx : 0.0;
-      werr[i] = row_active ? ls.err * kscale[(size_t)rc * q + i] : 0.0;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double mx = 0.0, er = 0.0;
-      for (int u = 0; u < q; ++u) {
-        mx = fmax(mx, wmax[u]);
-        er = fmax(er, werr[u]);
-      }
-      if (!(er <= ls.tol * mx)) {
-        const int slot = atomicAdd(ls.flag_count, 1);
-        ls.flag_sel[slot] = s;
-      }
-    }
+}
+
+// First pass of the reverse level switch, after cross_bwd_kernel: the truncation error of the cheaper level on row j is
+// err x kscale[j] (calibrated per unit row scale of the Vbar planes); restarts where it exceeds tol x max |gradient| are
+// listed for the second pass.  One thread per restart.
+__global__ void lsw_flag_bwd_kernel(const double* __restrict__ grad, const double* __restrict__ kscale, int S, int q, int p,
+                                    int d, LevelSwitch ls) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  double mx = 0.0, er = 0.0;
+  const double* g = grad + (size_t)s * (q - p) * d;
+  for (int t = 0; t < (q - p) * d; ++t) mx = fmax(mx, fabs(g[t]));
+  for (int i = p; i < q; ++i) er = fmax(er, ls.err * kscale[(size_t)s * q + i]);
+  if (!(er <= ls.tol * mx)) {
+    const int slot = atomicAdd(ls.flag_count, 1);
+    ls.flag_sel[slot] = s;
   }
 }

@@ -61,6 +61,7 @@ struct maf_ctx {
   int mu_alpha = 1;
   int vbar_tight = 0;              // MAF_VBAR_TIGHT=1: exact row maxima for the Vbar digit planes (one more sweep)
   Buf mu_part;                     // [column blocks of 1024][Jpad] partial sums of K10 . alpha
+  Buf row_add;                     // [Jpad] mubar per row of the Vbar planes (rank-one term of the reverse epilogue)
   // Level switch (common.cuh, struct LevelSwitch): both contractions first run with one digit plane less (21 products
   // instead of 28); restarts whose result does not tolerate the calibrated error of that level are recomputed with all
   // planes on compact rows.  MAF_LEVEL_SWITCH=0 / maf_set_level_switch turn it off (every restart on all planes).
@@ -72,9 +73,15 @@ struct maf_ctx {
   double lsw_err_fwd = 0.0;        // max |Sigma(cheaper level) - Sigma(all planes)| over the probe candidates
   double lsw_err_bwd = 0.0;        // max |grad(cheaper) - grad(all)| / row scale of Vbar over the probe candidates
   Buf Vt2, rowmax2;                // forward second pass: V^T rows / row maxima of the recomputed restarts (compact)
-  int *lsw_cnt = nullptr;          // device: [0] forward count, [1] reverse count, [2..3] unused
-  long long* lsw_stats = nullptr;  // device: restarts recomputed forward / reverse since the last reset
-  long long lsw_evaluated = 0;     // host: restarts that went through the switch since the last reset
+  int *lsw_cnt = nullptr;          // device: [0] forward count, [1] reverse count of the current chunk
+  long long* lsw_stats = nullptr;  // device: {tested forward, recomputed forward, tested reverse, recomputed reverse}
+  long long* lsw_host = nullptr;   // pinned mirror of lsw_stats, refreshed (asynchronously) at the end of every evaluation
+  // A direction whose cheaper level fails for more than 40 % of the restarts costs more than it saves (21 + 28 share
+  // products against 28): it then runs on all planes directly for the next 64 evaluations before the cheaper level is
+  // tried again.  Decided on the host from the mirror, between evaluations; the results never depend on it.
+  bool lsw_cheap_fwd = true, lsw_cheap_bwd = true;
+  long long lsw_base[4] = {0, 0, 0, 0};
+  int lsw_cool_fwd = 0, lsw_cool_bwd = 0;
   int *lsw_selF = nullptr, *lsw_slotF = nullptr, *lsw_selB = nullptr;
   size_t lsw_cap = 0;              // restarts the three lists were sized for
   size_t cap_train = 0;        // npad the factor buffers were sized for
@@ -458,7 +465,8 @@ static int oz_schedule(maf_ctx* ctx, int nN, int nJ2, int K, int tri, int sj, in
 
 static int launch_i8gemm(maf_ctx* ctx, int slot, int J, int N, int K, const Buf& Ap, const Buf& sA, const Buf& Tp,
                          const Buf& sT, double* C, int ldc, int tri, int ns, int lmax, double* rowmax = nullptr,
-                         bool* rowmax_done = nullptr, const int* nrows_dev = nullptr, int nrows_mul = 1) {
+                         bool* rowmax_done = nullptr, const int* nrows_dev = nullptr, int nrows_mul = 1,
+                         const double* row_add = nullptr, const double* col_add = nullptr) {
   if (rowmax_done) *rowmax_done = false;
   if (J % 128 || N % 128 || K % 128) return fail(ctx, "i8 gemm dims must be multiples of 128");
   if (tri != 0 && K != N) return fail(ctx, "triangular gemm needs K == N");
@@ -499,7 +507,12 @@ static int launch_i8gemm(maf_ctx* ctx, int slot, int J, int N, int K, const Buf&
     return 1;
   static const unsigned long long pol[3] = {OZ3_L2_NORMAL, OZ3_L2_EVICT_FIRST, OZ3_L2_EVICT_LAST};
   OzParams prm{K, ns, lmax, tri, ldc, ctx->oz_sj, pol[ctx->oz_hint_a % 3], pol[ctx->oz_hint_t % 3], ctx->oz_pf, nullptr, ctx->oz_dbg,
-               nullptr, nullptr, nullptr, nullptr, 1};
+               nullptr, nullptr, nullptr, nullptr, 1, nullptr, nullptr};
+  if (row_add) {
+    if (!(stash && variant == 4)) return fail(ctx, "the rank-one epilogue term needs the register-stash CTA-pair kernel");
+    prm.row_add = row_add;
+    prm.col_add = col_add;
+  }
   if (nrows_dev) {
     if (variant != 4) return fail(ctx, "a device-side row count needs the CTA-pair contraction kernel");
     prm.nrows_dev = nrows_dev;
@@ -758,7 +771,7 @@ extern "C" int maf_destroy(maf_ctx* ctx) {
                  &ctx->dmubar, &ctx->dSigbar, &ctx->dloss, &ctx->dgrad, &ctx->adam_X, &ctx->adam_m, &ctx->adam_v,
                  &ctx->adam_g, &ctx->adam_z, &ctx->fGamma, &ctx->fGammaT, &ctx->fmeans, &ctx->flevels, &ctx->fVG,
                  &ctx->fmubar, &ctx->ozA, &ctx->ozTL, &ctx->ozTU, &ctx->ozsA, &ctx->ozsTL, &ctx->ozsTU, &ctx->adam_zcur,
-                 &ctx->adam_coef, &ctx->adam_trace, &ctx->ozVmax, &ctx->mu_part, &ctx->Vt2, &ctx->rowmax2};
+                 &ctx->adam_coef, &ctx->adam_trace, &ctx->ozVmax, &ctx->mu_part, &ctx->Vt2, &ctx->rowmax2, &ctx->row_add};
   for (Buf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (ctx->d_argmin_idx) cudaFree(ctx->d_argmin_idx);
@@ -766,6 +779,7 @@ extern "C" int maf_destroy(maf_ctx* ctx) {
   if (ctx->adam_ctr) cudaFree(ctx->adam_ctr);
   for (void* b : {(void*)ctx->lsw_cnt, (void*)ctx->lsw_stats, (void*)ctx->lsw_selF, (void*)ctx->lsw_slotF, (void*)ctx->lsw_selB})
     if (b) cudaFree(b);
+  if (ctx->lsw_host) cudaFreeHost(ctx->lsw_host);
   for (auto& sc : ctx->oz_scheds) {
     cudaFree(sc.d_list);
     cudaFree(sc.d_begin);
@@ -1026,8 +1040,10 @@ static void launch_posterior(maf_ctx* ctx, int sc, const double* Vt, int npad, c
 static int lsw_ensure(maf_ctx* ctx, int sc, int Jpad, int npad) {
   if (!ctx->lsw_cnt) {
     CK(cudaMalloc((void**)&ctx->lsw_cnt, 4 * sizeof(int)));
-    CK(cudaMalloc((void**)&ctx->lsw_stats, 2 * sizeof(long long)));
-    CK(cudaMemsetAsync(ctx->lsw_stats, 0, 2 * sizeof(long long), ctx->stream));
+    CK(cudaMalloc((void**)&ctx->lsw_stats, 4 * sizeof(long long)));
+    CK(cudaMemsetAsync(ctx->lsw_stats, 0, 4 * sizeof(long long), ctx->stream));
+    CK(cudaHostAlloc((void**)&ctx->lsw_host, 4 * sizeof(long long), cudaHostAllocDefault));
+    memset(ctx->lsw_host, 0, 4 * sizeof(long long));
   }
   if ((size_t)sc > ctx->lsw_cap) {
     for (int** b : {&ctx->lsw_selF, &ctx->lsw_slotF, &ctx->lsw_selB}) {
@@ -1043,9 +1059,11 @@ static int lsw_ensure(maf_ctx* ctx, int sc, int Jpad, int npad) {
   return ensure(ctx, ctx->Vt2, (size_t)Jpad * npad) || ensure(ctx, ctx->rowmax2, (size_t)Jpad);
 }
 
-__global__ void lsw_accumulate_kernel(const int* __restrict__ cnt, long long* __restrict__ stats) {
-  stats[0] += cnt[0];
-  stats[1] += cnt[1];
+__global__ void lsw_accumulate_kernel(const int* __restrict__ cnt, long long* __restrict__ stats, int tested_fwd, int tested_bwd) {
+  stats[0] += tested_fwd;
+  stats[1] += cnt[0];
+  stats[2] += tested_bwd;
+  stats[3] += cnt[1];
 }
 
 // forward (+ optional backward) over one chunk of restarts
@@ -1057,23 +1075,27 @@ static int run_chunk(maf_ctx* ctx, const AcqDev& ap, bool posterior_only, bool c
   double* K10 = ctx->K10.p;
   double* Vt = ctx->Vt.p;
   const bool fused = ctx->i8_ready && (ctx->oz_fuse & 1), fused_bwd = ctx->i8_ready && (ctx->oz_fuse & 2);
-  const bool mu_alpha = fused && fused_bwd && ctx->mu_alpha;    // mean and its gradient outside the contractions
+  // mean and its gradient outside the contractions (the rank-one gradient term rides the register-stash epilogue)
+  const bool mu_alpha = fused && fused_bwd && ctx->mu_alpha && ctx->oz_variant == 5 && ctx->oz_ns >= 3;
   const int need_grad = (!posterior_only && dgrad != nullptr) ? 1 : 0;
   // level switch: cheaper level first, failing restarts again with all planes (see LevelSwitch in common.cuh)
   const bool lsw = mu_alpha && ctx->lsw_on && ctx->lsw_ready && !ctx->lsw_busy && ctx->dtype == MAF_F64 && ctx->oz_variant == 5 &&
-                   npad >= ctx->lsw_min_npad && ctx->oz_ns_fwd == ctx->oz_ns && ctx->oz_ns_bwd == ctx->oz_ns && ctx->oz_ns >= 4;
-  if (lsw && lsw_ensure(ctx, sc, Jpad, npad)) return 1;
-  const int ns_fwd = lsw ? ctx->oz_ns - 1 : std::min(ctx->oz_ns_fwd, ctx->oz_ns);
-  const int ns_bwd = lsw ? ctx->oz_ns - 1 : ctx->oz_ns_bwd;
+                   npad >= ctx->lsw_min_npad && ctx->oz_ns_fwd == ctx->oz_ns && ctx->oz_ns_bwd == ctx->oz_ns && ctx->oz_ns == 7;
+  const bool lswF = lsw && ctx->lsw_cheap_fwd, lswB = lsw && ctx->lsw_cheap_bwd && need_grad;
+  if ((lswF || lswB) && lsw_ensure(ctx, sc, Jpad, npad)) return 1;
+  const int ns_fwd = lswF ? ctx->oz_ns - 1 : std::min(ctx->oz_ns_fwd, ctx->oz_ns);
+  const int ns_bwd = lswB ? ctx->oz_ns - 1 : ctx->oz_ns_bwd;
   const int nparts = (npad + OZC_THREADS * 4 - 1) / (OZC_THREADS * 4);
-  if (mu_alpha && ensure(ctx, ctx->mu_part, (size_t)nparts * Jpad)) return 1;
+  if (mu_alpha && (ensure(ctx, ctx->mu_part, (size_t)nparts * Jpad) || ensure(ctx, ctx->row_add, (size_t)Jpad))) return 1;
+  const double* const radd = mu_alpha ? ctx->row_add.p : nullptr;
+  const double* const cadd = mu_alpha ? ctx->alpha : nullptr;
   const double* mu_part = mu_alpha ? ctx->mu_part.p : nullptr;
   // the Vbar producer needs the row maxima of V^T: the forward contraction's epilogue leaves them behind
   const bool want_rowmax = fused_bwd && ctx->oz_rowmax && need_grad;
   bool have_rowmax = false;
   if (want_rowmax && ensure(ctx, ctx->ozVmax, (size_t)Jpad)) return 1;
   double* const rowmax = want_rowmax ? ctx->ozVmax.p : nullptr;
-  if (lsw) CK(cudaMemsetAsync(ctx->lsw_cnt, 0, 4 * sizeof(int), ctx->stream));
+  if (lswF || lswB) CK(cudaMemsetAsync(ctx->lsw_cnt, 0, 4 * sizeof(int), ctx->stream));
   if (fused) {
     // K10 goes straight to digit planes (bounded by a^2: fixed row scale), FP64 K10 is never materialised
     const size_t bytes = (size_t)ctx->oz_ns * Jpad * npad;
@@ -1081,8 +1103,13 @@ static int run_chunk(maf_ctx* ctx, const AcqDev& ap, bool posterior_only, bool c
     {
       ProfScope ps(ctx, MAF_PROF_CROSS_FWD);
       dim3 grid(nparts, Jpad / OZC_TJ);
-      DISPATCH_DKN(d, ctx->mp.kernel_id, ns_fwd, cross_fwd_planes_kernel<D, KID, NSC><<<grid, OZC_THREADS, 0, ctx->stream>>>(dX, J, Jpad, ctx->X0s, n, npad, ctx->mp, ns_fwd,
-                                                                                  (int8_t*)ctx->ozA.p, ctx->ozsA.p, mu_alpha ? ctx->alpha : nullptr, ctx->mu_part.p));
+      if (mu_alpha) {
+        DISPATCH_DKN(d, ctx->mp.kernel_id, ns_fwd, cross_fwd_planes_kernel<D, KID, NSC, 1><<<grid, OZC_THREADS, 0, ctx->stream>>>(dX, J, Jpad, ctx->X0s, n, npad, ctx->mp, ns_fwd,
+                                                                                       (int8_t*)ctx->ozA.p, ctx->ozsA.p, ctx->alpha, ctx->mu_part.p));
+      } else {
+        DISPATCH_DKN(d, ctx->mp.kernel_id, ns_fwd, cross_fwd_planes_kernel<D, KID, NSC, 0><<<grid, OZC_THREADS, 0, ctx->stream>>>(dX, J, Jpad, ctx->X0s, n, npad, ctx->mp, ns_fwd,
+                                                                                       (int8_t*)ctx->ozA.p, ctx->ozsA.p));
+      }
       CKL();
     }
     if (launch_i8gemm(ctx, MAF_PROF_GEMM_FWD, Jpad, npad, npad, ctx->ozA, ctx->ozsA, ctx->ozTL, ctx->ozsTL, Vt, npad, 1,
@@ -1108,19 +1135,19 @@ static int run_chunk(maf_ctx* ctx, const AcqDev& ap, bool posterior_only, bool c
   {
     ProfScope ps(ctx, MAF_PROF_POSTERIOR);
     LevelSwitch ls{};
-    if (lsw) ls = LevelSwitch{nullptr, nullptr, ctx->lsw_cnt, ctx->lsw_selF, ctx->lsw_slotF, ctx->lsw_err_fwd, ctx->lsw_tol};
+    if (lswF) ls = LevelSwitch{nullptr, nullptr, ctx->lsw_cnt, ctx->lsw_selF, ctx->lsw_slotF, ctx->lsw_err_fwd, ctx->lsw_tol};
     DISPATCH_Q(q, launch_posterior<Q>(ctx, sc, Vt, npad, dX, mu, Sig, mu_part, nparts, Jpad, ls));
     CKL();
   }
   bool have_rowmax2 = false;
-  if (lsw) {
+  if (lswF) {
     // second pass of the forward switch: the listed restarts again with all planes, on compact rows
     const int nsf = ctx->oz_ns;
     {
       ProfScope ps(ctx, MAF_PROF_CROSS_FWD);
       dim3 grid(nparts, Jpad / OZC_TJ);
-      DISPATCH_DKN(d, ctx->mp.kernel_id, nsf, cross_fwd_planes_kernel<D, KID, NSC><<<grid, OZC_THREADS, 0, ctx->stream>>>(dX, J, Jpad, ctx->X0s, n, npad, ctx->mp, nsf,
-                                                                                  (int8_t*)ctx->ozA.p, ctx->ozsA.p, ctx->alpha, ctx->mu_part.p, ctx->lsw_selF, ctx->lsw_cnt, q));
+      DISPATCH_DK(d, ctx->mp.kernel_id, cross_fwd_planes_kernel<D, KID, 7, 2><<<grid, OZC_THREADS, 0, ctx->stream>>>(dX, J, Jpad, ctx->X0s, n, npad, ctx->mp, nsf,
+                                                                             (int8_t*)ctx->ozA.p, ctx->ozsA.p, ctx->alpha, ctx->mu_part.p, ctx->lsw_selF, ctx->lsw_cnt, q));
       CKL();
     }
     if (launch_i8gemm(ctx, MAF_PROF_GEMM_FWD, Jpad, npad, npad, ctx->ozA, ctx->ozsA, ctx->ozTL, ctx->ozsTL, ctx->Vt2.p, npad, 1,
@@ -1132,10 +1159,9 @@ static int run_chunk(maf_ctx* ctx, const AcqDev& ap, bool posterior_only, bool c
     CKL();
   }
   if (posterior_only) {
-    if (lsw) {
+    if (lswF) {
       ProfScope ps(ctx, MAF_PROF_ADAM);
-      lsw_accumulate_kernel<<<1, 1, 0, ctx->stream>>>(ctx->lsw_cnt, ctx->lsw_stats);
-      ctx->lsw_evaluated += sc;
+      lsw_accumulate_kernel<<<1, 1, 0, ctx->stream>>>(ctx->lsw_cnt, ctx->lsw_stats, sc, 0);
     }
     return 0;
   }
@@ -1157,10 +1183,9 @@ static int run_chunk(maf_ctx* ctx, const AcqDev& ap, bool posterior_only, bool c
     CKL();
   }
   if (!need_grad) {
-    if (lsw) {
+    if (lswF) {
       ProfScope ps(ctx, MAF_PROF_ADAM);
-      lsw_accumulate_kernel<<<1, 1, 0, ctx->stream>>>(ctx->lsw_cnt, ctx->lsw_stats);
-      ctx->lsw_evaluated += sc;
+      lsw_accumulate_kernel<<<1, 1, 0, ctx->stream>>>(ctx->lsw_cnt, ctx->lsw_stats, sc, 0);
     }
     return 0;
   }
@@ -1169,17 +1194,18 @@ static int run_chunk(maf_ctx* ctx, const AcqDev& ap, bool posterior_only, bool c
     // expansion rounded to that many digits, so the same buffer serves the shorter reverse contraction
     const size_t bytes = (size_t)ctx->oz_ns * Jpad * npad;
     if (ensure(ctx, ctx->ozA, (bytes + 7) / 8) || ensure(ctx, ctx->ozsA, (size_t)Jpad)) return 1;
-    const int* vslot = lsw ? ctx->lsw_slotF : nullptr;       // restarts whose V^T rows live in Vt2 (compact)
-    const double* vmax2 = (lsw && have_rowmax2) ? ctx->rowmax2.p : nullptr;
-    const double* vmax1 = (have_rowmax && (!lsw || have_rowmax2)) ? rowmax : nullptr;
+    const int* vslot = lswF ? ctx->lsw_slotF : nullptr;      // restarts whose V^T rows live in Vt2 (compact)
+    const double* vmax2 = (lswF && have_rowmax2) ? ctx->rowmax2.p : nullptr;
+    const double* vmax1 = (have_rowmax && (!lswF || have_rowmax2)) ? rowmax : nullptr;
     {
       ProfScope ps(ctx, MAF_PROF_VBAR);
       DISPATCH_Q(q, vbar_planes_kernel<Q><<<sc + (Jpad - J), VBP_THREADS, 0, ctx->stream>>>(Vt, npad, sc, Jpad, ctx->gamma, mu_alpha ? nullptr : mubar, Sigbar, ns_bwd,
-                                                                                   (int8_t*)ctx->ozA.p, ctx->ozsA.p, vmax1, ctx->vbar_tight, vslot, ctx->Vt2.p, vmax2));
+                                                                                   (int8_t*)ctx->ozA.p, ctx->ozsA.p, vmax1, ctx->vbar_tight, vslot, ctx->Vt2.p, vmax2,
+                                                                                   LevelSwitch{}, mubar, mu_alpha ? ctx->row_add.p : nullptr));
       CKL();
     }
     if (launch_i8gemm(ctx, MAF_PROF_GEMM_BWD, Jpad, npad, npad, ctx->ozA, ctx->ozsA, ctx->ozTU, ctx->ozsTU, K10, npad, 2,
-                      ns_bwd, ns_bwd + 1))
+                      ns_bwd, ns_bwd + 1, nullptr, nullptr, nullptr, 1, radd, cadd))
       return 1;
   } else {
     {
@@ -1198,37 +1224,42 @@ static int run_chunk(maf_ctx* ctx, const AcqDev& ap, bool posterior_only, bool c
   }
   {
     ProfScope ps(ctx, MAF_PROF_CROSS_BWD);
-    LevelSwitch ls{};
-    if (lsw) ls = LevelSwitch{nullptr, nullptr, ctx->lsw_cnt + 1, ctx->lsw_selB, nullptr, ctx->lsw_err_bwd, ctx->lsw_tol};
-    DISPATCH_DK(d, ctx->mp.kernel_id, cross_bwd_kernel<D, KID><<<sc, 32 * q, 0, ctx->stream>>>(dX, sc, q, p, ctx->X0s, n, npad, ctx->mp, K10, Sigbar, dgrad,
-                                                                                         mu_alpha ? ctx->alpha : nullptr, mubar, ctx->ozsA.p, ls));
+    DISPATCH_DK(d, ctx->mp.kernel_id, cross_bwd_kernel<D, KID, false><<<sc, 32 * q, 0, ctx->stream>>>(dX, sc, q, p, ctx->X0s, n, npad, ctx->mp, K10, Sigbar, dgrad));
     CKL();
   }
-  if (lsw) {
+  if (lswB) {
+    ProfScope ps(ctx, MAF_PROF_CROSS_BWD);
+    const LevelSwitch ls{nullptr, nullptr, ctx->lsw_cnt + 1, ctx->lsw_selB, nullptr, ctx->lsw_err_bwd, ctx->lsw_tol};
+    lsw_flag_bwd_kernel<<<(sc + 127) / 128, 128, 0, ctx->stream>>>(dgrad, ctx->ozsA.p, sc, q, p, d, ls);
+    CKL();
+  }
+  if (lswB) {
     // second pass of the reverse switch: Vbar planes of the listed restarts with all planes on compact rows, contraction
     // into the (now free) V^T buffer, gradient of those restarts again
     const int nsb = ctx->oz_ns;
     const LevelSwitch ls{ctx->lsw_selB, ctx->lsw_cnt + 1, nullptr, nullptr, nullptr, 0.0, 0.0};
-    const double* vmax2 = have_rowmax2 ? ctx->rowmax2.p : nullptr;
-    const double* vmax1 = (have_rowmax && have_rowmax2) ? rowmax : nullptr;
+    const double* vmax2 = (lswF && have_rowmax2) ? ctx->rowmax2.p : nullptr;
+    const double* vmax1 = (have_rowmax && (!lswF || have_rowmax2)) ? rowmax : nullptr;
     {
       ProfScope ps(ctx, MAF_PROF_VBAR);
       DISPATCH_Q(q, vbar_planes_kernel<Q><<<sc, VBP_THREADS, 0, ctx->stream>>>(Vt, npad, sc, Jpad, ctx->gamma, nullptr, Sigbar, nsb, (int8_t*)ctx->ozA.p,
-                                                                       ctx->ozsA.p, vmax1, ctx->vbar_tight, ctx->lsw_slotF, ctx->Vt2.p, vmax2, ls));
+                                                                       ctx->ozsA.p, vmax1, ctx->vbar_tight, lswF ? ctx->lsw_slotF : nullptr, ctx->Vt2.p, vmax2, ls,
+                                                                       mubar, ctx->row_add.p));
       CKL();
     }
     if (launch_i8gemm(ctx, MAF_PROF_GEMM_BWD, Jpad, npad, npad, ctx->ozA, ctx->ozsA, ctx->ozTU, ctx->ozsTU, Vt, npad, 2, nsb, nsb + 1,
-                      nullptr, nullptr, ctx->lsw_cnt + 1, q))
+                      nullptr, nullptr, ctx->lsw_cnt + 1, q, radd, cadd))
       return 1;
     {
       ProfScope ps(ctx, MAF_PROF_CROSS_BWD);
-      DISPATCH_DK(d, ctx->mp.kernel_id, cross_bwd_kernel<D, KID><<<sc, 32 * q, 0, ctx->stream>>>(dX, sc, q, p, ctx->X0s, n, npad, ctx->mp, Vt, Sigbar, dgrad,
-                                                                                           ctx->alpha, mubar, nullptr, ls));
+      DISPATCH_DK(d, ctx->mp.kernel_id, cross_bwd_kernel<D, KID, true><<<sc, 32 * q, 0, ctx->stream>>>(dX, sc, q, p, ctx->X0s, n, npad, ctx->mp, Vt, Sigbar, dgrad,
+                                                                                                 ctx->lsw_selB, ctx->lsw_cnt + 1));
       CKL();
     }
+  }
+  if (lswF || lswB) {
     ProfScope ps(ctx, MAF_PROF_ADAM);
-    lsw_accumulate_kernel<<<1, 1, 0, ctx->stream>>>(ctx->lsw_cnt, ctx->lsw_stats);
-    ctx->lsw_evaluated += sc;
+    lsw_accumulate_kernel<<<1, 1, 0, ctx->stream>>>(ctx->lsw_cnt, ctx->lsw_stats, lswF ? sc : 0, lswB ? sc : 0);
   }
   return 0;
 }
@@ -1239,6 +1270,32 @@ static int check_shape(maf_ctx* ctx, int S, int q, int p) {
   if (q < 1 || q > MAF_MAX_Q) return fail(ctx, "q=%d outside 1..%d", q, MAF_MAX_Q);
   if (p < 0 || p >= q) return fail(ctx, "p_pending=%d must satisfy 0 <= p < q=%d", p, q);
   return 0;
+}
+
+// Between evaluations: is the cheaper level of each direction still paying (see maf_ctx::lsw_cheap_fwd)?
+static void lsw_adapt(maf_ctx* ctx) {
+  if (!ctx->lsw_host || !ctx->lsw_ready || ctx->lsw_busy) return;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(ctx->stream, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) return;
+  const long long h[4] = {ctx->lsw_host[0], ctx->lsw_host[1], ctx->lsw_host[2], ctx->lsw_host[3]};
+  auto one = [&](bool& cheap, int& cool, int it, int ir) {
+    if (cheap) {
+      const long long tested = h[it] - ctx->lsw_base[it], redone = h[ir] - ctx->lsw_base[ir];
+      if (tested >= 256 && redone * 5 > tested * 2) {            // more than 40 % recomputed
+        cheap = false;
+        cool = 64;
+        ctx->generation++;
+      }
+      if (tested >= 256) ctx->lsw_base[it] = h[it], ctx->lsw_base[ir] = h[ir];
+    } else if (--cool <= 0) {
+      cheap = true;
+      ctx->lsw_base[it] = h[it];
+      ctx->lsw_base[ir] = h[ir];
+      ctx->generation++;
+    }
+  };
+  one(ctx->lsw_cheap_fwd, ctx->lsw_cool_fwd, 0, 1);
+  one(ctx->lsw_cheap_bwd, ctx->lsw_cool_bwd, 2, 3);
 }
 
 // All restarts, in chunks of at most chunk_rows candidate rows.  Device pointers; asynchronous.
@@ -1260,6 +1317,7 @@ static int run_all(maf_ctx* ctx, const maf_acq_params* prm, bool posterior_only,
   if (ensure(ctx, ctx->dmu, sq) || ensure(ctx, ctx->dmubar, sq) || ensure(ctx, ctx->dSig, sqq) ||
       ensure(ctx, ctx->dSigbar, sqq) || ensure(ctx, ctx->dchol, sqq))
     return 1;
+  lsw_adapt(ctx);
   int sc_max = (int)std::max<size_t>(1, ctx->chunk_rows / q);
   sc_max = std::min(sc_max, S);
   const size_t need = (size_t)round_up(sc_max * q, 256) * npad;
@@ -1273,6 +1331,8 @@ static int run_all(maf_ctx* ctx, const maf_acq_params* prm, bool posterior_only,
                   dgrad ? dgrad + (size_t)s0 * (q - p) * d : nullptr))
       return 1;
   }
+  if (ctx->lsw_stats && ctx->lsw_ready && !ctx->lsw_busy)
+    CK(cudaMemcpyAsync(ctx->lsw_host, ctx->lsw_stats, 4 * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
   ctx->last_S = S;
   ctx->last_q = q;
   ctx->last_has_chol = !posterior_only && !closed_form;
@@ -1317,6 +1377,8 @@ static int lsw_calibrate(maf_ctx* ctx, int n, const double* X0) {
   std::vector<double> v6(S), v7(S), g6((size_t)S * d), g7((size_t)S * d), sc6(S);
   maf_acq_params prm{MAF_ACQ_CB, 1, NAN, NAN, 2.0};
   ctx->lsw_busy = true;
+  const size_t chunk_rows_saved = ctx->chunk_rows;
+  ctx->chunk_rows = std::max<size_t>(ctx->chunk_rows, (size_t)S);    // one chunk: the row scales of all probes are read back
   int rc = 0;
   for (int pass = 0; pass < 2 && rc == 0; ++pass) {
     const int nsp = pass == 0 ? ns - 1 : ns;
@@ -1337,8 +1399,10 @@ static int lsw_calibrate(maf_ctx* ctx, int n, const double* X0) {
   }
   ctx->oz_ns_fwd = ctx->oz_ns_bwd = ns;
   ctx->oz_lmax_bwd = ns + 1;
+  ctx->chunk_rows = chunk_rows_saved;
   ctx->lsw_busy = false;
   ctx->last_S = 0;
+  ctx->lsw_cheap_fwd = ctx->lsw_cheap_bwd = true;
   if (rc) return rc;
   double ef = 0.0, eb = 0.0;
   for (int s = 0; s < S; ++s) {
@@ -1348,6 +1412,23 @@ static int lsw_calibrate(maf_ctx* ctx, int n, const double* X0) {
   }
   ctx->lsw_err_fwd = ef;
   ctx->lsw_err_bwd = eb;
+  // share of the uniform probes the per-restart test would send to the second pass: a direction that starts above 90 %
+  // (e.g. the squared-exponential kernel at n = 4096, cond(K00) ~ 1e9) begins on all planes.  The probes are single
+  // points; pools of q points tolerate more (max |Sigma_s| over q^2 entries), hence the generous threshold here -- the
+  // running statistics take over after the first evaluation.
+  int ff = 0, fb = 0;
+  for (int s = S / 2; s < S; ++s) {
+    double gm = 0.0;
+    for (int c = 0; c < d; ++c) gm = std::max(gm, std::fabs(g7[(size_t)s * d + c]));
+    ff += !(ef <= ctx->lsw_tol * std::fabs(v7[s]));
+    fb += !(eb * sc6[s] <= ctx->lsw_tol * gm);
+  }
+  ctx->lsw_cheap_fwd = ff * 10 <= (S / 2) * 9;
+  ctx->lsw_cheap_bwd = fb * 10 <= (S / 2) * 9;
+  ctx->lsw_cool_fwd = ctx->lsw_cheap_fwd ? 0 : 64;
+  ctx->lsw_cool_bwd = ctx->lsw_cheap_bwd ? 0 : 64;
+  if (ctx->lsw_host)
+    for (int u = 0; u < 4; ++u) ctx->lsw_base[u] = ctx->lsw_host[u];
   ctx->lsw_ready = true;
   return 0;
 }
@@ -1365,23 +1446,23 @@ extern "C" int maf_set_level_switch(maf_ctx* ctx, int on, double tol) {
 extern "C" int maf_level_switch_stats(maf_ctx* ctx, int64_t* counts, double* errs, int reset) {
   if (!ctx) return 1;
   CK(cudaSetDevice(ctx->device));
-  long long h[2] = {0, 0};
+  long long h[4] = {0, 0, 0, 0};
   if (ctx->lsw_stats) {
     CK(cudaMemcpyAsync(h, ctx->lsw_stats, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    if (reset) CK(cudaMemsetAsync(ctx->lsw_stats, 0, sizeof(h), ctx->stream));
+    if (reset) {
+      CK(cudaMemsetAsync(ctx->lsw_stats, 0, sizeof(h), ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      for (int u = 0; u < 4; ++u) ctx->lsw_host[u] = 0, ctx->lsw_base[u] = 0;
+    }
   }
-  if (counts) {
-    counts[0] = (int64_t)ctx->lsw_evaluated;
-    counts[1] = (int64_t)h[0];
-    counts[2] = (int64_t)h[1];
-  }
+  if (counts)
+    for (int u = 0; u < 4; ++u) counts[u] = (int64_t)h[u];
   if (errs) {
     errs[0] = ctx->lsw_ready ? ctx->lsw_err_fwd : NAN;
     errs[1] = ctx->lsw_ready ? ctx->lsw_err_bwd : NAN;
     errs[2] = ctx->lsw_tol;
   }
-  if (reset) ctx->lsw_evaluated = 0;
   return 0;
 }
 
@@ -1571,8 +1652,10 @@ extern "C" int maf_set_fantasies(maf_ctx* ctx, int F, const double* Y) {
 }
 
 // loss/grad (prm != null) or posterior (prm == null) over S single-point candidates, in chunks
+// dev: X, out_loss and out_grad are DEVICE pointers, nothing is copied and the stream is not synchronised (the batched
+// L-BFGS loop evaluates this way); otherwise host pointers.
 static int run_fantasies(maf_ctx* ctx, const maf_acq_params* prm, int S, const double* X, double* out_loss,
-                         double* out_grad, double* out_mu, double* out_var) {
+                         double* out_grad, double* out_mu, double* out_var, bool dev = false) {
   if (ctx->F < 1) return fail(ctx, "maf_set_fantasies must be called first");
   if (S < 1 || !X) return fail(ctx, "bad arguments");
   CK(cudaSetDevice(ctx->device));
@@ -1594,18 +1677,21 @@ static int run_fantasies(maf_ctx* ctx, const maf_acq_params* prm, int S, const d
   }
   const int sc_max = (int)std::min<size_t>(ctx->chunk_rows, (size_t)S);
   const int Jmax = round_up(sc_max, 256);
-  if (ensure(ctx, ctx->dX, (size_t)S * d) || ensure(ctx, ctx->K10, (size_t)Jmax * npad) ||
+  if ((!dev && ensure(ctx, ctx->dX, (size_t)S * d)) || ensure(ctx, ctx->K10, (size_t)Jmax * npad) ||
       ensure(ctx, ctx->Vt, (size_t)Jmax * npad) || ensure(ctx, ctx->fVG, (size_t)Jmax * Fpad) ||
       ensure(ctx, ctx->fmubar, (size_t)Jmax * Fpad) || ensure(ctx, ctx->dmu, (size_t)S) ||
       ensure(ctx, ctx->dSig, (size_t)S) || ensure(ctx, ctx->dSigbar, (size_t)S) || ensure(ctx, ctx->dloss, (size_t)S) ||
       ensure(ctx, ctx->dgrad, (size_t)S * d))
     return 1;
-  CK(cudaMemcpyAsync(ctx->dX.p, X, sizeof(double) * (size_t)S * d, cudaMemcpyHostToDevice, ctx->stream));
+  if (!dev) CK(cudaMemcpyAsync(ctx->dX.p, X, sizeof(double) * (size_t)S * d, cudaMemcpyHostToDevice, ctx->stream));
+  const double* const Xd = dev ? X : ctx->dX.p;
+  double* const lossd = dev ? out_loss : ctx->dloss.p;
+  double* const gradd = dev ? out_grad : ctx->dgrad.p;
   const int need_grad = out_grad != nullptr;
   for (int s0 = 0; s0 < S; s0 += sc_max) {
     const int sc = std::min(sc_max, S - s0);
     const int Jpad = round_up(sc, 256);
-    const double* dX = ctx->dX.p + (size_t)s0 * d;
+    const double* dX = Xd + (size_t)s0 * d;
     if (ctx->i8_ready) {
       // same contraction engine as the Monte-Carlo path: K10 straight to digit planes, INT8 products
       const size_t bytes = (size_t)ctx->oz_ns * Jpad * npad;
@@ -1641,7 +1727,7 @@ static int run_fantasies(maf_ctx* ctx, const maf_acq_params* prm, int S, const d
       ProfScope ps(ctx, MAF_PROF_MC);
       closed_form_fant_kernel<<<(sc + 3) / 4, 128, 0, ctx->stream>>>(
           sc, F, Fpad, ctx->fVG.p, ctx->fmeans.p, ctx->flevels.p, ctx->dSig.p + s0, ap, use_flevels, need_grad,
-          ctx->dloss.p + s0, ctx->fmubar.p, ctx->dSigbar.p + s0, prm ? nullptr : ctx->fVG.p);
+          lossd + s0, ctx->fmubar.p, ctx->dSigbar.p + s0, prm ? nullptr : ctx->fVG.p);
       CKL();
     }
     if (!prm && out_mu) {
@@ -1672,16 +1758,17 @@ static int run_fantasies(maf_ctx* ctx, const maf_acq_params* prm, int S, const d
     }
     {
       ProfScope ps(ctx, MAF_PROF_CROSS_BWD);
-      DISPATCH_DK(d, ctx->mp.kernel_id, cross_bwd_kernel<D, KID><<<sc, 32, 0, ctx->stream>>>(dX, sc, 1, 0, ctx->X0s, n, npad, ctx->mp, ctx->K10.p,
-                                                                     ctx->dSigbar.p + s0, ctx->dgrad.p + (size_t)s0 * d));
+      DISPATCH_DK(d, ctx->mp.kernel_id, cross_bwd_kernel<D, KID, false><<<sc, 32, 0, ctx->stream>>>(dX, sc, 1, 0, ctx->X0s, n, npad, ctx->mp, ctx->K10.p,
+                                                                     ctx->dSigbar.p + s0, gradd + (size_t)s0 * d));
       CKL();
     }
   }
+  ctx->last_S = 0;   // the per-restart extras buffers were reused
+  if (dev) return 0;
   if (out_loss) CK(cudaMemcpyAsync(out_loss, ctx->dloss.p, sizeof(double) * S, cudaMemcpyDeviceToHost, ctx->stream));
   if (out_grad) CK(cudaMemcpyAsync(out_grad, ctx->dgrad.p, sizeof(double) * (size_t)S * d, cudaMemcpyDeviceToHost, ctx->stream));
   if (out_var) CK(cudaMemcpyAsync(out_var, ctx->dSig.p, sizeof(double) * S, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  ctx->last_S = 0;   // the per-restart extras buffers were reused
   return 0;
 }
 

@@ -105,6 +105,11 @@ struct OzParams {
   // to whole 256-row blocks) are contracted; tiles of later row blocks are skipped by all three roles.  null = all rows.
   const int* nrows_dev;
   int nrows_mul;    // rows = *nrows_dev x nrows_mul (restarts x pool size)
+  // register-stash epilogue only: C[j][r] += row_add[j] * col_add[r] (one FMA on the rounded product, exactly what a
+  // consumer adding the rank-one term to the stored C would compute).  The reverse contraction uses it for the mean part
+  // of d loss / d K10, mubar_j alpha_r, which never passes through the digit planes.  null = nothing added.
+  const double* row_add;
+  const double* col_add;
 };
 #define OZ_TILE_EXPLICIT 0x40000000
 
@@ -395,37 +400,44 @@ ozaki_slice_rows_kernel(const double* __restrict__ X, int ldx, int R, int Rpad, 
 #ifndef OZC_UNROLL
 #define OZC_UNROLL 2
 #endif
-// NS > 0: compile-time digit count (the FP64-grade configuration); NS == 0: run-time ns.
-template <int D, int KID, int NS>
+// NS > 0: compile-time digit count (the FP64-grade configurations); NS == 0: run-time ns.
+// MODE 0: digit planes only.
+// MODE 1: also the posterior mean the exact FP64 way, mu_j = m + sum_k K10[j][k] alpha_k with alpha = K00^-1 (y0 - m)
+//         (Means = mean_fn + Beta . resid, gaussian_process.py:204-208): every kernel value is in a register here anyway.
+//         The partial sum of this CTA's 1024 columns goes to mu_part[blockIdx.x][j].  Every thread parks its 4-column
+//         partial in shared memory (no dependent shuffle chain in the element loop: the chain cost 2.1 ms per step at the
+//         headline size); after every OZC_RG rows warp w folds row w of the group.  Fixed summation order (thread partials
+//         strided by lane, shuffle tree, column blocks in index order): results do not depend on scheduling.
+// MODE 2: MODE 1 on the compact rows of the level switch's second pass: row r = pos q + i holds candidate row
+//         sel[pos] q + i of X for pos < *sel_count; J is ignored.
+template <int D, int KID, int NS, int MODE = 0>
 __global__ void __launch_bounds__(OZC_THREADS, (D > 0 && D <= 8) ? OZC_MINB : 1)
 cross_fwd_planes_kernel(const double* __restrict__ X, int J, int Jpad, const double* __restrict__ X0s, int n, int npad,
                         ModelParams mp, int ns_rt, int8_t* __restrict__ planes, double* __restrict__ scales,
                         const double* __restrict__ alpha = nullptr, double* __restrict__ mu_part = nullptr,
                         const int* __restrict__ sel = nullptr, const int* __restrict__ sel_count = nullptr, int q = 1) {
-  // sel != nullptr (second pass of the level switch): compact row r = pos q + i holds candidate row sel[pos] q + i of
-  // X for pos < *sel_count; J is ignored.
-  // alpha != nullptr: the posterior mean goes the exact FP64 way, mu_j = m + sum_k K10[j][k] alpha_k with
-  // alpha = K00^-1 (y0 - m) (Means = mean_fn + Beta . resid, gaussian_process.py:204-208): every kernel value is in a
-  // register here anyway.  The partial sum of this CTA's 1024 columns goes to mu_part[blockIdx.x][j] (fixed summation
-  // order: lanes by shuffle tree, warps and column blocks in index order, so results do not depend on scheduling).
   constexpr int DD = D > 0 ? D : MAF_MAX_D;
+  constexpr bool ALPHA = MODE >= 1, SEL = MODE == 2;
   const int d = D > 0 ? D : mp.d;
   const int ns = NS > 0 ? NS : ns_rt;
   __shared__ double xs[OZC_TJ][DD];
   __shared__ double etab_sh[MAF_ETAB_WORDS];
-  __shared__ double msum[OZC_THREADS / 32][OZC_TJ];
+  constexpr int OZC_RG = OZC_THREADS / 32;                   // rows per reduction group = warps per CTA
+  static_assert(OZC_TJ % OZC_RG == 0, "row groups");
+  __shared__ double psum[ALPHA ? OZC_RG : 1][ALPHA ? OZC_THREADS : 1];
+  __shared__ double msum[ALPHA ? OZC_TJ : 1];
   maf_fill_etab(etab_sh, threadIdx.x, blockDim.x);
-  const double* etab = etab_sh + (threadIdx.x & 31);
+  const double* etab = etab_sh + MAF_ETAB_LANE(threadIdx.x);
   const int k = (blockIdx.x * OZC_THREADS + threadIdx.x) * 4;
   const int j0 = blockIdx.y * OZC_TJ;
-  if (sel != nullptr) {
+  if (SEL) {
     J = __ldg(sel_count) * q;
     if (j0 >= J) return;                                     // nothing selected in this row block (rows stay stale, unread)
   }
   for (int t = threadIdx.x; t < OZC_TJ * d; t += OZC_THREADS) {
     int jj = t / d, c = t - jj * d;
     int j = j0 + jj;
-    if (sel != nullptr && j < J) {
+    if (SEL && j < J) {
       const int pos = j / q;
       j = __ldg(sel + pos) * q + (j - pos * q);
     }
@@ -434,29 +446,29 @@ cross_fwd_planes_kernel(const double* __restrict__ X, int J, int Jpad, const dou
   const int e = oz_exponent_for(mp.amp2);
   if (blockIdx.x == 0 && threadIdx.x < OZC_TJ) scales[j0 + threadIdx.x] = (j0 + (int)threadIdx.x < J) ? ldexp(1.0, e) : 1.0;
   __syncthreads();
-  const bool active = k < npad;                              // npad is a multiple of 128, the column block is 1024 wide
-  // a^2 2^(8 ns - 1 - e) per column, 0 on the pad columns k >= n (their digits must be zero): no per-element predicate
-  const double sc = mp.amp2 * ldexp(1.0, -e + 8 * ns - 1);
-  double x0[4][DD], cs[4], al[4];
-#pragma unroll
-  for (int t = 0; t < 4; ++t) {
-    cs[t] = (active && (k + t) < n) ? sc : 0.0;
-    al[t] = (alpha != nullptr && active) ? alpha[k + t] : 0.0;
-#pragma unroll
-    for (int c = 0; c < DD; ++c) x0[t][c] = (c < d && active) ? X0s[(size_t)c * npad + k + t] : 0.0;
-  }
-  const size_t plane_stride = (size_t)Jpad * npad;
   const int jend = min(OZC_TJ, J - j0);                      // rows >= J of the last row block: zero digits
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int UNRJ = OZC_UNROLL;
-  if (!active) {                                             // whole warps (npad is a multiple of 128): nothing to add
-    if (alpha != nullptr && lane == 0)
-      for (int jj = 0; jj < OZC_TJ; ++jj) msum[warp][jj] = 0.0;
-  } else {
+  const bool active = k < npad;                              // whole warps (npad is a multiple of 128)
+  if (!ALPHA && !active) return;
+  {
+    // a^2 2^(8 ns - 1 - e) per column, 0 on the pad columns k >= n (their digits must be zero): no per-element predicate
+    const double sc = mp.amp2 * ldexp(1.0, -e + 8 * ns - 1);
+    double x0[4][DD], cs[4], al[ALPHA ? 4 : 1];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      cs[t] = (active && (k + t) < n) ? sc : 0.0;
+      if (ALPHA) al[t] = active ? alpha[k + t] : 0.0;
+#pragma unroll
+      for (int c = 0; c < DD; ++c) x0[t][c] = (c < d && active) ? X0s[(size_t)c * npad + k + t] : 0.0;
+    }
+    const size_t plane_stride = (size_t)Jpad * npad;
+    constexpr int UNRJ = OZC_UNROLL;
+    const int jloop = ALPHA ? OZC_TJ : jend;                 // ALPHA: whole groups (barriers inside); rows >= jend add 0
 #pragma unroll UNRJ
-    for (int jj = 0; jj < jend; ++jj) {
+    for (int jj = 0; jj < jloop; ++jj) {
       long long I[4];
       double pm = 0.0;
+      if (!ALPHA || (active && jj < jend)) {
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         double r2 = 0.0;
@@ -468,31 +480,34 @@ cross_fwd_planes_kernel(const double* __restrict__ X, int J, int Jpad, const dou
           }
         }
         const double v = kern_val_fast<KID>(r2, etab) * cs[t];
-        pm = fma(v, al[t], pm);
+        if (ALPHA) pm = fma(v, al[t], pm);
         I[t] = __double2ll_rn(v);
       }
       int8_t* dst = planes + (size_t)(j0 + jj) * npad + k;
       if constexpr (NS > 0) oz_emit_digits4_t<(NS > 0 ? NS : 1)>(I, dst, plane_stride);
       else oz_emit_digits4(I, ns, dst, plane_stride);
-      if (alpha != nullptr) {
-        pm = warp_sum(pm);
-        if (lane == 0) msum[warp][jj] = pm;
       }
-    }
-  }
-  if (active)
-    for (int jj = (jend > 0 ? jend : 0); jj < OZC_TJ; ++jj)
-      for (int i = 0; i < ns; ++i) *reinterpret_cast<unsigned*>(planes + i * plane_stride + (size_t)(j0 + jj) * npad + k) = 0u;
-  if (alpha != nullptr) {
-    __syncthreads();
-    if (threadIdx.x < OZC_TJ) {
-      double a = 0.0;
-      if ((int)threadIdx.x < jend) {
+      if (ALPHA) {
+        psum[jj % OZC_RG][threadIdx.x] = pm;
+        if (jj % OZC_RG == OZC_RG - 1) {                     // group complete: warp w folds the group's row w
+          __syncthreads();
+          double a = 0.0;
 #pragma unroll
-        for (int w = 0; w < OZC_THREADS / 32; ++w) a += msum[w][threadIdx.x];
+          for (int u = 0; u < OZC_THREADS / 32; ++u) a += psum[warp][lane + 32 * u];
+          a = warp_sum(a);
+          if (lane == 0) msum[jj - (OZC_RG - 1) + warp] = a;
+          __syncthreads();
+        }
       }
-      mu_part[(size_t)blockIdx.x * Jpad + j0 + threadIdx.x] = a * ldexp(1.0, e - 8 * ns + 1);   // undo the fixed-point factor (exact)
     }
+    if (active)
+      for (int jj = (jend > 0 ? jend : 0); jj < OZC_TJ; ++jj)
+        for (int i = 0; i < ns; ++i) *reinterpret_cast<unsigned*>(planes + i * plane_stride + (size_t)(j0 + jj) * npad + k) = 0u;
+  }
+  if (ALPHA) {
+    __syncthreads();
+    if (threadIdx.x < OZC_TJ)                                // undo the fixed-point factor (exact)
+      mu_part[(size_t)blockIdx.x * Jpad + j0 + threadIdx.x] = ((int)threadIdx.x < jend ? msum[threadIdx.x] : 0.0) * ldexp(1.0, e - 8 * ns + 1);
   }
 }
 
@@ -512,7 +527,10 @@ vbar_planes_kernel(const double* __restrict__ Vt, int npad, int S, int Jpad, con
                    const double* __restrict__ mubar, const double* __restrict__ Sigbar, int ns,
                    int8_t* __restrict__ planes, double* __restrict__ scales, const double* __restrict__ vmax = nullptr,
                    int tight = 0, const int* __restrict__ vslot = nullptr, const double* __restrict__ Vt2 = nullptr,
-                   const double* __restrict__ vmax2 = nullptr, LevelSwitch ls = LevelSwitch{}) {
+                   const double* __restrict__ vmax2 = nullptr, LevelSwitch ls = LevelSwitch{},
+                   const double* __restrict__ mubar_src = nullptr, double* __restrict__ row_add = nullptr) {
+  // row_add != nullptr: row_add[row] = mubar_src[s][i] for the rows this CTA writes (the reverse contraction's epilogue adds
+  // row_add[j] alpha[r]: the mean part of d loss / d K10); 0 on the pad rows.
   // vslot != nullptr: restarts whose forward contraction was redone with all planes (level switch) keep their V^T rows
   // at compact position vslot[s] of Vt2 (row maxima in vmax2).  ls.sel != nullptr: this is the second pass of the REVERSE
   // switch; CTA r serves restart ls.sel[r] and writes compact rows r q .. r q + q - 1.
@@ -537,9 +555,13 @@ vbar_planes_kernel(const double* __restrict__ Vt, int npad, int S, int Jpad, con
     if (r >= Jpad) return;
     for (int i = 0; i < ns; ++i)
       for (int k = tid * 4; k < npad; k += VBP_THREADS * 4) *reinterpret_cast<int*>(planes + i * plane_stride + (size_t)r * npad + k) = 0;
-    if (tid == 0) scales[r] = 1.0;
+    if (tid == 0) {
+      scales[r] = 1.0;
+      if (row_add != nullptr) row_add[r] = 0.0;
+    }
     return;
   }
+  if (row_add != nullptr && tid < Q) row_add[(size_t)rc * Q + tid] = mubar_src[(size_t)s * Q + tid];
   const double* sb = Sigbar + (size_t)s * Q * Q;
   for (int t = tid; t < Q * Q; t += VBP_THREADS) {
     int i = t / Q, j = t - i * Q;

@@ -315,15 +315,19 @@ __device__ __forceinline__ void oz4_epilogue_stash(const double* __restrict__ sA
         double rm[2][2] = {{0.0, 0.0}, {0.0, 0.0}};          // |C| maxima of this lane's four rows (p.rowmax)
 #pragma unroll
         for (int gq = 0; gq < NG; ++gq) {
-          double2 sc[2];
+          double2 sc[2], ca[2];
 #pragma unroll
-          for (int n = 0; n < 2; ++n) sc[n] = __ldg(reinterpret_cast<const double2*>(sT + x.r0 + part * CW + gq * 16 + fc + 8 * n));
+          for (int n = 0; n < 2; ++n) {
+            sc[n] = __ldg(reinterpret_cast<const double2*>(sT + x.r0 + part * CW + gq * 16 + fc + 8 * n));
+            ca[n] = p.col_add ? __ldg(reinterpret_cast<const double2*>(p.col_add + x.r0 + part * CW + gq * 16 + fc + 8 * n)) : make_double2(0.0, 0.0);
+          }
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
               const size_t j = (size_t)(j0 + quarter * 32 + h * 16 + fr + 8 * e);
               const double sa = __ldg(sA + j) * w;
+              const double ra = p.row_add ? __ldg(p.row_add + j) : 0.0;
               double* crow = C + j * p.ldc + x.r0 + part * CW + gq * 16 + fc;
 #pragma unroll
               for (int n = 0; n < 2; ++n) {
@@ -337,7 +341,7 @@ __device__ __forceinline__ void oz4_epilogue_stash(const double* __restrict__ sA
                   v1 = __longlong_as_double(H[idx + 1]);
                 }
                 // written once, read by the next kernel only after the whole 2 GB result: streaming store (evict-first)
-                const double o0 = v0 * sc[n].x * sa, o1 = v1 * sc[n].y * sa;
+                const double o0 = fma(ra, ca[n].x, v0 * sc[n].x * sa), o1 = fma(ra, ca[n].y, v1 * sc[n].y * sa);
                 __stcs(reinterpret_cast<double2*>(crow + 8 * n), make_double2(o0, o1));
                 if (p.rowmax) rm[h][e] = fmax(rm[h][e], fmax(fabs(o0), fabs(o1)));
               }

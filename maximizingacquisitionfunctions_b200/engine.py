@@ -331,10 +331,11 @@ class Engine:
         self._fingerprint = None
 
     def level_switch_stats(self, reset: bool = False):
-        counts = np.zeros(3, dtype=np.int64)
+        counts = np.zeros(4, dtype=np.int64)
         errs = np.zeros(3)
         self._ck(self._lib.maf_level_switch_stats(self._ctx, counts.ctypes.data_as(C.c_void_p), nat.ptr(errs), 1 if reset else 0))
-        return {"restarts": int(counts[0]), "recomputed_forward": int(counts[1]), "recomputed_reverse": int(counts[2]),
+        return {"tested_forward": int(counts[0]), "recomputed_forward": int(counts[1]), "tested_reverse": int(counts[2]),
+                "recomputed_reverse": int(counts[3]), "restarts": int(max(counts[0], counts[2])),
                 "err_cov_abs": float(errs[0]), "err_grad_per_scale": float(errs[1]), "tol": float(errs[2])}
 
     def gemm_nt_i8(self, A: np.ndarray, T: np.ndarray, tri: int = 0, ns: int = 7, lmax: int = 8) -> np.ndarray:

@@ -56,8 +56,8 @@ def main():
                         mu, cov, _ = e.last_extras(S, q)
                         lo, go = ref[name]
                         rec = {"kernel": kernel_id, "workload": wl, "acq": name, "switch": on, "stats": st,
-                               "share_fwd": st["recomputed_forward"] / max(st["restarts"], 1),
-                               "share_bwd": st["recomputed_reverse"] / max(st["restarts"], 1),
+                               "share_fwd": st["recomputed_forward"] / max(st["tested_forward"], 1),
+                               "share_bwd": st["recomputed_reverse"] / max(st["tested_reverse"], 1),
                                "loss": rel(lg, lo), "loss_per_restart": per_restart(lg.reshape(S, 1), lo.reshape(S, 1)),
                                "grad": rel(gg, go), "grad_per_restart": per_restart(gg, go),
                                "mu": rel(mu, mo), "mu_per_restart": per_restart(mu, mo), "cov": rel(cov, co),

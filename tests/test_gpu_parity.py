@@ -611,3 +611,93 @@ def test_digit_switch_api(eng):
     from maximizingacquisitionfunctions_b200.engine import MafError
     with pytest.raises(MafError):
         eng.set_digits(8, 7)
+
+
+# ---------------------------------------------------------------- level switch of the contractions
+def _near_problem(n, d, q, S, M, kernel_id="matern52", seed=0):
+    gp, X0, y0, X, z = orc.synthetic_problem(n, d, q, S, M, seed=seed, kernel_id=kernel_id)
+    X[: S // 2] = np.clip(X0[: (S // 2) * q].reshape(S // 2, q, d) + 1e-3 * np.random.RandomState(7).randn(S // 2, q, d), 0, 1)
+    return gp, X0, y0, X, z
+
+
+def test_level_switch_keeps_the_bar_per_restart():
+    """Default engine (level switch on) at the headline size, half of the candidates 1e-3 from training points: the
+    restarts the cheaper level cannot serve are recomputed on all planes inside the call (statistics say so) and value,
+    gradient, mean and covariance stay within 1e-9 of the oracle per tensor AND per restart."""
+    from maximizingacquisitionfunctions_b200.engine import Engine
+    n, d, q, S, M = 4096, 6, 8, 64, 128
+    gp, X0, y0, X, z = _near_problem(n, d, q, S, M)
+    ts = orc.prepare_train(gp, X0, y0)
+    level = float(np.median(y0))
+    e = Engine(0)
+    try:
+        e.set_model("matern52", np.full(d, math.sqrt(d) / 4), 1.0, 1e-3, 0.0, 1e-6)
+        e.set_train(X0, y0)
+        st0 = e.level_switch_stats(reset=True)
+        assert st0["err_cov_abs"] > 0 and st0["err_grad_per_scale"] > 0 and st0["tol"] == 2.5e-10
+        for okw, gkw in ((("ei",), {"level": level}), (("cb",), {}), (("sr",), {})):
+            lo, go = orc.value_and_grad(ts, orc.Acq(okw[0], **gkw), X, z)
+            lg, gg = e.value_and_grad(prm(okw[0], **gkw), X, z)
+            mu, cov, _ = e.last_extras(S, q)
+            with torch.no_grad():
+                mo, co = orc.posterior(ts, torch.as_tensor(X), full_cov=True)
+            assert relerr(lg, lo) < TOL and relerr(gg, go) < TOL and relerr(mu, mo.numpy()) < TOL and relerr(cov, co.numpy()) < TOL
+            assert per_restart_err(gg, go) < TOL and per_restart_err(cov, co.numpy()) < TOL and per_restart_err(mu, mo.numpy()) < TOL
+            assert int(np.argmin(lg)) == int(np.argmin(lo))
+        st = e.level_switch_stats()
+        assert st["tested_forward"] == 3 * S and st["recomputed_forward"] >= 3 * (S // 2) - 3     # the near half at least
+        assert st["recomputed_forward"] <= st["tested_forward"] and st["recomputed_reverse"] <= st["tested_reverse"]
+    finally:
+        e.close()
+
+
+def test_level_switch_is_invisible_to_chunking_and_can_be_switched_off():
+    """Results with the switch on do not depend on how the restarts are chunked (a restart's result depends on that restart
+    only), and agree with the switch-off results to the tolerance the switch promises."""
+    from maximizingacquisitionfunctions_b200.engine import Engine
+    n, d, q, S, M = 1024, 4, 3, 300, 64
+    gp, X0, y0, X, z = _near_problem(n, d, q, S, M, seed=4)
+    out = {}
+    for tag, env, on in (("a", None, True), ("b", "256", True), ("off", None, False)):
+        if env:
+            os.environ["MAF_CHUNK_ROWS"] = env
+        try:
+            e = Engine(0)
+            e.set_level_switch(on)
+            e.set_model("matern52", np.full(d, math.sqrt(d) / 4), 1.0, 1e-3, 0.0, 1e-6)
+            e.set_train(X0, y0)
+            out[tag] = e.value_and_grad(prm("cb"), X, z) + e.last_extras(S, q)[:2] + (e.level_switch_stats(),)
+            e.close()
+        finally:
+            os.environ.pop("MAF_CHUNK_ROWS", None)
+    for u in range(4):
+        assert np.array_equal(out["a"][u], out["b"][u])
+    assert out["a"][4]["tested_forward"] == S and out["off"][4]["tested_forward"] == 0
+    assert relerr(out["a"][0], out["off"][0]) < 1e-9 and relerr(out["a"][1], out["off"][1]) < 1e-9
+    assert per_restart_err(out["a"][1], out["off"][1]) < 1e-9 and per_restart_err(out["a"][3], out["off"][3]) < 1e-9
+
+
+def test_level_switch_inside_the_replayed_adam_loop():
+    """The switch decides on the device, so a captured optimizer step replays it: the replayed loop equals the host-driven
+    loop bit for bit with the switch on."""
+    from maximizingacquisitionfunctions_b200.engine import Engine
+    n, d, q, S, M, T = 1024, 6, 2, 40, 32, 6
+    gp, X0, y0, X, z = orc.synthetic_problem(n, d, q, S, M, seed=9)
+    zs = np.random.RandomState(3).randn(T, M, q)
+    res = []
+    for graph in ("1", "0"):
+        os.environ["MAF_GRAPH"] = graph
+        try:
+            e = Engine(0)
+            e.set_model("matern52", np.full(d, math.sqrt(d) / 4), 1.0, 1e-3, 0.0, 1e-6)
+            e.set_train(X0, y0)
+            e.adam_begin(prm("sr"), X)
+            tr = e.adam_steps(zs, want_trace=True)
+            res.append((e.adam_end(), tr, e.level_switch_stats()))
+            e.close()
+        finally:
+            os.environ.pop("MAF_GRAPH", None)
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    for key in ("tested_forward", "recomputed_forward", "tested_reverse", "recomputed_reverse"):
+        assert res[0][2][key] == res[1][2][key]
+    assert res[0][2]["tested_forward"] == T * S and res[0][2]["tested_reverse"] == T * S     # the switch was live in both
