@@ -181,6 +181,24 @@ int maf_adam_steps(maf_ctx* ctx, int steps, int M, const double* z_steps, double
 int maf_adam_peek(maf_ctx* ctx, double* X_out);   /* current iterate, loop stays open */
 int maf_adam_end(maf_ctx* ctx, double* X_out);
 
+/* ---- multi-start L-BFGS loop ------------------------------------------- */
+/* Replaces bayesian_optimization._optimize_inputs_scipy (src/agents/bayesian_optimization.py:485-555:
+ * ScipyOptimizerInterface, method 'L-BFGS-B', bounds (0, 1), fixed base samples), the default subroutine for pools of
+ * one point (:311-313), of suggest_answers (:938-1048) and of the incremental greedy construction
+ * (scripts/run_bayesopt_incremental.py:138-218).  The reference minimises mean_s loss_s jointly; the objective is
+ * separable over restarts, so every restart runs its own box-constrained L-BFGS here (history 10, projected Armijo
+ * backtracking; csrc/lbfgs.cuh), all restarts in lock step, one value+gradient evaluation per iteration, and nothing
+ * leaves the device between iterations (the host looks at a counter every 8 iterations: all converged? out of time?).
+ * X[S][q][d] host, in: starts (pending rows first), out: the best (= last accepted) iterate of every restart;
+ * z[M][q] fixed base samples (NULL with q == 1: closed form); fantasies != 0: the fantasy-conditioned closed form of
+ * maf_set_fantasies (q == 1).  Stops per restart on |projected gradient|_inf <= pgtol or on an accepted step improving
+ * the loss by <= ftol * max(|f|, |f'|, 1) (SciPy's factr test).  out_loss[S]; out_info[2] = {evaluations per restart,
+ * restarts not converged}; out_trace[maxiter][S] (NULL to skip): the loss of every evaluated trial point, rows
+ * [0, out_info[0]) valid.  time_limit_s: NaN / inf for none. */
+int maf_lbfgs_run(maf_ctx* ctx, const maf_acq_params* prm, int S, int q, int p_pending, double* X, int M,
+                  const double* z, int fantasies, int maxiter, double ftol, double pgtol, double time_limit_s,
+                  double* out_loss, int32_t* out_info, double* out_trace);
+
 /* ---- selection --------------------------------------------------------- */
 /* np.argmin semantics (first minimum; src/agents/bayesian_optimization.py:152) over
  * a host loss vector is the caller's; this is the device-side variant over the losses

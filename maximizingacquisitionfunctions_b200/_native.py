@@ -53,6 +53,8 @@ SIGNATURES = {
     "maf_adam_steps": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp]),
     "maf_adam_peek": (C.c_int, [_vp, _vp]),
     "maf_adam_end": (C.c_int, [_vp, _vp]),
+    "maf_lbfgs_run": (C.c_int, [_vp, C.POINTER(AcqParams), C.c_int, C.c_int, C.c_int, _vp, C.c_int, _vp, C.c_int, C.c_int,
+                                C.c_double, C.c_double, C.c_double, _vp, _vp, _vp]),
     "maf_argmin_last": (C.c_int, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
     "maf_best_record_dev": (C.c_int, [_vp, C.c_int64, _vp]),
     "maf_profile_enable": (C.c_int, [_vp, C.c_int]),

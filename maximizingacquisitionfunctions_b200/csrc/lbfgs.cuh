@@ -12,6 +12,13 @@
 // backtracking line search on [0, 1]^D with the Armijo test along the projected path, curvature pairs skipped unless
 // s.y > 1e-10 |s| |y|.  A restart stops when its projected gradient is below pgtol, when an accepted step improves the
 // loss by less than ftol * max(|f|, |f'|, 1) (SciPy's factr test), or when the step has shrunk to nothing.
+// Where the loss has no positive curvature along the step (the far tail of -EI is concave: s.y <= 0, no pair can be
+// stored) the restart is in steepest-descent mode and the trial DISTANCE grows eightfold after every accepted step
+// (backtracking still halves it on failure).  Starts in the flat tail of an improvement-type loss (|loss| ~ 1e-40 and a
+// gradient to match) stop at once under these absolute tests -- as they do, in effect, inside the reference's joint
+// problem, whose `best S (iterate, restart) pairs over the whole trajectory` rule (:541-550) then fills their places with
+// further iterates of the restarts that did move; sample_starts draws starts in proportion to the marginal loss, so such
+// starts are rare.
 #pragma once
 #include "common.cuh"
 
@@ -24,7 +31,7 @@ struct LbfgsState {
   double* g;        // [S][D]
   double* dir;      // [S][D]   search direction of the running line search
   double* step;     // [S]      current step length
-  double* gd;       // [S]      directional derivative g . dir at the accepted iterate
+  double* gd;       // [S]      steepest-descent mode: length of the last accepted move
   double* hs;       // [S][LB_M][D]
   double* hy;       // [S][LB_M][D]
   double* rho;      // [S][LB_M]
@@ -98,6 +105,7 @@ __global__ void lbfgs_step_kernel(LbfgsState st, int S, int q, int p, int d, dou
       st.hpos[s] = (slot + 1) % LB_M;
       st.hcount[s] = min(st.hcount[s] + 1, LB_M);
     }
+    st.gd[s] = sqrt(ss);
     st.iters[s] += 1;
     const double fo = st.f[s];
     if (fo - fn <= ftol * fmax(fmax(fabs(fo), fabs(fn)), 1.0)) st.status[s] = 2;
@@ -162,10 +170,16 @@ __global__ void lbfgs_step_kernel(LbfgsState st, int S, int q, int p, int d, dou
       gd += g[t] * dir[t];
     }
   }
-  // first step of a fresh model: length 1 / |g| like SciPy; afterwards the quasi-Newton unit step
-  double a = (st.hcount[s] == 0) ? fmin(1.0, 1.0 / sqrt(fmax(gnorm, 1e-300))) : 1.0;
+  // no curvature model (first step, or negative curvature so far): steepest descent over a trial distance L -- first
+  // min(1, |g|) (SciPy's first step), then 8 x the last accepted move, at most the diagonal of the box; with a model:
+  // the quasi-Newton unit step
+  double a = 1.0;
+  if (st.hcount[s] == 0) {
+    const double gn2 = sqrt(fmax(gnorm, 1e-300));
+    const double L = first ? fmin(1.0, gn2) : fmin(8.0 * st.gd[s], sqrt((double)D));
+    a = L / gn2;
+  }
   st.step[s] = a;
-  st.gd[s] = gd;
   bool moved = false;
   for (int t = 0; t < D; ++t) {
     const double v = fmin(fmax(x[t] + a * dir[t], 0.0), 1.0);

@@ -13,6 +13,7 @@
 #include "factor.cuh"
 #include "fit_kernels.cuh"
 #include "gemm_f64.cuh"
+#include "lbfgs.cuh"
 #include "mc_kernels.cuh"
 #include "ozaki_i8.cuh"
 #include "ozaki_i8_v3.cuh"
@@ -128,6 +129,11 @@ struct maf_ctx {
   std::vector<OzSched> oz_scheds;  // balanced static tile schedules of the CTA-pair kernel, one per launch shape
   int oz_sched = 1;                // MAF_OZ_SCHED=0: round-robin
   double oz_sched_ovh = 1.5;       // per-tile overhead of the cost model, in k-chunks (MAF_OZ_SCHED_OVH)
+  // batched L-BFGS (lbfgs.cuh)
+  Buf lb_X, lb_ft, lb_gt, lb_x, lb_f, lb_g, lb_dir, lb_step, lb_gd, lb_hs, lb_hy, lb_rho, lb_trace;
+  int* lb_int = nullptr;           // device: hcount, hpos, status, iters [S each] + active [1]
+  size_t lb_int_cap = 0;
+  int* lb_active_host = nullptr;   // pinned mirror of the active counter
   // replayed optimizer steps: one CUDA graph per session (MAF_GRAPH=0: every step launched from the host)
   int graph_on = 1;
   long long generation = 0;        // bumped whenever a device buffer moves or the model / training set / engine changes
@@ -771,6 +777,8 @@ extern "C" int maf_destroy(maf_ctx* ctx) {
                  &ctx->dmubar, &ctx->dSigbar, &ctx->dloss, &ctx->dgrad, &ctx->adam_X, &ctx->adam_m, &ctx->adam_v,
                  &ctx->adam_g, &ctx->adam_z, &ctx->fGamma, &ctx->fGammaT, &ctx->fmeans, &ctx->flevels, &ctx->fVG,
                  &ctx->fmubar, &ctx->ozA, &ctx->ozTL, &ctx->ozTU, &ctx->ozsA, &ctx->ozsTL, &ctx->ozsTU, &ctx->adam_zcur,
+                 &ctx->lb_X, &ctx->lb_ft, &ctx->lb_gt, &ctx->lb_x, &ctx->lb_f, &ctx->lb_g, &ctx->lb_dir, &ctx->lb_step, &ctx->lb_gd,
+                 &ctx->lb_hs, &ctx->lb_hy, &ctx->lb_rho, &ctx->lb_trace,
                  &ctx->adam_coef, &ctx->adam_trace, &ctx->ozVmax, &ctx->mu_part, &ctx->Vt2, &ctx->rowmax2, &ctx->row_add};
   for (Buf* b : bufs)
     if (b->p) cudaFree(b->p);
@@ -780,6 +788,8 @@ extern "C" int maf_destroy(maf_ctx* ctx) {
   for (void* b : {(void*)ctx->lsw_cnt, (void*)ctx->lsw_stats, (void*)ctx->lsw_selF, (void*)ctx->lsw_slotF, (void*)ctx->lsw_selB})
     if (b) cudaFree(b);
   if (ctx->lsw_host) cudaFreeHost(ctx->lsw_host);
+  if (ctx->lb_int) cudaFree(ctx->lb_int);
+  if (ctx->lb_active_host) cudaFreeHost(ctx->lb_active_host);
   for (auto& sc : ctx->oz_scheds) {
     cudaFree(sc.d_list);
     cudaFree(sc.d_begin);
@@ -2041,6 +2051,112 @@ extern "C" int maf_adam_end(maf_ctx* ctx, double* X_out) {
   if (X_out) CK(cudaMemcpyAsync(X_out, ctx->adam_X.p, nx * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->adam_on = false;
+  return 0;
+}
+
+// ---- batched L-BFGS on the device -----------------------------------------------------------------
+__global__ void lbfgs_finish_kernel(LbfgsState st, int S, int q, int p, int d, double* __restrict__ Xt) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  const int D = (q - p) * d;
+  for (int t = 0; t < D; ++t) Xt[((size_t)s * q + p) * d + t] = st.x[(size_t)s * D + t];
+}
+
+extern "C" int maf_lbfgs_run(maf_ctx* ctx, const maf_acq_params* prm, int S, int q, int p_pending, double* X, int M,
+                             const double* z, int fantasies, int maxiter, double ftol, double pgtol, double time_limit_s,
+                             double* out_loss, int32_t* out_info, double* out_trace) {
+  if (!ctx) return 1;
+  if (!prm || !X) return fail(ctx, "null pointer");
+  if (check_shape(ctx, S, q, p_pending)) return 1;
+  if (maxiter < 1) return fail(ctx, "maxiter must be >= 1");
+  if (fantasies && (q != 1 || ctx->F < 1)) return fail(ctx, "fantasy-conditioned losses are closed-form (q == 1) and need maf_set_fantasies");
+  const bool closed = !fantasies && q == 1 && z == nullptr;
+  if (!fantasies && !closed && (z == nullptr || M < 1)) return fail(ctx, "base samples z[M][q] are required for the Monte-Carlo path");
+  CK(cudaSetDevice(ctx->device));
+  const int d = ctx->mp.d, p = p_pending, D = (q - p) * d;
+  if (D > LB_MAX_D) return fail(ctx, "(q - p) d = %d exceeds %d", D, LB_MAX_D);
+  const size_t nx = (size_t)S * q * d, nd = (size_t)S * D;
+  if (ensure(ctx, ctx->lb_X, nx) || ensure(ctx, ctx->lb_ft, (size_t)S) || ensure(ctx, ctx->lb_gt, nd) || ensure(ctx, ctx->lb_x, nd) ||
+      ensure(ctx, ctx->lb_f, (size_t)S) || ensure(ctx, ctx->lb_g, nd) || ensure(ctx, ctx->lb_dir, nd) || ensure(ctx, ctx->lb_step, (size_t)S) ||
+      ensure(ctx, ctx->lb_gd, (size_t)S) || ensure(ctx, ctx->lb_hs, nd * LB_M) || ensure(ctx, ctx->lb_hy, nd * LB_M) ||
+      ensure(ctx, ctx->lb_rho, (size_t)S * LB_M) || (out_trace && ensure(ctx, ctx->lb_trace, (size_t)maxiter * S)))
+    return 1;
+  if ((size_t)S > ctx->lb_int_cap) {
+    if (ctx->lb_int) CK(cudaFree(ctx->lb_int));
+    ctx->lb_int = nullptr;
+    CK(cudaMalloc((void**)&ctx->lb_int, sizeof(int) * (4 * (size_t)S + 1)));
+    ctx->lb_int_cap = (size_t)S;
+  }
+  if (!ctx->lb_active_host) CK(cudaHostAlloc((void**)&ctx->lb_active_host, sizeof(int), cudaHostAllocDefault));
+  int* ib = ctx->lb_int;
+  const size_t cap = ctx->lb_int_cap;
+  LbfgsState st{ctx->lb_x.p, ctx->lb_f.p, ctx->lb_g.p, ctx->lb_dir.p, ctx->lb_step.p, ctx->lb_gd.p, ctx->lb_hs.p, ctx->lb_hy.p,
+                ctx->lb_rho.p, ib, ib + cap, ib + 2 * cap, ib + 3 * cap, ib + 4 * cap};
+  CK(cudaMemcpyAsync(ctx->lb_X.p, X, nx * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(st.active, &S, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  const double* dz = nullptr;
+  if (!fantasies && !closed) {
+    if (ensure(ctx, ctx->dz, (size_t)M * q)) return 1;
+    CK(cudaMemcpyAsync(ctx->dz.p, z, sizeof(double) * M * q, cudaMemcpyHostToDevice, ctx->stream));
+    dz = ctx->dz.p;
+  }
+  CK(cudaStreamSynchronize(ctx->stream));                         // &S is a stack address
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
+  if (time_limit_s == time_limit_s && time_limit_s < 1e30) {
+    CK(cudaEventCreate(&t0));
+    CK(cudaEventCreate(&t1));
+    CK(cudaEventRecord(t0, ctx->stream));
+  }
+  int it = 0, active = S, rc = 0;
+  for (; it < maxiter && rc == 0; ++it) {
+    if (fantasies)
+      rc = run_fantasies(ctx, prm, S, ctx->lb_X.p, ctx->lb_ft.p, ctx->lb_gt.p, nullptr, nullptr, true);
+    else
+      rc = run_all(ctx, prm, false, S, q, p, ctx->lb_X.p, M, dz, nullptr, nullptr, ctx->lb_ft.p, ctx->lb_gt.p);
+    if (rc) break;
+    if (out_trace)
+      CK(cudaMemcpyAsync(ctx->lb_trace.p + (size_t)it * S, ctx->lb_ft.p, sizeof(double) * S, cudaMemcpyDeviceToDevice, ctx->stream));
+    {
+      ProfScope ps(ctx, MAF_PROF_ADAM);
+      lbfgs_step_kernel<<<(S + 127) / 128, 128, 0, ctx->stream>>>(st, S, q, p, d, ctx->lb_X.p, ctx->lb_ft.p, ctx->lb_gt.p, it == 0 ? 1 : 0, ftol, pgtol);
+      CKL();
+    }
+    if ((it & 7) == 7 || it + 1 == maxiter) {                     // every 8 iterations: anything left to do? out of time?
+      CK(cudaMemcpyAsync(ctx->lb_active_host, st.active, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      if (t0) CK(cudaEventRecord(t1, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      active = *ctx->lb_active_host;
+      if (active <= 0) {
+        ++it;
+        break;
+      }
+      if (t0) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, t0, t1));
+        if ((double)ms * 1e-3 >= time_limit_s) {
+          ++it;
+          break;
+        }
+      }
+    }
+  }
+  if (t0) cudaEventDestroy(t0), cudaEventDestroy(t1);
+  if (rc) return rc;
+  {
+    ProfScope ps(ctx, MAF_PROF_ADAM);
+    lbfgs_finish_kernel<<<(S + 127) / 128, 128, 0, ctx->stream>>>(st, S, q, p, d, ctx->lb_X.p);
+    CKL();
+  }
+  CK(cudaMemcpyAsync(X, ctx->lb_X.p, nx * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (out_loss) CK(cudaMemcpyAsync(out_loss, ctx->lb_f.p, sizeof(double) * S, cudaMemcpyDeviceToHost, ctx->stream));
+  if (out_trace) CK(cudaMemcpyAsync(out_trace, ctx->lb_trace.p, sizeof(double) * (size_t)it * S, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->lb_active_host, st.active, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (out_info) {
+    out_info[0] = it;                                             // value+gradient evaluations of every restart
+    out_info[1] = std::max(0, *ctx->lb_active_host);              // restarts that had not converged
+  }
+  ctx->last_S = 0;
   return 0;
 }
 

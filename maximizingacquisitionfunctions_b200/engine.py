@@ -293,6 +293,30 @@ class Engine:
         self._ck(self._lib.maf_adam_steps(self._ctx, steps, M, nat.ptr(z_steps), nat.ptr(trace)))
         return trace
 
+    # -- batched L-BFGS loop ---------------------------------------------------------------------------
+    def lbfgs_run(self, prm: nat.AcqParams, X: np.ndarray, z: Optional[np.ndarray] = None, p_pending: int = 0,
+                  fantasies: bool = False, maxiter: int = 1000, ftol: float = 1e6 * np.finfo("float64").eps,
+                  pgtol: float = 1e-5, time_limit: float = float("inf"), want_trace: bool = True):
+        """Per-restart box-constrained L-BFGS on the device (maf_lbfgs_run).  X[S][q][d] starts (pending rows first);
+        returns (X_best[S][q][d], losses[S], trace[evals][S] | None, info dict)."""
+        X = np.array(nat.as_f64(X))                      # in/out buffer
+        S, q, d = X.shape
+        assert d == self.d
+        M = 0
+        if z is not None:
+            z = nat.as_f64(z)
+            assert z.ndim == 2 and z.shape[1] == q
+            M = int(z.shape[0])
+        loss = np.empty(S)
+        info = np.zeros(2, dtype=np.int32)
+        trace = np.empty((int(maxiter), S)) if want_trace else None
+        tl = float("nan") if (time_limit is None or not np.isfinite(time_limit)) else float(time_limit)
+        self._ck(self._lib.maf_lbfgs_run(self._ctx, C.byref(prm), S, q, int(p_pending), nat.ptr(X), M, nat.ptr(z),
+                                         1 if fantasies else 0, int(maxiter), float(ftol), float(pgtol), tl, nat.ptr(loss),
+                                         info.ctypes.data_as(C.c_void_p), nat.ptr(trace)))
+        self.last_eval_shape = None
+        return X, loss, (None if trace is None else trace[:int(info[0])]), {"evaluations": int(info[0]), "not_converged": int(info[1])}
+
     def adam_peek(self) -> np.ndarray:
         X = np.empty(self._adam_shape)
         self._ck(self._lib.maf_adam_peek(self._ctx, nat.ptr(X)))

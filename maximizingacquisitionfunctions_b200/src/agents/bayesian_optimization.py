@@ -338,10 +338,32 @@ class bayesian_optimization(search_agent):
         config = self.update_dict(self.configs["scipy"], config, as_copy=True)
         method = config.pop("method", "L-BFGS-B")
         config.pop("var_to_bounds", None)
+        on_device = config.pop("device", True)
         handle = inputs_new
         shape = handle.value.shape
         S = shape[0]
         inputs_seq, loss_seq, start_time = [], [], self.timer()
+
+        # L-BFGS-B on the device: the objective mean_s loss_s is separable over restarts (they only share SciPy's line
+        # search), so every restart runs its own box-constrained L-BFGS inside the library (maf_lbfgs_run), all restarts
+        # in lock step and with no host round trip per evaluation.  config={"device": False} keeps the joint SciPy loop
+        # below (host L-BFGS-B driving device value + gradient), as do other `method`s.
+        eng = handle.model.bind(handle.inputs_old, handle.outputs_old)
+        if on_device and method == "L-BFGS-B" and hasattr(eng, "lbfgs_run"):
+            pools, p = handle.pools()
+            fantasies = np.ndim(handle.inputs_old) == 4
+            prm = handle.loss_fn.acq_params(outputs_old=None if fantasies else handle.outputs_old, **handle.loss_kwargs)
+            rvs = None if pools.shape[-2] == 1 else feed_dict.get("fantasy_rvs", None)
+            if pools.shape[-2] > 1 and rvs is None:
+                raise ValueError("base samples (feed_dict['fantasy_rvs']) are required for pools of more than one point")
+            X, losses, trace, info = eng.lbfgs_run(
+                prm, pools, None if rvs is None else np.asarray(rvs, dtype=np.float64), p_pending=p, fantasies=fantasies,
+                maxiter=int(config.get("maxiter", 1000)), ftol=float(config.get("ftol", 1e6 * np.finfo("float64").eps)),
+                pgtol=float(config.get("gtol", 1e-5)), time_limit=time_limit)
+            handle.assign(X[:, p:, :])
+            loss_seq = np.ravel(trace) if trace is not None else np.ravel(losses)
+            logger.info("L-BFGS (device) evaluated {:d} losses in {:.3e}s".format(len(loss_seq), self.timer() - start_time))
+            return loss_seq
 
         class _Timeout(Exception):
             pass

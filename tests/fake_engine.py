@@ -123,6 +123,110 @@ class FakeEngine:
                 var = v.numpy().reshape(-1)
         return np.asarray(mus), var
 
+    def lbfgs_run(self, prm, X, z=None, p_pending=0, fantasies=False, maxiter=1000, ftol=1e6 * np.finfo("float64").eps,
+                  pgtol=1e-5, time_limit=float("inf"), want_trace=True):
+        """TEST-ONLY restatement of csrc/lbfgs.cuh (per-restart box-constrained L-BFGS, all restarts in lock step) on the
+        oracle's value + gradient, so that the host logic above it can be compared engine against engine."""
+        LB_M = 10
+        X = np.array(X, dtype=np.float64)
+        S, q, d = X.shape
+        p = int(p_pending)
+        D = (q - p) * d
+
+        def evaluate(Xp):
+            if fantasies:
+                l, g = self.fantasies_value_and_grad(prm, Xp[:, 0, :])
+                return np.asarray(l), np.asarray(g).reshape(S, D)
+            l, g = self.value_and_grad(prm, Xp, z, p_pending=p)
+            return np.asarray(l).reshape(S), np.asarray(g).reshape(S, D)
+
+        x = np.zeros((S, D)); f = np.zeros(S); g = np.zeros((S, D)); dirn = np.zeros((S, D)); step = np.zeros(S)
+        HS = np.zeros((S, LB_M, D)); HY = np.zeros((S, LB_M, D)); rho = np.zeros((S, LB_M))
+        hcount = np.zeros(S, dtype=int); hpos = np.zeros(S, dtype=int); status = np.zeros(S, dtype=int)
+        moved_len = np.zeros(S)
+        trace, evals, active = [], 0, S
+        held = lambda xv, gv: ((xv <= 0.0) & (gv > 0.0)) | ((xv >= 1.0) & (gv < 0.0))
+        for it in range(int(maxiter)):
+            ft, gt = evaluate(X)
+            evals += 1
+            trace.append(ft.copy())
+            Xt = X[:, p:, :].reshape(S, D)                      # view of the trainable rows
+            for s in range(S):
+                first = it == 0
+                if not first and status[s] != 0:
+                    continue
+                xt, fn, gn = Xt[s], ft[s], gt[s]
+                if not first:
+                    gdx = float(np.dot(g[s], xt - x[s]))
+                    if not (fn == fn and fn <= f[s] + 1e-4 * gdx):
+                        step[s] *= 0.5
+                        v = np.clip(x[s] + step[s] * dirn[s], 0.0, 1.0)
+                        moved = bool(np.any(v != x[s]))
+                        Xt[s] = v
+                        if step[s] < 1e-12 or not moved:
+                            Xt[s] = x[s]
+                            status[s] = 3
+                            active -= 1
+                        continue
+                    sv, yv = xt - x[s], gn - g[s]
+                    sy, ss, yy = float(np.dot(sv, yv)), float(np.dot(sv, sv)), float(np.dot(yv, yv))
+                    slot = hpos[s]
+                    HS[s, slot], HY[s, slot] = sv, yv
+                    if sy > 1e-10 * math.sqrt(ss * yy) and sy > 0.0:
+                        rho[s, slot] = 1.0 / sy
+                        hpos[s] = (slot + 1) % LB_M
+                        hcount[s] = min(hcount[s] + 1, LB_M)
+                    moved_len[s] = math.sqrt(ss)
+                    if f[s] - fn <= ftol * max(abs(f[s]), abs(fn), 1.0):
+                        status[s] = 2
+                f[s] = fn
+                x[s] = xt.copy()
+                g[s] = gn.copy()
+                pg = x[s] - np.clip(x[s] - g[s], 0.0, 1.0)
+                if status[s] == 0 and np.abs(pg).max() <= pgtol:
+                    status[s] = 1
+                if status[s] != 0:
+                    active -= 1
+                    continue
+                hc, hp = hcount[s], hpos[s]
+                hd = held(x[s], g[s])
+                dv = np.where(hd, 0.0, g[s])
+                al = np.zeros(LB_M)
+                for u in range(hc):
+                    k = (hp - 1 - u + 2 * LB_M) % LB_M
+                    a = rho[s, k] * float(np.dot(HS[s, k], dv))
+                    al[u] = a
+                    dv = dv - a * HY[s, k]
+                if hc > 0:
+                    k = (hp - 1 + LB_M) % LB_M
+                    dv = dv * (1.0 / (rho[s, k] * float(np.dot(HY[s, k], HY[s, k]))))
+                for u in range(hc - 1, -1, -1):
+                    k = (hp - 1 - u + 2 * LB_M) % LB_M
+                    b = rho[s, k] * float(np.dot(HY[s, k], dv))
+                    dv = dv + (al[u] - b) * HS[s, k]
+                dv = np.where(hd, 0.0, -dv)
+                gd = float(np.dot(g[s], dv))
+                gnorm = float(np.sum(np.where(hd, 0.0, g[s] * g[s])))
+                if not gd < 0.0:
+                    hcount[s] = 0
+                    dv = np.where(hd, 0.0, -g[s])
+                a = 1.0
+                if hcount[s] == 0:
+                    gn2 = math.sqrt(max(gnorm, 1e-300))
+                    L = min(1.0, gn2) if first else min(8.0 * moved_len[s], math.sqrt(float(D)))
+                    a = L / gn2
+                step[s], dirn[s] = a, dv
+                v = np.clip(x[s] + a * dv, 0.0, 1.0)
+                if not np.any(v != x[s]):
+                    status[s] = 1
+                    active -= 1
+                Xt[s] = v
+            X[:, p:, :] = Xt.reshape(S, q - p, d)
+            if active <= 0:
+                break
+        X[:, p:, :] = x.reshape(S, q - p, d)
+        return X, f.copy(), (np.asarray(trace) if want_trace else None), {"evaluations": evals, "not_converged": max(active, 0)}
+
     def last_extras(self, S, q, want_chol=True):
         return self._last
 

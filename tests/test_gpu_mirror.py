@@ -172,3 +172,60 @@ def test_random_subroutine_on_the_cuda_engine():
     assert xqg.shape == (2, 3) and x1g.shape == (1, 3)
     assert np.array_equal(xqg, xqr) and abs(lqg - lqr) < 1e-9 * max(1.0, abs(lqr))
     assert np.array_equal(x1g, x1r) and abs(l1g - l1r) < 1e-9 * max(1.0, abs(l1r))
+
+
+def _lbfgs_problem(d=3, n=48, seed=21, loss="negative_ei", **kw):
+    agent, X0, Y0 = build(d, n, "hartmann3" if d == 3 else "braninhoo", seed, loss, **kw)
+    # starts the way the agent draws them: in proportion to the marginal loss (flat-tail starts are rare)
+    starts = agent.sample_starts(16, 1, None, X0, Y0, eval_limit=2048)
+    return agent, X0, Y0, starts
+
+
+def test_device_lbfgs_matches_its_restatement_and_beats_the_starts():
+    """maf_lbfgs_run (per-restart box-constrained L-BFGS inside the library, no host round trip per evaluation) against
+    the test-only NumPy restatement of the same algorithm on the oracle engine: closed form (q = 1), Monte-Carlo with
+    fixed base samples and one pending point, and the fantasy-conditioned closed form of the incremental greedy path."""
+    def flow():
+        agent, X0, Y0, starts = _lbfgs_problem()
+        eng = agent.model.bind(X0, Y0)
+        prm = agent.loss_fn.acq_params(outputs_old=Y0)
+        X1, f1, tr1, info1 = eng.lbfgs_run(prm, starts, None, maxiter=40)
+        z = np.random.RandomState(5).randn(64, 2)
+        pend = X0[[int(np.argmax(Y0))]] + 0.01
+        pools = np.concatenate([np.broadcast_to(pend, (len(starts), 1, 3)), starts], axis=1)
+        X2, f2, tr2, info2 = eng.lbfgs_run(prm, pools, z, p_pending=1, maxiter=30)
+        F = 8
+        Yf = Y0[None, None] + 0.05 * np.random.RandomState(6).randn(F, 1, len(Y0), 1)
+        Xf = np.tile(X0[None, None], (F, 1, 1, 1))
+        engf = agent.model.bind(Xf, Yf)
+        X3, f3, tr3, info3 = engf.lbfgs_run(agent.loss_fn.acq_params(outputs_old=None), starts, None, fantasies=True, maxiter=30)
+        return X1, f1, tr1[0], X2, f2, tr2[0], X3, f3, tr3[0]
+    g, r = run_both(flow)
+    for k in (0, 3, 6):                                     # iterates, final losses, start losses of the three runs
+        assert g[k].shape == r[k].shape
+        assert np.abs(g[k] - r[k]).max() < 1e-5, k
+        assert np.abs(g[k + 1] - r[k + 1]).max() < 1e-7 * max(1.0, np.abs(r[k + 1]).max())
+        assert np.abs(g[k + 2] - r[k + 2]).max() < 1e-9 * max(1.0, np.abs(r[k + 2]).max())
+        assert np.all(g[k + 1] <= g[k + 2] + 1e-15)         # monotone per restart
+        assert g[k + 1].min() < g[k + 2].min()              # and the best restart improved
+        assert np.all(g[k] >= 0) and np.all(g[k] <= 1)
+    assert np.array_equal(g[3][:, 0], np.broadcast_to(g[3][0, 0], g[3][:, 0].shape))     # pending row untouched
+
+
+def test_device_lbfgs_is_no_worse_than_host_scipy_on_the_cuda_engine():
+    """Same starts, CUDA engine: the device loop against the reference-style joint SciPy L-BFGS-B driving device
+    value + gradient (config device=False).  The device loop finds an optimum at least as good."""
+    runtime.set_engine_factory(None)
+    runtime.release_engines()
+    try:
+        agent, X0, Y0, starts = _lbfgs_problem(seed=23)
+        best = {}
+        for device in (True, False):
+            handle = agent.appraise_inputs(None, starts, X0, Y0, inputs_as_var=True)[0]
+            agent._optimize_inputs_scipy(None, handle, handle, dict(), config={"maxiter": 100, "device": device})
+            best[device] = float(np.ravel(handle.evaluate(None)[0]).min())
+        assert best[True] <= best[False] + 1e-6 * max(1.0, abs(best[False]))
+        ans, (m, v) = agent.suggest_answers(2, X0, Y0, None, num_starts=32, num_options=512, config={"maxiter": 30}, in_order=True)
+        assert ans.shape == (2, 3) and m[0] <= m[1] and m[0] <= float(Y0.min()) + 0.1
+    finally:
+        runtime.release_engines()

@@ -310,3 +310,35 @@ def test_fantasies_are_rebound_after_the_training_set_was_reloaded():
     agent.model.predict(cand[:, 0], X0, Y0)                           # SAME inputs as the fantasy set, 2-D outputs
     l_c = np.ravel(agent.loss_fn(cand, Xf, Yf, model=agent.model)[0])
     assert np.array_equal(l_a, l_c)
+
+
+def test_device_lbfgs_restatement_is_no_worse_than_joint_scipy():
+    """The per-restart L-BFGS that replaces the joint SciPy L-BFGS-B (here: its test-only restatement on the oracle engine)
+    finds the optimum the reference-style joint run finds from the same starts, and never leaves a restart worse than
+    it started.  (The joint route returns the best S (iterate, restart) pairs of the whole trajectory, several iterates of
+    one restart included, so only the best value is comparable.)"""
+    agent, X0, Y0 = make(d=2, n=30, seed=4)
+    starts = np.random.RandomState(3).rand(12, 1, 2)
+    out = {}
+    for device in (True, False):
+        handle = agent.appraise_inputs(None, starts, X0, Y0, inputs_as_var=True)[0]
+        seq = agent._optimize_inputs_scipy(None, handle, handle, dict(), config={"maxiter": 60, "device": device})
+        losses = np.ravel(handle.evaluate(None)[0])
+        assert handle.value.shape == starts.shape and np.all(handle.value >= 0) and np.all(handle.value <= 1)
+        out[device] = (losses, len(seq))
+    start_losses = np.ravel(agent.loss_fn(starts, X0, Y0, model=agent.model)[0])
+    assert np.all(out[True][0] <= start_losses + 1e-15)            # monotone per restart
+    assert out[True][0].min() <= out[False][0].min() + 1e-6        # best optimum found: no worse than the joint run
+
+
+def test_device_lbfgs_restatement_with_pending_points_and_fixed_samples():
+    agent, X0, Y0 = make(d=2, n=20, seed=6, loss="simple_regret")
+    pend = X0[[int(np.argmax(Y0))]] + 0.01             # a poor pending point: the new point decides the loss
+    starts = np.random.RandomState(2).rand(5, 1, 2)
+    handle, feed = agent.appraise_inputs(None, starts, X0, Y0, inputs_pend=pend, inputs_as_var=True,
+                                         loss_kwargs={"num_fantasies": 32})[:2]
+    before = np.ravel(handle.evaluate(feed)[0])
+    agent._optimize_inputs_scipy(None, handle, handle, feed, config={"maxiter": 25})
+    after = np.ravel(handle.evaluate(feed)[0])
+    assert np.all(after <= before + 1e-12) and after.min() < before.min()
+    assert handle.value.shape == (5, 1, 2)
