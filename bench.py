@@ -199,6 +199,40 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+AGENT_CONFIGS = [
+    # BASELINE configs 1-3 through the product API (agent.suggest_inputs: starts by the closed-form sweep, Adam on the
+    # device, re-evaluation with 1024 base samples, arg-min); a fixed optimizer budget instead of the scripts' time limit
+    ("C1 Hartmann-3 qEI q=2 n=32 S=64 M=128", dict(task="hartmann3", d=3, n=32, q=2, S=64, M=128, loss="negative_ei", kw={}, steps=100)),
+    ("C2 Branin qPI(tau=0.01) q=4 n=256 S=1024 M=256", dict(task="braninhoo", d=2, n=256, q=4, S=1024, M=256, loss="negative_pi", kw={"temperature": 0.01}, steps=50)),
+    ("C3 Hartmann-6 qEI q=8 n=1024 S=4096 M=128", dict(task="hartmann6", d=6, n=1024, q=8, S=4096, M=128, loss="negative_ei", kw={}, steps=25)),
+]
+
+
+def agent_suggest_inputs_times(device):
+    """Wall time of agent.suggest_inputs (second call; the first one warms buffers and graphs up) for C1-C3."""
+    from maximizingacquisitionfunctions_b200 import runtime, tasks
+    from maximizingacquisitionfunctions_b200.src import agents, losses, models
+    out = []
+    for name, c in AGENT_CONFIGS:
+        rng = np.random.RandomState(0)
+        X0 = rng.rand(c["n"], c["d"])
+        Y0 = getattr(tasks, c["task"])(X0) + math.sqrt(1e-3) * rng.randn(c["n"], 1)
+        model = models.gaussian_process(kernel_id="matern52", seed=1, log_lenscales=np.log(math.sqrt(c["d"]) / 4) * np.ones(c["d"]),
+                                        log_amplitude=0.0, log_noise=np.log(1e-3), mean=0.0, device=device)
+        loss_fn = getattr(losses, c["loss"])(seed=2, num_fantasies=1024, **c["kw"])
+        agent = agents.bayesian_optimization(loss_fn=loss_fn, model=model, seed=3, timer=time.perf_counter)
+        cfg = {"step_limit": c["steps"], "batch_size": c["M"]}
+        wall = []
+        for _ in range(2):
+            t0 = time.perf_counter()
+            agent.suggest_inputs(c["q"], X0, Y0, None, num_to_optimize=c["S"], subroutine=agent._optimize_inputs_sgd, config=cfg)
+            wall.append(time.perf_counter() - t0)
+        out.append({"config": name, "adam_steps": c["steps"], "wall_s": wall[1], "first_call_wall_s": wall[0],
+                    "evals_per_s": c["steps"] * c["S"] * c["q"] * c["M"] / wall[1]})
+        runtime.release_engines()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -207,6 +241,7 @@ def main():
     ap.add_argument("--impl", type=str, default="b200", choices=["b200", "reference"])
     ap.add_argument("--restarts", type=int, default=WORKLOAD["S_per_gpu"], help="restarts per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-agent", action="store_true", help="skip the agent-level suggest_inputs timings (C1-C3)")
     ap.add_argument("--level", type=str, default=WORKLOAD["level"],
                     help="qEI improvement threshold: 'median' (of y0; default, non-degenerate), 'min' (reference default) or a number")
     ap.add_argument("--gemm", type=str, default=os.environ.get("MAF_BENCH_GEMM", DEFAULT_GEMM), choices=["f64", "i8"],
@@ -392,6 +427,13 @@ def main():
         cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": "S=%d restarts (of %d), one value+autograd-gradient pass in %.1f s, same n/d/q/M/z" % (S_cpu, S, dt)}
 
+    agent_times = None
+    if rank == 0 and ws == 1 and not args.no_agent:
+        try:
+            agent_times = agent_suggest_inputs_times(local)
+        except Exception as exc:                            # reported, never fatal for the headline
+            agent_times = {"error": repr(exc)}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": args.steps, "warmup": args.warmup,
@@ -411,7 +453,7 @@ def main():
                 "tol": lsw["tol"], "calibrated_err_cov_abs": lsw["err_cov_abs"], "calibrated_err_grad_per_scale": lsw["err_grad_per_scale"],
                 "products_forward_avg": pairs_f, "products_reverse_avg": pairs_b,
                 "note": "both contractions first keep 6 of 7 digit planes (21 exact products); restarts whose own result does not tolerate the calibrated error of that level within tol are recomputed on all planes (28) inside the same call"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "adam_loop": adam_loop, "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "adam_loop": adam_loop, "agent_suggest_inputs": agent_times, "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     eng.close()

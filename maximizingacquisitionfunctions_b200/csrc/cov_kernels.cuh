@@ -101,8 +101,12 @@ cross_bwd_kernel(const double* __restrict__ X, int S, int q, int p,
                                  const double* __restrict__ Kbar /*[S*q][npad]*/,
                                  const double* __restrict__ Sigbar /*[S][q][q]*/,
                                  double* __restrict__ grad /*[S][q-p][d]*/,
-                                 const int* __restrict__ sel = nullptr, const int* __restrict__ sel_count = nullptr) {
-  // SEL (second pass of the reverse level switch): CTA r serves restart sel[r] from compact Kbar rows r q + i.
+                                 const int* __restrict__ sel = nullptr, const int* __restrict__ sel_count = nullptr,
+                                 int kq = 0) {
+  // One warp per trainable row (block = 32 (q - p) threads).  Kbar holds kq rows per pool: kq = q (all rows, pending
+  // ones included and ignored; kq = 0 means q) or kq = q - p (pending points contracted once elsewhere: trainable rows
+  // only); pool row i lives at row blockIdx.x kq + i - (q - kq).
+  // SEL (second pass of the reverse level switch): CTA r serves restart sel[r] from compact Kbar rows.
   // (With the mean computed as m + K10 . alpha the mean part of d loss / d K10, mubar_j alpha_k, is added to Kbar by the
   // reverse contraction's epilogue in FP64: this kernel always sees the complete Kbar.)
   constexpr int DD = D > 0 ? D : MAF_MAX_D;
@@ -112,14 +116,15 @@ cross_bwd_kernel(const double* __restrict__ X, int S, int q, int p,
   const double* etab = etab_sh + MAF_ETAB_LANE(threadIdx.x);
   __syncthreads();
   int s = blockIdx.x;
-  size_t krow0 = (size_t)s * q;
+  if (kq == 0) kq = q;
+  size_t krow0 = (size_t)s * kq;
   if (SEL) {
     if ((int)blockIdx.x >= __ldg(sel_count)) return;
     s = __ldg(sel + blockIdx.x);
   }
-  const int i = threadIdx.x >> 5;
+  const int i = p + (threadIdx.x >> 5);                      // warp w <-> trainable row p + w
   const int lane = threadIdx.x & 31;
-  if (i >= q || i < p) return;
+  if (i >= q) return;
   const size_t j = (size_t)s * q + i;
   double xi[DD], acc[DD];
 #pragma unroll
@@ -127,7 +132,7 @@ cross_bwd_kernel(const double* __restrict__ X, int S, int q, int p,
     xi[c] = (c < d) ? X[j * d + c] * mp.inv_ls[c] : 0.0;
     acc[c] = 0.0;
   }
-  const double* kb = Kbar + (krow0 + i) * npad;
+  const double* kb = Kbar + (krow0 + i - (q - kq)) * npad;
   constexpr int UNR = CROSS_BWD_UNROLL;
 #pragma unroll UNR
   for (int k = lane; k < n; k += 32) {
@@ -179,13 +184,13 @@ cross_bwd_kernel(const double* __restrict__ X, int S, int q, int p,
 // err x kscale[j] (calibrated per unit row scale of the Vbar planes); restarts where it exceeds tol x max |gradient| are
 // listed for the second pass.  One thread per restart.
 __global__ void lsw_flag_bwd_kernel(const double* __restrict__ grad, const double* __restrict__ kscale, int S, int q, int p,
-                                    int d, LevelSwitch ls) {
+                                    int d, LevelSwitch ls, int kq) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= S) return;
   double mx = 0.0, er = 0.0;
   const double* g = grad + (size_t)s * (q - p) * d;
   for (int t = 0; t < (q - p) * d; ++t) mx = fmax(mx, fabs(g[t]));
-  for (int i = p; i < q; ++i) er = fmax(er, ls.err * kscale[(size_t)s * q + i]);
+  for (int i = p; i < q; ++i) er = fmax(er, ls.err * kscale[(size_t)s * kq + i - (q - kq)]);
   if (!(er <= ls.tol * mx)) {
     const int slot = atomicAdd(ls.flag_count, 1);
     ls.flag_sel[slot] = s;

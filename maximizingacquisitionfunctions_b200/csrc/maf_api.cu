@@ -63,6 +63,12 @@ struct maf_ctx {
   int vbar_tight = 0;              // MAF_VBAR_TIGHT=1: exact row maxima for the Vbar digit planes (one more sweep)
   Buf mu_part;                     // [column blocks of 1024][Jpad] partial sums of K10 . alpha
   Buf row_add;                     // [Jpad] mubar per row of the Vbar planes (rank-one term of the reverse epilogue)
+  // Pending points (rows 0..p-1 of every pool, identical for all restarts: pools = concat(tile(Xpend), new),
+  // bayesian_optimization.py:1106-1123) are contracted ONCE per evaluation, on all digit planes: V^T rows, mean partial
+  // sums and row maxima of the shared block; the restarts only carry their q - p trainable rows through both contractions.
+  Buf Vp, mu_part_p, rowmax_p;
+  bool pend_shared = false;        // the caller's pools were checked: identical pending rows (host entry points)
+  int pend_dedupe = 1;             // MAF_PEND_DEDUPE=0: every restart contracts its own copy of the pending rows (A/B)
   // Level switch (common.cuh, struct LevelSwitch): both contractions first run with one digit plane less (21 products
   // instead of 28); restarts whose result does not tolerate the calibrated error of that level are recomputed with all
   // planes on compact rows.  MAF_LEVEL_SWITCH=0 / maf_set_level_switch turn it off (every restart on all planes).
@@ -745,6 +751,7 @@ extern "C" int maf_create(int device, int dtype, maf_ctx** out) {
   if (const char* ma = getenv("MAF_MU_ALPHA")) ctx->mu_alpha = atoi(ma);
   if (const char* vt = getenv("MAF_VBAR_TIGHT")) ctx->vbar_tight = atoi(vt);
   if (const char* lw = getenv("MAF_LEVEL_SWITCH")) ctx->lsw_on = atoi(lw);
+  if (const char* pdd = getenv("MAF_PEND_DEDUPE")) ctx->pend_dedupe = atoi(pdd);
   if (const char* lt = getenv("MAF_LEVEL_SWITCH_TOL")) ctx->lsw_tol = atof(lt);
   if (const char* ln = getenv("MAF_LEVEL_SWITCH_MIN_N")) ctx->lsw_min_npad = atoi(ln);
   if (const char* nf = getenv("MAF_OZ_NS_FWD")) {
@@ -779,7 +786,7 @@ extern "C" int maf_destroy(maf_ctx* ctx) {
                  &ctx->fmubar, &ctx->ozA, &ctx->ozTL, &ctx->ozTU, &ctx->ozsA, &ctx->ozsTL, &ctx->ozsTU, &ctx->adam_zcur,
                  &ctx->lb_X, &ctx->lb_ft, &ctx->lb_gt, &ctx->lb_x, &ctx->lb_f, &ctx->lb_g, &ctx->lb_dir, &ctx->lb_step, &ctx->lb_gd,
                  &ctx->lb_hs, &ctx->lb_hy, &ctx->lb_rho, &ctx->lb_trace,
-                 &ctx->adam_coef, &ctx->adam_trace, &ctx->ozVmax, &ctx->mu_part, &ctx->Vt2, &ctx->rowmax2, &ctx->row_add};
+                 &ctx->adam_coef, &ctx->adam_trace, &ctx->ozVmax, &ctx->mu_part, &ctx->Vt2, &ctx->rowmax2, &ctx->row_add, &ctx->Vp, &ctx->mu_part_p, &ctx->rowmax_p};
   for (Buf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (ctx->d_argmin_idx) cudaFree(ctx->d_argmin_idx);
@@ -1038,12 +1045,21 @@ static int resolve_acq(maf_ctx* ctx, const maf_acq_params* prm, AcqDev* out) {
 // posterior mean / covariance of one chunk: register-accumulating kernel for Q <= 8, shared-memory slab beyond
 template <int Q>
 static void launch_posterior(maf_ctx* ctx, int sc, const double* Vt, int npad, const double* dX, double* mu, double* Sig,
-                             const double* mu_part, int nparts, int Jpad, LevelSwitch ls = LevelSwitch{}) {
+                             const double* mu_part, int nparts, int Jpad, LevelSwitch ls = LevelSwitch{}, int pd = 0) {
   const double* gam = mu_part ? nullptr : ctx->gamma;         // mean from K10 . alpha: no gamma sweep
-  if constexpr (Q <= 8)
-    posterior_reg_kernel<Q><<<sc, POST_REG_THREADS, 0, ctx->stream>>>(Vt, npad, gam, dX, ctx->mp, ctx->mean_val, mu, Sig, mu_part, nparts, Jpad, ls);
-  else
-    posterior_kernel<Q><<<sc, POST_THREADS, 0, ctx->stream>>>(Vt, npad, gam, dX, ctx->mp, ctx->mean_val, mu, Sig, mu_part, nparts, Jpad, ls);
+  if constexpr (Q <= 8) {
+    if (pd > 0)
+      posterior_reg_kernel<Q, true><<<sc, POST_REG_THREADS, 0, ctx->stream>>>(Vt, npad, gam, dX, ctx->mp, ctx->mean_val, mu, Sig, mu_part, nparts, Jpad, ls,
+                                                                              pd, ctx->Vp.p, ctx->mu_part_p.p, 256);
+    else
+      posterior_reg_kernel<Q, false><<<sc, POST_REG_THREADS, 0, ctx->stream>>>(Vt, npad, gam, dX, ctx->mp, ctx->mean_val, mu, Sig, mu_part, nparts, Jpad, ls);
+  } else {
+    if (pd > 0)
+      posterior_kernel<Q, true><<<sc, POST_THREADS, 0, ctx->stream>>>(Vt, npad, gam, dX, ctx->mp, ctx->mean_val, mu, Sig, mu_part, nparts, Jpad, ls,
+                                                                      pd, ctx->Vp.p, ctx->mu_part_p.p, 256);
+    else
+      posterior_kernel<Q, false><<<sc, POST_THREADS, 0, ctx->stream>>>(Vt, npad, gam, dX, ctx->mp, ctx->mean_val, mu, Sig, mu_part, nparts, Jpad, ls);
+  }
 }
 
 // lists and compact buffers of the level switch for chunks of up to `sc` restarts / `Jpad` candidate rows
@@ -1079,9 +1095,12 @@ __global__ void lsw_accumulate_kernel(const int* __restrict__ cnt, long long* __
 // forward (+ optional backward) over one chunk of restarts
 static int run_chunk(maf_ctx* ctx, const AcqDev& ap, bool posterior_only, bool closed_form, int sc, int q, int p,
                      const double* dX, int M, const double* dz, const double* dw, const double* dinc, double* mu,
-                     double* Sig, double* chol, double* mubar, double* Sigbar, double* dloss, double* dgrad) {
+                     double* Sig, double* chol, double* mubar, double* Sigbar, double* dloss, double* dgrad, bool ded) {
+  // ded: the p pending rows were contracted once by run_all (ctx->Vp ...); only the q - p trainable rows of every pool
+  // go through the contractions here
   const int d = ctx->mp.d, n = ctx->n, npad = ctx->npad;
-  const int J = sc * q, Jpad = round_up(J, 256);     // 256: one row block per CTA pair of the INT8 contraction
+  const int pd = ded ? p : 0, qn = q - pd;
+  const int J = sc * qn, Jpad = round_up(J, 256);    // 256: one row block per CTA pair of the INT8 contraction
   double* K10 = ctx->K10.p;
   double* Vt = ctx->Vt.p;
   const bool fused = ctx->i8_ready && (ctx->oz_fuse & 1), fused_bwd = ctx->i8_ready && (ctx->oz_fuse & 2);
@@ -1115,7 +1134,7 @@ static int run_chunk(maf_ctx* ctx, const AcqDev& ap, bool posterior_only, bool c
       dim3 grid(nparts, Jpad / OZC_TJ);
       if (mu_alpha) {
         DISPATCH_DKN(d, ctx->mp.kernel_id, ns_fwd, cross_fwd_planes_kernel<D, KID, NSC, 1><<<grid, OZC_THREADS, 0, ctx->stream>>>(dX, J, Jpad, ctx->X0s, n, npad, ctx->mp, ns_fwd,
-                                                                                       (int8_t*)ctx->ozA.p, ctx->ozsA.p, ctx->alpha, ctx->mu_part.p));
+                                                                                       (int8_t*)ctx->ozA.p, ctx->ozsA.p, ctx->alpha, ctx->mu_part.p, nullptr, nullptr, q, pd));
       } else {
         DISPATCH_DKN(d, ctx->mp.kernel_id, ns_fwd, cross_fwd_planes_kernel<D, KID, NSC, 0><<<grid, OZC_THREADS, 0, ctx->stream>>>(dX, J, Jpad, ctx->X0s, n, npad, ctx->mp, ns_fwd,
                                                                                        (int8_t*)ctx->ozA.p, ctx->ozsA.p));
@@ -1146,7 +1165,7 @@ static int run_chunk(maf_ctx* ctx, const AcqDev& ap, bool posterior_only, bool c
     ProfScope ps(ctx, MAF_PROF_POSTERIOR);
     LevelSwitch ls{};
     if (lswF) ls = LevelSwitch{nullptr, nullptr, ctx->lsw_cnt, ctx->lsw_selF, ctx->lsw_slotF, ctx->lsw_err_fwd, ctx->lsw_tol};
-    DISPATCH_Q(q, launch_posterior<Q>(ctx, sc, Vt, npad, dX, mu, Sig, mu_part, nparts, Jpad, ls));
+    DISPATCH_Q(q, launch_posterior<Q>(ctx, sc, Vt, npad, dX, mu, Sig, mu_part, nparts, Jpad, ls, pd));
     CKL();
   }
   bool have_rowmax2 = false;
@@ -1157,15 +1176,15 @@ static int run_chunk(maf_ctx* ctx, const AcqDev& ap, bool posterior_only, bool c
       ProfScope ps(ctx, MAF_PROF_CROSS_FWD);
       dim3 grid(nparts, Jpad / OZC_TJ);
       DISPATCH_DK(d, ctx->mp.kernel_id, cross_fwd_planes_kernel<D, KID, 7, 2><<<grid, OZC_THREADS, 0, ctx->stream>>>(dX, J, Jpad, ctx->X0s, n, npad, ctx->mp, nsf,
-                                                                             (int8_t*)ctx->ozA.p, ctx->ozsA.p, ctx->alpha, ctx->mu_part.p, ctx->lsw_selF, ctx->lsw_cnt, q));
+                                                                             (int8_t*)ctx->ozA.p, ctx->ozsA.p, ctx->alpha, ctx->mu_part.p, ctx->lsw_selF, ctx->lsw_cnt, q, pd));
       CKL();
     }
     if (launch_i8gemm(ctx, MAF_PROF_GEMM_FWD, Jpad, npad, npad, ctx->ozA, ctx->ozsA, ctx->ozTL, ctx->ozsTL, ctx->Vt2.p, npad, 1,
-                      nsf, nsf + 1, want_rowmax ? ctx->rowmax2.p : nullptr, &have_rowmax2, ctx->lsw_cnt, q))
+                      nsf, nsf + 1, want_rowmax ? ctx->rowmax2.p : nullptr, &have_rowmax2, ctx->lsw_cnt, qn))
       return 1;
     ProfScope ps(ctx, MAF_PROF_POSTERIOR);
     const LevelSwitch ls{ctx->lsw_selF, ctx->lsw_cnt, nullptr, nullptr, nullptr, 0.0, 0.0};
-    DISPATCH_Q(q, launch_posterior<Q>(ctx, sc, ctx->Vt2.p, npad, dX, mu, Sig, mu_part, nparts, Jpad, ls));
+    DISPATCH_Q(q, launch_posterior<Q>(ctx, sc, ctx->Vt2.p, npad, dX, mu, Sig, mu_part, nparts, Jpad, ls, pd));
     CKL();
   }
   if (posterior_only) {
@@ -1209,9 +1228,10 @@ static int run_chunk(maf_ctx* ctx, const AcqDev& ap, bool posterior_only, bool c
     const double* vmax1 = (have_rowmax && (!lswF || have_rowmax2)) ? rowmax : nullptr;
     {
       ProfScope ps(ctx, MAF_PROF_VBAR);
-      DISPATCH_Q(q, vbar_planes_kernel<Q><<<sc + (Jpad - J), VBP_THREADS, 0, ctx->stream>>>(Vt, npad, sc, Jpad, ctx->gamma, mu_alpha ? nullptr : mubar, Sigbar, ns_bwd,
+      DISPATCH_Q(q, (pd > 0 ? vbar_planes_kernel<Q, true> : vbar_planes_kernel<Q, false>)<<<sc + (Jpad - J), VBP_THREADS, 0, ctx->stream>>>(Vt, npad, sc, Jpad, ctx->gamma, mu_alpha ? nullptr : mubar, Sigbar, ns_bwd,
                                                                                    (int8_t*)ctx->ozA.p, ctx->ozsA.p, vmax1, ctx->vbar_tight, vslot, ctx->Vt2.p, vmax2,
-                                                                                   LevelSwitch{}, mubar, mu_alpha ? ctx->row_add.p : nullptr));
+                                                                                   LevelSwitch{}, mubar, mu_alpha ? ctx->row_add.p : nullptr,
+                                                                                   pd, ctx->Vp.p, ctx->rowmax_p.p));
       CKL();
     }
     if (launch_i8gemm(ctx, MAF_PROF_GEMM_BWD, Jpad, npad, npad, ctx->ozA, ctx->ozsA, ctx->ozTU, ctx->ozsTU, K10, npad, 2,
@@ -1234,13 +1254,14 @@ static int run_chunk(maf_ctx* ctx, const AcqDev& ap, bool posterior_only, bool c
   }
   {
     ProfScope ps(ctx, MAF_PROF_CROSS_BWD);
-    DISPATCH_DK(d, ctx->mp.kernel_id, cross_bwd_kernel<D, KID, false><<<sc, 32 * q, 0, ctx->stream>>>(dX, sc, q, p, ctx->X0s, n, npad, ctx->mp, K10, Sigbar, dgrad));
+    DISPATCH_DK(d, ctx->mp.kernel_id, cross_bwd_kernel<D, KID, false><<<sc, 32 * (q - p), 0, ctx->stream>>>(dX, sc, q, p, ctx->X0s, n, npad, ctx->mp, K10, Sigbar, dgrad,
+                                                                                                     nullptr, nullptr, qn));
     CKL();
   }
   if (lswB) {
     ProfScope ps(ctx, MAF_PROF_CROSS_BWD);
     const LevelSwitch ls{nullptr, nullptr, ctx->lsw_cnt + 1, ctx->lsw_selB, nullptr, ctx->lsw_err_bwd, ctx->lsw_tol};
-    lsw_flag_bwd_kernel<<<(sc + 127) / 128, 128, 0, ctx->stream>>>(dgrad, ctx->ozsA.p, sc, q, p, d, ls);
+    lsw_flag_bwd_kernel<<<(sc + 127) / 128, 128, 0, ctx->stream>>>(dgrad, ctx->ozsA.p, sc, q, p, d, ls, qn);
     CKL();
   }
   if (lswB) {
@@ -1252,18 +1273,18 @@ static int run_chunk(maf_ctx* ctx, const AcqDev& ap, bool posterior_only, bool c
     const double* vmax1 = (have_rowmax && (!lswF || have_rowmax2)) ? rowmax : nullptr;
     {
       ProfScope ps(ctx, MAF_PROF_VBAR);
-      DISPATCH_Q(q, vbar_planes_kernel<Q><<<sc, VBP_THREADS, 0, ctx->stream>>>(Vt, npad, sc, Jpad, ctx->gamma, nullptr, Sigbar, nsb, (int8_t*)ctx->ozA.p,
+      DISPATCH_Q(q, (pd > 0 ? vbar_planes_kernel<Q, true> : vbar_planes_kernel<Q, false>)<<<sc, VBP_THREADS, 0, ctx->stream>>>(Vt, npad, sc, Jpad, ctx->gamma, nullptr, Sigbar, nsb, (int8_t*)ctx->ozA.p,
                                                                        ctx->ozsA.p, vmax1, ctx->vbar_tight, lswF ? ctx->lsw_slotF : nullptr, ctx->Vt2.p, vmax2, ls,
-                                                                       mubar, ctx->row_add.p));
+                                                                       mubar, ctx->row_add.p, pd, ctx->Vp.p, ctx->rowmax_p.p));
       CKL();
     }
     if (launch_i8gemm(ctx, MAF_PROF_GEMM_BWD, Jpad, npad, npad, ctx->ozA, ctx->ozsA, ctx->ozTU, ctx->ozsTU, Vt, npad, 2, nsb, nsb + 1,
-                      nullptr, nullptr, ctx->lsw_cnt + 1, q, radd, cadd))
+                      nullptr, nullptr, ctx->lsw_cnt + 1, qn, radd, cadd))
       return 1;
     {
       ProfScope ps(ctx, MAF_PROF_CROSS_BWD);
-      DISPATCH_DK(d, ctx->mp.kernel_id, cross_bwd_kernel<D, KID, true><<<sc, 32 * q, 0, ctx->stream>>>(dX, sc, q, p, ctx->X0s, n, npad, ctx->mp, Vt, Sigbar, dgrad,
-                                                                                                 ctx->lsw_selB, ctx->lsw_cnt + 1));
+      DISPATCH_DK(d, ctx->mp.kernel_id, cross_bwd_kernel<D, KID, true><<<sc, 32 * (q - p), 0, ctx->stream>>>(dX, sc, q, p, ctx->X0s, n, npad, ctx->mp, Vt, Sigbar, dgrad,
+                                                                                                       ctx->lsw_selB, ctx->lsw_cnt + 1, qn));
       CKL();
     }
   }
@@ -1309,9 +1330,41 @@ static void lsw_adapt(maf_ctx* ctx) {
 }
 
 // All restarts, in chunks of at most chunk_rows candidate rows.  Device pointers; asynchronous.
+// Host pools X[S][q][d]: do all restarts carry the same p pending rows (bit for bit)?
+static bool pending_rows_shared(const double* X, int S, int q, int p, int d) {
+  if (p <= 0) return false;
+  const size_t row = (size_t)q * d, len = (size_t)p * d * sizeof(double);
+  for (int s = 1; s < S; ++s)
+    if (memcmp(X, X + (size_t)s * row, len) != 0) return false;
+  return true;
+}
+
+// V^T rows, mean partial sums and row maxima of the p pending points (rows 0..p-1 of the first pool), on all planes
+static int run_pending_block(maf_ctx* ctx, const double* dX, int q, int p) {
+  const int d = ctx->mp.d, n = ctx->n, npad = ctx->npad, ns = ctx->oz_ns, Jp = 256;
+  const int nparts = (npad + OZC_THREADS * 4 - 1) / (OZC_THREADS * 4);
+  const size_t bytes = (size_t)ns * Jp * npad;
+  if (ensure(ctx, ctx->ozA, (bytes + 7) / 8) || ensure(ctx, ctx->ozsA, (size_t)Jp) || ensure(ctx, ctx->Vp, (size_t)Jp * npad) ||
+      ensure(ctx, ctx->mu_part_p, (size_t)nparts * Jp) || ensure(ctx, ctx->rowmax_p, (size_t)Jp))
+    return 1;
+  {
+    ProfScope ps(ctx, MAF_PROF_CROSS_FWD);
+    dim3 grid(nparts, Jp / OZC_TJ);
+    DISPATCH_DKN(d, ctx->mp.kernel_id, ns, cross_fwd_planes_kernel<D, KID, NSC, 1><<<grid, OZC_THREADS, 0, ctx->stream>>>(dX, p, Jp, ctx->X0s, n, npad, ctx->mp, ns,
+                                                                               (int8_t*)ctx->ozA.p, ctx->ozsA.p, ctx->alpha, ctx->mu_part_p.p));
+    CKL();
+  }
+  bool done = false;
+  if (launch_i8gemm(ctx, MAF_PROF_GEMM_FWD, Jp, npad, npad, ctx->ozA, ctx->ozsA, ctx->ozTL, ctx->ozsTL, ctx->Vp.p, npad, 1, ns, ns + 1,
+                    ctx->rowmax_p.p, &done))
+    return 1;
+  if (!done) return fail(ctx, "the shared pending block needs the register-stash contraction kernel");
+  return 0;
+}
+
 static int run_all(maf_ctx* ctx, const maf_acq_params* prm, bool posterior_only, int S, int q, int p,
                    const double* dX, int M, const double* dz, const double* dw, const double* dinc,
-                   double* dloss, double* dgrad) {
+                   double* dloss, double* dgrad, bool pend_shared = false) {
   if (check_shape(ctx, S, q, p)) return 1;
   CK(cudaSetDevice(ctx->device));
   AcqDev ap{};
@@ -1328,17 +1381,22 @@ static int run_all(maf_ctx* ctx, const maf_acq_params* prm, bool posterior_only,
       ensure(ctx, ctx->dSigbar, sqq) || ensure(ctx, ctx->dchol, sqq))
     return 1;
   lsw_adapt(ctx);
-  int sc_max = (int)std::max<size_t>(1, ctx->chunk_rows / q);
+  // pending points contracted once: the INT8 engine with both fused producers and the exact-mean route only
+  const bool ded = pend_shared && ctx->pend_dedupe && p > 0 && !posterior_only && ctx->i8_ready && (ctx->oz_fuse & 3) == 3 && ctx->mu_alpha &&
+                   ctx->oz_variant == 5 && ctx->oz_ns >= 3 && ctx->oz_rowmax;
+  const int qrows = ded ? q - p : q;                              // candidate rows per restart through the contractions
+  int sc_max = (int)std::max<size_t>(1, ctx->chunk_rows / qrows);
   sc_max = std::min(sc_max, S);
-  const size_t need = (size_t)round_up(sc_max * q, 256) * npad;
+  const size_t need = (size_t)round_up(sc_max * qrows, 256) * npad;
   if (ensure(ctx, ctx->K10, need) || ensure(ctx, ctx->Vt, need)) return 1;
+  if (ded && run_pending_block(ctx, dX, q, p)) return 1;
   for (int s0 = 0; s0 < S; s0 += sc_max) {
     const int sc = std::min(sc_max, S - s0);
     const size_t oq = (size_t)s0 * q, oqq = oq * q;
     if (run_chunk(ctx, ap, posterior_only, closed_form, sc, q, p, dX + oq * d, M, dz, dw, dinc, ctx->dmu.p + oq,
                   ctx->dSig.p + oqq, closed_form ? nullptr : ctx->dchol.p + oqq, ctx->dmubar.p + oq,
                   ctx->dSigbar.p + oqq, dloss ? dloss + s0 : nullptr,
-                  dgrad ? dgrad + (size_t)s0 * (q - p) * d : nullptr))
+                  dgrad ? dgrad + (size_t)s0 * (q - p) * d : nullptr, ded))
       return 1;
   }
   if (ctx->lsw_stats && ctx->lsw_ready && !ctx->lsw_busy)
@@ -1545,7 +1603,7 @@ extern "C" int maf_acq_value_grad(maf_ctx* ctx, const maf_acq_params* prm, int S
     }
   }
   if (run_all(ctx, prm, false, S, q, p_pending, ctx->dX.p, M, dz, dw, dinc, ctx->dloss.p,
-              out_grad ? ctx->dgrad.p : nullptr))
+              out_grad ? ctx->dgrad.p : nullptr, pending_rows_shared(X, S, q, p_pending, d)))
     return 1;
   CK(cudaMemcpyAsync(out_loss, ctx->dloss.p, sizeof(double) * S, cudaMemcpyDeviceToHost, ctx->stream));
   if (out_grad) CK(cudaMemcpyAsync(out_grad, ctx->dgrad.p, sizeof(double) * ng, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1862,6 +1920,7 @@ extern "C" int maf_adam_begin(maf_ctx* ctx, const maf_acq_params* prm, int S, in
   ctx->adam_S = S;
   ctx->adam_q = q;
   ctx->adam_p = p_pending;
+  ctx->pend_shared = pending_rows_shared(X, S, q, p_pending, d);   // the update kernels never touch the pending rows
   ctx->adam_lr = lr;
   ctx->adam_b1 = beta1;
   ctx->adam_b2 = beta2;
@@ -1898,7 +1957,7 @@ static int adam_step_body(maf_ctx* ctx, bool closed, int M, size_t zsz, bool tra
     CKL();
   }
   if (run_all(ctx, &ctx->adam_prm, false, S, q, p, ctx->adam_X.p, M, closed ? nullptr : ctx->adam_zcur.p, nullptr, nullptr,
-              ctx->dloss.p, ctx->adam_g.p))
+              ctx->dloss.p, ctx->adam_g.p, ctx->pend_shared))
     return 1;
   {
     ProfScope ps(ctx, MAF_PROF_ADAM);
@@ -2010,7 +2069,7 @@ extern "C" int maf_adam_steps(maf_ctx* ctx, int steps, int M, const double* z_st
   for (int t = 0; t < steps && rc == 0; ++t) {
     double* lossp = dtrace ? dtrace + (size_t)t * S : ctx->dloss.p;
     rc = run_all(ctx, &ctx->adam_prm, false, S, q, p, ctx->adam_X.p, M, closed ? nullptr : ctx->adam_z.p + zsz * t,
-                 nullptr, nullptr, lossp, ctx->adam_g.p);
+                 nullptr, nullptr, lossp, ctx->adam_g.p, ctx->pend_shared);
     if (rc) break;
     const double coef = adam_next_coef(ctx);
     ProfScope ps(ctx, MAF_PROF_ADAM);
@@ -2107,12 +2166,13 @@ extern "C" int maf_lbfgs_run(maf_ctx* ctx, const maf_acq_params* prm, int S, int
     CK(cudaEventCreate(&t1));
     CK(cudaEventRecord(t0, ctx->stream));
   }
+  const bool lb_shared = pending_rows_shared(X, S, q, p, d);
   int it = 0, active = S, rc = 0;
   for (; it < maxiter && rc == 0; ++it) {
     if (fantasies)
       rc = run_fantasies(ctx, prm, S, ctx->lb_X.p, ctx->lb_ft.p, ctx->lb_gt.p, nullptr, nullptr, true);
     else
-      rc = run_all(ctx, prm, false, S, q, p, ctx->lb_X.p, M, dz, nullptr, nullptr, ctx->lb_ft.p, ctx->lb_gt.p);
+      rc = run_all(ctx, prm, false, S, q, p, ctx->lb_X.p, M, dz, nullptr, nullptr, ctx->lb_ft.p, ctx->lb_gt.p, lb_shared);
     if (rc) break;
     if (out_trace)
       CK(cudaMemcpyAsync(ctx->lb_trace.p + (size_t)it * S, ctx->lb_ft.p, sizeof(double) * S, cudaMemcpyDeviceToDevice, ctx->stream));

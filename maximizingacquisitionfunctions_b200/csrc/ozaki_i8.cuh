@@ -408,16 +408,20 @@ ozaki_slice_rows_kernel(const double* __restrict__ X, int ldx, int R, int Rpad, 
 //         partial in shared memory (no dependent shuffle chain in the element loop: the chain cost 2.1 ms per step at the
 //         headline size); after every OZC_RG rows warp w folds row w of the group.  Fixed summation order (thread partials
 //         strided by lane, shuffle tree, column blocks in index order): results do not depend on scheduling.
-// MODE 2: MODE 1 on the compact rows of the level switch's second pass: row r = pos q + i holds candidate row
-//         sel[pos] q + i of X for pos < *sel_count; J is ignored.
+// MODE 2: MODE 1 on the compact rows of the level switch's second pass: row r = pos (q - p) + i holds candidate row
+//         sel[pos] q + p + i of X for pos < *sel_count; J is ignored.
+// p > 0 (pending points, shared by every restart and contracted once elsewhere): only the q - p trainable rows of
+//         each pool are produced; row j = s (q - p) + i holds candidate row s q + p + i of X.
 template <int D, int KID, int NS, int MODE = 0>
 __global__ void __launch_bounds__(OZC_THREADS, (D > 0 && D <= 8) ? OZC_MINB : 1)
 cross_fwd_planes_kernel(const double* __restrict__ X, int J, int Jpad, const double* __restrict__ X0s, int n, int npad,
                         ModelParams mp, int ns_rt, int8_t* __restrict__ planes, double* __restrict__ scales,
                         const double* __restrict__ alpha = nullptr, double* __restrict__ mu_part = nullptr,
-                        const int* __restrict__ sel = nullptr, const int* __restrict__ sel_count = nullptr, int q = 1) {
+                        const int* __restrict__ sel = nullptr, const int* __restrict__ sel_count = nullptr, int q = 1,
+                        int p = 0) {
   constexpr int DD = D > 0 ? D : MAF_MAX_D;
   constexpr bool ALPHA = MODE >= 1, SEL = MODE == 2;
+  const int qn = q - p;
   const int d = D > 0 ? D : mp.d;
   const int ns = NS > 0 ? NS : ns_rt;
   __shared__ double xs[OZC_TJ][DD];
@@ -431,15 +435,15 @@ cross_fwd_planes_kernel(const double* __restrict__ X, int J, int Jpad, const dou
   const int k = (blockIdx.x * OZC_THREADS + threadIdx.x) * 4;
   const int j0 = blockIdx.y * OZC_TJ;
   if (SEL) {
-    J = __ldg(sel_count) * q;
+    J = __ldg(sel_count) * qn;
     if (j0 >= J) return;                                     // nothing selected in this row block (rows stay stale, unread)
   }
   for (int t = threadIdx.x; t < OZC_TJ * d; t += OZC_THREADS) {
     int jj = t / d, c = t - jj * d;
     int j = j0 + jj;
-    if (SEL && j < J) {
-      const int pos = j / q;
-      j = __ldg(sel + pos) * q + (j - pos * q);
+    if ((SEL || p > 0) && j < J) {
+      const int pos = j / qn;
+      j = (SEL ? __ldg(sel + pos) : pos) * q + p + (j - pos * qn);
     }
     xs[jj][c] = (j0 + jj < J) ? X[(size_t)j * d + c] * mp.inv_ls[c] : 0.0;
   }
@@ -521,14 +525,18 @@ cross_fwd_planes_kernel(const double* __restrict__ X, int J, int Jpad, const dou
 #ifndef VBP_MINB
 #define VBP_MINB 4
 #endif
-template <int Q>
+template <int Q, bool DED = false>
 __global__ void __launch_bounds__(VBP_THREADS, Q <= 8 ? VBP_MINB : 1)
 vbar_planes_kernel(const double* __restrict__ Vt, int npad, int S, int Jpad, const double* __restrict__ gamma,
                    const double* __restrict__ mubar, const double* __restrict__ Sigbar, int ns,
                    int8_t* __restrict__ planes, double* __restrict__ scales, const double* __restrict__ vmax = nullptr,
                    int tight = 0, const int* __restrict__ vslot = nullptr, const double* __restrict__ Vt2 = nullptr,
                    const double* __restrict__ vmax2 = nullptr, LevelSwitch ls = LevelSwitch{},
-                   const double* __restrict__ mubar_src = nullptr, double* __restrict__ row_add = nullptr) {
+                   const double* __restrict__ mubar_src = nullptr, double* __restrict__ row_add = nullptr,
+                   int p_rt = 0, const double* __restrict__ Vp = nullptr, const double* __restrict__ vmaxp = nullptr) {
+  const int p = DED ? p_rt : 0;                             // DED = false: no shared block, the row selects fold away
+  // p > 0: the first p rows of every pool are pending points; their V^T rows are shared (Vp[p][npad], row maxima vmaxp)
+  // and only the q - p trainable rows exist in Vt / Vt2 and are written here (rows rc (Q - p) + i - p).
   // row_add != nullptr: row_add[row] = mubar_src[s][i] for the rows this CTA writes (the reverse contraction's epilogue adds
   // row_add[j] alpha[r]: the mean part of d loss / d K10); 0 on the pad rows.
   // vslot != nullptr: restarts whose forward contraction was redone with all planes (level switch) keep their V^T rows
@@ -546,12 +554,13 @@ vbar_planes_kernel(const double* __restrict__ Vt, int npad, int S, int Jpad, con
   const int tid = threadIdx.x;
   const int rc = blockIdx.x;                                // row group written (compact position in the second pass)
   int s = rc;                                               // restart served
+  const int qn = Q - p;                                     // rows per restart in Vt / the planes
   const size_t plane_stride = (size_t)Jpad * npad;
   if (ls.sel != nullptr) {
     if (rc >= __ldg(ls.sel_count)) return;                  // (pad rows of the compact block stay stale: never read back)
     s = __ldg(ls.sel + rc);
-  } else if (s >= S) {                                      // pad rows [S Q, Jpad): zero digits, unit scale
-    const int r = S * Q + (s - S);
+  } else if (s >= S) {                                      // pad rows [S qn, Jpad): zero digits, unit scale
+    const int r = S * qn + (s - S);
     if (r >= Jpad) return;
     for (int i = 0; i < ns; ++i)
       for (int k = tid * 4; k < npad; k += VBP_THREADS * 4) *reinterpret_cast<int*>(planes + i * plane_stride + (size_t)r * npad + k) = 0;
@@ -561,7 +570,7 @@ vbar_planes_kernel(const double* __restrict__ Vt, int npad, int S, int Jpad, con
     }
     return;
   }
-  if (row_add != nullptr && tid < Q) row_add[(size_t)rc * Q + tid] = mubar_src[(size_t)s * Q + tid];
+  if (row_add != nullptr && tid >= p && tid < Q) row_add[(size_t)rc * qn + tid - p] = mubar_src[(size_t)s * Q + tid];
   const double* sb = Sigbar + (size_t)s * Q * Q;
   for (int t = tid; t < Q * Q; t += VBP_THREADS) {
     int i = t / Q, j = t - i * Q;
@@ -570,8 +579,11 @@ vbar_planes_kernel(const double* __restrict__ Vt, int npad, int S, int Jpad, con
   if (tid < Q) mb[tid] = mubar != nullptr ? mubar[(size_t)s * Q + tid] : 0.0;
   __syncthreads();
   const int vs = vslot != nullptr ? __ldg(vslot + s) : -1;
-  const double* V = vs >= 0 ? Vt2 + (size_t)vs * Q * npad : Vt + (size_t)s * Q * npad;
-  if (vs >= 0 && vmax != nullptr) vmax = vmax2 + (size_t)vs * Q - (size_t)s * Q;   // indexed by s Q + j below
+  // row j of this restart: pending rows from the shared block, trainable rows from Vt (or Vt2 after a forward redo)
+  const double* Vn = (vs >= 0 ? Vt2 + (size_t)vs * qn * npad : Vt + (size_t)s * qn * npad) - (size_t)p * npad;
+  const double* vmn = vmax == nullptr ? nullptr : (vs >= 0 ? vmax2 + (size_t)vs * qn : vmax + (size_t)s * qn) - p;
+#define VBP_ROW(j) ((DED && (j) < p) ? Vp + (size_t)(j) * npad : Vn + (size_t)(j) * npad)
+#define VBP_VMAX(j) ((DED && (j) < p) ? vmaxp[j] : vmn[j])
   double mx[Q], gx = 0.0;
 #pragma unroll
   for (int i = 0; i < Q; ++i) mx[i] = 0.0;
@@ -581,7 +593,7 @@ vbar_planes_kernel(const double* __restrict__ Vt, int npad, int S, int Jpad, con
     for (int k = tid * 2; k < npad; k += VBP_THREADS * 2) {
       double2 v[Q];
 #pragma unroll
-      for (int i = 0; i < Q; ++i) v[i] = *reinterpret_cast<const double2*>(V + (size_t)i * npad + k);
+      for (int i = 0; i < Q; ++i) v[i] = *reinterpret_cast<const double2*>(VBP_ROW(i) + k);
       double2 g = make_double2(0.0, 0.0);
       if (mubar != nullptr) g = *reinterpret_cast<const double2*>(gamma + k);
 #pragma unroll 1
@@ -606,7 +618,7 @@ vbar_planes_kernel(const double* __restrict__ Vt, int npad, int S, int Jpad, con
   } else {
     for (int k = tid; k < npad; k += VBP_THREADS) {
 #pragma unroll
-      for (int i = 0; i < Q; ++i) mx[i] = fmax(mx[i], fabs(V[(size_t)i * npad + k]));
+      for (int i = 0; i < Q; ++i) mx[i] = fmax(mx[i], fabs(VBP_ROW(i)[k]));
       if (mubar != nullptr) gx = fmax(gx, fabs(gamma[k]));
     }
   }
@@ -632,13 +644,13 @@ vbar_planes_kernel(const double* __restrict__ Vt, int npad, int S, int Jpad, con
       for (int j = 0; j < Q; ++j) {
         double vm = red[0][j];
         for (int w = 1; w < VBP_THREADS / 32; ++w) vm = fmax(vm, red[w][j]);
-        if (vmax) vm = vmax[(size_t)s * Q + j];
+        if (vmax) vm = VBP_VMAX(j);
         bound += fabs(W[tid][j]) * vm;
       }
     }
     const int e = oz_exponent_for(bound);
     // an all-zero row (no gradient reaches it) gets scale 0: its product is exactly 0 and carries no truncation error
-    scales[(size_t)rc * Q + tid] = bound > 0.0 ? ldexp(1.0, e) : 0.0;
+    if (tid >= p) scales[(size_t)rc * qn + tid - p] = bound > 0.0 ? ldexp(1.0, e) : 0.0;
     sinv[tid] = ldexp(1.0, -e + 8 * ns - 1);
   }
   __syncthreads();
@@ -648,11 +660,11 @@ vbar_planes_kernel(const double* __restrict__ Vt, int npad, int S, int Jpad, con
     if (k >= npad) continue;
     double2 v[Q];
 #pragma unroll
-    for (int i = 0; i < Q; ++i) v[i] = *reinterpret_cast<const double2*>(V + (size_t)i * npad + k);
+    for (int i = 0; i < Q; ++i) v[i] = *reinterpret_cast<const double2*>(VBP_ROW(i) + k);
     double2 g = make_double2(0.0, 0.0);
     if (mubar != nullptr) g = *reinterpret_cast<const double2*>(gamma + k);
 #pragma unroll 1
-    for (int i = 0; i < Q; ++i) {
+    for (int i = p; i < Q; ++i) {                             // trainable rows only: pending rows have no gradient
       double o0 = mb[i] * g.x, o1 = mb[i] * g.y;
 #pragma unroll
       for (int j = 0; j < Q; ++j) {
@@ -660,7 +672,9 @@ vbar_planes_kernel(const double* __restrict__ Vt, int npad, int S, int Jpad, con
         o1 -= W[i][j] * v[j].y;
       }
       const long long I[2] = {__double2ll_rn(o0 * sinv[i]), __double2ll_rn(o1 * sinv[i])};
-      oz_emit_digits2(I, ns, planes + ((size_t)rc * Q + i) * npad + k, plane_stride);
+      oz_emit_digits2(I, ns, planes + ((size_t)rc * qn + i - p) * npad + k, plane_stride);
     }
   }
+#undef VBP_ROW
+#undef VBP_VMAX
 }

@@ -17,12 +17,17 @@
 
 // One CTA per restart.  The q x POST_TK slab of V^T is staged in shared memory once and
 // every warp accumulates the Gram rows it owns (warp w -> rows w and w+8).
-template <int Q>
+template <int Q, bool DED = false>
 __global__ void __launch_bounds__(POST_THREADS)
 posterior_kernel(const double* __restrict__ Vt, int npad, const double* __restrict__ gamma,
                  const double* __restrict__ X, ModelParams mp, double mean,
                  double* __restrict__ mu, double* __restrict__ Sig,
-                 const double* __restrict__ mu_part = nullptr, int nparts = 0, int Jpad = 0, LevelSwitch ls = LevelSwitch{}) {
+                 const double* __restrict__ mu_part = nullptr, int nparts = 0, int Jpad = 0, LevelSwitch ls = LevelSwitch{},
+                 int p_rt = 0, const double* __restrict__ Vp = nullptr, const double* __restrict__ mu_part_p = nullptr,
+                 int Jpad_p = 0) {
+  const int p = DED ? p_rt : 0;                  // DED = false: no shared block, the row selects below fold away
+  // p > 0: rows 0..p-1 of every pool are pending points shared by all restarts; their V^T rows come from Vp[p][npad]
+  // (contracted once), their mean partial sums from mu_part_p, and Vt holds only the q - p trainable rows per restart.
   __shared__ double tile[Q][POST_TK];
   __shared__ double gs[POST_TK];
   __shared__ double G[Q][Q];
@@ -35,7 +40,8 @@ posterior_kernel(const double* __restrict__ Vt, int npad, const double* __restri
     s = __ldg(ls.sel + r);
   }
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const double* V = Vt + (size_t)r * Q * npad;
+  const int qn = Q - p;
+  const double* V = Vt + (size_t)r * qn * npad - (size_t)p * npad;      // trainable row i at V + i npad
   const int i0 = warp, i1 = warp + 8;
   double acc0[Q], acc1[Q], m0 = 0.0, m1 = 0.0;
 #pragma unroll
@@ -45,7 +51,7 @@ posterior_kernel(const double* __restrict__ Vt, int npad, const double* __restri
     __syncthreads();
     const int k = k0 + tid;
 #pragma unroll
-    for (int i = 0; i < Q; ++i) tile[i][tid] = (k < npad) ? V[(size_t)i * npad + k] : 0.0;
+    for (int i = 0; i < Q; ++i) tile[i][tid] = (k < npad) ? ((DED && i < p) ? Vp : V)[(size_t)i * npad + k] : 0.0;
     gs[tid] = (k < npad && gamma != nullptr) ? gamma[k] : 0.0;
     __syncthreads();
     for (int kk = lane; kk < POST_TK; kk += 32) {
@@ -103,7 +109,8 @@ posterior_kernel(const double* __restrict__ Vt, int npad, const double* __restri
     double m = mus[tid];
     if (mu_part != nullptr) {                         // mean from K10 . alpha (cross_fwd_planes_kernel), column blocks in order
       m = 0.0;
-      for (int b = 0; b < nparts; ++b) m += mu_part[(size_t)b * Jpad + (size_t)r * Q + tid];
+      for (int b = 0; b < nparts; ++b)
+        m += (DED && tid < p) ? mu_part_p[(size_t)b * Jpad_p + tid] : mu_part[(size_t)b * Jpad + (size_t)r * qn + tid - p];
     }
     mu[(size_t)s * Q + tid] = mean + m;
   }
@@ -125,12 +132,15 @@ posterior_kernel(const double* __restrict__ Vt, int npad, const double* __restri
 // Same result for Q <= 8 without the shared-memory slab (ncu: posterior_kernel runs at 94 % of the L1/shared
 // pipe): one thread owns a strided set of training columns, keeps its Q values of V^T in registers and accumulates the
 // Q (Q+1)/2 Gram entries and the Q mean terms there; one block reduction at the end.  Streams V^T once (HBM-bound).
-template <int Q>
+template <int Q, bool DED = false>
 __global__ void __launch_bounds__(POST_REG_THREADS)
 posterior_reg_kernel(const double* __restrict__ Vt, int npad, const double* __restrict__ gamma,
                      const double* __restrict__ X, ModelParams mp, double mean,
                      double* __restrict__ mu, double* __restrict__ Sig,
-                     const double* __restrict__ mu_part = nullptr, int nparts = 0, int Jpad = 0, LevelSwitch ls = LevelSwitch{}) {
+                     const double* __restrict__ mu_part = nullptr, int nparts = 0, int Jpad = 0, LevelSwitch ls = LevelSwitch{},
+                     int p_rt = 0, const double* __restrict__ Vp = nullptr, const double* __restrict__ mu_part_p = nullptr,
+                     int Jpad_p = 0) {
+  const int p = DED ? p_rt : 0;                  // DED = false: no shared block, the row selects below fold away
   constexpr int NG = Q * (Q + 1) / 2;
   __shared__ double red[POST_REG_THREADS / 32][NG + Q];
   __shared__ double G[Q][Q];
@@ -143,7 +153,8 @@ posterior_reg_kernel(const double* __restrict__ Vt, int npad, const double* __re
     s = __ldg(ls.sel + r);
   }
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const double* V = Vt + (size_t)r * Q * npad;
+  const int qn = Q - p;
+  const double* V = Vt + (size_t)r * qn * npad - (size_t)p * npad;      // trainable row i at V + i npad
   double acc[NG], m[Q];
 #pragma unroll
   for (int t = 0; t < NG; ++t) acc[t] = 0.0;
@@ -152,7 +163,7 @@ posterior_reg_kernel(const double* __restrict__ Vt, int npad, const double* __re
   for (int k = tid; k < npad; k += POST_REG_THREADS) {
     double v[Q];
 #pragma unroll
-    for (int i = 0; i < Q; ++i) v[i] = V[(size_t)i * npad + k];
+    for (int i = 0; i < Q; ++i) v[i] = ((DED && i < p) ? Vp : V)[(size_t)i * npad + k];
     const double g = gamma != nullptr ? gamma[k] : 0.0;      // nullptr: the mean comes from mu_part
 #pragma unroll
     for (int i = 0; i < Q; ++i) {
@@ -203,7 +214,8 @@ posterior_reg_kernel(const double* __restrict__ Vt, int npad, const double* __re
     double m = mus[tid];
     if (mu_part != nullptr) {
       m = 0.0;
-      for (int b = 0; b < nparts; ++b) m += mu_part[(size_t)b * Jpad + (size_t)r * Q + tid];
+      for (int b = 0; b < nparts; ++b)
+        m += (DED && tid < p) ? mu_part_p[(size_t)b * Jpad_p + tid] : mu_part[(size_t)b * Jpad + (size_t)r * qn + tid - p];
     }
     mu[(size_t)s * Q + tid] = mean + m;
   }

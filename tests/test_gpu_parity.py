@@ -701,3 +701,27 @@ def test_level_switch_inside_the_replayed_adam_loop():
     for key in ("tested_forward", "recomputed_forward", "tested_reverse", "recomputed_reverse"):
         assert res[0][2][key] == res[1][2][key]
     assert res[0][2]["tested_forward"] == T * S and res[0][2]["tested_reverse"] == T * S     # the switch was live in both
+
+
+def test_pending_rows_shared_block_and_per_restart_fallback(eng):
+    """Pending points shared by all restarts are contracted once (the pools of the agent: concat(tile(Xpend), new));
+    pools whose first p rows differ from restart to restart are legal through the C ABI too and take the per-restart
+    route.  Both against the oracle; the shared route must also agree with the per-restart route on the same pools."""
+    n, d, q, p, S, M = 300, 3, 5, 2, 40, 48
+    ts, X0, y0, X, z = setup_problem(eng, n, d, q, S, M, seed=12)
+    shared = X.copy()
+    shared[:, :p] = X[0, :p]
+    lo, go = orc.value_and_grad(ts, orc.Acq("cb"), shared[:, p:], z, X_pend=shared[0, :p])
+    lg, gg = eng.value_and_grad(prm("cb"), shared, z, p_pending=p)
+    assert gg.shape == (S, q - p, d) and relerr(lg, lo) < TOL and relerr(gg, go) < TOL
+    mu, cov, chol = eng.last_extras(S, q)
+    with torch.no_grad():
+        mo, co = orc.posterior(ts, torch.as_tensor(shared), full_cov=True)
+    assert relerr(mu, mo.numpy()) < TOL and relerr(cov, co.numpy()) < TOL
+    # different "pending" rows per restart: gradient of the trainable rows of the full-pool problem
+    lo2, go2 = orc.value_and_grad(ts, orc.Acq("cb"), X, z)
+    lg2, gg2 = eng.value_and_grad(prm("cb"), X, z, p_pending=p)
+    assert relerr(lg2, lo2) < TOL and relerr(gg2, go2[:, p:]) < TOL
+    # one restart of the shared pools evaluated alone (S = 1: trivially shared) equals its row in the batch
+    l1, g1 = eng.value_and_grad(prm("cb"), shared[7:8], z, p_pending=p)
+    assert relerr(l1, lg[7:8]) < 1e-12 and relerr(g1, gg[7:8]) < 1e-10

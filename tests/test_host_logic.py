@@ -147,3 +147,21 @@ def test_suggest_inputs_shards_restarts_over_ranks(tmp_path):
     for (x1, l1, i1), (x2, l2, i2) in zip(one, two):
         assert i1 == i2
         assert np.array_equal(np.asarray(x1), np.asarray(x2)) and l1 == l2
+
+
+def test_fast_weighted_draw_equals_numpy_legacy_choice():
+    """sample_starts draws its index sets with a cached cumulative sum; the result must be the one
+    RandomState.choice(n, k, p=w, replace=False) gives from the same stream (collisions and redraws included)."""
+    from maximizingacquisitionfunctions_b200.src.agents.bayesian_optimization import _choice_without_replacement
+    rs = np.random.RandomState(0)
+    for n, k in ((5, 1), (5, 3), (6, 6), (1000, 1), (1000, 4), (17, 9)):
+        w = rs.rand(n) ** 6 + 1e-16                      # heavy-tailed: collisions are frequent for small n
+        w /= w.sum()
+        raw = np.cumsum(w)
+        cdf = raw / raw[-1]
+        for seed in range(40):
+            a = np.random.RandomState(seed).choice(n, k, p=w, replace=False)
+            b = _choice_without_replacement(np.random.RandomState(seed), w, cdf, k)              # NumPy's redraw rounds
+            c = _choice_without_replacement(np.random.RandomState(seed), w, cdf, k, raw)         # step-function redraws
+            assert a.dtype.kind == b.dtype.kind and np.array_equal(a, b), (n, k, seed)
+            assert np.array_equal(a, c), (n, k, seed)
