@@ -20,7 +20,7 @@
 #include "ozaki_i8_v4.cuh"
 #include "posterior.cuh"
 
-#define MAF_VERSION_STR "maf_b200 0.1 (sm_100a, fp64 DMMA)"
+#define MAF_VERSION_STR "maf_b200 0.2 (sm_100a; INT8 digit-plane contractions on tcgen05, FP64 DMMA fallback)"
 
 struct ProfSlot {
   std::vector<cudaEvent_t> ev;   // pairs (start, stop)
