@@ -354,14 +354,17 @@ def main():
     flops_per_step = 2.0 * npad * npad * q * S            # n^2 q per triangular GEMM, two GEMMs (this rank's restarts)
     peak64, peak64_src = load_fp64_peak()
     fp64_equiv = flops_per_step * args.steps / (gemm_ms * 1e-3) * 1e-12 if gemm_ms > 0 else 0.0
-    common = {"kernel_ms_per_launch": gemm_ms / max(gemm_launches, 1), "kernel_share_of_step": gemm_ms / ms,
+    common = {"kernel_ms_per_launch": gemm_ms / max(gemm_launches, 1), "kernel_launches_per_step": gemm_launches / args.steps,
+              "kernel_ms_per_step": gemm_ms / args.steps, "kernel_share_of_step": gemm_ms / ms,
               "per_kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()}}
     if args.gemm == "i8":
         # every algorithmic FP64 flop is OZ_PAIRS exact int8 digit-plane products on the tcgen05 i8 pipe
         peak8, peak8_src, peak8_issue = load_i8_peak()
         achieved = fp64_equiv * pairs
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peak8, "unit": "TOP/s", "frac": achieved / peak8,
-                    "traffic": load_traffic("i8"), "kernel": "ozaki_i8_gemm_v4_kernel<%d,%d,1> forward / <%d,%d,1> reverse (tcgen05.mma.cta_group::2 kind::i8, TMA, TMEM; persistent CTA pairs, register-stash epilogue)" % (ns_f, ns_f + 1, ns_b, ns_b + 1),
+                    "traffic": load_traffic("i8"), "kernel": ("ozaki_i8_gemm_v4_kernel<%d,%d,1> (first pass of the level switch, every restart) and <%d,%d,1> (second pass, the recomputed restarts on compact rows)" % (ns_f - 1, ns_f, ns_f, ns_f + 1) if lsw["restarts"] else
+                               "ozaki_i8_gemm_v4_kernel<%d,%d,1> forward / <%d,%d,1> reverse" % (ns_f, ns_f + 1, ns_b, ns_b + 1)) +
+                              " (tcgen05.mma.cta_group::2 kind::i8, TMA, TMEM; persistent CTA pairs, register-stash epilogue)",
                     "peak_source": peak8_src,
                     "peak_note": "the driver's sustained cuBLAS bf16 figure is itself power-capped (1335 MHz median), so "
                                  "frac can exceed 1 when this kernel holds higher clocks under the same 1 kW cap; "

@@ -35,11 +35,16 @@ struct Oz3 {
   // parity (4 smax(0) <= NSLOT); when that does not fit (single-pass configurations) only the T tiles are.
   static constexpr int NLEV = LMAX - 1;
   static constexpr int NPASS = (NLEV + 3) / 4;
-  static constexpr int N0 = NLEV - 4 * (NPASS - 1);           // levels of the first pass
+  // levels of the first pass.  OZ3_N0_6: override for the six-level configuration <6,7> (default 2: levels 2-3 | 4-7;
+  // 3: levels 2-4 | 5-7), measured in profiles/r02_i8gemm_pass_split_ns6.txt
+#ifndef OZ3_N0_6
+#define OZ3_N0_6 2
+#endif
+  static constexpr int N0 = (NLEV == 6) ? OZ3_N0_6 : NLEV - 4 * (NPASS - 1);
   static constexpr int NSLOT = (2 * NS > 12) ? 2 * NS : 12;
   static constexpr int SMEM_BYTES = NSLOT * OZ3_TILE_BYTES + 1024;
   __host__ __device__ static constexpr int lo(int pass) { return pass == 0 ? 2 : 2 + N0 + 4 * (pass - 1); }
-  __host__ __device__ static constexpr int hi(int pass) { return pass == 0 ? 2 + N0 - 1 : lo(pass) + 3; }
+  __host__ __device__ static constexpr int hi(int pass) { return pass == 0 ? 2 + N0 - 1 : (lo(pass) + 3 < LMAX ? lo(pass) + 3 : LMAX); }
   __host__ __device__ static constexpr int smax(int pass) { return (NS < hi(pass) - 1) ? NS : hi(pass) - 1; }
   __host__ __device__ static constexpr int wlo(int pass, int i) { return (lo(pass) - i > 1) ? lo(pass) - i : 1; }
   __host__ __device__ static constexpr int whi(int pass, int i) { return (hi(pass) - i < NS) ? hi(pass) - i : NS; }
