@@ -348,24 +348,32 @@ class bayesian_optimization(search_agent):
         pools, p = handle.pools()
         S, q, d = pools.shape
         if np.ndim(handle.inputs_old) == 4:
-            raise NotImplementedError("Adam on fantasy-padded observations; use the L-BFGS-B subroutine (q == 1 default)")
+            return self._sgd_on_fantasies(handle, kind, lr, step_limit, time_limit)
         eng = handle.model.bind(handle.inputs_old, handle.outputs_old)
         prm = handle.loss_fn.acq_params(outputs_old=handle.outputs_old, **handle.loss_kwargs)
         eng.adam_begin(prm, pools, p_pending=p, lr=lr, method=kind, momentum=0.9)     # resets slots + step (:444-451)
 
         start_time = self.timer()
+        # steps per library call (= between looks at the clock).  Without a time limit: 16.  With one: 4 to begin with,
+        # then as many as fit a twentieth of the remaining time (at most 256), so that small problems -- a device step of
+        # tens of microseconds -- are not bound by one host round trip every four steps.
+        adaptive = block is None and np.isfinite(time_limit) and not use_averaging
         if block is None:
-            block = 16 if np.isinf(time_limit) else 4     # steps between looks at the clock
+            block = 16 if np.isinf(time_limit) else 4
         if use_averaging:
             block = 1
         loss_seq, mean_x, done = [], None, 0
         world_size = mdist.active()[1]
         while done < step_limit:
-            timed_out = self.timer() - start_time >= time_limit
+            now = self.timer() - start_time
+            timed_out = now >= time_limit
             if world_size > 1 and np.isfinite(time_limit):
                 timed_out = mdist.any_rank(timed_out)        # ranks stop after the same step: same host-RNG state
             if timed_out:
                 break
+            if adaptive and done and world_size == 1:
+                per_step = max(now / done, 1e-7)
+                block = int(min(256, max(4, (time_limit - now) / 20 / per_step)))
             k = int(min(block, step_limit - done))
             if q == 1:                                      # deterministic closed-form loss, no base samples
                 trace = eng.adam_steps(None, want_trace=True, steps=k)
@@ -387,6 +395,38 @@ class bayesian_optimization(search_agent):
         handle.assign(x[:, p:, :])
         loss_seq = np.concatenate([np.ravel(t) for t in loss_seq]) if loss_seq else np.empty([0])
         logger.info("SGD evaluated {:d} losses in {:.3e}s".format(len(loss_seq), self.timer() - start_time))
+        return loss_seq
+
+    def _sgd_on_fantasies(self, handle, kind, lr, step_limit, time_limit):
+        """`--subroutine sgd` on fantasy-padded (rank-4) observations, which the reference accepts (its sgd route sees the
+        mean over fantasies of the closed-form loss, src/models/gaussian_process.py:195-206): the same TF-1 Adam /
+        GradientDescent / Momentum updates and clip as on the device, driven from the host on the device's
+        fantasy-conditioned value + gradient (one call per step; the default subroutine for pools of one point, L-BFGS,
+        runs entirely on the device)."""
+        x = np.array(handle.value, dtype=np.float64)                    # [S, 1, d]
+        eng = handle.model.bind(handle.inputs_old, handle.outputs_old)
+        prm = handle.loss_fn.acq_params(outputs_old=None, **handle.loss_kwargs)
+        m, v, acc = np.zeros_like(x), np.zeros_like(x), np.zeros_like(x)
+        b1, b2, eps, b1p, b2p = 0.9, 0.999, 1e-8, 1.0, 1.0
+        loss_seq, start_time = [], self.timer()
+        for t in range(int(step_limit)):
+            if self.timer() - start_time >= time_limit:
+                break
+            losses, g = eng.fantasies_value_and_grad(prm, x[:, 0, :])
+            g = np.reshape(g, x.shape)
+            loss_seq.append(np.ravel(losses))
+            if kind == "adam":
+                b1p, b2p = b1p * b1, b2p * b2
+                m += (g - m) * (1 - b1)
+                v += (g * g - v) * (1 - b2)
+                x = x - lr * np.sqrt(1 - b2p) / (1 - b1p) * m / (np.sqrt(v) + eps)
+            else:
+                acc = (0.9 if kind == "momentum" else 0.0) * acc + g
+                x = x - lr * float(t + 1) ** -0.7 * acc
+            x = np.clip(x, 0.0, 1.0)
+        handle.assign(x)
+        loss_seq = np.concatenate(loss_seq) if loss_seq else np.empty([0])
+        logger.info("SGD (fantasy-conditioned) evaluated {:d} losses in {:.3e}s".format(len(loss_seq), self.timer() - start_time))
         return loss_seq
 
     # ------------------------------------------------------------------------------------------

@@ -725,3 +725,26 @@ def test_pending_rows_shared_block_and_per_restart_fallback(eng):
     # one restart of the shared pools evaluated alone (S = 1: trivially shared) equals its row in the batch
     l1, g1 = eng.value_and_grad(prm("cb"), shared[7:8], z, p_pending=p)
     assert relerr(l1, lg[7:8]) < 1e-12 and relerr(g1, gg[7:8]) < 1e-10
+
+
+def test_two_engines_on_two_devices_in_one_process():
+    """cudaFuncSetAttribute opt-ins (dynamic shared memory of the factorisation, the Monte-Carlo kernel at q = 16, the
+    contraction kernels) are per device: a second engine on another GPU of the same process must work like the first."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    from maximizingacquisitionfunctions_b200.engine import Engine
+    n, d, q, S, M = 1100, 3, 16, 12, 32
+    gp, X0, y0, X, z = orc.synthetic_problem(n, d, q, S, M, seed=6)
+    ts = orc.prepare_train(gp, X0, y0)
+    lo, go = orc.value_and_grad(ts, orc.Acq("sr"), X, z)
+    engines = [Engine(0), Engine(1)]
+    try:
+        for e in engines:
+            e.set_model("matern52", np.full(d, math.sqrt(d) / 4), 1.0, 1e-3, 0.0, 1e-6)
+            e.set_train(X0, y0)
+        for e in reversed(engines):
+            lg, gg = e.value_and_grad(prm("sr"), X, z)
+            assert relerr(lg, lo) < TOL and relerr(gg, go) < TOL
+    finally:
+        for e in engines:
+            e.close()

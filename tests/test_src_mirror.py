@@ -342,3 +342,19 @@ def test_device_lbfgs_restatement_with_pending_points_and_fixed_samples():
     after = np.ravel(handle.evaluate(feed)[0])
     assert np.all(after <= before + 1e-12) and after.min() < before.min()
     assert handle.value.shape == (5, 1, 2)
+
+
+def test_sgd_subroutine_on_fantasy_padded_observations():
+    """`--subroutine sgd` with rank-4 observations (the reference accepts it): Adam on the fantasy-averaged closed form."""
+    agent, X0, Y0 = make(d=2, n=16, seed=8, loss="confidence_bound", beta=2.0)
+    F = 4
+    rng = np.random.RandomState(2)
+    Xf = np.tile(X0[None, None], (F, 1, 1, 1))
+    Yf = Y0[None, None] + 0.05 * rng.randn(F, 1, len(Y0), 1)
+    starts = rng.rand(6, 1, 2)
+    handle = agent.appraise_inputs(None, starts, Xf, Yf, inputs_as_var=True)[0]
+    before = np.ravel(handle.evaluate(None)[0])
+    seq = agent._optimize_inputs_sgd(None, handle, handle, config={"step_limit": 15, "learning_rate": 0.02})
+    after = np.ravel(handle.evaluate(None)[0])
+    assert len(seq) == 15 * 6 and handle.value.shape == (6, 1, 2)
+    assert after.mean() < before.mean() and np.all(handle.value >= 0) and np.all(handle.value <= 1)
