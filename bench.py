@@ -455,7 +455,7 @@ def main():
                 "tested_reverse": lsw["tested_reverse"], "recomputed_reverse": lsw["recomputed_reverse"],
                 "tol": lsw["tol"], "calibrated_err_cov_abs": lsw["err_cov_abs"], "calibrated_err_grad_per_scale": lsw["err_grad_per_scale"],
                 "products_forward_avg": pairs_f, "products_reverse_avg": pairs_b,
-                "note": "both contractions first keep 6 of 7 digit planes (21 exact products); restarts whose own result does not tolerate the calibrated error of that level within tol are recomputed on all planes (28) inside the same call"},
+                "note": "both contractions first keep %d of %d digit planes (%d exact products); restarts whose own result does not tolerate the calibrated error of that level within tol are recomputed on all planes (%d) inside the same call" % (ns_f - 1, ns_f, (ns_f - 1) * ns_f // 2, ns_f * (ns_f + 1) // 2)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "adam_loop": adam_loop, "agent_suggest_inputs": agent_times, "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

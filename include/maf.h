@@ -245,8 +245,8 @@ int maf_set_gemm_mode(maf_ctx* ctx, int mode);
  * Kbar10 = Vbar^T L0^-1.  7 / 7 (28 + 28 exact products) is the FP64-grade default, 3 <= ns <= 7 (5 / 5 in MAF_F32 mode).
  * Accuracy studies and the level switch of the host layer use it; takes effect at the next evaluation. */
 int maf_set_digits(maf_ctx* ctx, int ns_fwd, int ns_bwd);
-/* Level switch (default on in MAF_F64 mode for n >= 1024; MAF_LEVEL_SWITCH=0 turns it off): both contractions first keep
- * one digit plane less (21 instead of 28 exact products).  maf_set_train measures the error that level leaves on the
+/* Level switch (default on for n >= 1024; MAF_LEVEL_SWITCH=0 turns it off): both contractions first keep
+ * one digit plane less (21 instead of 28 exact products; MAF_F32 mode: 10 instead of 15, tol 2.5e-5).  maf_set_train measures the error that level leaves on the
  * posterior covariance and on the gradient against the full level on 512 probe candidates; every restart whose own result
  * (max |Sigma_s|, max |gradient_s|) does not tolerate that error within `tol` (relative; default 2.5e-10, a quarter of
  * the 1e-9 parity bar; NaN keeps the current value) is recomputed with all planes, on the device, inside the same call.

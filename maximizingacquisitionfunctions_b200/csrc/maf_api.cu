@@ -727,6 +727,7 @@ extern "C" int maf_create(int device, int dtype, maf_ctx** out) {
     ctx->oz_ns_bwd = 5;
     ctx->oz_lmax_bwd = 6;
     ctx->oz_ns_fwd = 5;
+    ctx->lsw_tol = 2.5e-5;         // level switch: 4 planes first (10 products), a quarter of this mode's 1e-4 bar
   }
   CK(cudaSetDevice(device));
   cudaDeviceProp prop;
@@ -1108,8 +1109,8 @@ static int run_chunk(maf_ctx* ctx, const AcqDev& ap, bool posterior_only, bool c
   const bool mu_alpha = fused && fused_bwd && ctx->mu_alpha && ctx->oz_variant == 5 && ctx->oz_ns >= 3;
   const int need_grad = (!posterior_only && dgrad != nullptr) ? 1 : 0;
   // level switch: cheaper level first, failing restarts again with all planes (see LevelSwitch in common.cuh)
-  const bool lsw = mu_alpha && ctx->lsw_on && ctx->lsw_ready && !ctx->lsw_busy && ctx->dtype == MAF_F64 && ctx->oz_variant == 5 &&
-                   npad >= ctx->lsw_min_npad && ctx->oz_ns_fwd == ctx->oz_ns && ctx->oz_ns_bwd == ctx->oz_ns && ctx->oz_ns == 7;
+  const bool lsw = mu_alpha && ctx->lsw_on && ctx->lsw_ready && !ctx->lsw_busy && ctx->oz_variant == 5 &&
+                   npad >= ctx->lsw_min_npad && ctx->oz_ns_fwd == ctx->oz_ns && ctx->oz_ns_bwd == ctx->oz_ns && ctx->oz_ns >= 4;
   const bool lswF = lsw && ctx->lsw_cheap_fwd, lswB = lsw && ctx->lsw_cheap_bwd && need_grad;
   if ((lswF || lswB) && lsw_ensure(ctx, sc, Jpad, npad)) return 1;
   const int ns_fwd = lswF ? ctx->oz_ns - 1 : std::min(ctx->oz_ns_fwd, ctx->oz_ns);
@@ -1175,8 +1176,13 @@ static int run_chunk(maf_ctx* ctx, const AcqDev& ap, bool posterior_only, bool c
     {
       ProfScope ps(ctx, MAF_PROF_CROSS_FWD);
       dim3 grid(nparts, Jpad / OZC_TJ);
-      DISPATCH_DK(d, ctx->mp.kernel_id, cross_fwd_planes_kernel<D, KID, 7, 2><<<grid, OZC_THREADS, 0, ctx->stream>>>(dX, J, Jpad, ctx->X0s, n, npad, ctx->mp, nsf,
-                                                                             (int8_t*)ctx->ozA.p, ctx->ozsA.p, ctx->alpha, ctx->mu_part.p, ctx->lsw_selF, ctx->lsw_cnt, q, pd));
+      if (nsf == 7) {
+        DISPATCH_DK(d, ctx->mp.kernel_id, cross_fwd_planes_kernel<D, KID, 7, 2><<<grid, OZC_THREADS, 0, ctx->stream>>>(dX, J, Jpad, ctx->X0s, n, npad, ctx->mp, nsf,
+                                                                               (int8_t*)ctx->ozA.p, ctx->ozsA.p, ctx->alpha, ctx->mu_part.p, ctx->lsw_selF, ctx->lsw_cnt, q, pd));
+      } else {                                               // MAF_F32 mode (5 planes): run-time digit count
+        DISPATCH_DK(d, ctx->mp.kernel_id, cross_fwd_planes_kernel<D, KID, 0, 2><<<grid, OZC_THREADS, 0, ctx->stream>>>(dX, J, Jpad, ctx->X0s, n, npad, ctx->mp, nsf,
+                                                                               (int8_t*)ctx->ozA.p, ctx->ozsA.p, ctx->alpha, ctx->mu_part.p, ctx->lsw_selF, ctx->lsw_cnt, q, pd));
+      }
       CKL();
     }
     if (launch_i8gemm(ctx, MAF_PROF_GEMM_FWD, Jpad, npad, npad, ctx->ozA, ctx->ozsA, ctx->ozTL, ctx->ozsTL, ctx->Vt2.p, npad, 1,
@@ -1416,7 +1422,7 @@ static int run_all(maf_ctx* ctx, const maf_acq_params* prm, bool posterior_only,
 // are evaluated later; the per-restart test in the kernels compares it with what each restart's own result tolerates.
 static int lsw_calibrate(maf_ctx* ctx, int n, const double* X0) {
   ctx->lsw_ready = false;
-  const bool eligible = ctx->lsw_on && ctx->i8_ready && (ctx->oz_fuse & 3) == 3 && ctx->mu_alpha && ctx->dtype == MAF_F64 &&
+  const bool eligible = ctx->lsw_on && ctx->i8_ready && (ctx->oz_fuse & 3) == 3 && ctx->mu_alpha &&
                         ctx->oz_variant == 5 && ctx->npad >= ctx->lsw_min_npad && ctx->oz_ns >= 4 &&
                         ctx->oz_ns_fwd == ctx->oz_ns && ctx->oz_ns_bwd == ctx->oz_ns;
   if (!eligible) return 0;
