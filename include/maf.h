@@ -34,6 +34,8 @@
  *   MAF_LEVEL_SWITCH=0|1 error-bounded level switch of the two contractions (default 1, see maf_set_level_switch);
  *                        MAF_LEVEL_SWITCH_TOL=<rel> its tolerance (default 2.5e-10), MAF_LEVEL_SWITCH_MIN_N=<n> smallest padded
  *                        training-set size it applies to (default 1024)
+ *   MAF_CENTRE_K10=0|1   digit planes of K10 - a^2/2 with the rank-one term added back by the forward epilogue (default 1: one more
+ *                        bit of fixed-point range, half the truncation error) or of K10 itself
  *   MAF_PEND_DEDUPE=0|1  pending points shared by all restarts are contracted once per evaluation (default 1)
  *   MAF_VBAR_TIGHT=0|1   row scales of the Vbar digit planes from the true row maxima (one more sweep; default 0)
  *   MAF_OZ_HINTS=<a><t>  L2 policy of the A / T plane loads, 0 normal, 1 evict-first, 2 evict-last (default 22)

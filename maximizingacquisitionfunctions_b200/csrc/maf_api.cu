@@ -56,6 +56,9 @@ struct maf_ctx {
   double mean_val = 0.0, y_min = 0.0;
   double *X0s = nullptr, *L0 = nullptr, *Linv = nullptr, *LinvT = nullptr, *gamma = nullptr;
   double* alpha = nullptr;         // K00^-1 (y0 - m), refined (maf_set_train); [npad], zero on the pad
+  double* linv_rowsum = nullptr;   // L0^-1 1 (ones on the n real columns); [npad]: the add-back of the centred K10 planes
+  Buf row_add_fwd;                 // [Jpad] a^2/2 per valid candidate row (0 on pad rows), written by cross_fwd_planes_kernel
+  int centre_k10 = 0;              // MAF_CENTRE_K10=1: planes of K10 - a^2/2 (one more bit of range); 0: planes of K10 itself
   // Posterior mean by the exact FP64 route mu = m + K10 . alpha inside the cross-covariance kernel, its gradient
   // mubar_j alpha_k added inside cross_bwd_kernel: the mean no longer passes through the digit-sliced contractions
   // (INT8 engine with both fused producers only; MAF_MU_ALPHA=0 restores mu = m + V^T gamma).
@@ -753,6 +756,7 @@ extern "C" int maf_create(int device, int dtype, maf_ctx** out) {
   if (const char* vt = getenv("MAF_VBAR_TIGHT")) ctx->vbar_tight = atoi(vt);
   if (const char* lw = getenv("MAF_LEVEL_SWITCH")) ctx->lsw_on = atoi(lw);
   if (const char* pdd = getenv("MAF_PEND_DEDUPE")) ctx->pend_dedupe = atoi(pdd);
+  if (const char* ck = getenv("MAF_CENTRE_K10")) ctx->centre_k10 = atoi(ck);
   if (const char* lt = getenv("MAF_LEVEL_SWITCH_TOL")) ctx->lsw_tol = atof(lt);
   if (const char* ln = getenv("MAF_LEVEL_SWITCH_MIN_N")) ctx->lsw_min_npad = atoi(ln);
   if (const char* nf = getenv("MAF_OZ_NS_FWD")) {
@@ -778,7 +782,7 @@ extern "C" int maf_destroy(maf_ctx* ctx) {
   if (!ctx) return 0;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  double* raw[] = {ctx->X0s, ctx->L0, ctx->Linv, ctx->LinvT, ctx->gamma, ctx->alpha, ctx->d_argmin_val};
+  double* raw[] = {ctx->X0s, ctx->L0, ctx->Linv, ctx->LinvT, ctx->gamma, ctx->alpha, ctx->linv_rowsum, ctx->d_argmin_val};
   for (double* b : raw)
     if (b) cudaFree(b);
   Buf* bufs[] = {&ctx->K10, &ctx->Vt, &ctx->dX, &ctx->dz, &ctx->dw, &ctx->dinc, &ctx->dmu, &ctx->dSig, &ctx->dchol,
@@ -787,7 +791,7 @@ extern "C" int maf_destroy(maf_ctx* ctx) {
                  &ctx->fmubar, &ctx->ozA, &ctx->ozTL, &ctx->ozTU, &ctx->ozsA, &ctx->ozsTL, &ctx->ozsTU, &ctx->adam_zcur,
                  &ctx->lb_X, &ctx->lb_ft, &ctx->lb_gt, &ctx->lb_x, &ctx->lb_f, &ctx->lb_g, &ctx->lb_dir, &ctx->lb_step, &ctx->lb_gd,
                  &ctx->lb_hs, &ctx->lb_hy, &ctx->lb_rho, &ctx->lb_trace,
-                 &ctx->adam_coef, &ctx->adam_trace, &ctx->ozVmax, &ctx->mu_part, &ctx->Vt2, &ctx->rowmax2, &ctx->row_add, &ctx->Vp, &ctx->mu_part_p, &ctx->rowmax_p};
+                 &ctx->adam_coef, &ctx->adam_trace, &ctx->ozVmax, &ctx->mu_part, &ctx->Vt2, &ctx->rowmax2, &ctx->row_add, &ctx->Vp, &ctx->mu_part_p, &ctx->rowmax_p, &ctx->row_add_fwd};
   for (Buf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (ctx->d_argmin_idx) cudaFree(ctx->d_argmin_idx);
@@ -883,7 +887,7 @@ extern "C" int maf_set_train(maf_ctx* ctx, int n, const double* X0, const double
   const int npad = round_up(n, 128);
   ctx->train_set = false;
   if ((size_t)npad != ctx->cap_train || d != ctx->cap_train_d) {
-    double** bufs[] = {&ctx->X0s, &ctx->L0, &ctx->Linv, &ctx->LinvT, &ctx->gamma, &ctx->alpha};
+    double** bufs[] = {&ctx->X0s, &ctx->L0, &ctx->Linv, &ctx->LinvT, &ctx->gamma, &ctx->alpha, &ctx->linv_rowsum};
     for (double** b : bufs) {
       if (*b) CK(cudaFree(*b));
       *b = nullptr;
@@ -896,6 +900,7 @@ extern "C" int maf_set_train(maf_ctx* ctx, int n, const double* X0, const double
     CK(cudaMalloc((void**)&ctx->LinvT, sizeof(double) * nn));
     CK(cudaMalloc((void**)&ctx->gamma, sizeof(double) * npad));
     CK(cudaMalloc((void**)&ctx->alpha, sizeof(double) * npad));
+    CK(cudaMalloc((void**)&ctx->linv_rowsum, sizeof(double) * npad));
     ctx->cap_train = npad;
     ctx->cap_train_d = d;
   }
@@ -962,6 +967,16 @@ extern "C" int maf_set_train(maf_ctx* ctx, int n, const double* X0, const double
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaFree(res));
     CK(cudaFree(tmp));
+  }
+  {
+    // L0^-1 1 over the n real columns (add-back of the centred cross-covariance planes)
+    std::vector<double> ones(npad, 0.0);
+    for (int i = 0; i < n; ++i) ones[i] = 1.0;
+    CK(cudaMemcpyAsync(drho, ones.data(), sizeof(double) * npad, cudaMemcpyHostToDevice, ctx->stream));
+    ProfScope ps(ctx, MAF_PROF_CROSS_FWD);
+    trmv_lower_kernel<<<(npad + 7) / 8, 256, 0, ctx->stream>>>(ctx->Linv, drho, npad, ctx->linv_rowsum);
+    CKL();
+    CK(cudaStreamSynchronize(ctx->stream));                      // `ones` goes out of scope
   }
   ctx->i8_ready = false;
   if (ctx->gemm_i8 && npad <= 8192) {   // int32 level accumulators hold K <= 8192; larger n keeps the DMMA contraction
@@ -1116,7 +1131,9 @@ static int run_chunk(maf_ctx* ctx, const AcqDev& ap, bool posterior_only, bool c
   const int ns_fwd = lswF ? ctx->oz_ns - 1 : std::min(ctx->oz_ns_fwd, ctx->oz_ns);
   const int ns_bwd = lswB ? ctx->oz_ns - 1 : ctx->oz_ns_bwd;
   const int nparts = (npad + OZC_THREADS * 4 - 1) / (OZC_THREADS * 4);
-  if (mu_alpha && (ensure(ctx, ctx->mu_part, (size_t)nparts * Jpad) || ensure(ctx, ctx->row_add, (size_t)Jpad))) return 1;
+  if (mu_alpha && (ensure(ctx, ctx->mu_part, (size_t)nparts * Jpad) || ensure(ctx, ctx->row_add, (size_t)Jpad) ||
+                   ensure(ctx, ctx->row_add_fwd, (size_t)Jpad)))
+    return 1;
   const double* const radd = mu_alpha ? ctx->row_add.p : nullptr;
   const double* const cadd = mu_alpha ? ctx->alpha : nullptr;
   const double* mu_part = mu_alpha ? ctx->mu_part.p : nullptr;
@@ -1135,7 +1152,7 @@ static int run_chunk(maf_ctx* ctx, const AcqDev& ap, bool posterior_only, bool c
       dim3 grid(nparts, Jpad / OZC_TJ);
       if (mu_alpha) {
         DISPATCH_DKN(d, ctx->mp.kernel_id, ns_fwd, cross_fwd_planes_kernel<D, KID, NSC, 1><<<grid, OZC_THREADS, 0, ctx->stream>>>(dX, J, Jpad, ctx->X0s, n, npad, ctx->mp, ns_fwd,
-                                                                                       (int8_t*)ctx->ozA.p, ctx->ozsA.p, ctx->alpha, ctx->mu_part.p, nullptr, nullptr, q, pd));
+                                                                                       (int8_t*)ctx->ozA.p, ctx->ozsA.p, ctx->alpha, ctx->mu_part.p, nullptr, nullptr, q, pd, ctx->centre_k10 ? ctx->row_add_fwd.p : nullptr));
       } else {
         DISPATCH_DKN(d, ctx->mp.kernel_id, ns_fwd, cross_fwd_planes_kernel<D, KID, NSC, 0><<<grid, OZC_THREADS, 0, ctx->stream>>>(dX, J, Jpad, ctx->X0s, n, npad, ctx->mp, ns_fwd,
                                                                                        (int8_t*)ctx->ozA.p, ctx->ozsA.p));
@@ -1143,7 +1160,8 @@ static int run_chunk(maf_ctx* ctx, const AcqDev& ap, bool posterior_only, bool c
       CKL();
     }
     if (launch_i8gemm(ctx, MAF_PROF_GEMM_FWD, Jpad, npad, npad, ctx->ozA, ctx->ozsA, ctx->ozTL, ctx->ozsTL, Vt, npad, 1,
-                      ns_fwd, ns_fwd + 1, rowmax, &have_rowmax))
+                      ns_fwd, ns_fwd + 1, rowmax, &have_rowmax, nullptr, 1, (mu_alpha && ctx->centre_k10) ? ctx->row_add_fwd.p : nullptr,
+                      (mu_alpha && ctx->centre_k10) ? ctx->linv_rowsum : nullptr))
       return 1;
   } else {
     {
@@ -1178,15 +1196,16 @@ static int run_chunk(maf_ctx* ctx, const AcqDev& ap, bool posterior_only, bool c
       dim3 grid(nparts, Jpad / OZC_TJ);
       if (nsf == 7) {
         DISPATCH_DK(d, ctx->mp.kernel_id, cross_fwd_planes_kernel<D, KID, 7, 2><<<grid, OZC_THREADS, 0, ctx->stream>>>(dX, J, Jpad, ctx->X0s, n, npad, ctx->mp, nsf,
-                                                                               (int8_t*)ctx->ozA.p, ctx->ozsA.p, ctx->alpha, ctx->mu_part.p, ctx->lsw_selF, ctx->lsw_cnt, q, pd));
+                                                                               (int8_t*)ctx->ozA.p, ctx->ozsA.p, ctx->alpha, ctx->mu_part.p, ctx->lsw_selF, ctx->lsw_cnt, q, pd, ctx->centre_k10 ? ctx->row_add_fwd.p : nullptr));
       } else {                                               // MAF_F32 mode (5 planes): run-time digit count
         DISPATCH_DK(d, ctx->mp.kernel_id, cross_fwd_planes_kernel<D, KID, 0, 2><<<grid, OZC_THREADS, 0, ctx->stream>>>(dX, J, Jpad, ctx->X0s, n, npad, ctx->mp, nsf,
-                                                                               (int8_t*)ctx->ozA.p, ctx->ozsA.p, ctx->alpha, ctx->mu_part.p, ctx->lsw_selF, ctx->lsw_cnt, q, pd));
+                                                                               (int8_t*)ctx->ozA.p, ctx->ozsA.p, ctx->alpha, ctx->mu_part.p, ctx->lsw_selF, ctx->lsw_cnt, q, pd, ctx->centre_k10 ? ctx->row_add_fwd.p : nullptr));
       }
       CKL();
     }
     if (launch_i8gemm(ctx, MAF_PROF_GEMM_FWD, Jpad, npad, npad, ctx->ozA, ctx->ozsA, ctx->ozTL, ctx->ozsTL, ctx->Vt2.p, npad, 1,
-                      nsf, nsf + 1, want_rowmax ? ctx->rowmax2.p : nullptr, &have_rowmax2, ctx->lsw_cnt, qn))
+                      nsf, nsf + 1, want_rowmax ? ctx->rowmax2.p : nullptr, &have_rowmax2, ctx->lsw_cnt, qn,
+                      ctx->centre_k10 ? ctx->row_add_fwd.p : nullptr, ctx->centre_k10 ? ctx->linv_rowsum : nullptr))
       return 1;
     ProfScope ps(ctx, MAF_PROF_POSTERIOR);
     const LevelSwitch ls{ctx->lsw_selF, ctx->lsw_cnt, nullptr, nullptr, nullptr, 0.0, 0.0};
@@ -1351,18 +1370,21 @@ static int run_pending_block(maf_ctx* ctx, const double* dX, int q, int p) {
   const int nparts = (npad + OZC_THREADS * 4 - 1) / (OZC_THREADS * 4);
   const size_t bytes = (size_t)ns * Jp * npad;
   if (ensure(ctx, ctx->ozA, (bytes + 7) / 8) || ensure(ctx, ctx->ozsA, (size_t)Jp) || ensure(ctx, ctx->Vp, (size_t)Jp * npad) ||
-      ensure(ctx, ctx->mu_part_p, (size_t)nparts * Jp) || ensure(ctx, ctx->rowmax_p, (size_t)Jp))
+      ensure(ctx, ctx->mu_part_p, (size_t)nparts * Jp) || ensure(ctx, ctx->rowmax_p, (size_t)Jp) ||
+      ensure(ctx, ctx->row_add_fwd, (size_t)Jp))
     return 1;
   {
     ProfScope ps(ctx, MAF_PROF_CROSS_FWD);
     dim3 grid(nparts, Jp / OZC_TJ);
     DISPATCH_DKN(d, ctx->mp.kernel_id, ns, cross_fwd_planes_kernel<D, KID, NSC, 1><<<grid, OZC_THREADS, 0, ctx->stream>>>(dX, p, Jp, ctx->X0s, n, npad, ctx->mp, ns,
-                                                                               (int8_t*)ctx->ozA.p, ctx->ozsA.p, ctx->alpha, ctx->mu_part_p.p));
+                                                                               (int8_t*)ctx->ozA.p, ctx->ozsA.p, ctx->alpha, ctx->mu_part_p.p, nullptr, nullptr, 1, 0,
+                                                                               ctx->centre_k10 ? ctx->row_add_fwd.p : nullptr));
     CKL();
   }
   bool done = false;
   if (launch_i8gemm(ctx, MAF_PROF_GEMM_FWD, Jp, npad, npad, ctx->ozA, ctx->ozsA, ctx->ozTL, ctx->ozsTL, ctx->Vp.p, npad, 1, ns, ns + 1,
-                    ctx->rowmax_p.p, &done))
+                    ctx->rowmax_p.p, &done, nullptr, 1, ctx->centre_k10 ? ctx->row_add_fwd.p : nullptr,
+                    ctx->centre_k10 ? ctx->linv_rowsum : nullptr))
     return 1;
   if (!done) return fail(ctx, "the shared pending block needs the register-stash contraction kernel");
   return 0;

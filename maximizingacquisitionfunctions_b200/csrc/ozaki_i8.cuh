@@ -412,13 +412,19 @@ ozaki_slice_rows_kernel(const double* __restrict__ X, int ldx, int R, int Rpad, 
 //         sel[pos] q + p + i of X for pos < *sel_count; J is ignored.
 // p > 0 (pending points, shared by every restart and contracted once elsewhere): only the q - p trainable rows of
 //         each pool are produced; row j = s (q - p) + i holds candidate row s q + p + i of X.
+// MODE >= 1 also CENTRES the operand: cross-covariances lie in (0, a^2], so the planes hold K10 - a^2/2 in (-a^2/2, a^2/2]
+//         and the fixed row scale halves -- one more bit of the fixed-point range, i.e. half the truncation error of every
+//         level, for free.  The contraction's epilogue adds the rank-one term back, (a^2/2) (L0^-1 1)_r: row_add[j] = a^2/2
+//         (written here, 0 on pad rows), col_add = ctx->linv_rowsum.  L0^-1 1 is the whitened constant function: O(1)
+//         entries, so the add-back rounds at the FP64 floor.
 template <int D, int KID, int NS, int MODE = 0>
 __global__ void __launch_bounds__(OZC_THREADS, (D > 0 && D <= 8) ? OZC_MINB : 1)
 cross_fwd_planes_kernel(const double* __restrict__ X, int J, int Jpad, const double* __restrict__ X0s, int n, int npad,
                         ModelParams mp, int ns_rt, int8_t* __restrict__ planes, double* __restrict__ scales,
                         const double* __restrict__ alpha = nullptr, double* __restrict__ mu_part = nullptr,
                         const int* __restrict__ sel = nullptr, const int* __restrict__ sel_count = nullptr, int q = 1,
-                        int p = 0) {
+                        int p = 0, double* __restrict__ row_add = nullptr) {
+  // (row_add == nullptr: not centred)
   constexpr int DD = D > 0 ? D : MAF_MAX_D;
   constexpr bool ALPHA = MODE >= 1, SEL = MODE == 2;
   const int qn = q - p;
@@ -447,8 +453,13 @@ cross_fwd_planes_kernel(const double* __restrict__ X, int J, int Jpad, const dou
     }
     xs[jj][c] = (j0 + jj < J) ? X[(size_t)j * d + c] * mp.inv_ls[c] : 0.0;
   }
-  const int e = oz_exponent_for(mp.amp2);
-  if (blockIdx.x == 0 && threadIdx.x < OZC_TJ) scales[j0 + threadIdx.x] = (j0 + (int)threadIdx.x < J) ? ldexp(1.0, e) : 1.0;
+  const bool centred = ALPHA && row_add != nullptr;
+  const double centre = centred ? 0.5 * mp.amp2 : 0.0;
+  const int e = oz_exponent_for(centred ? centre : mp.amp2);
+  if (blockIdx.x == 0 && threadIdx.x < OZC_TJ) {
+    scales[j0 + threadIdx.x] = (j0 + (int)threadIdx.x < J) ? ldexp(1.0, e) : 1.0;
+    if (centred) row_add[j0 + threadIdx.x] = (j0 + (int)threadIdx.x < J) ? centre : 0.0;
+  }
   __syncthreads();
   const int jend = min(OZC_TJ, J - j0);                      // rows >= J of the last row block: zero digits
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -457,10 +468,12 @@ cross_fwd_planes_kernel(const double* __restrict__ X, int J, int Jpad, const dou
   {
     // a^2 2^(8 ns - 1 - e) per column, 0 on the pad columns k >= n (their digits must be zero): no per-element predicate
     const double sc = mp.amp2 * ldexp(1.0, -e + 8 * ns - 1);
-    double x0[4][DD], cs[4], al[ALPHA ? 4 : 1];
+    const double coff = centre * ldexp(1.0, -e + 8 * ns - 1);
+    double x0[4][DD], cs[4], co[ALPHA ? 4 : 1], al[ALPHA ? 4 : 1];
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
       cs[t] = (active && (k + t) < n) ? sc : 0.0;
+      if (ALPHA) co[t] = (active && (k + t) < n) ? coff : 0.0;   // pad columns: zero digits
       if (ALPHA) al[t] = active ? alpha[k + t] : 0.0;
 #pragma unroll
       for (int c = 0; c < DD; ++c) x0[t][c] = (c < d && active) ? X0s[(size_t)c * npad + k + t] : 0.0;
@@ -485,7 +498,7 @@ cross_fwd_planes_kernel(const double* __restrict__ X, int J, int Jpad, const dou
         }
         const double v = kern_val_fast<KID>(r2, etab) * cs[t];
         if (ALPHA) pm = fma(v, al[t], pm);
-        I[t] = __double2ll_rn(v);
+        I[t] = __double2ll_rn(ALPHA ? v - co[t] : v);
       }
       int8_t* dst = planes + (size_t)(j0 + jj) * npad + k;
       if constexpr (NS > 0) oz_emit_digits4_t<(NS > 0 ? NS : 1)>(I, dst, plane_stride);
