@@ -58,7 +58,7 @@ struct maf_ctx {
   double* alpha = nullptr;         // K00^-1 (y0 - m), refined (maf_set_train); [npad], zero on the pad
   double* linv_rowsum = nullptr;   // L0^-1 1 (ones on the n real columns); [npad]: the add-back of the centred K10 planes
   Buf row_add_fwd;                 // [Jpad] a^2/2 per valid candidate row (0 on pad rows), written by cross_fwd_planes_kernel
-  int centre_k10 = 0;              // MAF_CENTRE_K10=1: planes of K10 - a^2/2 (one more bit of range); 0: planes of K10 itself
+  int centre_k10 = 1;              // MAF_CENTRE_K10=0: planes of K10 itself (fixed scale a^2, one bit less of range)
   // Posterior mean by the exact FP64 route mu = m + K10 . alpha inside the cross-covariance kernel, its gradient
   // mubar_j alpha_k added inside cross_bwd_kernel: the mean no longer passes through the digit-sliced contractions
   // (INT8 engine with both fused producers only; MAF_MU_ALPHA=0 restores mu = m + V^T gamma).
