@@ -16,6 +16,7 @@ CONFIGS = [
     ("C2 Branin qPI(tau=0.01) q=4 n=256 S=1024 M=256", dict(n=256, d=2, q=4, S=1024, M=256, acq="pi", kw={"temperature": 0.01}, task="braninhoo")),
     ("C2 Branin qSR q=4 n=256 S=1024 M=256", dict(n=256, d=2, q=4, S=1024, M=256, acq="sr", kw={}, task="braninhoo")),
     ("C3 Hartmann-6 qEI q=8 n=1024 S=4096 M=128", dict(n=1024, d=6, q=8, S=4096, M=128, acq="ei", kw={}, task="hartmann6")),
+    ("C3 Hartmann-6 qEI(level=median y0: no restart identically 0) q=8 n=1024 S=4096 M=128", dict(n=1024, d=6, q=8, S=4096, M=128, acq="ei", kw={}, task="hartmann6", level="median")),
     ("C4 Levy d=6 qLCB(beta=2) q=16 n=2048 S=8192 M=128 (joint pass)", dict(n=2048, d=6, q=16, S=8192, M=128, acq="cb", kw={"beta": 2.0, "lower": True}, task="levy")),
     ("C5 synthetic d=6 qEI(level=median y0) q=8 n=4096 S=8192 (1/8 of 65536) M=1024", dict(n=4096, d=6, q=8, S=8192, M=1024, acq="ei", kw={}, task=None, level="median")),
 ]
