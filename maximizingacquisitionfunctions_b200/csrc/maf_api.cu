@@ -599,11 +599,14 @@ static int launch_i8gemm(maf_ctx* ctx, int slot, int J, int N, int K, const Buf&
       std::vector<long long> h(8 * 128);
       CK(cudaStreamSynchronize(ctx->stream));
       CK(cudaMemcpy(h.data(), prm.stats, sizeof(long long) * 8 * 128, cudaMemcpyDeviceToHost));
-      double tot = 0, full = 0, acc = 0, epi = 0, f[4] = {0, 0, 0, 0};
+      double tot = 0, full = 0, acc = 0, epi = 0, f[4] = {0, 0, 0, 0}, tmin = 1e30, tmax = 0;
       for (long long c = 0; c < pairs; ++c) {
+        tmin = std::min(tmin, (double)h[8 * c]);
+        tmax = std::max(tmax, (double)h[8 * c]);
         tot += h[8 * c]; full += h[8 * c + 1]; acc += h[8 * c + 2]; epi += h[8 * c + 3];
         for (int u = 0; u < 4; ++u) f[u] += h[8 * c + 4 + u];
       }
+      fprintf(stderr, "[oz4 stats] busiest/mean pair %.4f idlest/mean %.4f\n", tmax * pairs / tot, tmin * pairs / tot);
       fprintf(stderr, "[oz4 stats] tri=%d pairs=%lld tiles/pair=%.1f  issuer cycles: total %.0f  wait-operands %.1f%% (pass0 first chunk %.1f%%, later %.1f%%; pass1 first %.1f%%, later %.1f%%)  wait-epilogue %.1f%%  | epilogue body (1 warp) %.1f%% of total\n",
               tri, pairs, (double)ntiles2 / pairs, tot / pairs, 100 * full / tot, 100 * f[0] / tot, 100 * f[1] / tot, 100 * f[2] / tot,
               100 * f[3] / tot, 100 * acc / tot, 100 * epi / tot);

@@ -20,18 +20,19 @@ def main():
     dA = eng.alloc(A.nbytes).upload(A)
     dT = eng.alloc(T.nbytes).upload(T)
     dC = eng.alloc(A.nbytes)
+    ns = int(os.environ.get("OZ_BENCH_NS", "7"))                 # digit planes (levels <= ns + 1)
     for tri, name in ((0, "full"), (1, "lower")):
         eng.profile_enable(True)
         eng.profile_reset()
         for rep in range(3):
-            eng._ck(lib.maf_gemm_nt_i8_dev(ctx, J, N, N, dA.ptr, N, dT.ptr, N, dC.ptr, N, tri, 7, 8))
+            eng._ck(lib.maf_gemm_nt_i8_dev(ctx, J, N, N, dA.ptr, N, dT.ptr, N, dC.ptr, N, tri, ns, ns + 1))
         prof = eng.profile_read()
         eng.profile_enable(False)
         ms = prof["gemm_fwd"][0] / 3
         flops = 2.0 * J * N * N * (1.0 if tri == 0 else 0.5)
         print(json.dumps({"bench": "maf_gemm_nt_i8", "tri": name, "J": J, "N": N, "gemm_ms": ms,
                           "slice_ms": prof["cross_fwd"][0] / 3, "fp64_equiv_tflops_algorithmic": flops / ms * 1e-9,
-                          "int8_tops": flops * 28 / ms * 1e-9 * (1.0 if tri == 0 else (1 + 128.0 / N))}), flush=True)
+                          "ns": ns, "int8_tops": flops * (ns * (ns + 1) // 2) / ms * 1e-9 * (1.0 if tri == 0 else (1 + 128.0 / N))}), flush=True)
     eng.close()
 
 
