@@ -183,6 +183,31 @@ __device__ __forceinline__ double kern_dr2_fast(double r2, const double* __restr
   return below ? 0.0 : -1.5 * g;
 }
 
+// kappa(r2) and d kappa / d r2 from one sqrt and one exp: the same arithmetic as kern_val_fast / kern_dr2_fast, so the
+// pair is bit-identical to calling both.  The forward covariance kernel stores the derivative (see cross_bwd_g_kernel).
+template <int KID>
+__device__ __forceinline__ double kern_val_dr2_fast(double r2, const double* __restrict__ tab, double& g) {
+  if (KID == MAF_KERNEL_SE) {
+    const double E = maf_exp_neg_fast(0.5 * r2, tab);
+    g = -0.5 * E;
+    return E;
+  }
+  const bool below = __double2hiint(r2) < 0x3CB00000;        // r2 < eps: value clamped, gradient blocked
+  const double rc = below ? MAF_EPS_F64 : r2;
+  if (KID == MAF_KERNEL_MATERN52) {
+    const double u = 5.0 * rc;
+    const double r = maf_sqrt_fast(u);
+    const double E = maf_exp_neg_fast(r, tab);
+    const double gg = (1.0 + r) * E;
+    g = below ? 0.0 : -(5.0 / 6.0) * gg;
+    return fma(u, MAF_FC[7], 1.0 + r) * E;
+  }
+  const double r = maf_sqrt_fast(3.0 * rc);
+  const double E = maf_exp_neg_fast(r, tab);
+  g = below ? 0.0 : -1.5 * E;
+  return (1.0 + r) * E;
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

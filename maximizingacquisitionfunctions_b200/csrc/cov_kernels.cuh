@@ -180,6 +180,137 @@ cross_bwd_kernel(const double* __restrict__ X, int S, int q, int p,
   }
 }
 
+// ---------------------------------------------------------------------------
+// Backward on stored kernel derivatives: the forward covariance kernel left G[j][k] = kappa'(r2_jk) behind
+// (cross_fwd_planes_kernel, gout), so the element costs two streamed loads and 13 FP64 instructions instead of a
+// square root and an exponential (40): the kernel moves from the FP64 pipe to the HBM stream (Kbar + G, 16 B per pair).
+// One CTA per restart, R trainable rows per warp: a training point's coordinates are loaded once per R rows.
+// Row layout of Kbar as in cross_bwd_kernel (kq rows per pool, compact positions in the second pass of the level
+// switch); G always lives at the restart's own rows.
+// ---------------------------------------------------------------------------
+#ifndef CROSS_BWD_G_R
+#define CROSS_BWD_G_R 2
+#endif
+#ifndef CROSS_BWD_G_MINB
+#define CROSS_BWD_G_MINB 2
+#endif
+#ifndef CROSS_BWD_G_UNROLL
+#define CROSS_BWD_G_UNROLL 1
+#endif
+#ifndef CROSS_BWD_G_VEC
+#define CROSS_BWD_G_VEC 2
+#endif
+template <int D, int KID, int R, bool SEL = false>
+__global__ void __launch_bounds__(32 * ((MAF_MAX_Q + R - 1) / R), CROSS_BWD_G_MINB)
+cross_bwd_g_kernel(const double* __restrict__ X, int S, int q, int p, const double* __restrict__ X0s, int n, int npad,
+                   ModelParams mp, const double* __restrict__ Kbar, const double* __restrict__ G,
+                   const double* __restrict__ Sigbar, double* __restrict__ grad, const int* __restrict__ sel,
+                   const int* __restrict__ sel_count, int kq) {
+  static_assert(D > 0, "compile-time dimension only");
+  __shared__ double etab_sh[MAF_ETAB_WORDS];
+  maf_fill_etab(etab_sh, threadIdx.x, blockDim.x);
+  const double* etab = etab_sh + MAF_ETAB_LANE(threadIdx.x);
+  __syncthreads();
+  int s = blockIdx.x;
+  if (kq == 0) kq = q;
+  const size_t krow0 = (size_t)s * kq;                         // rows of Kbar: position of this CTA
+  if (SEL) {
+    if ((int)blockIdx.x >= __ldg(sel_count)) return;
+    s = __ldg(sel + blockIdx.x);
+  }
+  const size_t grow0 = (size_t)s * kq;                         // rows of G: the restart itself
+  const int lane = threadIdx.x & 31;
+  const int i0 = p + (threadIdx.x >> 5) * R;                   // first row of this warp
+  if (i0 >= q) return;
+  double xi[R][D], acc[R][D];
+  const double* kb[R];
+  const double* gb[R];
+#pragma unroll
+  for (int rr = 0; rr < R; ++rr) {
+    const int i = min(i0 + rr, q - 1);                         // a missing last row repeats the previous one (never stored)
+    const size_t j = (size_t)s * q + i;
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+      xi[rr][c] = X[j * D + c] * mp.inv_ls[c];
+      acc[rr][c] = 0.0;
+    }
+    kb[rr] = Kbar + (krow0 + i - (q - kq)) * npad;
+    gb[rr] = G + (grow0 + i - (q - kq)) * npad;
+  }
+  constexpr int UNRG = CROSS_BWD_G_UNROLL;
+#if CROSS_BWD_G_VEC == 2
+  // two training points per lane and 16-byte loads (rows are 1 KB aligned: npad is a multiple of 128); the odd last
+  // column of an odd n is masked, pad columns are never read past n rounded up to 2
+  const int n2 = n & ~1;
+#pragma unroll UNRG
+  for (int k = 2 * lane; k < n2; k += 64) {
+    double2 x0[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) x0[c] = *reinterpret_cast<const double2*>(X0s + (size_t)c * npad + k);
+#pragma unroll
+    for (int rr = 0; rr < R; ++rr) {
+      const double2 kv = __ldcs(reinterpret_cast<const double2*>(kb[rr] + k));
+      const double2 gv = __ldcs(reinterpret_cast<const double2*>(gb[rr] + k));
+      const double g0 = kv.x * gv.x, g1 = kv.y * gv.y;
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        acc[rr][c] = fma(g0, xi[rr][c] - x0[c].x, acc[rr][c]);
+        acc[rr][c] = fma(g1, xi[rr][c] - x0[c].y, acc[rr][c]);
+      }
+    }
+  }
+  if ((n & 1) && lane == 0) {
+    const int k = n - 1;
+#pragma unroll
+    for (int rr = 0; rr < R; ++rr) {
+      const double g = kb[rr][k] * gb[rr][k];
+#pragma unroll
+      for (int c = 0; c < D; ++c) acc[rr][c] = fma(g, xi[rr][c] - X0s[(size_t)c * npad + k], acc[rr][c]);
+    }
+  }
+#else
+#pragma unroll UNRG
+  for (int k = lane; k < n; k += 32) {
+    double x0[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) x0[c] = X0s[(size_t)c * npad + k];
+#pragma unroll
+    for (int rr = 0; rr < R; ++rr) {
+      const double g = __ldcs(kb[rr] + k) * __ldcs(gb[rr] + k);
+#pragma unroll
+      for (int c = 0; c < D; ++c) acc[rr][c] = fma(g, xi[rr][c] - x0[c], acc[rr][c]);
+    }
+  }
+#endif
+#pragma unroll
+  for (int rr = 0; rr < R; ++rr) {
+    const int i = i0 + rr;
+    if (i < q) {                                               // warp-uniform
+      // self-covariance term (K11 = a^2 kappa(r2(X_s, X_s)); diagonal has zero gradient)
+      if (lane < q && lane != i) {
+        const double* xo = X + ((size_t)s * q + lane) * D;
+        double xj[D];
+        double r2 = 0.0;
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+          xj[c] = xo[c] * mp.inv_ls[c];
+          const double df = xi[rr][c] - xj[c];
+          r2 += df * df;
+        }
+        const double* sb = Sigbar + (size_t)s * q * q;
+        const double g = (sb[i * q + lane] + sb[lane * q + i]) * kern_dr2_fast<KID>(r2, etab);
+#pragma unroll
+        for (int c = 0; c < D; ++c) acc[rr][c] += g * (xi[rr][c] - xj[c]);
+      }
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        const double v = warp_sum(acc[rr][c]);
+        if (lane == 0) grad[((size_t)s * (q - p) + (i - p)) * D + c] = 2.0 * mp.amp2 * mp.inv_ls[c] * v;
+      }
+    }
+  }
+}
+
 // First pass of the reverse level switch, after cross_bwd_kernel: the truncation error of the cheaper level on row j is
 // err x kscale[j] (calibrated per unit row scale of the Vbar planes); restarts where it exceeds tol x max |gradient| are
 // listed for the second pass.  One thread per restart.

@@ -133,6 +133,8 @@ struct maf_ctx {
   Buf ozA, ozTL, ozTU;             // digit planes (int8, sized in doubles): candidates / Linv / LinvT
   Buf ozsA, ozsTL, ozsTU;          // row scales
   Buf ozVmax;                      // row maxima of V^T left by the forward contraction's epilogue
+  Buf Gk;                          // d kappa / d r2 of every (candidate row, training point) pair, left by the forward covariance kernel
+  int g_route = 1;                 // MAF_G_ROUTE=0: the reverse covariance kernel recomputes the derivative (sqrt + exp per pair)
   int oz_rowmax = 1;               // MAF_OZ_ROWMAX=0: the Vbar producer sweeps V^T for them
   struct OzSched { int nN, nJ2, tri, sj, pairs, groups; int* d_list; int* d_begin; };
   std::vector<OzSched> oz_scheds;  // balanced static tile schedules of the CTA-pair kernel, one per launch shape
@@ -750,6 +752,7 @@ extern "C" int maf_create(int device, int dtype, maf_ctx** out) {
     if (h[0] && h[1]) ctx->oz_hint_t = h[1] - '0';
   }
   if (const char* pf = getenv("MAF_OZ_PF")) ctx->oz_pf = atoi(pf);
+  if (const char* gr2 = getenv("MAF_G_ROUTE")) ctx->g_route = atoi(gr2);
   if (const char* sc = getenv("MAF_OZ_SCHED")) ctx->oz_sched = atoi(sc);
   if (const char* so = getenv("MAF_OZ_SCHED_OVH")) ctx->oz_sched_ovh = atof(so);
   if (const char* sg = getenv("MAF_OZ_GROUPS")) ctx->oz_groups = atoi(sg);
@@ -794,7 +797,7 @@ extern "C" int maf_destroy(maf_ctx* ctx) {
                  &ctx->fmubar, &ctx->ozA, &ctx->ozTL, &ctx->ozTU, &ctx->ozsA, &ctx->ozsTL, &ctx->ozsTU, &ctx->adam_zcur,
                  &ctx->lb_X, &ctx->lb_ft, &ctx->lb_gt, &ctx->lb_x, &ctx->lb_f, &ctx->lb_g, &ctx->lb_dir, &ctx->lb_step, &ctx->lb_gd,
                  &ctx->lb_hs, &ctx->lb_hy, &ctx->lb_rho, &ctx->lb_trace,
-                 &ctx->adam_coef, &ctx->adam_trace, &ctx->ozVmax, &ctx->mu_part, &ctx->Vt2, &ctx->rowmax2, &ctx->row_add, &ctx->Vp, &ctx->mu_part_p, &ctx->rowmax_p, &ctx->row_add_fwd};
+                 &ctx->adam_coef, &ctx->adam_trace, &ctx->ozVmax, &ctx->mu_part, &ctx->Vt2, &ctx->rowmax2, &ctx->row_add, &ctx->Vp, &ctx->mu_part_p, &ctx->rowmax_p, &ctx->row_add_fwd, &ctx->Gk};
   for (Buf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (ctx->d_argmin_idx) cudaFree(ctx->d_argmin_idx);
@@ -1146,6 +1149,10 @@ static int run_chunk(maf_ctx* ctx, const AcqDev& ap, bool posterior_only, bool c
   if (want_rowmax && ensure(ctx, ctx->ozVmax, (size_t)Jpad)) return 1;
   double* const rowmax = want_rowmax ? ctx->ozVmax.p : nullptr;
   if (lswF || lswB) CK(cudaMemsetAsync(ctx->lsw_cnt, 0, 4 * sizeof(int), ctx->stream));
+  // kernel derivatives stored by the forward covariance kernel for the reverse one (cross_bwd_g_kernel)
+  const bool groute = mu_alpha && ctx->g_route && need_grad && d >= 1 && d <= 8;
+  if (groute && ensure(ctx, ctx->Gk, (size_t)Jpad * npad)) return 1;
+  double* const gout = groute ? ctx->Gk.p : nullptr;
   if (fused) {
     // K10 goes straight to digit planes (bounded by a^2: fixed row scale), FP64 K10 is never materialised
     const size_t bytes = (size_t)ctx->oz_ns * Jpad * npad;
@@ -1153,7 +1160,10 @@ static int run_chunk(maf_ctx* ctx, const AcqDev& ap, bool posterior_only, bool c
     {
       ProfScope ps(ctx, MAF_PROF_CROSS_FWD);
       dim3 grid(nparts, Jpad / OZC_TJ);
-      if (mu_alpha) {
+      if (groute) {
+        DISPATCH_DKN(d, ctx->mp.kernel_id, ns_fwd, cross_fwd_planes_kernel<D, KID, NSC, 3><<<grid, OZC_THREADS, 0, ctx->stream>>>(dX, J, Jpad, ctx->X0s, n, npad, ctx->mp, ns_fwd,
+                                                                                       (int8_t*)ctx->ozA.p, ctx->ozsA.p, ctx->alpha, ctx->mu_part.p, nullptr, nullptr, q, pd, ctx->centre_k10 ? ctx->row_add_fwd.p : nullptr, gout));
+      } else if (mu_alpha) {
         DISPATCH_DKN(d, ctx->mp.kernel_id, ns_fwd, cross_fwd_planes_kernel<D, KID, NSC, 1><<<grid, OZC_THREADS, 0, ctx->stream>>>(dX, J, Jpad, ctx->X0s, n, npad, ctx->mp, ns_fwd,
                                                                                        (int8_t*)ctx->ozA.p, ctx->ozsA.p, ctx->alpha, ctx->mu_part.p, nullptr, nullptr, q, pd, ctx->centre_k10 ? ctx->row_add_fwd.p : nullptr));
       } else {
@@ -1282,8 +1292,14 @@ static int run_chunk(maf_ctx* ctx, const AcqDev& ap, bool posterior_only, bool c
   }
   {
     ProfScope ps(ctx, MAF_PROF_CROSS_BWD);
-    DISPATCH_DK(d, ctx->mp.kernel_id, cross_bwd_kernel<D, KID, false><<<sc, 32 * (q - p), 0, ctx->stream>>>(dX, sc, q, p, ctx->X0s, n, npad, ctx->mp, K10, Sigbar, dgrad,
+    if (groute) {
+      constexpr int R = CROSS_BWD_G_R;
+      DISPATCH_DK(d, ctx->mp.kernel_id, cross_bwd_g_kernel<(D > 0 ? D : 1), KID, R, false><<<sc, 32 * ((q - p + R - 1) / R), 0, ctx->stream>>>(
+                      dX, sc, q, p, ctx->X0s, n, npad, ctx->mp, K10, gout, Sigbar, dgrad, nullptr, nullptr, qn));
+    } else {
+      DISPATCH_DK(d, ctx->mp.kernel_id, cross_bwd_kernel<D, KID, false><<<sc, 32 * (q - p), 0, ctx->stream>>>(dX, sc, q, p, ctx->X0s, n, npad, ctx->mp, K10, Sigbar, dgrad,
                                                                                                      nullptr, nullptr, qn));
+    }
     CKL();
   }
   if (lswB) {
@@ -1311,8 +1327,14 @@ static int run_chunk(maf_ctx* ctx, const AcqDev& ap, bool posterior_only, bool c
       return 1;
     {
       ProfScope ps(ctx, MAF_PROF_CROSS_BWD);
-      DISPATCH_DK(d, ctx->mp.kernel_id, cross_bwd_kernel<D, KID, true><<<sc, 32 * (q - p), 0, ctx->stream>>>(dX, sc, q, p, ctx->X0s, n, npad, ctx->mp, Vt, Sigbar, dgrad,
+      if (groute) {
+        constexpr int R = CROSS_BWD_G_R;
+        DISPATCH_DK(d, ctx->mp.kernel_id, cross_bwd_g_kernel<(D > 0 ? D : 1), KID, R, true><<<sc, 32 * ((q - p + R - 1) / R), 0, ctx->stream>>>(
+                        dX, sc, q, p, ctx->X0s, n, npad, ctx->mp, Vt, gout, Sigbar, dgrad, ctx->lsw_selB, ctx->lsw_cnt + 1, qn));
+      } else {
+        DISPATCH_DK(d, ctx->mp.kernel_id, cross_bwd_kernel<D, KID, true><<<sc, 32 * (q - p), 0, ctx->stream>>>(dX, sc, q, p, ctx->X0s, n, npad, ctx->mp, Vt, Sigbar, dgrad,
                                                                                                        ctx->lsw_selB, ctx->lsw_cnt + 1, qn));
+      }
       CKL();
     }
   }

@@ -408,6 +408,7 @@ ozaki_slice_rows_kernel(const double* __restrict__ X, int ldx, int R, int Rpad, 
 //         partial in shared memory (no dependent shuffle chain in the element loop: the chain cost 2.1 ms per step at the
 //         headline size); after every OZC_RG rows warp w folds row w of the group.  Fixed summation order (thread partials
 //         strided by lane, shuffle tree, column blocks in index order): results do not depend on scheduling.
+// MODE 3: MODE 1 that also stores the kernel derivative of every pair for the reverse covariance kernel (gout).
 // MODE 2: MODE 1 on the compact rows of the level switch's second pass: row r = pos (q - p) + i holds candidate row
 //         sel[pos] q + p + i of X for pos < *sel_count; J is ignored.
 // p > 0 (pending points, shared by every restart and contracted once elsewhere): only the q - p trainable rows of
@@ -423,10 +424,12 @@ cross_fwd_planes_kernel(const double* __restrict__ X, int J, int Jpad, const dou
                         ModelParams mp, int ns_rt, int8_t* __restrict__ planes, double* __restrict__ scales,
                         const double* __restrict__ alpha = nullptr, double* __restrict__ mu_part = nullptr,
                         const int* __restrict__ sel = nullptr, const int* __restrict__ sel_count = nullptr, int q = 1,
-                        int p = 0, double* __restrict__ row_add = nullptr) {
+                        int p = 0, double* __restrict__ row_add = nullptr, double* __restrict__ gout = nullptr) {
   // (row_add == nullptr: not centred)
+  // MODE 3: MODE 1 + gout, d kappa / d r2 of every (row, training point) pair, [Jpad][npad] FP64, written once and read once
+  // by cross_bwd_g_kernel: the reverse kernel then neither recomputes r2 nor takes a square root or an exponential.
   constexpr int DD = D > 0 ? D : MAF_MAX_D;
-  constexpr bool ALPHA = MODE >= 1, SEL = MODE == 2;
+  constexpr bool ALPHA = MODE >= 1, SEL = MODE == 2, GST = MODE == 3;
   const int qn = q - p;
   const int d = D > 0 ? D : mp.d;
   const int ns = NS > 0 ? NS : ns_rt;
@@ -485,6 +488,7 @@ cross_fwd_planes_kernel(const double* __restrict__ X, int J, int Jpad, const dou
     for (int jj = 0; jj < jloop; ++jj) {
       long long I[4];
       double pm = 0.0;
+      double gv[GST ? 4 : 1];
       if (!ALPHA || (active && jj < jend)) {
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
@@ -496,9 +500,16 @@ cross_fwd_planes_kernel(const double* __restrict__ X, int J, int Jpad, const dou
             r2 += df * df;
           }
         }
-        const double v = kern_val_fast<KID>(r2, etab) * cs[t];
+        double v;
+        if constexpr (GST) v = kern_val_dr2_fast<KID>(r2, etab, gv[t]) * cs[t];
+        else v = kern_val_fast<KID>(r2, etab) * cs[t];
         if (ALPHA) pm = fma(v, al[t], pm);
         I[t] = __double2ll_rn(ALPHA ? v - co[t] : v);
+      }
+      if constexpr (GST) {
+        double* gd = gout + (size_t)(j0 + jj) * npad + k;
+        __stcs(reinterpret_cast<double2*>(gd), make_double2(gv[0], gv[1]));
+        __stcs(reinterpret_cast<double2*>(gd + 2), make_double2(gv[2], gv[3]));
       }
       int8_t* dst = planes + (size_t)(j0 + jj) * npad + k;
       if constexpr (NS > 0) oz_emit_digits4_t<(NS > 0 ? NS : 1)>(I, dst, plane_stride);

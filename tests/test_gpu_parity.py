@@ -677,6 +677,43 @@ def test_level_switch_is_invisible_to_chunking_and_can_be_switched_off():
     assert per_restart_err(out["a"][1], out["off"][1]) < 1e-9 and per_restart_err(out["a"][3], out["off"][3]) < 1e-9
 
 
+@pytest.mark.parametrize("kernel_id", ["matern52", "matern32", "squared_exponential"])
+def test_stored_kernel_derivatives_route_equals_the_recomputing_kernel(kernel_id):
+    """The forward covariance kernel leaves d kappa / d r2 of every pair behind and the reverse kernel streams it
+    (cross_bwd_g_kernel, default) instead of recomputing square root and exponential per pair (MAF_G_ROUTE=0): same
+    arithmetic for the derivative, so values are identical and gradients agree to rounding; both within the bar of
+    the oracle.  Odd n (masked last column of the two-column loop), shared pending rows, per-restart pending rows, a
+    candidate ON a training point (gradient blocked by the clamp), and the second pass of the reverse level switch."""
+    from maximizingacquisitionfunctions_b200.engine import Engine
+    n, d, q, S, M = 1153, 5, 5, 96, 64
+    gp, X0, y0, X, z = _near_problem(n, d, q, S, M, kernel_id=kernel_id, seed=11)
+    X[3, 1] = X0[17]                                          # r2 = 0 against one training point
+    ts = orc.prepare_train(gp, X0, y0)
+    Xp = X.copy()
+    Xp[:, :2] = X[0, :2]                                      # two shared pending rows
+    out = {}
+    for route in ("1", "0"):
+        os.environ["MAF_G_ROUTE"] = route
+        try:
+            e = Engine(0)
+            e.set_model(kernel_id, np.full(d, math.sqrt(d) / 4), 1.0, 1e-3, 0.0, 1e-6)
+            e.set_train(X0, y0)
+            out[route] = (e.value_and_grad(prm("cb"), X, z), e.value_and_grad(prm("ei", level=float(np.median(y0))), Xp, z, p_pending=2),
+                          e.value_and_grad(prm("sr"), X, z, p_pending=1), e.level_switch_stats())
+            e.close()
+        finally:
+            os.environ.pop("MAF_G_ROUTE", None)
+    for u in range(3):
+        assert np.array_equal(out["1"][u][0], out["0"][u][0])                     # losses never see the reverse kernel
+        # different summation order over the training points (two columns per lane): rounding of cancelling sums only
+        assert relerr(out["1"][u][1], out["0"][u][1]) < 1e-11 and per_restart_err(out["1"][u][1], out["0"][u][1]) < 1e-10
+    lo, go = orc.value_and_grad(ts, orc.Acq("cb"), X, z)
+    assert relerr(out["1"][0][0], lo) < TOL and relerr(out["1"][0][1], go) < TOL and per_restart_err(out["1"][0][1], go) < TOL
+    lo, go = orc.value_and_grad(ts, orc.Acq("ei", level=float(np.median(y0))), Xp[:, 2:], z, X_pend=Xp[0, :2])
+    assert relerr(out["1"][1][0], lo) < TOL and relerr(out["1"][1][1], go) < TOL
+    assert out["1"][2][1].shape == (S, q - 1, d)              # pools with their own pending row: trainable rows only
+
+
 def test_level_switch_inside_the_replayed_adam_loop():
     """The switch decides on the device, so a captured optimizer step replays it: the replayed loop equals the host-driven
     loop bit for bit with the switch on."""
