@@ -36,6 +36,8 @@
  *                        training-set size it applies to (default 1024)
  *   MAF_CENTRE_K10=0|1   digit planes of K10 - a^2/2 with the rank-one term added back by the forward epilogue (default 1: one more
  *                        bit of fixed-point range, half the truncation error) or of K10 itself
+ *   MAF_G_ROUTE=0|1      the forward covariance kernel stores d kappa / d r2 of every (candidate, training point) pair and the
+ *                        reverse one streams it (default 1) instead of recomputing square root and exponential per pair
  *   MAF_PEND_DEDUPE=0|1  pending points shared by all restarts are contracted once per evaluation (default 1)
  *   MAF_VBAR_TIGHT=0|1   row scales of the Vbar digit planes from the true row maxima (one more sweep; default 0)
  *   MAF_OZ_HINTS=<a><t>  L2 policy of the A / T plane loads, 0 normal, 1 evict-first, 2 evict-last (default 22)
