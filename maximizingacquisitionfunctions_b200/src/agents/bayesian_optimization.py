@@ -680,20 +680,25 @@ class bayesian_optimization(search_agent):
         if losses_op is None:
             losses_op = self.appraise_inputs(sess=sess, inputs_new=np.empty([0, 1, input_dim]), inputs_old=inputs_old,
                                              outputs_old=outputs_old, feed_dict=feed_dict, **kwargs)[0]
-        options, losses = [], []
-        start_time = self.timer()
+        losses = []
         total_shards, k = eval_limit // shard_size, 0
+        # every shard is one access to the reseeding host RNG, exactly like the reference's loop; the uniforms land in one
+        # preallocated block (no per-call stacking) and the number of shards per device sweep doubles while the clock allows
+        options = np.empty((total_shards * shard_size, input_dim))
         rank, world_size = mdist.active()
+        g_call = int(shards_per_call)
+        start_time = self.timer()
         while k < total_shards:
-            timed_out = self.timer() - start_time > time_limit
+            timed_out = k > 0 and self.timer() - start_time > time_limit      # at least one sweep: the draws need weights
             if world_size > 1 and np.isfinite(time_limit):
                 timed_out = mdist.any_rank(timed_out)        # every rank leaves the sweep after the same shard
             if timed_out:
                 break
-            g = int(min(shards_per_call, total_shards - k))
-            batch = [self.rng.rand(shard_size, input_dim) for _ in range(g)]
-            options.extend(batch)
-            cand = np.vstack(batch)[:, None, :]
+            g = int(min(g_call, total_shards - k))
+            block = options[k * shard_size:(k + g) * shard_size]
+            for i in range(g):
+                block[i * shard_size:(i + 1) * shard_size] = self.rng.rand(shard_size, input_dim)
+            cand = block[:, None, :]
             if world_size > 1:                               # independent candidates: each rank scores its slice
                 lo, hi = mdist.shard_range(len(cand), rank, world_size)
                 l = losses_op.evaluate(None, inputs_new=cand[lo:hi])[0] if hi > lo else np.empty([0])
@@ -702,8 +707,11 @@ class bayesian_optimization(search_agent):
                 l = losses_op.evaluate(None, inputs_new=cand)[0]
             losses.append(np.atleast_1d(np.squeeze(l)))
             k += g
-        losses = np.hstack(losses)
-        options = np.vstack(options)
+            t_call = (self.timer() - start_time) / max(k, 1) * g          # seconds per sweep at this size
+            if world_size == 1 and g_call < 1024 and 4 * t_call < time_limit - (self.timer() - start_time):
+                g_call *= 2                                               # (ranks keep the fixed size: same shards everywhere)
+        losses = np.hstack(losses) if losses else np.empty([0])
+        options = options[:k * shard_size]
         num_options = len(options)
         logger.info("Evaluated {:d} marginal losses in {:.3e}s".format(num_options, self.timer() - start_time))
 
