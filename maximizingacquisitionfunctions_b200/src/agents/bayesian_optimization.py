@@ -695,6 +695,7 @@ class bayesian_optimization(search_agent):
             if timed_out:
                 break
             g = int(min(g_call, total_shards - k))
+            g = 1 << (g.bit_length() - 1)                    # a power of two: sweeps stay exact multiples of the loss's shard size
             block = options[k * shard_size:(k + g) * shard_size]
             for i in range(g):
                 block[i * shard_size:(i + 1) * shard_size] = self.rng.rand(shard_size, input_dim)

@@ -74,6 +74,30 @@ def test_sample_starts_stream_and_shape():
     assert all(any(np.array_equal(pt, o) for o in opts) for pt in starts.reshape(-1, 2))
 
 
+def test_sample_starts_sweeps_stay_powers_of_two():
+    """Without a time limit the sweep doubles its shards per device call (64, 128, ... 1024); a remainder that is not a
+    power of two is split, so that every sweep stays an exact multiple of the loss's shard size (exact_sharding of the
+    reference's sharded_fn, src/misc/sharded_fn.py:56-83) -- 1536 shards used to end in one sweep of 576 x 256 candidates.
+    The stream is the reference's whatever the grouping: shard k is RandomState(seed + k).rand(256, d)."""
+    agent, X0, Y0 = make()
+    s0 = int(agent.seed)
+    sizes = []
+    handle = agent.appraise_inputs(sess=None, inputs_new=np.empty([0, 1, 2]), inputs_old=X0, outputs_old=Y0)[0]
+    evaluate = handle.evaluate
+
+    def spy(feed_dict, inputs_new=None, **kw):
+        sizes.append(len(inputs_new))
+        return evaluate(feed_dict, inputs_new=inputs_new, **kw)
+
+    handle.evaluate = spy
+    starts = agent.sample_starts(5, 2, None, X0, Y0, losses_op=handle, eval_limit=1536 * 256, shard_size=256)
+    assert sizes == [g * 256 for g in (64, 128, 256, 512, 512, 64)]
+    pts = starts.reshape(-1, 2)
+    assert starts.shape == (5, 2, 2) and pts.min() >= 0 and pts.max() <= 1
+    opts = np.vstack([np.random.RandomState(s0 + k).rand(256, 2) for k in range(1, 1537)])
+    assert all((opts == pt).all(axis=1).any() for pt in pts)
+
+
 @pytest.mark.parametrize("loss,kw", [("negative_ei", {}), ("negative_pi", {"temperature": 0.01}),
                                      ("simple_regret", {}), ("confidence_bound", {"beta": 2.0})])
 def test_suggest_inputs_sgd_improves_and_returns_argmin(loss, kw):
