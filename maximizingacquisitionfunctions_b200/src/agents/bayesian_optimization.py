@@ -686,7 +686,7 @@ class bayesian_optimization(search_agent):
         # preallocated block (no per-call stacking) and the number of shards per device sweep doubles while the clock allows
         options = np.empty((total_shards * shard_size, input_dim))
         rank, world_size = mdist.active()
-        g_call = int(shards_per_call)
+        g_call = max(1, int(shards_per_call))
         start_time = self.timer()
         while k < total_shards:
             timed_out = k > 0 and self.timer() - start_time > time_limit      # at least one sweep: the draws need weights
